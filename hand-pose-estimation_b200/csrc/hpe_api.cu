@@ -1,0 +1,442 @@
+// hpe_api.cu -- the C ABI of include/hpe.h: handles, host<->device staging, launches.
+// No compute happens on the host and nothing here falls back to a CPU path.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "hpe_internal.h"
+
+static thread_local char g_err[512] = "ok";
+
+int hpe_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+namespace {
+
+// grow-only device workspace per host thread (staging for the host-pointer entry points)
+struct Workspace {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int device = -1;
+    cudaError_t reserve(size_t want)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev == device && want <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0; device = dev;
+        e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+};
+thread_local Workspace g_ws;
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+int check_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return hpe_set_error(HPE_ERR_CUDA, "no CUDA device: libhpe_b200 has no CPU fallback (%s)",
+                             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return HPE_OK;
+}
+
+int check_slot(const hpe_obs *o, int first, int count)
+{
+    if (!o) return hpe_set_error(HPE_ERR_ARG, "observation handle is NULL");
+    if (first < 0 || count < 0 || first + count > o->v.capacity)
+        return hpe_set_error(HPE_ERR_ARG, "slots [%d,%d) outside capacity %d", first, first + count, o->v.capacity);
+    return HPE_OK;
+}
+
+// slots must hold a usable observation before any cost / PSO call
+int check_filled(const hpe_obs *o, int first, int count)
+{
+    std::vector<FrameMeta> meta(count);
+    HPE_CUDA(cudaMemcpy(meta.data(), o->v.meta + first, sizeof(FrameMeta) * count, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < count; ++i)
+        if (!meta[i].ok)
+            return hpe_set_error(HPE_ERR_STATE, "observation slot %d is empty or has no hand pixel", first + i);
+    return HPE_OK;
+}
+
+PsoDev make_pso(const hpe_pso_params *p, int num_p)
+{
+    PsoDev d;
+    memcpy(d.lb, p->lb, sizeof d.lb);
+    memcpy(d.ub, p->ub, sizeof d.ub);
+    memcpy(d.std, p->std, sizeof d.std);
+    d.maxiter = p->maxiter;
+    d.num_p = num_p;
+    return d;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *hpe_last_error_string(void) { return g_err; }
+int hpe_version(void) { return 100; }
+
+int hpe_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// handmodel
+// ------------------------------------------------------------------------------------------
+int hpe_model_create(const double geo_cm[20], const double spacing_cm[5], const double cmc_deg[5],
+                     const int tb_spheres[4], const int fg_spheres[4], const double rad_cm[HPE_NSPH],
+                     hpe_model **out)
+{
+    if (!geo_cm || !spacing_cm || !cmc_deg || !tb_spheres || !fg_spheres || !rad_cm || !out)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_model_create: NULL argument");
+    static const int tb_ref[4] = {2, 2, 2, 2}, fg_ref[4] = {4, 2, 2, 2};
+    if (memcmp(tb_spheres, tb_ref, sizeof tb_ref) || memcmp(fg_spheres, fg_ref, sizeof fg_ref))
+        return hpe_set_error(HPE_ERR_ARG, "sphere layout must be thumb {2,2,2,2}, finger {4,2,2,2} "
+                                          "(the reference's fixed 8x3/10x3 matrices, src/handmodel.cpp:272-274)");
+    hpe_model *m = new (std::nothrow) hpe_model;
+    if (!m) return hpe_set_error(HPE_ERR_ARG, "out of host memory");
+    memset(m, 0, sizeof *m);
+    cudaGetDevice(&m->device);
+    DevModel &d = m->dm;
+    const double PI = std::acos(-1.0);
+    memcpy(d.geo, geo_cm, sizeof d.geo);
+    for (int i = 0; i < HPE_NSPH; ++i) { d.rad[i] = rad_cm[i]; d.radf[i] = (float)rad_cm[i]; }
+    // the matrices the digits latch behind setCMCTrans: src/fingermodel.cpp:106-132,
+    // src/thumbmodel.cpp:112-138 (spacing is a float member, so spacing*spacing is a float product)
+    for (int k = 0; k < 5; ++k) {
+        double nCMC = cmc_deg[k] / 180.0 * PI;
+        double L = geo_cm[4 * k];
+        float sp = (float)spacing_cm[k];
+        double a = std::sqrt(L * L + sp * sp - 2 * L * sp * std::cos(nCMC));
+        double beta = std::asin(std::sin(nCMC) * sp / a);
+        double *b = d.base[k];
+        b[0] = std::cos(nCMC); b[1] = -std::sin(nCMC); b[2] = 0; b[3] = L * std::cos(nCMC);
+        b[4] = std::sin(nCMC); b[5] = std::cos(nCMC);  b[6] = 0; b[7] = L * std::sin(nCMC);
+        b[8] = 0; b[9] = 0; b[10] = 1; b[11] = 0;
+        if (k == 0) {
+            d.backt[k][0] = -a * std::cos(beta);
+            d.backt[k][1] = -a * std::sin(beta);
+        } else {
+            d.backt[k][0] = -L * std::sin(nCMC) * std::cos(beta);
+            d.backt[k][1] = -L * std::sin(nCMC) * std::sin(beta);
+        }
+    }
+    double pCMC = cmc_deg[0] / 180.0 * PI + PI;     // src/thumbmodel.cpp:149
+    d.tc = std::cos(pCMC);
+    d.ts = std::sin(pCMC);
+    *out = m;
+    return HPE_OK;
+}
+
+int hpe_model_destroy(hpe_model *m)
+{
+    delete m;
+    return HPE_OK;
+}
+
+int hpe_fk_batch(const hpe_model *m, const double *theta, int64_t n, double *spheres, double *joints)
+{
+    if (!m || (!theta && n > 0) || n < 0) return hpe_set_error(HPE_ERR_ARG, "hpe_fk_batch: bad argument");
+    if (n == 0) return HPE_OK;
+    if (int rc = check_device()) return rc;
+    size_t b_th = align_up(sizeof(double) * n * HPE_NDOF), b_sp = align_up(sizeof(double) * n * HPE_NSPH * 3),
+           b_jt = align_up(sizeof(double) * n * HPE_NJOINT * 3);
+    HPE_CUDA(g_ws.reserve(b_th + b_sp + b_jt));
+    char *base = (char *)g_ws.p;
+    double *d_th = (double *)base, *d_sp = (double *)(base + b_th), *d_jt = (double *)(base + b_th + b_sp);
+    HPE_CUDA(cudaMemcpyAsync(d_th, theta, sizeof(double) * n * HPE_NDOF, cudaMemcpyHostToDevice, 0));
+    HPE_CUDA(hpe_launch_fk(m->dm, d_th, n, spheres ? d_sp : nullptr, joints ? d_jt : nullptr, 0));
+    if (spheres) HPE_CUDA(cudaMemcpyAsync(spheres, d_sp, sizeof(double) * n * HPE_NSPH * 3, cudaMemcpyDeviceToHost, 0));
+    if (joints) HPE_CUDA(cudaMemcpyAsync(joints, d_jt, sizeof(double) * n * HPE_NJOINT * 3, cudaMemcpyDeviceToHost, 0));
+    HPE_CUDA(cudaStreamSynchronize(0));
+    return HPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// observedmodel
+// ------------------------------------------------------------------------------------------
+int hpe_obs_create(int capacity, int num_samples, double focal, hpe_obs **out)
+{
+    if (!out || capacity <= 0) return hpe_set_error(HPE_ERR_ARG, "hpe_obs_create: bad argument");
+    if (num_samples <= 0 || num_samples > HPE_MAXPTS)
+        return hpe_set_error(HPE_ERR_ARG, "num_samples must be in [1,%d]", HPE_MAXPTS);
+    if (int rc = check_device()) return rc;
+    hpe_obs *o = new (std::nothrow) hpe_obs;
+    if (!o) return hpe_set_error(HPE_ERR_ARG, "out of host memory");
+    memset(o, 0, sizeof *o);
+    cudaGetDevice(&o->device);
+    ObsView &v = o->v;
+    v.capacity = capacity;
+    v.n_pts = num_samples;
+    v.focal = focal;
+    v.cx = HPE_W / 2.;     // img_center << imH/2. << imW/2., src/observedmodel.cpp:56
+    v.cy = HPE_H / 2.;
+    size_t npix = (size_t)HPE_W * HPE_H;
+    cudaError_t e = cudaMalloc(&v.depth_mm, sizeof(float) * npix * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&v.dt_px, sizeof(float) * npix * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&v.cloud, sizeof(double) * 3 * num_samples * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&v.meta, sizeof(FrameMeta) * capacity);
+    if (e == cudaSuccess) e = cudaMemset(v.meta, 0, sizeof(FrameMeta) * capacity);
+    if (e != cudaSuccess) {
+        hpe_obs_destroy(o);
+        return hpe_set_error(HPE_ERR_CUDA, "hpe_obs_create(%d frames): %s", capacity, cudaGetErrorString(e));
+    }
+    *out = o;
+    return HPE_OK;
+}
+
+int hpe_obs_destroy(hpe_obs *o)
+{
+    if (!o) return HPE_OK;
+    cudaFree(o->v.depth_mm); cudaFree(o->v.dt_px); cudaFree(o->v.cloud); cudaFree(o->v.meta);
+    delete o;
+    return HPE_OK;
+}
+
+int hpe_obs_num_samples(const hpe_obs *o) { return o ? o->v.n_pts : 0; }
+float *hpe_obs_depth_dev(hpe_obs *o) { return o ? o->v.depth_mm : nullptr; }
+
+static int observe_and_check(hpe_obs *o, int first, int count)
+{
+    HPE_CUDA(hpe_launch_observe(o->v, first, count, nullptr, 0));
+    std::vector<FrameMeta> meta(count);
+    HPE_CUDA(cudaMemcpy(meta.data(), o->v.meta + first, sizeof(FrameMeta) * count, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < count; ++i)
+        if (!meta[i].ok)
+            return hpe_set_error(HPE_ERR_EMPTY_FRAME, "frame in slot %d has no hand pixel", first + i);
+    return HPE_OK;
+}
+
+int hpe_obs_upload(hpe_obs *o, const float *depth_mm, int first, int count)
+{
+    if (int rc = check_slot(o, first, count)) return rc;
+    if (!depth_mm && count > 0) return hpe_set_error(HPE_ERR_ARG, "hpe_obs_upload: NULL frames");
+    if (count == 0) return HPE_OK;
+    size_t npix = (size_t)HPE_W * HPE_H;
+    HPE_CUDA(cudaMemcpyAsync(o->v.depth_mm + npix * first, depth_mm, sizeof(float) * npix * count,
+                             cudaMemcpyHostToDevice, 0));
+    return observe_and_check(o, first, count);
+}
+
+int hpe_obs_upload_dev(hpe_obs *o, const float *depth_mm_dev, int first, int count)
+{
+    if (int rc = check_slot(o, first, count)) return rc;
+    if (count == 0) return HPE_OK;
+    size_t npix = (size_t)HPE_W * HPE_H;
+    if (depth_mm_dev && depth_mm_dev != o->v.depth_mm + npix * first)
+        HPE_CUDA(cudaMemcpyAsync(o->v.depth_mm + npix * first, depth_mm_dev, sizeof(float) * npix * count,
+                                 cudaMemcpyDeviceToDevice, 0));
+    return observe_and_check(o, first, count);
+}
+
+int hpe_obs_set(hpe_obs *o, int slot, const float *depth_mm, const float *dt_px, const double *cloud, double scale)
+{
+    if (int rc = check_slot(o, slot, 1)) return rc;
+    if (!depth_mm || !dt_px || !cloud) return hpe_set_error(HPE_ERR_ARG, "hpe_obs_set: NULL argument");
+    size_t npix = (size_t)HPE_W * HPE_H;
+    const int np = o->v.n_pts;
+    std::vector<double> soa(3 * (size_t)np);
+    for (int k = 0; k < np; ++k)
+        for (int c = 0; c < 3; ++c) soa[(size_t)c * np + k] = cloud[k * 3 + c];
+    int n_hand = 0;
+    for (size_t k = 0; k < npix; ++k) n_hand += depth_mm[k] != 0.0f;
+    FrameMeta meta;
+    meta.scale = scale; meta.dt_max = 0.0; meta.n_hand = n_hand; meta.ok = 1;
+    HPE_CUDA(cudaMemcpy(o->v.depth_mm + npix * slot, depth_mm, sizeof(float) * npix, cudaMemcpyHostToDevice));
+    HPE_CUDA(cudaMemcpy(o->v.dt_px + npix * slot, dt_px, sizeof(float) * npix, cudaMemcpyHostToDevice));
+    HPE_CUDA(cudaMemcpy(o->v.cloud + (size_t)3 * np * slot, soa.data(), sizeof(double) * 3 * np, cudaMemcpyHostToDevice));
+    HPE_CUDA(cudaMemcpy(o->v.meta + slot, &meta, sizeof meta, cudaMemcpyHostToDevice));
+    HPE_CUDA(hpe_launch_dtmax(o->v, slot, 0));
+    HPE_CUDA(cudaStreamSynchronize(0));
+    return HPE_OK;
+}
+
+int hpe_obs_get(const hpe_obs *o, int slot, double *cloud, float *dt_px, double *scale, int *n_hand, float *dt_max)
+{
+    if (int rc = check_slot(o, slot, 1)) return rc;
+    size_t npix = (size_t)HPE_W * HPE_H;
+    const int np = o->v.n_pts;
+    FrameMeta meta;
+    HPE_CUDA(cudaMemcpy(&meta, o->v.meta + slot, sizeof meta, cudaMemcpyDeviceToHost));
+    if (scale) *scale = meta.scale;
+    if (n_hand) *n_hand = meta.n_hand;
+    if (dt_max) *dt_max = (float)meta.dt_max;
+    if (!meta.ok) return hpe_set_error(HPE_ERR_STATE, "observation slot %d is empty or has no hand pixel", slot);
+    if (cloud) {
+        std::vector<double> soa(3 * (size_t)np);
+        HPE_CUDA(cudaMemcpy(soa.data(), o->v.cloud + (size_t)3 * np * slot, sizeof(double) * 3 * np, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < np; ++k)
+            for (int c = 0; c < 3; ++c) cloud[k * 3 + c] = soa[(size_t)c * np + k];
+    }
+    if (dt_px) HPE_CUDA(cudaMemcpy(dt_px, o->v.dt_px + npix * slot, sizeof(float) * npix, cudaMemcpyDeviceToHost));
+    return HPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// costfunc
+// ------------------------------------------------------------------------------------------
+int hpe_cost_batch_dev(const hpe_model *m, const hpe_obs *o, int slot, const double *theta_dev, int64_t n,
+                       int with_collision, double *cost_dev, double *terms_dev, void *stream)
+{
+    if (!m || n < 0) return hpe_set_error(HPE_ERR_ARG, "hpe_cost_batch_dev: bad argument");
+    if (int rc = check_slot(o, slot, 1)) return rc;
+    if (n == 0) return HPE_OK;
+    if (!theta_dev) return hpe_set_error(HPE_ERR_ARG, "hpe_cost_batch_dev: NULL theta");
+    HPE_CUDA(hpe_launch_cost(m->dm, o->v, slot, theta_dev, n, with_collision != 0, cost_dev, terms_dev, nullptr,
+                             nullptr, (cudaStream_t)stream));
+    return HPE_OK;
+}
+
+static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
+                     const int32_t *frozen, int32_t *match_out, double *align, double *depth, double *colli)
+{
+    if (!m || n < 0 || (!theta && n > 0)) return hpe_set_error(HPE_ERR_ARG, "cost: bad argument");
+    if (int rc = check_slot(o, slot, 1)) return rc;
+    if (n == 0) return HPE_OK;
+    if (int rc = check_filled(o, slot, 1)) return rc;
+    const int np = o->v.n_pts;
+    size_t b_th = align_up(sizeof(double) * n * HPE_NDOF), b_tm = align_up(sizeof(double) * n * 3),
+           b_fr = align_up(sizeof(int32_t) * np), b_mo = match_out ? align_up(sizeof(int32_t) * n * np) : 0;
+    HPE_CUDA(g_ws.reserve(b_th + b_tm + b_fr + b_mo));
+    char *base = (char *)g_ws.p;
+    double *d_th = (double *)base, *d_tm = (double *)(base + b_th);
+    int32_t *d_fr = (int32_t *)(base + b_th + b_tm), *d_mo = (int32_t *)(base + b_th + b_tm + b_fr);
+    HPE_CUDA(cudaMemcpyAsync(d_th, theta, sizeof(double) * n * HPE_NDOF, cudaMemcpyHostToDevice, 0));
+    if (frozen) HPE_CUDA(cudaMemcpyAsync(d_fr, frozen, sizeof(int32_t) * np, cudaMemcpyHostToDevice, 0));
+    HPE_CUDA(hpe_launch_cost(m->dm, o->v, slot, d_th, n, colli != nullptr, nullptr, d_tm, frozen ? d_fr : nullptr,
+                             match_out ? d_mo : nullptr, 0));
+    std::vector<double> tm;
+    if (align || depth || colli) {
+        tm.resize((size_t)n * 3);
+        HPE_CUDA(cudaMemcpyAsync(tm.data(), d_tm, sizeof(double) * n * 3, cudaMemcpyDeviceToHost, 0));
+    }
+    if (match_out) HPE_CUDA(cudaMemcpyAsync(match_out, d_mo, sizeof(int32_t) * n * np, cudaMemcpyDeviceToHost, 0));
+    HPE_CUDA(cudaStreamSynchronize(0));
+    for (int64_t i = 0; i < n && !tm.empty(); ++i) {
+        if (align) align[i] = tm[i * 3];
+        if (depth) depth[i] = tm[i * 3 + 1];
+        if (colli) colli[i] = tm[i * 3 + 2];
+    }
+    return HPE_OK;
+}
+
+int hpe_cost_batch(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n, double *align,
+                   double *depth, double *colli)
+{
+    return cost_host(m, o, slot, theta, n, nullptr, nullptr, align, depth, colli);
+}
+
+int hpe_cost_batch_frozen(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
+                          const int32_t *match, double *align, double *depth, double *colli)
+{
+    if (!match) return hpe_set_error(HPE_ERR_ARG, "hpe_cost_batch_frozen: NULL match");
+    return cost_host(m, o, slot, theta, n, match, nullptr, align, depth, colli);
+}
+
+int hpe_correspondences(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n, int32_t *match)
+{
+    if (!match) return hpe_set_error(HPE_ERR_ARG, "hpe_correspondences: NULL match");
+    return cost_host(m, o, slot, theta, n, nullptr, match, nullptr, nullptr, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// PSO
+// ------------------------------------------------------------------------------------------
+static int pso_host(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                    const double *x0, int n_x0, int first, int count, const uint64_t *seeds, double *bestp,
+                    double *best_cost, double *trace, int chain)
+{
+    if (!m || !p || !x0 || !bestp || num_particles < 1 || p->maxiter < 1)
+        return hpe_set_error(HPE_ERR_ARG, "pso: bad argument");
+    if (int rc = check_slot(o, first, count)) return rc;
+    if (count == 0) return HPE_OK;
+    if (int rc = check_filled(o, first, count)) return rc;
+    const int tl = p->maxiter > 1 ? p->maxiter - 1 : 1;
+    size_t b_x0 = align_up(sizeof(double) * n_x0 * HPE_NDOF), b_sd = align_up(sizeof(uint64_t) * count),
+           b_bp = align_up(sizeof(double) * count * HPE_NDOF), b_bc = align_up(sizeof(double) * count),
+           b_tr = align_up(sizeof(double) * count * tl);
+    HPE_CUDA(g_ws.reserve(b_x0 + b_sd + b_bp + b_bc + b_tr));
+    char *base = (char *)g_ws.p;
+    double *d_x0 = (double *)base;
+    uint64_t *d_sd = (uint64_t *)(base + b_x0);
+    double *d_bp = (double *)(base + b_x0 + b_sd), *d_bc = (double *)(base + b_x0 + b_sd + b_bp),
+           *d_tr = (double *)(base + b_x0 + b_sd + b_bp + b_bc);
+    HPE_CUDA(cudaMemcpyAsync(d_x0, x0, sizeof(double) * n_x0 * HPE_NDOF, cudaMemcpyHostToDevice, 0));
+    if (seeds) HPE_CUDA(cudaMemcpyAsync(d_sd, seeds, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, 0));
+    cudaError_t e = hpe_launch_pso(m->dm, o->v, make_pso(p, num_particles), d_x0, first, count, seeds ? d_sd : nullptr,
+                                   d_bp, d_bc, trace ? d_tr : nullptr, chain, 0);
+    if (e != cudaSuccess)
+        return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
+                             "pso launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));
+    HPE_CUDA(cudaMemcpyAsync(bestp, d_bp, sizeof(double) * count * HPE_NDOF, cudaMemcpyDeviceToHost, 0));
+    if (best_cost) HPE_CUDA(cudaMemcpyAsync(best_cost, d_bc, sizeof(double) * count, cudaMemcpyDeviceToHost, 0));
+    if (trace && p->maxiter > 1)
+        HPE_CUDA(cudaMemcpyAsync(trace, d_tr, sizeof(double) * count * (p->maxiter - 1), cudaMemcpyDeviceToHost, 0));
+    HPE_CUDA(cudaStreamSynchronize(0));
+    return HPE_OK;
+}
+
+int hpe_pso_evolve(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                   const double *x0, int first, int count, const uint64_t *seeds, double *bestp, double *best_cost,
+                   double *trace)
+{
+    return pso_host(m, o, p, num_particles, x0, count, first, count, seeds, bestp, best_cost, trace, 0);
+}
+
+int hpe_track_sequence(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                       const double x0[HPE_NDOF], int first, int n_frames, uint64_t seed, double *poses, double *costs)
+{
+    if (n_frames < 0) return hpe_set_error(HPE_ERR_ARG, "hpe_track_sequence: bad frame count");
+    std::vector<uint64_t> seeds((size_t)(n_frames > 0 ? n_frames : 1), seed);
+    return pso_host(m, o, p, num_particles, x0, 1, first, n_frames, seeds.data(), poses, costs, nullptr, 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic frames
+// ------------------------------------------------------------------------------------------
+int hpe_render_dev(const hpe_model *m, const double *theta_dev, int64_t n, double focal, float *depth_mm_dev,
+                   void *stream)
+{
+    if (!m || n < 0 || ((!theta_dev || !depth_mm_dev) && n > 0))
+        return hpe_set_error(HPE_ERR_ARG, "hpe_render_dev: bad argument");
+    HPE_CUDA(hpe_launch_render(m->dm, theta_dev, n, focal, depth_mm_dev, (cudaStream_t)stream));
+    return HPE_OK;
+}
+
+int hpe_render(const hpe_model *m, const double *theta, int64_t n, double focal, float *depth_mm)
+{
+    if (!m || n < 0 || ((!theta || !depth_mm) && n > 0)) return hpe_set_error(HPE_ERR_ARG, "hpe_render: bad argument");
+    if (n == 0) return HPE_OK;
+    if (int rc = check_device()) return rc;
+    size_t npix = (size_t)HPE_W * HPE_H;
+    size_t b_th = align_up(sizeof(double) * n * HPE_NDOF);
+    HPE_CUDA(g_ws.reserve(b_th + sizeof(float) * npix * n));
+    double *d_th = (double *)g_ws.p;
+    float *d_fr = (float *)((char *)g_ws.p + b_th);
+    HPE_CUDA(cudaMemcpyAsync(d_th, theta, sizeof(double) * n * HPE_NDOF, cudaMemcpyHostToDevice, 0));
+    HPE_CUDA(hpe_launch_render(m->dm, d_th, n, focal, d_fr, 0));
+    HPE_CUDA(cudaMemcpyAsync(depth_mm, d_fr, sizeof(float) * npix * n, cudaMemcpyDeviceToHost, 0));
+    HPE_CUDA(cudaStreamSynchronize(0));
+    return HPE_OK;
+}
+
+}  // extern "C"

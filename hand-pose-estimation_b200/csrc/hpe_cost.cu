@@ -1,0 +1,211 @@
+// hpe_cost.cu -- batched handmodel::build_hand_model and costfunc::cal_cost/cal_cost2 kernels,
+// plus the sphere-model ray-caster used to synthesise Subject1-format frames.
+#include "hpe_eval.cuh"
+#include "hpe_internal.h"
+
+namespace {
+
+constexpr int COST_WARPS = 8;
+
+// ---------------------------------------------------------------------------------------
+// handmodel::build_hand_model for n poses (src/handmodel.cpp:259-298): thread = (pose, digit)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160) fk_kernel(DevModel m, const double *__restrict__ theta, int64_t n,
+                                                  double *__restrict__ spheres, double *__restrict__ joints)
+{
+    __shared__ DevModel Ms;
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 8); i += blockDim.x)
+        reinterpret_cast<double *>(&Ms)[i] = reinterpret_cast<const double *>(&m)[i];
+    __syncthreads();
+    int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t pose = item / 5;
+    int d = (int)(item - pose * 5);
+    if (pose >= n) return;
+    const double *th = theta + pose * HPE_NDOF;
+    double J[5][3], S[10][3];
+    fk_digit(Ms, d, th, J);
+    int cnt = digit_spheres(d, J, S);
+    int first = digit_first_sphere(d);
+    if (spheres) {
+        double *out = spheres + (pose * HPE_NSPH + first) * 3;
+        for (int i = 0; i < cnt; ++i) {
+            out[i * 3 + 0] = S[i][0];
+            out[i * 3 + 1] = -S[i][1];   // sphere_centres.cols(1,2) *= -1, src/handmodel.cpp:288
+            out[i * 3 + 2] = -S[i][2];
+        }
+    }
+    if (joints) {
+        // hand_joints rows: 0 = g_pos, 1-16 = index..little joints 1..4, 17-20 = thumb (:291-296)
+        double *out = joints + pose * HPE_NJOINT * 3;
+        if (d == 0) { out[0] = th[3]; out[1] = th[4]; out[2] = th[5]; }
+        int row = d == 0 ? 17 : 1 + 4 * (d - 1);
+        for (int j = 1; j < 5; ++j)
+            for (int k = 0; k < 3; ++k) out[(row + j - 1) * 3 + k] = J[j][k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// cal_cost / cal_cost2 for n poses against one frame.  Poses are split evenly over all
+// warps of the grid; a warp walks its range in groups of HPE_GROUP.
+// ---------------------------------------------------------------------------------------
+struct __align__(16) CostSmem {
+    DevModel M;
+    double rad[HPE_NSPH];
+    double cloud[3 * HPE_MAXPTS];
+    __align__(16) unsigned char ws[COST_WARPS * HPE_GROUP * HPE_WS_BYTES_PER_SLOT];
+};
+
+template <bool WITH_COLLI>
+__global__ void __launch_bounds__(COST_WARPS * 32, 2)
+cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, int64_t n,
+            double *__restrict__ cost, double *__restrict__ terms, const int32_t *__restrict__ frozen,
+            int32_t *__restrict__ match_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const FrameView F = frame_view(o, slot);
+
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 8); i += blockDim.x)
+        reinterpret_cast<double *>(&sm.M)[i] = reinterpret_cast<const double *>(&m)[i];
+    for (int i = threadIdx.x; i < 3 * F.n_pts; i += blockDim.x) sm.cloud[i] = F.cloud[i];
+    __syncthreads();
+    if (threadIdx.x < HPE_NSPH) sm.rad[threadIdx.x] = sm.M.rad[threadIdx.x];
+    __syncthreads();
+
+    LanePoints P;
+    load_lane_points(F, lane, P);
+    const WarpScratch ws = warp_scratch(sm.ws, warp, HPE_GROUP);
+
+    const int64_t total_warps = (int64_t)gridDim.x * COST_WARPS;
+    const int64_t gw = (int64_t)blockIdx.x * COST_WARPS + warp;
+    const int64_t lo = n * gw / total_warps, hi = n * (gw + 1) / total_warps;
+
+    for (int64_t p0 = lo; p0 < hi; p0 += HPE_GROUP) {
+        int cnt = (int)min((int64_t)HPE_GROUP, hi - p0);
+        group_fk(sm.M, [&](int g) { return theta + (p0 + g) * HPE_NDOF; }, cnt, ws, lane);
+        for (int g = 0; g < cnt; ++g) {
+            double depth = depth_lanes(sm.rad, F, ws, g, lane);
+            int idx[HPE_PPL];
+            if (frozen) {
+#pragma unroll
+                for (int q = 0; q < HPE_PPL; ++q) {
+                    int k = lane + 32 * q;
+                    idx[q] = k < F.n_pts ? frozen[k] : 0;
+                }
+            } else {
+                match_sweep(ws.sph4 + g * HPE_NSPH, P, F.n_pts, lane, idx);
+            }
+            if (match_out) {
+#pragma unroll
+                for (int q = 0; q < HPE_PPL; ++q) {
+                    int k = lane + 32 * q;
+                    if (k < F.n_pts) match_out[(p0 + g) * F.n_pts + k] = idx[q];
+                }
+            }
+            double align = align_lanes(sm.rad, ws, g, sm.cloud, F.n_pts, lane, idx);
+            double colli = 0.0;
+            if (WITH_COLLI) colli = warp_sum(collision_lane(sm.rad, ws.sphd + (size_t)g * HPE_NSPH * 3, lane));
+            if (lane == 0) {
+                if (cost) cost[p0 + g] = WITH_COLLI ? align + depth + colli : align + depth;
+                if (terms) {
+                    terms[(p0 + g) * 3 + 0] = align;
+                    terms[(p0 + g) * 3 + 1] = depth;
+                    terms[(p0 + g) * 3 + 2] = colli;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Synthetic frames: ray-cast the 48 spheres at pose theta[f] into frame f.  One CTA per
+// frame; FP64 so that the frame equals the oracle's renderer up to FK rounding.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) render_kernel(DevModel m, const double *__restrict__ theta, double focal,
+                                                      float *__restrict__ depth_mm)
+{
+    __shared__ DevModel Ms;
+    __shared__ double S[HPE_NSPH][4];   // x,y,z (un-negated), cc = |c|^2 - r^2
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 8); i += blockDim.x)
+        reinterpret_cast<double *>(&Ms)[i] = reinterpret_cast<const double *>(&m)[i];
+    __syncthreads();
+    const double *th = theta + (size_t)blockIdx.x * HPE_NDOF;
+    if (threadIdx.x < 5) {
+        double J[5][3], C[10][3];
+        int d = threadIdx.x;
+        fk_digit(Ms, d, th, J);
+        int cnt = digit_spheres(d, J, C);
+        int first = digit_first_sphere(d);
+        for (int i = 0; i < cnt; ++i) {
+            double r = Ms.rad[first + i];
+            S[first + i][0] = C[i][0]; S[first + i][1] = C[i][1]; S[first + i][2] = C[i][2];
+            S[first + i][3] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C[i][0], C[i][0]), __dmul_rn(C[i][1], C[i][1])),
+                                                  __dmul_rn(C[i][2], C[i][2])), -__dmul_rn(r, r));
+        }
+    }
+    __syncthreads();
+    float *out = depth_mm + (size_t)blockIdx.x * HPE_W * HPE_H;
+    for (int pix = threadIdx.x; pix < HPE_W * HPE_H; pix += blockDim.x) {
+        int v = pix / HPE_W, u = pix - v * HPE_W;
+        double dx = __ddiv_rn((double)u - HPE_W / 2., focal), dy = __ddiv_rn((double)v - HPE_H / 2., focal);
+        double a = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), 1.0);
+        double best = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll 4
+        for (int j = 0; j < HPE_NSPH; ++j) {
+            double b = __dadd_rn(__dadd_rn(__dmul_rn(dx, S[j][0]), __dmul_rn(dy, S[j][1])), S[j][2]);
+            double disc = __dadd_rn(__dmul_rn(b, b), -__dmul_rn(a, S[j][3]));
+            if (disc >= 0) {
+                double t = __ddiv_rn(__dadd_rn(b, -sqrt(disc)), a);
+                if (t > 0 && t < best) best = t;
+            }
+        }
+        out[pix] = best < 1e300 ? (float)__dmul_rn(best, 10.0) : 0.0f;
+    }
+}
+
+}  // namespace
+
+cudaError_t hpe_launch_fk(const DevModel &m, const double *theta_dev, int64_t n, double *spheres_dev,
+                          double *joints_dev, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    int64_t items = n * 5;
+    int blocks = (int)((items + 159) / 160);
+    fk_kernel<<<blocks, 160, 0, st>>>(m, theta_dev, n, spheres_dev, joints_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const double *theta_dev,
+                            int64_t n, bool with_colli, double *cost_dev, double *terms_dev,
+                            const int32_t *frozen_match_dev, int32_t *match_out_dev, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(cost_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
+        cudaFuncSetAttribute(cost_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
+    }
+    int64_t groups = (n + HPE_GROUP - 1) / HPE_GROUP;
+    int64_t want = (groups + COST_WARPS - 1) / COST_WARPS;
+    int blocks = (int)(want < 2LL * sms ? want : 2LL * sms);
+    if (with_colli)
+        cost_kernel<true><<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev,
+                                                                              terms_dev, frozen_match_dev, match_out_dev);
+    else
+        cost_kernel<false><<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev,
+                                                                               terms_dev, frozen_match_dev, match_out_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_t n, double focal,
+                              float *depth_dev, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    render_kernel<<<(unsigned)n, 256, 0, st>>>(m, theta_dev, focal, depth_dev);
+    return cudaGetLastError();
+}

@@ -1,0 +1,260 @@
+// hpe_device.cuh -- device-side building blocks shared by the kernels.
+//
+// Precision policy ("reference precision"): the reference computes everything in double
+// except the point->sphere matcher, which runs in float32 inside cv::BFMatcher
+// (src/costfunc.cpp:321-334).  We keep exactly that split: forward kinematics,
+// projection/depth term and the alignment sum in FP64 (a few % of the instructions), the
+// 250x48 distance sweep in FP32 with OpenCV's operation order, so match indices are
+// bit-identical and costs agree with the reference arithmetic to ~1e-13 relative.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define HPE_NDOF 26
+#define HPE_NSPH 48
+#define HPE_NJOINT 21
+#define HPE_W 320
+#define HPE_H 240
+#define HPE_GROUP 6          // poses evaluated together by one warp (6 poses x 5 digits = 30 FK lanes)
+#define HPE_MAXPTS 256       // 8 points per lane
+#define HPE_PPL 8
+
+struct DevModel {
+    double base[5][12];      // pose-independent CMC link (finger T01 / thumb Trf), 3x4 row-major
+    double backt[5][2];      // translation (x,y) of the reverse link T10 (its z is 0)
+    double geo[20];          // segment lengths, cm
+    double rad[HPE_NSPH];
+    float  radf[HPE_NSPH];
+    double tc, ts;           // cos/sin of the thumb's pCMC = CMC + pi (src/thumbmodel.cpp:149)
+};
+
+// One observed frame (observedmodel after next_frame), device pointers.
+struct FrameView {
+    const float  *depth_mm;  // [240][320]
+    const float  *dt_px;     // [240][320]
+    const double *cloud;     // [3][n_pts] SoA: X, -Y, -Z
+    double scale;            // cm per pixel
+    double dt_max;           // disttrans.max()
+    double focal, cx, cy;
+    int    n_pts;
+};
+
+// ---------------------------------------------------------------------------------------
+// Forward kinematics of one digit (src/fingermodel.cpp:70-182,270-317,
+// src/thumbmodel.cpp:76-195,276-318).  All lanes run the same code: the thumb's tilted
+// second link degenerates to the finger's planar link with (cp,sp) = (1,0).
+// ---------------------------------------------------------------------------------------
+struct Aff {   // 3x4 affine map, rotation r (row-major) + translation t
+    double r00, r01, r02, r10, r11, r12, r20, r21, r22, tx, ty, tz;
+};
+
+__device__ __forceinline__ double hpe_deg2rad(double d)
+{
+    // reference: angle/180.0*PI (src/fingermodel.cpp:203-205); one multiply differs from it
+    // by <= 1 ulp of the angle
+    return d * 0.017453292519943295769236907684886;
+}
+
+// cur <- cur * [[c,-s,0,L c],[s,c,0,L s],[0,0,1,0]]
+__device__ __forceinline__ void aff_planar(Aff &a, double c, double s, double L)
+{
+    double n00 = a.r00 * c + a.r01 * s, n01 = a.r01 * c - a.r00 * s;
+    double n10 = a.r10 * c + a.r11 * s, n11 = a.r11 * c - a.r10 * s;
+    double n20 = a.r20 * c + a.r21 * s, n21 = a.r21 * c - a.r20 * s;
+    a.r00 = n00; a.r01 = n01; a.r10 = n10; a.r11 = n11; a.r20 = n20; a.r21 = n21;
+    a.tx += L * n00; a.ty += L * n10; a.tz += L * n20;
+}
+
+// Global pose T00 * Rz(t0+180) * Ry(t1) * Rx(t2)  (src/fingermodel.cpp:157-180, :289)
+__device__ __forceinline__ void aff_global(Aff &g, const double *th)
+{
+    double sz, cz, sy, cy, sx, cx;
+    sincos(hpe_deg2rad(th[0] + 180.0), &sz, &cz);
+    sincos(hpe_deg2rad(th[1]), &sy, &cy);
+    sincos(hpe_deg2rad(th[2]), &sx, &cx);
+    // Rz*Ry = [[cz cy, -sz, cz sy],[sz cy, cz, sz sy],[-sy, 0, cy]]
+    double a00 = cz * cy, a01 = -sz, a02 = cz * sy;
+    double a10 = sz * cy, a11 = cz, a12 = sz * sy;
+    double a20 = -sy, a22 = cy;
+    // (Rz*Ry)*Rx, Rx = [[1,0,0],[0,cx,-sx],[0,sx,cx]]
+    g.r00 = a00; g.r01 = a01 * cx + a02 * sx; g.r02 = a02 * cx - a01 * sx;
+    g.r10 = a10; g.r11 = a11 * cx + a12 * sx; g.r12 = a12 * cx - a11 * sx;
+    g.r20 = a20; g.r21 = a22 * sx;            g.r22 = a22 * cx;
+    g.tx = th[3]; g.ty = th[4]; g.tz = th[5];
+}
+
+// joints J[0..4] of digit d (0 = thumb) for pose th[26]
+__device__ __forceinline__ void fk_digit(const DevModel &M, int d, const double *th, double J[5][3])
+{
+    Aff cur;
+    aff_global(cur, th);
+    // cur <- cur * base[d]   (general 3x4 product; base has r[2][*] = (0,0,1), t.z = 0)
+    {
+        const double *b = M.base[d];
+        double c = b[0], s = b[4];          // base = planar(CMC, L): [[c,-s,0,Lc],[s,c,0,Ls]]
+        double n00 = cur.r00 * c + cur.r01 * s, n01 = cur.r01 * c - cur.r00 * s;
+        double n10 = cur.r10 * c + cur.r11 * s, n11 = cur.r11 * c - cur.r10 * s;
+        double n20 = cur.r20 * c + cur.r21 * s, n21 = cur.r21 * c - cur.r20 * s;
+        cur.tx += cur.r00 * b[3] + cur.r01 * b[7];
+        cur.ty += cur.r10 * b[3] + cur.r11 * b[7];
+        cur.tz += cur.r20 * b[3] + cur.r21 * b[7];
+        cur.r00 = n00; cur.r01 = n01; cur.r10 = n10; cur.r11 = n11; cur.r20 = n20; cur.r21 = n21;
+    }
+    J[1][0] = cur.tx; J[1][1] = cur.ty; J[1][2] = cur.tz;
+    {   // joint 0 = (cur * T10).col(3)
+        double bx = M.backt[d][0], by = M.backt[d][1];
+        J[0][0] = cur.r00 * bx + cur.r01 * by + cur.tx;
+        J[0][1] = cur.r10 * bx + cur.r11 * by + cur.ty;
+        J[0][2] = cur.r20 * bx + cur.r21 * by + cur.tz;
+    }
+    const double *ang = th + 6 + 4 * d;
+    const double *L = M.geo + 4 * d;
+    double s1, c1, s2, c2;
+    sincos(hpe_deg2rad(ang[0]), &s1, &c1);
+    sincos(hpe_deg2rad(ang[1]), &s2, &c2);
+    double cp = d == 0 ? M.tc : 1.0, sp = d == 0 ? M.ts : 0.0;
+    {   // S = twist(a0) * X(a1), X = [[c2,-s2 cp, s2 sp, L c2],[s2, c2 cp, -c2 sp, L s2],[0, sp, cp, 0]]
+        double x00 = c2, x01 = -s2 * cp, x02 = s2 * sp, x03 = L[1] * c2;
+        double x10 = s2, x11 = c2 * cp, x12 = -c2 * sp, x13 = L[1] * s2;
+        double x21 = sp, x22 = cp;
+        // twist = [[c1,0,-s1],[s1,0,c1],[0,-1,0]]
+        double s00 = c1 * x00, s01 = c1 * x01 - s1 * x21, s02 = c1 * x02 - s1 * x22, s03 = c1 * x03;
+        double s10 = s1 * x00, s11 = s1 * x01 + c1 * x21, s12 = s1 * x02 + c1 * x22, s13 = s1 * x03;
+        double s20 = -x10, s21 = -x11, s22 = -x12, s23 = -x13;
+        Aff n;
+        n.r00 = cur.r00 * s00 + cur.r01 * s10 + cur.r02 * s20;
+        n.r01 = cur.r00 * s01 + cur.r01 * s11 + cur.r02 * s21;
+        n.r02 = cur.r00 * s02 + cur.r01 * s12 + cur.r02 * s22;
+        n.tx  = cur.r00 * s03 + cur.r01 * s13 + cur.r02 * s23 + cur.tx;
+        n.r10 = cur.r10 * s00 + cur.r11 * s10 + cur.r12 * s20;
+        n.r11 = cur.r10 * s01 + cur.r11 * s11 + cur.r12 * s21;
+        n.r12 = cur.r10 * s02 + cur.r11 * s12 + cur.r12 * s22;
+        n.ty  = cur.r10 * s03 + cur.r11 * s13 + cur.r12 * s23 + cur.ty;
+        n.r20 = cur.r20 * s00 + cur.r21 * s10 + cur.r22 * s20;
+        n.r21 = cur.r20 * s01 + cur.r21 * s11 + cur.r22 * s21;
+        n.r22 = cur.r20 * s02 + cur.r21 * s12 + cur.r22 * s22;
+        n.tz  = cur.r20 * s03 + cur.r21 * s13 + cur.r22 * s23 + cur.tz;
+        cur = n;
+    }
+    J[2][0] = cur.tx; J[2][1] = cur.ty; J[2][2] = cur.tz;
+    double s3, c3, s4, c4;
+    sincos(hpe_deg2rad(ang[2]), &s3, &c3);
+    sincos(hpe_deg2rad(ang[3]), &s4, &c4);
+    aff_planar(cur, c3, s3, L[2]);
+    J[3][0] = cur.tx; J[3][1] = cur.ty; J[3][2] = cur.tz;
+    // last link: only the translation is needed
+    J[4][0] = cur.tx + L[3] * (cur.r00 * c4 + cur.r01 * s4);
+    J[4][1] = cur.ty + L[3] * (cur.r10 * c4 + cur.r11 * s4);
+    J[4][2] = cur.tz + L[3] * (cur.r20 * c4 + cur.r21 * s4);
+}
+
+// Sphere centres of a digit from its joints (src/fingermodel.cpp:208-267,
+// src/thumbmodel.cpp:227-274), un-negated frame.  Returns the count (8 thumb / 10 finger);
+// first sphere index of digit d is d == 0 ? 0 : 8 + 10*(d-1)  (src/handmodel.cpp:282-286).
+__device__ __forceinline__ int digit_spheres(int d, const double J[5][3], double S[10][3])
+{
+    const double t = 1. / 3.;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (d == 0) {
+            S[0][k] = 0.5 * J[0][k] + 0.5 * J[1][k];
+            S[1][k] = J[1][k];
+        } else {
+            S[0][k] = J[0][k];
+            S[1][k] = (1. - t) * J[0][k] + t * J[1][k];
+            S[2][k] = (1. - t * 2) * J[0][k] + (t * 2) * J[1][k];
+            S[3][k] = J[1][k];
+        }
+    }
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double mid = 0.5 * J[i][k] + 0.5 * J[i + 1][k];
+            if (d == 0) { S[2 * i][k] = mid; S[2 * i + 1][k] = J[i + 1][k]; }
+            else        { S[2 + 2 * i][k] = mid; S[3 + 2 * i][k] = J[i + 1][k]; }
+        }
+    }
+    return d == 0 ? 8 : 10;
+}
+
+__device__ __forceinline__ int digit_first_sphere(int d) { return d == 0 ? 0 : 8 + 10 * (d - 1); }
+
+// ---------------------------------------------------------------------------------------
+// depth term of one sphere (src/costfunc.cpp:251-300), un-negated centre (x,y,z), radius r
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double depth_term(const FrameView &F, double x, double y, double z, double r)
+{
+    // K*c without FMA contraction: row0 = f*x + cx*z, row1 = f*y + cy*z, row2 = z
+    double pu = __ddiv_rn(__dadd_rn(__dmul_rn(F.focal, x), __dmul_rn(F.cx, z)), z);
+    double pv = __ddiv_rn(__dadd_rn(__dmul_rn(F.focal, y), __dmul_rn(F.cy, z)), z);
+    double dx = floor(pu), dy = floor(pv);
+    bool inside = dx >= 0.0 && dx < (double)HPE_W && dy >= 0.0 && dy < (double)HPE_H;
+    double v;
+    if (inside) {
+        int at = (int)dy * HPE_W + (int)dx;
+        double d_jc = __ddiv_rn((double)__ldg(F.depth_mm + at), 10.0);
+        if (d_jc != 0.0) {
+            v = fmax(0.0, d_jc - z);
+        } else {
+            v = __dadd_rn(__dmul_rn((double)__ldg(F.dt_px + at), F.scale), r);
+        }
+    } else {
+        v = __dadd_rn(__dmul_rn(F.dt_max, F.scale), r);
+    }
+    return __dmul_rn(v, v);
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (DESIGN.md "RNG"); counter = (elem_pair, particle,
+// generation, stream), key = 64-bit seed.  Replayed bit-for-bit by the CPU oracle.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2,
+                                           uint32_t c3, uint32_t out[4])
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo)
+{
+    uint64_t k = ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
+    return (double)k * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void uniform2(uint64_t seed, uint32_t elem_pair, uint32_t particle,
+                                         uint32_t gen, uint32_t stream, double u[2])
+{
+    uint32_t w[4];
+    philox4x32(seed, elem_pair, particle, gen, stream, w);
+    u[0] = u53(w[0], w[1]);
+    u[1] = u53(w[2], w[3]);
+}
+
+__device__ __forceinline__ void normal2(uint64_t seed, uint32_t elem_pair, uint32_t particle,
+                                        uint32_t gen, double z[2])
+{
+    double u[2];
+    uniform2(seed, elem_pair, particle, gen, 0u, u);
+    double u1 = u[0] + 1.0 / 9007199254740992.0;
+    double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincos(6.283185307179586476925286766559 * u[1], &s, &c);
+    z[0] = r * c;
+    z[1] = r * s;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

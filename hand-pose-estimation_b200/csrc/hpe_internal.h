@@ -1,0 +1,81 @@
+// hpe_internal.h -- host-side handle layouts and launch wrappers shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hpe.h"
+#include "hpe_device.cuh"
+
+// per-frame scalars produced by the observation kernels (device resident)
+struct FrameMeta {
+    double scale;     // cm per pixel (src/observedmodel.cpp:195-202)
+    double dt_max;    // disttrans.max() (src/costfunc.cpp:298)
+    int    n_hand;    // non-zero pixels
+    int    ok;        // 1 once the slot holds a usable observation
+};
+
+// device view of an hpe_obs, passed to kernels by value
+struct ObsView {
+    float     *depth_mm;  // [capacity][240][320]
+    float     *dt_px;     // [capacity][240][320]
+    double    *cloud;     // [capacity][3][n_pts]
+    FrameMeta *meta;      // [capacity]
+    double focal, cx, cy;
+    int n_pts;
+    int capacity;
+};
+
+__device__ __forceinline__ FrameView frame_view(const ObsView &o, int slot)
+{
+    FrameView f;
+    f.depth_mm = o.depth_mm + (size_t)slot * HPE_W * HPE_H;
+    f.dt_px = o.dt_px + (size_t)slot * HPE_W * HPE_H;
+    f.cloud = o.cloud + (size_t)slot * 3 * o.n_pts;
+    f.scale = o.meta[slot].scale;
+    f.dt_max = o.meta[slot].dt_max;
+    f.focal = o.focal; f.cx = o.cx; f.cy = o.cy;
+    f.n_pts = o.n_pts;
+    return f;
+}
+
+struct hpe_model {
+    DevModel dm;
+    int device;
+};
+
+struct hpe_obs {
+    ObsView v;
+    int device;
+    void *scratch;        // chamfer / compaction workspace
+    size_t scratch_bytes;
+};
+
+struct PsoDev {           // constants of one pso_evolve call, passed by value
+    double lb[HPE_NDOF], ub[HPE_NDOF], std[HPE_NDOF];
+    int maxiter;
+    int num_p;
+};
+
+int hpe_set_error(int code, const char *fmt, ...);
+#define HPE_CUDA(call)                                                                           \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return hpe_set_error(HPE_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                   \
+                                 cudaGetErrorString(e_), __FILE__, __LINE__);                    \
+    } while (0)
+
+// launch wrappers (defined in the kernel .cu files); all asynchronous on `st`
+cudaError_t hpe_launch_fk(const DevModel &m, const double *theta_dev, int64_t n, double *spheres_dev,
+                          double *joints_dev, cudaStream_t st);
+cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const double *theta_dev,
+                            int64_t n, bool with_colli, double *cost_dev, double *terms_dev,
+                            const int32_t *frozen_match_dev, int32_t *match_out_dev, cudaStream_t st);
+cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *scratch, cudaStream_t st);
+cudaError_t hpe_launch_dtmax(const ObsView &o, int slot, cudaStream_t st);
+cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
+                           int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
+                           double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st);
+cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_t n, double focal,
+                              float *depth_dev, cudaStream_t st);
+size_t hpe_observe_scratch_bytes(int count);

@@ -1,0 +1,243 @@
+// hpe_obs.cu -- observedmodel::next_frame on the device (src/observedmodel.cpp:420-430):
+//   cloud_kernel   load_data + depth_to_ptncloud (:272-310, :110-219): raster-order compaction of
+//                  the non-zero pixels, back-projection, FP64 scale estimate, stride subsample
+//   chamfer_kernel invert_depthmap + dist_transform (:313-369): OpenCV's 5x5 chamfer DIST_L2
+// One CTA per frame; frames are independent.
+#include "hpe_internal.h"
+
+namespace {
+
+constexpr int OBS_THREADS = 1024;
+constexpr int NPIX = HPE_W * HPE_H;            // 76,800
+constexpr int PIX_PER_WARP = NPIX / 32;        // 2,400 = 75 * 32
+
+__global__ void __launch_bounds__(OBS_THREADS) cloud_kernel(ObsView o, int first)
+{
+    const int slot = first + blockIdx.x;
+    const float *__restrict__ depth = o.depth_mm + (size_t)slot * NPIX;
+    double *__restrict__ cloud = o.cloud + (size_t)slot * 3 * o.n_pts;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int warp_tot[32];
+    __shared__ int warp_base[32];
+    __shared__ double red_sum[32];
+    __shared__ int red_cnt[32];
+    __shared__ int n_total;
+
+    // pass 1: non-zero pixels per warp-owned contiguous span (raster order is preserved)
+    int cnt = 0;
+    for (int it = 0; it < PIX_PER_WARP / 32; ++it) {
+        int pix = warp * PIX_PER_WARP + it * 32 + lane;
+        unsigned b = __ballot_sync(0xffffffffu, depth[pix] != 0.0f);
+        cnt += __popc(b);
+    }
+    if (lane == 0) warp_tot[warp] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+        int v = warp_tot[lane], s = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += t;
+        }
+        warp_base[lane] = s - v;
+        if (lane == 31) n_total = s;
+    }
+    __syncthreads();
+    const int n = n_total;
+    if (n == 0) {
+        if (threadIdx.x == 0) {
+            o.meta[slot].n_hand = 0; o.meta[slot].ok = 0;
+            o.meta[slot].scale = 0.0; o.meta[slot].dt_max = 0.0;
+        }
+        return;
+    }
+    // :204-217  sample_f = n / num_samples (integer), idx = k * sample_f
+    const int sample_f = n / o.n_pts;
+    const double rad = 2.0;
+    double ssum = 0.0;
+    int scnt = 0;
+    int run = warp_base[warp];
+    for (int it = 0; it < PIX_PER_WARP / 32; ++it) {
+        int pix = warp * PIX_PER_WARP + it * 32 + lane;
+        float mm = depth[pix];
+        bool nz = mm != 0.0f;
+        unsigned b = __ballot_sync(0xffffffffu, nz);
+        int rank = run + __popc(b & ((1u << lane) - 1u));
+        run += __popc(b);
+        if (nz) {
+            int v = pix / HPE_W, u = pix - v * HPE_W;
+            double Z = __ddiv_rn((double)mm, 10.0);                            // :300-303 mm -> cm
+            double X = __ddiv_rn(__dmul_rn((double)u - o.cx, Z), o.focal);     // :139-140
+            double Y = __ddiv_rn(__dmul_rn((double)v - o.cy, Z), o.focal);
+            // scale estimate :171-202, K*(X,Y,Z) with row0 = f*X + cx*Z, no FMA contraction
+            double cu = floor(__ddiv_rn(__dadd_rn(__dmul_rn(o.focal, X), __dmul_rn(o.cx, Z)), Z));
+            double eu = floor(__ddiv_rn(__dadd_rn(__dmul_rn(o.focal, __dadd_rn(X, rad)), __dmul_rn(o.cx, Z)), Z));
+            double dist = fabs(eu - cu);   // the row-1 difference is identically zero
+            if (dist != 0.0) { ssum += __ddiv_rn(rad, dist); scnt++; }
+            if (sample_f > 0) {
+                int k = rank / sample_f;
+                if (k * sample_f == rank && k < o.n_pts) {
+                    cloud[k] = X; cloud[o.n_pts + k] = -Y; cloud[2 * o.n_pts + k] = -Z;
+                }
+            } else if (rank == 0) {
+                for (int k = 0; k < o.n_pts; ++k) {
+                    cloud[k] = X; cloud[o.n_pts + k] = -Y; cloud[2 * o.n_pts + k] = -Z;
+                }
+            }
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
+        scnt += __shfl_xor_sync(0xffffffffu, scnt, d);
+    }
+    if (lane == 0) { red_sum[warp] = ssum; red_cnt[warp] = scnt; }
+    __syncthreads();
+    if (warp == 0) {
+        double s = red_sum[lane];
+        int c = red_cnt[lane];
+        for (int d = 16; d > 0; d >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, d);
+            c += __shfl_xor_sync(0xffffffffu, c, d);
+        }
+        if (lane == 0) {
+            o.meta[slot].scale = s / (double)c;   // arma::mean(cmPerPixel), :202
+            o.meta[slot].n_hand = n;
+            o.meta[slot].ok = 1;
+        }
+    }
+}
+
+// 5x5 chamfer metric in OpenCV's Q16 fixed point: a = 65536 (axis), b = 91750 (diagonal),
+// c = 143976 (knight).  Distance between two pixels with |dx|,|dy| = closed form below; the
+// two-pass raster algorithm of cv::distanceTransform computes exactly min over feature
+// pixels of this metric (checked against cv2 in tests/).
+__device__ __forceinline__ unsigned chamfer_metric(int dx, int dy)
+{
+    int mx = max(dx, dy), mn = min(dx, dy);
+    return 2 * mn <= mx ? (unsigned)(mn * 143976 + (mx - 2 * mn) * 65536)
+                        : (unsigned)((mx - mn) * 143976 + (2 * mn - mx) * 91750);
+}
+
+// Row decomposition: h[i][j] = |j - j'| to the nearest hand pixel of row i; the metric is
+// monotone in |dx| for fixed |dy|, so DT(i,j) = min_i' metric(h[i'][j], |i-i'|), searched
+// outwards from row i and cut off once |i-i'| * a >= best.
+__global__ void __launch_bounds__(OBS_THREADS) chamfer_kernel(ObsView o, int first)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned short *h = reinterpret_cast<unsigned short *>(smem_raw);   // [240][320]
+    __shared__ float red_max[32];
+    const int slot = first + blockIdx.x;
+    if (!o.meta[slot].ok) return;
+    const float *__restrict__ depth = o.depth_mm + (size_t)slot * NPIX;
+    float *__restrict__ dt = o.dt_px + (size_t)slot * NPIX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // 1-D distance along each row: a warp owns rows warp, warp+32, ...; lanes own 10-pixel runs
+    for (int i = warp; i < HPE_H; i += 32) {
+        const float *row = depth + i * HPE_W;
+        // nearest hand pixel at or left of each position: scan over the row in 10 chunks of 32
+        int carry = -100000;   // column of the last hand pixel seen so far
+        for (int c = 0; c < HPE_W / 32; ++c) {
+            int j = c * 32 + lane;
+            bool nz = row[j] != 0.0f;
+            unsigned b = __ballot_sync(0xffffffffu, nz);
+            unsigned le = b & (0xffffffffu >> (31 - lane));        // hand pixels at lanes <= mine
+            int left = le ? c * 32 + (31 - __clz(le)) : carry;
+            int dl = j - left;
+            h[i * HPE_W + j] = (unsigned short)min(dl, 65535);
+            if (b) carry = c * 32 + (31 - __clz(b));
+        }
+        __syncwarp();
+        carry = 100000;
+        for (int c = HPE_W / 32 - 1; c >= 0; --c) {
+            int j = c * 32 + lane;
+            bool nz = row[j] != 0.0f;
+            unsigned b = __ballot_sync(0xffffffffu, nz);
+            unsigned ge = b & (0xffffffffu << lane);
+            int right = ge ? c * 32 + (__ffs(ge) - 1) : carry;
+            int dr = right - j;
+            int cur = h[i * HPE_W + j];
+            h[i * HPE_W + j] = (unsigned short)min(min(dr, cur), 65535);
+            if (b) carry = c * 32 + (__ffs(b) - 1);
+        }
+    }
+    __syncthreads();
+
+    float vmax = 0.f;
+    for (int pix = threadIdx.x; pix < NPIX; pix += OBS_THREADS) {
+        int i = pix / HPE_W, j = pix - i * HPE_W;
+        unsigned best = 0xffffffffu;
+        int h0 = h[pix];
+        if (h0 == 0) {
+            best = 0;
+        } else {
+            if (h0 < 65535) best = chamfer_metric(h0, 0);
+            for (int dy = 1; dy < HPE_H; ++dy) {
+                if ((unsigned)dy * 65536u >= best) break;
+                int up = i - dy, dn = i + dy;
+                if (up < 0 && dn >= HPE_H) break;
+                if (up >= 0) {
+                    int hh = h[up * HPE_W + j];
+                    if (hh < 65535) best = min(best, chamfer_metric(hh, dy));
+                }
+                if (dn < HPE_H) {
+                    int hh = h[dn * HPE_W + j];
+                    if (hh < 65535) best = min(best, chamfer_metric(hh, dy));
+                }
+            }
+        }
+        // OpenCV: d[j] = (float)(t0 * scale), unsigned -> float (RN) then * 2^-16
+        float v = __uint2float_rn(best) * (1.f / 65536.f);
+        dt[pix] = v;
+        vmax = fmaxf(vmax, v);
+    }
+    for (int d = 16; d > 0; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    if (lane == 0) red_max[warp] = vmax;
+    __syncthreads();
+    if (warp == 0) {
+        float v = red_max[lane];
+        for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+        if (lane == 0) o.meta[slot].dt_max = (double)v;
+    }
+}
+
+// disttrans.max() for a slot whose distance transform was injected by the caller
+__global__ void __launch_bounds__(1024) dtmax_kernel(ObsView o, int slot)
+{
+    __shared__ float red_max[32];
+    const float *dt = o.dt_px + (size_t)slot * NPIX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float vmax = dt[0];
+    for (int pix = threadIdx.x; pix < NPIX; pix += blockDim.x) vmax = fmaxf(vmax, dt[pix]);
+    for (int d = 16; d > 0; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    if (lane == 0) red_max[warp] = vmax;
+    __syncthreads();
+    if (warp == 0) {
+        float v = red_max[lane];
+        for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+        if (lane == 0) o.meta[slot].dt_max = (double)v;
+    }
+}
+
+}  // namespace
+
+size_t hpe_observe_scratch_bytes(int) { return 0; }
+
+cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *, cudaStream_t st)
+{
+    if (count <= 0) return cudaSuccess;
+    static bool attr = false;
+    const int smem = HPE_W * HPE_H * (int)sizeof(unsigned short);
+    if (!attr) {
+        cudaFuncSetAttribute(chamfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr = true;
+    }
+    cloud_kernel<<<count, OBS_THREADS, 0, st>>>(o, first);
+    chamfer_kernel<<<count, OBS_THREADS, smem, st>>>(o, first);
+    return cudaGetLastError();
+}
+
+cudaError_t hpe_launch_dtmax(const ObsView &o, int slot, cudaStream_t st)
+{
+    dtmax_kernel<<<1, 1024, 0, st>>>(o, slot);
+    return cudaGetLastError();
+}

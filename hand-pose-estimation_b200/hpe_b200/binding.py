@@ -1,0 +1,305 @@
+"""ctypes binding of include/hpe.h and the Python mirror of the reference's host classes."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import defaults as D
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class HpeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"hpe status {code}: {msg}")
+        self.code = code
+
+
+def library_path():
+    return os.path.join(os.path.dirname(_HERE), "libhpe_b200.so")
+
+
+class PsoParams(C.Structure):
+    """hpe_pso_params: the arguments of PSO::set_pso_params (src/PSO.cpp:38-54)."""
+    _fields_ = [("ub", C.c_double * 26), ("lb", C.c_double * 26), ("std", C.c_double * 26),
+                ("w", C.c_double), ("c1", C.c_double), ("c2", C.c_double), ("maxiter", C.c_int),
+                ("minstep", C.c_double), ("minfunc", C.c_double)]
+
+
+def lib():
+    """Load libhpe_b200.so; fails loudly when it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise HpeError(-1, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "or `make -C hand-pose-estimation_b200` (there is no CPU fallback)")
+        L = C.CDLL(path)
+        L.hpe_last_error_string.restype = C.c_char_p
+        L.hpe_obs_depth_dev.restype = C.c_void_p
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise HpeError(rc, lib().hpe_last_error_string().decode())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t=C.c_double):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def device_count():
+    return int(lib().hpe_device_count())
+
+
+class handmodel:
+    """handmodel(h_geo, h_spacing, tb_spheres, fg_spheres, h_CMC, sphR), src/handmodel.cpp:10-27."""
+
+    def __init__(self, h_geo=None, h_spacing=None, tb_spheres=None, fg_spheres=None, h_CMC=None, sphR=None):
+        self._geo = _f64(D.HGEO_CM if h_geo is None else h_geo)
+        self._spacing = _f64(D.SPACING if h_spacing is None else h_spacing)
+        self._cmc = _f64(D.CMC if h_CMC is None else h_CMC)
+        self._tb = np.ascontiguousarray(D.TB_N if tb_spheres is None else tb_spheres, dtype=np.int32)
+        self._fg = np.ascontiguousarray(D.FG_N if fg_spheres is None else fg_spheres, dtype=np.int32)
+        self._rad = _f64(D.RAD_CM if sphR is None else sphR)
+        for name, arr, n in (("h_geo", self._geo, 20), ("h_spacing", self._spacing, 5), ("h_CMC", self._cmc, 5),
+                             ("tb_spheres", self._tb, 4), ("fg_spheres", self._fg, 4), ("sphR", self._rad, 48)):
+            if arr.shape != (n,):
+                raise HpeError(1, f"{name} must have shape ({n},)")
+        self._h = C.c_void_p()
+        _check(lib().hpe_model_create(_p(self._geo), _p(self._spacing), _p(self._cmc), _p(self._tb, C.c_int),
+                                      _p(self._fg, C.c_int), _p(self._rad), C.byref(self._h)))
+        self.hand_joints = np.zeros((21, 3))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.hpe_model_destroy(self._h)
+            self._h = None
+
+    def get_radii(self):
+        return self._rad
+
+    def get_spheres_radii(self):
+        return self._rad.copy()
+
+    def get_hand_geo(self):
+        return self._geo.copy()
+
+    def get_hand_CMC(self):
+        return self._cmc.copy()
+
+    def get_spacing(self):
+        return self._spacing.copy()
+
+    def build_hand_model(self, h_theta):
+        """theta (26,) -> sphere centres (48,3), negated y,z; records hand_joints (21,3)
+        (src/handmodel.cpp:259-298)."""
+        S, J = self.build_hand_models(np.asarray(h_theta, dtype=np.float64).reshape(1, 26))
+        self.hand_joints = J[0]
+        return S[0]
+
+    def build_hand_models(self, thetas):
+        th = _f64(thetas).reshape(-1, 26)
+        n = th.shape[0]
+        S = np.empty((n, 48, 3))
+        J = np.empty((n, 21, 3))
+        _check(lib().hpe_fk_batch(self._h, _p(th), C.c_int64(n), _p(S), _p(J)))
+        return S, J
+
+
+class observedmodel:
+    """A batch of observed frames on the device.  `capacity` frames; slot 0 is "the current
+    frame" for the single-frame methods that mirror the reference."""
+
+    def __init__(self, capacity=1, num_samples=D.NUM_SAMPLES, focal=D.FOCAL):
+        self._h = C.c_void_p()
+        self.capacity = int(capacity)
+        self.num_samples = int(num_samples)
+        self.focal = float(focal)
+        self.path = ""
+        _check(lib().hpe_obs_create(self.capacity, self.num_samples, C.c_double(self.focal), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.hpe_obs_destroy(self._h)
+            self._h = None
+
+    # -- reference-style single-frame API (src/observedmodel.cpp:42-64, 420-430) --
+    def init_observation(self, dpath, dfname, mm_to_cm=True, imW=240, imH=320, foclen=D.FOCAL, downsample=True):
+        if (imW, imH) != (240, 320) or not mm_to_cm or not downsample or float(foclen) != self.focal:
+            raise HpeError(1, "only the reference configuration is supported: imW=240, imH=320, "
+                              "mm_to_cm=true, downsample=true, focal as given to the constructor")
+        self.path = dpath
+        return self.next_frame(dfname)
+
+    def next_frame(self, next_name):
+        """load_data (raw float32[240*320] file) + get_observed, slot 0."""
+        full = os.path.join(self.path, next_name) if self.path else next_name
+        data = np.fromfile(full, dtype="<f4")
+        if data.size != D.W * D.H:
+            raise HpeError(1, f"{full}: expected {D.W * D.H} float32 values, found {data.size}")
+        self.upload(data.reshape(1, D.H, D.W))
+        return self
+
+    # -- batched API --
+    def upload(self, depth_mm, first=0):
+        fr = np.ascontiguousarray(depth_mm, dtype=np.float32).reshape(-1, D.H, D.W)
+        _check(lib().hpe_obs_upload(self._h, _p(fr, C.c_float), int(first), int(fr.shape[0])))
+
+    def upload_dev(self, dev_ptr, first, count):
+        _check(lib().hpe_obs_upload_dev(self._h, C.c_void_p(dev_ptr), int(first), int(count)))
+
+    def set(self, slot, depth_mm, dt_px, cloud, scale):
+        depth_mm = np.ascontiguousarray(depth_mm, dtype=np.float32).reshape(D.H, D.W)
+        dt_px = np.ascontiguousarray(dt_px, dtype=np.float32).reshape(D.H, D.W)
+        cloud = _f64(cloud).reshape(self.num_samples, 3)
+        _check(lib().hpe_obs_set(self._h, int(slot), _p(depth_mm, C.c_float), _p(dt_px, C.c_float), _p(cloud),
+                                 C.c_double(scale)))
+
+    def get(self, slot=0):
+        cloud = np.empty((self.num_samples, 3))
+        dt = np.empty((D.H, D.W), dtype=np.float32)
+        scale, n_hand, dt_max = C.c_double(), C.c_int(), C.c_float()
+        _check(lib().hpe_obs_get(self._h, int(slot), _p(cloud), _p(dt, C.c_float), C.byref(scale), C.byref(n_hand),
+                                 C.byref(dt_max)))
+        return {"cloud": cloud, "dt": dt, "scale": scale.value, "n_hand": n_hand.value, "dt_max": dt_max.value}
+
+    def depth_dev_ptr(self):
+        return lib().hpe_obs_depth_dev(self._h)
+
+    def get_ptncloud(self, slot=0):
+        return self.get(slot)["cloud"]
+
+    def get_disttran(self, slot=0):
+        return self.get(slot)["dt"].astype(np.float64)
+
+    def get_img_scale(self, slot=0):
+        return self.get(slot)["scale"]
+
+    def get_imgW(self):
+        return 240
+
+    def get_imgH(self):
+        return 320
+
+    def get_focal_len(self):
+        return self.focal
+
+
+class costfunc:
+    """costfunc(handmodel*, observedmodel*): non-owning references (src/costfunc.cpp:16-29)."""
+
+    def __init__(self, handM, observed):
+        self.hand = handM
+        self.observation = observed
+
+    def cal_cost(self, theta, slot=0):
+        a, d, _ = self.cal_cost_batch(np.asarray(theta, dtype=np.float64).reshape(1, 26), slot)
+        return float(a[0] + d[0])
+
+    def cal_cost2(self, theta, matchId=None, compute_corr=True, debug=False, slot=0):
+        th = _f64(theta).reshape(1, 26)
+        if compute_corr:
+            if matchId is not None:
+                matchId[:] = self.compute_correspondences(th, slot)[0]
+            a, d, c = self.cal_cost_batch(th, slot, with_collision=True)
+        else:
+            a, d, c = self.cal_cost_frozen_batch(th, matchId, slot)
+        if debug:
+            print(a[0]); print(d[0]); print(c[0], "\n")
+        return float(a[0] + d[0] + c[0])
+
+    def cal_cost_batch(self, thetas, slot=0, with_collision=False):
+        th = _f64(thetas).reshape(-1, 26)
+        n = th.shape[0]
+        a, d = np.empty(n), np.empty(n)
+        c = np.empty(n) if with_collision else None
+        _check(lib().hpe_cost_batch(self.hand._h, self.observation._h, int(slot), _p(th), C.c_int64(n), _p(a), _p(d),
+                                    _p(c)))
+        return a, d, (c if with_collision else np.zeros(n))
+
+    def cal_cost_frozen_batch(self, thetas, matchId, slot=0):
+        th = _f64(thetas).reshape(-1, 26)
+        n = th.shape[0]
+        m = np.ascontiguousarray(matchId, dtype=np.int32)
+        a, d, c = np.empty(n), np.empty(n), np.empty(n)
+        _check(lib().hpe_cost_batch_frozen(self.hand._h, self.observation._h, int(slot), _p(th), C.c_int64(n),
+                                           _p(m, C.c_int32), _p(a), _p(d), _p(c)))
+        return a, d, c
+
+    def compute_correspondences(self, thetas, slot=0):
+        th = _f64(thetas).reshape(-1, 26)
+        n = th.shape[0]
+        m = np.empty((n, self.observation.num_samples), dtype=np.int32)
+        _check(lib().hpe_correspondences(self.hand._h, self.observation._h, int(slot), _p(th), C.c_int64(n),
+                                         _p(m, C.c_int32)))
+        return m
+
+    def cal_cost_dev(self, theta_dev_ptr, n, cost_dev_ptr, terms_dev_ptr=None, slot=0, with_collision=False,
+                     stream=None):
+        """device pointers in, device pointers out, asynchronous on `stream`."""
+        _check(lib().hpe_cost_batch_dev(self.hand._h, self.observation._h, int(slot), C.c_void_p(theta_dev_ptr),
+                                        C.c_int64(n), int(with_collision), C.c_void_p(cost_dev_ptr),
+                                        C.c_void_p(terms_dev_ptr or 0), C.c_void_p(stream or 0)))
+
+
+class PSO:
+    """PSO: set_pso_params + pso_evolve (src/PSO.cpp:38-54, 717-886)."""
+
+    def __init__(self):
+        self.params = PsoParams()
+        self.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, 100, 1e-6, 1e-6)
+
+    def set_pso_params(self, upperbound, lowerbound, std, omega, phip, phig, maxiter, minstep, minfunc):
+        p = self.params
+        p.ub[:] = list(_f64(upperbound))
+        p.lb[:] = list(_f64(lowerbound))
+        p.std[:] = list(_f64(std))
+        p.w, p.c1, p.c2 = float(omega), float(phip), float(phig)
+        p.maxiter = int(maxiter)
+        p.minstep, p.minfunc = float(minstep), float(minfunc)
+
+    def pso_evolve(self, optfunc, x0, num_particles, seed=1000, slot=0):
+        """one swarm on frame `slot`; returns bestp (26,) like the reference's out-argument."""
+        bestp, _, _ = self.pso_evolve_batch(optfunc, np.asarray(x0, dtype=np.float64).reshape(1, 26), num_particles,
+                                            seeds=[seed], first=slot)
+        return bestp[0]
+
+    def pso_evolve_batch(self, optfunc, x0, num_particles, seeds=None, first=0, want_trace=True):
+        x0 = _f64(x0).reshape(-1, 26)
+        count = x0.shape[0]
+        bestp = np.empty((count, 26))
+        best = np.empty(count)
+        tl = max(self.params.maxiter - 1, 1)
+        trace = np.empty((count, tl)) if want_trace else None
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        _check(lib().hpe_pso_evolve(optfunc.hand._h, optfunc.observation._h, C.byref(self.params), int(num_particles),
+                                    _p(x0), int(first), int(count), _p(sd, C.c_uint64), _p(bestp), _p(best),
+                                    _p(trace)))
+        if trace is not None:
+            trace = trace[:, :self.params.maxiter - 1]
+        return bestp, best, trace
+
+    def track_sequence(self, optfunc, x0, num_particles, n_frames, seed=1000, first=0):
+        x0 = _f64(x0).reshape(26)
+        poses = np.empty((n_frames, 26))
+        costs = np.empty(n_frames)
+        _check(lib().hpe_track_sequence(optfunc.hand._h, optfunc.observation._h, C.byref(self.params),
+                                        int(num_particles), _p(x0), int(first), int(n_frames), C.c_uint64(seed),
+                                        _p(poses), _p(costs)))
+        return poses, costs
+
+
+def render_frames(hand, thetas, focal=D.FOCAL):
+    """Synthetic Subject1-format frames (float32 mm, 0 = background) of the sphere model."""
+    th = _f64(thetas).reshape(-1, 26)
+    out = np.empty((th.shape[0], D.H, D.W), dtype=np.float32)
+    _check(lib().hpe_render(hand._h, _p(th), C.c_int64(th.shape[0]), C.c_double(focal), _p(out, C.c_float)))
+    return out

@@ -1,0 +1,151 @@
+/*
+ * hpe.h -- C ABI of libhpe_b200.so, the B200 (sm_100a) implementation of the
+ * particle-swarm hot path of hjurong/hand-pose-estimation.
+ *
+ * The reference has no FFI layer: its boundary is the C++ class API
+ * (handmodel / observedmodel / costfunc / PSO).  Each entry point below names
+ * the reference interface it replaces (file:line relative to the reference
+ * root).  hpe_classes.hpp wraps these in C++ classes with the reference's
+ * names; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function
+ * returns an hpe_status (0 = ok); the caller owns every buffer; opaque handles
+ * own device memory on the CUDA device that was current when they were
+ * created; a handle is not thread-safe, distinct handles are independent.
+ * There is no CPU fallback: without a CUDA device every compute call returns
+ * HPE_ERR_CUDA.
+ *
+ * Units follow the reference after its mm->cm conversion: lengths in cm,
+ * angles in degrees, depth frames in mm (the on-disk format), distance
+ * transform in pixels.
+ */
+#ifndef HPE_B200_ABI_H
+#define HPE_B200_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPE_NDOF 26
+#define HPE_NSPH 48
+#define HPE_NJOINT 21
+#define HPE_IMG_W 320
+#define HPE_IMG_H 240
+
+typedef enum {
+    HPE_OK = 0,
+    HPE_ERR_ARG = 1,          /* bad pointer / size / unsupported sphere layout */
+    HPE_ERR_CUDA = 2,         /* CUDA runtime error or no device */
+    HPE_ERR_EMPTY_FRAME = 3,  /* a frame without hand pixels (reference: Armadillo bounds error) */
+    HPE_ERR_STATE = 4         /* handle used before it was filled */
+} hpe_status;
+
+typedef struct hpe_model hpe_model; /* handmodel + 4 fingermodel + thumbmodel geometry */
+typedef struct hpe_obs hpe_obs;     /* a batch of observedmodel states (frames) on the device */
+
+/* PSO::set_pso_params (src/PSO.cpp:38-54).  w,c1,c2,minstep,minfunc are accepted
+ * for signature fidelity and ignored, exactly as pso_evolve ignores them
+ * (src/PSO.cpp:769-774 hard-codes W1, C1, C2, nK=3). */
+typedef struct {
+    double ub[HPE_NDOF];
+    double lb[HPE_NDOF];
+    double std[HPE_NDOF];
+    double w, c1, c2;
+    int    maxiter;          /* counts the initial evaluation (src/PSO.cpp:766,778) */
+    double minstep, minfunc;
+} hpe_pso_params;
+
+const char *hpe_last_error_string(void);
+int hpe_version(void);
+/* number of CUDA devices visible; 0 when there is none */
+int hpe_device_count(void);
+
+/* ---- handmodel (src/handmodel.h:9-32) --------------------------------- */
+/* handmodel::handmodel(h_geo, h_spacing, tb_spheres, fg_spheres, h_CMC, sphR),
+ * src/handmodel.cpp:10-27.  spacing is narrowed to float as fingermodel.h:43 does.
+ * Only the reference's sphere layout {2,2,2,2}/{4,2,2,2} is accepted (its
+ * fixed-size matrices allow no other, src/handmodel.cpp:272-274). */
+int hpe_model_create(const double geo_cm[20], const double spacing_cm[5], const double cmc_deg[5],
+                     const int tb_spheres[4], const int fg_spheres[4], const double rad_cm[HPE_NSPH],
+                     hpe_model **out);
+int hpe_model_destroy(hpe_model *m);
+
+/* handmodel::build_hand_model + hand_joints (src/handmodel.cpp:259-298) for n poses.
+ * theta: host n*26.  spheres: host n*48*3 in the negated-y,z frame (may be NULL).
+ * joints: host n*21*3, not negated (may be NULL). */
+int hpe_fk_batch(const hpe_model *m, const double *theta, int64_t n, double *spheres, double *joints);
+
+/* ---- observedmodel (src/observedmodel.h:34-68) ------------------------ */
+/* Capacity for `capacity` frames; num_samples = 250 in the reference
+ * (src/observedmodel.cpp:210); focal = 241.42 (src/testmodel.cpp:60). */
+int hpe_obs_create(int capacity, int num_samples, double focal, hpe_obs **out);
+int hpe_obs_destroy(hpe_obs *o);
+/* observedmodel::next_frame for `count` frames (src/observedmodel.cpp:420-430 =
+ * load_data :272-310 + depth_to_ptncloud :110-219 + dist_transform :340-369), all on
+ * the device.  depth_mm: HOST float32 [count][240][320] in the file layout
+ * (value at y*320+x, mm, 0 = background).  Frames are stored in slots first..first+count-1. */
+int hpe_obs_upload(hpe_obs *o, const float *depth_mm, int first, int count);
+/* same with the frames already in device memory */
+int hpe_obs_upload_dev(hpe_obs *o, const float *depth_mm_dev, int first, int count);
+/* inject an externally preprocessed observation into one slot (host pointers):
+ * depth_mm [240*320], dt_px [240*320], cloud [n_pts*3] = (X,-Y,-Z), scale. */
+int hpe_obs_set(hpe_obs *o, int slot, const float *depth_mm, const float *dt_px, const double *cloud,
+                double scale);
+/* getters: get_ptncloud / get_disttran / get_img_scale (src/observedmodel.cpp:375-417).
+ * Any output may be NULL.  cloud: n_pts*3, dt_px: 240*320. */
+int hpe_obs_get(const hpe_obs *o, int slot, double *cloud, float *dt_px, double *scale, int *n_hand,
+                float *dt_max);
+int hpe_obs_num_samples(const hpe_obs *o);
+/* device pointer to the stored depth frames [capacity][240][320] (for on-device generators) */
+float *hpe_obs_depth_dev(hpe_obs *o);
+
+/* ---- costfunc (src/costfunc.h:25-41) ---------------------------------- */
+/* costfunc::cal_cost / cal_cost2 for n poses against frame `slot`
+ * (src/costfunc.cpp:89-127, 31-86): align = align_models (:346-377) after
+ * compute_correspondences (:306-343), depth = depth_penalty (:227-304),
+ * colli = self_collision_penalty (:130-197, only computed when colli != NULL).
+ * cal_cost = align + depth; cal_cost2 = align + depth + colli.  HOST pointers; any
+ * output may be NULL. */
+int hpe_cost_batch(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
+                   double *align, double *depth, double *colli);
+/* same on DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be NULL).
+ * cost receives align+depth(+colli when with_collision); terms (n*3, may be NULL). */
+int hpe_cost_batch_dev(const hpe_model *m, const hpe_obs *o, int slot, const double *theta_dev,
+                       int64_t n, int with_collision, double *cost_dev, double *terms_dev,
+                       void *stream);
+/* cal_cost2(theta, matchId, compute_corr=false): frozen correspondences (src/costfunc.cpp:53-58).
+ * match: host n_pts int32 shared by all n poses. */
+int hpe_cost_batch_frozen(const hpe_model *m, const hpe_obs *o, int slot, const double *theta,
+                          int64_t n, const int32_t *match, double *align, double *depth, double *colli);
+/* compute_correspondences for n poses: match host n*n_pts int32 */
+int hpe_correspondences(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
+                        int32_t *match);
+
+/* ---- PSO (src/PSO.h:56-68) -------------------------------------------- */
+/* PSO::pso_evolve (src/PSO.cpp:717-886) for `count` independent swarms, swarm b fitted to
+ * frame slot first+b with initial pose x0[b].  seeds: count values or NULL (every swarm
+ * uses 1000, the constant at src/PSO.cpp:722).  Outputs (host): bestp count*26,
+ * best_cost count (gbest_cost), trace count*(maxiter-1) = bcost_evo (may be NULL). */
+int hpe_pso_evolve(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                   const double *x0, int first, int count, const uint64_t *seeds, double *bestp,
+                   double *best_cost, double *trace);
+/* the tracking loop of test_full without refine_init_pose (src/testmodel.cpp:117-138):
+ * frame k starts from the best pose of frame k-1.  poses: n_frames*26, costs: n_frames. */
+int hpe_track_sequence(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p,
+                       int num_particles, const double x0[HPE_NDOF], int first, int n_frames,
+                       uint64_t seed, double *poses, double *costs);
+
+/* ---- synthetic frames (also the overlay of src/costfunc.cpp:439-473) ---- */
+/* ray-cast the sphere model at n poses into depth frames (mm, 0 = background).
+ * theta_dev: device n*26; depth_mm_dev: device n*240*320. */
+int hpe_render_dev(const hpe_model *m, const double *theta_dev, int64_t n, double focal,
+                   float *depth_mm_dev, void *stream);
+/* host convenience: theta host n*26 -> depth_mm host n*240*320 */
+int hpe_render(const hpe_model *m, const double *theta, int64_t n, double focal, float *depth_mm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
