@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the PSO hot path on B200.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): 65,536 random
+poses scored by costfunc::cal_cost (FK + 48-sphere matching + alignment + depth term) against
+one synthetic 320x240 Subject1-format frame; a "step" is one pass over the 65,536 poses.
+
+  value   evaluations/s, poses resident in HBM, CUDA events around K kernel launches
+  e2e     evaluations/s through the host-pointer C ABI (hpe_cost_batch): pinned host poses
+          copied in and the three cost terms copied out inside every step
+  roofline  FP32 (non-tensor) pipe: algorithmic flop of SURVEY 8(d) / kernel time against the
+          FFMA peak measured on this device by hpe_measure_fp32_peak
+  cpu_baseline  the CPU oracle (double, OpenMP over poses) on a bounded sample, rank 0, N=1
+
+`--impl reference` times the reference's own CPU path: the reference cannot be compiled here
+(Armadillo/OpenCV/GLUT absent), so it is the oracle port on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "hand-pose-estimation_b200"))
+
+METRIC = "pso_cost_evals_per_sec"
+UNIT = "evals/s"
+N_POSES = 65536
+ROTATE = 16                      # pose sets cycled through: 16 x 13.6 MB = 218 MB > 126 MB L2
+
+
+def flops_per_eval(n_pts):
+    # align 8*48*N + 4*N, depth 576, FK 2480
+    return 8 * 48 * n_pts + 4 * n_pts + 576 + 2480
+
+
+def synth_truth(D, rng):
+    return np.clip(D.X0 + rng.normal(size=26) * D.STD * 0.5, D.LB, D.UB)
+
+
+def pose_sets(D, truth, n_sets, seed):
+    rng = np.random.default_rng(seed)
+    return truth + rng.normal(size=(n_sets, N_POSES, 26)) * D.STD     # unclipped, like generate_particles
+
+
+class ClockSampler:
+    """nvidia-smi sampling (every 100 ms) of SM clock and throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def cpu_baseline(n_pts, seconds=12.0, reference_arm=False, steps=0, warmup=0):
+    """the oracle port timed on the host cores (OPENBLAS_NUM_THREADS=1 mirrors README.md:53)"""
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    from hpe_b200 import defaults as D
+    om = orc.make_model()
+    truth = synth_truth(D, np.random.default_rng(20140528))
+    depth = orc.render_depth(om, truth)
+    obs = orc.Observation(depth, num_samples=n_pts)
+    th = pose_sets(D, truth, 1, 2)[0]
+    cores = orc.num_threads()
+    if reference_arm:
+        for _ in range(warmup):
+            orc.cost_batch(om, obs, th, collision=False)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            orc.cost_batch(om, obs, th, collision=False)
+        dt = time.perf_counter() - t0
+        return {"value": steps * N_POSES / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{steps} steps x {N_POSES} poses (the full workload), oracle port, OpenMP"}, dt
+    t0 = time.perf_counter()
+    orc.cost_batch(om, obs, th[:4096], collision=False)
+    rate = 4096 / (time.perf_counter() - t0)
+    n = int(min(max(rate * seconds, 4096), 8 * N_POSES))
+    reps, rem = divmod(n, N_POSES)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        orc.cost_batch(om, obs, th, collision=False)
+    if rem:
+        orc.cost_batch(om, obs, th[:rem], collision=False)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} of the workload's poses (same frame, {n_pts} points), oracle port, OpenMP, {dt:.1f} s"}, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    base, dt = cpu_baseline(args.npts, reference_arm=True, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (f32 matcher)",
+            "data": "synthetic", "config": workload_config(args), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference needs Armadillo+OpenCV+GLUT and cannot be built here: oracle port on host cores"}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "configs[1] CostFunc batch check: 65,536 random poses x 1 synthetic 320x240 frame "
+                        "(cal_cost = FK + 48-sphere match + align + depth)",
+            "poses_per_step": N_POSES, "n_pts": args.npts, "spheres": 48, "dof": 26,
+            "l2": f"{ROTATE} pose sets ({ROTATE * N_POSES * 26 * 8 / 1e6:.0f} MB) cycled, larger than the 126 MB L2",
+            "parallelism": f"poses x{args.gpus} (independent, no collective)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--npts", type=int, default=256)
+    ap.add_argument("--no-extras", action="store_true", help="skip the 250-point and frames/s side measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import hpe_b200
+    from hpe_b200 import defaults as D
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- inputs: one synthetic frame per rank (rendered + preprocessed on the device) ----
+    hand = hpe_b200.handmodel()
+    truth = synth_truth(D, np.random.default_rng(20140528 + rank))
+    frame = hpe_b200.render_frames(hand, truth[None])
+    obs = hpe_b200.observedmodel(capacity=1, num_samples=args.npts)
+    obs.upload(frame)
+    cf = hpe_b200.costfunc(hand, obs)
+    sets_host = pose_sets(D, truth, ROTATE, 2 + rank)
+    theta_dev = torch.from_numpy(sets_host).cuda()                    # [ROTATE][N_POSES][26] f64 in HBM
+    cost_dev = torch.empty(N_POSES, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    set_bytes = N_POSES * 26 * 8
+
+    def step_dev(i):
+        cf.cal_cost_dev(theta_dev.data_ptr() + (i % ROTATE) * set_bytes, N_POSES, cost_dev.data_ptr(), stream=stream)
+
+    peak_tf, mhz = hpe_b200.binding.measure_fp32_peak()
+
+    # ---- device-resident throughput ----
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_dev(i)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = world * N_POSES / (ms_step * 1e-3)
+
+    # ---- end to end through the host-pointer ABI (pinned host buffers, copies inside) ----
+    th_pin = torch.from_numpy(sets_host).pin_memory()
+    out_pin = torch.empty(3, N_POSES, dtype=torch.float64).pin_memory()
+    lib = hpe_b200.lib()
+    import ctypes as C
+
+    def step_e2e(i):
+        rc = lib.hpe_cost_batch(hand._h, obs._h, 0, C.c_void_p(th_pin.data_ptr() + (i % ROTATE) * set_bytes),
+                                C.c_int64(N_POSES), C.c_void_p(out_pin[0].data_ptr()),
+                                C.c_void_p(out_pin[1].data_ptr()), None)
+        if rc != 0:
+            raise RuntimeError(lib.hpe_last_error_string().decode())
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * N_POSES * args.steps / e2e_s
+    # the e2e result must equal the device-resident one for the same pose set
+    step_dev(args.steps - 1)
+    torch.cuda.synchronize()
+    dev_cost = cost_dev.cpu().numpy()
+    host_cost = (out_pin[0] + out_pin[1]).numpy()
+    assert np.array_equal(dev_cost, host_cost), "e2e and device-resident results differ"
+
+    extras = {}
+    if not args.no_extras:
+        # same kernel on the reference's 250 points (the parity configuration)
+        obs250 = hpe_b200.observedmodel(capacity=1, num_samples=250)
+        obs250.upload(frame)
+        cf250 = hpe_b200.costfunc(hand, obs250)
+        for i in range(3):
+            cf250.cal_cost_dev(theta_dev.data_ptr(), N_POSES, cost_dev.data_ptr(), stream=stream)
+        barrier()
+        e0.record()
+        for i in range(10):
+            cf250.cal_cost_dev(theta_dev.data_ptr() + (i % ROTATE) * set_bytes, N_POSES, cost_dev.data_ptr(),
+                               stream=stream)
+        e1.record()
+        barrier()
+        extras["evals_per_sec_250pts"] = world * N_POSES * 10 / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+        # tracked frames/s: independent 64 x 30 swarms, one per frame (configs[4] shape, bounded batch)
+        n_fr = 148 * 8
+        rng = np.random.default_rng(5 + rank)
+        truths = np.stack([synth_truth(D, rng) for _ in range(n_fr)])
+        frames_dev = torch.empty(n_fr, D.H, D.W, dtype=torch.float32, device="cuda")
+        th_dev = torch.from_numpy(truths).cuda()
+        hpe_b200.binding.render_dev(hand, th_dev.data_ptr(), n_fr, frames_dev.data_ptr())
+        obsb = hpe_b200.observedmodel(capacity=n_fr, num_samples=250)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        obsb.upload_dev(frames_dev.data_ptr(), 0, n_fr)
+        torch.cuda.synchronize()
+        extras["observe_frames_per_sec"] = world * n_fr / max_over_ranks(time.perf_counter() - t0)
+        pso = hpe_b200.PSO()
+        pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, 30, 1e-8, 1e-8)
+        x0 = truths + rng.normal(size=truths.shape) * D.STD * 0.3
+        cfb = hpe_b200.costfunc(hand, obsb)
+        pso.pso_evolve_batch(cfb, x0[:64], 64, want_trace=False)
+        barrier()
+        t0 = time.perf_counter()
+        bestp, best, _ = pso.pso_evolve_batch(cfb, x0, 64, want_trace=False)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        extras["pso_frames_per_sec"] = world * n_fr / dt
+        extras["pso_evals_per_sec"] = world * n_fr * 64 * 30 / dt
+        extras["pso_batch"] = f"{n_fr} frames x 64 particles x 30 generations per GPU, host x0 in, best pose out"
+        extras["pso_median_final_cost"] = float(np.median(best))
+
+    if rank == 0:
+        flop = flops_per_eval(args.npts)
+        achieved = flop * N_POSES / (ms_step * 1e-3) * 1e-12
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "cost_kernel_dram_bytes.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 matcher + f64 FK/depth/align (the reference's own split)",
+                "data": "synthetic", "config": workload_config(args),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POSES * 26 * 8,
+                        "d2h_bytes_per_step": N_POSES * 2 * 8},
+                "gpu_launches": args.steps,
+                "clocks": clocks,
+                "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": achieved / peak_tf, "traffic": traffic,
+                             "peak_source": "hpe_measure_fp32_peak: register-only FFMA kernel on this device "
+                                            "(MEASURED_PEAKS.json has no FP32 non-tensor figure)",
+                             "flop_per_eval": flop, "kernel": "cost_kernel<false>", "kernel_ms": ms_step},
+                "extras": extras}
+        if world == 1:
+            line["cpu_baseline"], _ = cpu_baseline(args.npts)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -324,18 +324,12 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
     if (frozen) HPE_CUDA(cudaMemcpyAsync(d_fr, frozen, sizeof(int32_t) * np, cudaMemcpyHostToDevice, 0));
     HPE_CUDA(hpe_launch_cost(m->dm, o->v, slot, d_th, n, colli != nullptr, nullptr, d_tm, frozen ? d_fr : nullptr,
                              match_out ? d_mo : nullptr, 0));
-    std::vector<double> tm;
-    if (align || depth || colli) {
-        tm.resize((size_t)n * 3);
-        HPE_CUDA(cudaMemcpyAsync(tm.data(), d_tm, sizeof(double) * n * 3, cudaMemcpyDeviceToHost, 0));
-    }
+    // the kernel writes the terms as three arrays: copy each straight into the caller's buffer
+    if (align) HPE_CUDA(cudaMemcpyAsync(align, d_tm, sizeof(double) * n, cudaMemcpyDeviceToHost, 0));
+    if (depth) HPE_CUDA(cudaMemcpyAsync(depth, d_tm + n, sizeof(double) * n, cudaMemcpyDeviceToHost, 0));
+    if (colli) HPE_CUDA(cudaMemcpyAsync(colli, d_tm + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, 0));
     if (match_out) HPE_CUDA(cudaMemcpyAsync(match_out, d_mo, sizeof(int32_t) * n * np, cudaMemcpyDeviceToHost, 0));
     HPE_CUDA(cudaStreamSynchronize(0));
-    for (int64_t i = 0; i < n && !tm.empty(); ++i) {
-        if (align) align[i] = tm[i * 3];
-        if (depth) depth[i] = tm[i * 3 + 1];
-        if (colli) colli[i] = tm[i * 3 + 2];
-    }
     return HPE_OK;
 }
 

@@ -109,9 +109,9 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
             if (lane == 0) {
                 if (cost) cost[p0 + g] = WITH_COLLI ? align + depth + colli : align + depth;
                 if (terms) {
-                    terms[(p0 + g) * 3 + 0] = align;
-                    terms[(p0 + g) * 3 + 1] = depth;
-                    terms[(p0 + g) * 3 + 2] = colli;
+                    terms[p0 + g] = align;           // SoA: align[n] | depth[n] | colli[n]
+                    terms[n + p0 + g] = depth;
+                    terms[2 * n + p0 + g] = colli;
                 }
             }
         }

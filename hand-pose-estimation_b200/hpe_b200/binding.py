@@ -297,6 +297,19 @@ class PSO:
         return poses, costs
 
 
+def measure_fp32_peak():
+    """(TFLOP/s, implied SM MHz) of a register-only FFMA kernel on the current device."""
+    tf, mhz = C.c_double(), C.c_double()
+    _check(lib().hpe_measure_fp32_peak(C.byref(tf), C.byref(mhz)))
+    return tf.value, mhz.value
+
+
+def render_dev(hand, theta_dev_ptr, n, depth_dev_ptr, focal=D.FOCAL, stream=None):
+    """device poses (n*26 f64) -> device frames (n*240*320 f32), asynchronous"""
+    _check(lib().hpe_render_dev(hand._h, C.c_void_p(theta_dev_ptr), C.c_int64(n), C.c_double(focal),
+                                C.c_void_p(depth_dev_ptr), C.c_void_p(stream or 0)))
+
+
 def render_frames(hand, thetas, focal=D.FOCAL):
     """Synthetic Subject1-format frames (float32 mm, 0 = background) of the sphere model."""
     th = _f64(thetas).reshape(-1, 26)

@@ -111,7 +111,8 @@ float *hpe_obs_depth_dev(hpe_obs *o);
 int hpe_cost_batch(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
                    double *align, double *depth, double *colli);
 /* same on DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be NULL).
- * cost receives align+depth(+colli when with_collision); terms (n*3, may be NULL). */
+ * cost receives align+depth(+colli when with_collision); terms (may be NULL) receives three
+ * arrays of n: align | depth | colli. */
 int hpe_cost_batch_dev(const hpe_model *m, const hpe_obs *o, int slot, const double *theta_dev,
                        int64_t n, int with_collision, double *cost_dev, double *terms_dev,
                        void *stream);
@@ -144,6 +145,12 @@ int hpe_render_dev(const hpe_model *m, const double *theta_dev, int64_t n, doubl
                    float *depth_mm_dev, void *stream);
 /* host convenience: theta host n*26 -> depth_mm host n*240*320 */
 int hpe_render(const hpe_model *m, const double *theta, int64_t n, double focal, float *depth_mm);
+
+/* ---- measurement ---- */
+/* FP32 (non-tensor) FFMA peak of the current device in TFLOP/s, measured with a
+ * register-only FFMA kernel; the denominator of the cost kernel's roofline (the
+ * driver-written MEASURED_PEAKS.json carries only HBM and bf16-tensor figures). */
+int hpe_measure_fp32_peak(double *tflops, double *sm_mhz_est);
 
 #ifdef __cplusplus
 }

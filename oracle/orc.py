@@ -1,4 +1,6 @@
-"""ctypes wrapper over oracle/libhpe_oracle.so (the CPU oracle: test infrastructure only)."""
+"""ctypes wrapper over oracle/libhpe_oracle.so -- the CPU oracle: test infrastructure only.
+Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs;
+never by the product package."""
 import ctypes as C
 import os
 import subprocess
@@ -153,14 +155,18 @@ def cal_cost2(model, obs, theta, match=None):
     return tot, terms, match
 
 
-def cost_batch(model, obs, theta, diagnostics=False):
+def cost_batch(model, obs, theta, diagnostics=False, collision=True):
     theta = f64(theta).reshape(-1, 26)
     n = theta.shape[0]
-    a, d, c = np.empty(n), np.empty(n), np.empty(n)
+    a, d = np.empty(n), np.empty(n)
+    c = np.empty(n) if collision else None
     fm = np.empty(n) if diagnostics else None
     mg = np.empty(n) if diagnostics else None
-    lib().orc_cost_batch(C.byref(model), C.byref(obs.o), _p(theta), C.c_int64(n), _p(a), _p(d), _p(c),
+    lib().orc_cost_batch(C.byref(model), C.byref(obs.o), _p(theta), C.c_int64(n), _p(a), _p(d),
+                         _p(c) if collision else None,
                          _p(fm) if diagnostics else None, _p(mg) if diagnostics else None)
+    if c is None:
+        c = np.zeros(n)
     return (a, d, c, fm, mg) if diagnostics else (a, d, c)
 
 
