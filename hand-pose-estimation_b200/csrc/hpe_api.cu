@@ -92,6 +92,13 @@ extern "C" {
 const char *hpe_last_error_string(void) { return g_err; }
 int hpe_version(void) { return 100; }
 
+int hpe_set_matcher(int mode)
+{
+    if (mode != 0 && mode != 1) return hpe_set_error(HPE_ERR_ARG, "matcher mode must be 0 or 1");
+    g_hpe_matcher = mode;
+    return HPE_OK;
+}
+
 int hpe_device_count(void)
 {
     int n = 0;

@@ -6,6 +6,11 @@
 namespace {
 
 constexpr int COST_WARPS = 8;
+}  // namespace
+
+int g_hpe_matcher = 0;   // 0 = certified two-sweep matcher, 1 = direct form on all 48 spheres (cross-check)
+
+namespace {
 
 // ---------------------------------------------------------------------------------------
 // handmodel::build_hand_model for n poses (src/handmodel.cpp:259-298): thread = (pose, digit)
@@ -49,32 +54,26 @@ __global__ void __launch_bounds__(160) fk_kernel(DevModel m, const double *__res
 // warps of the grid; a warp walks its range in groups of HPE_GROUP.
 // ---------------------------------------------------------------------------------------
 struct __align__(16) CostSmem {
-    DevModel M;
-    double rad[HPE_NSPH];
-    double cloud[3 * HPE_MAXPTS];
-    __align__(16) unsigned char ws[COST_WARPS * HPE_GROUP * HPE_WS_BYTES_PER_SLOT];
+    FrameSmem fs;
+    __align__(16) unsigned char ws[COST_WARPS * HPE_WS_BYTES(HPE_GROUP)];
 };
 
 template <bool WITH_COLLI>
 __global__ void __launch_bounds__(COST_WARPS * 32, 2)
 cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, int64_t n,
             double *__restrict__ cost, double *__restrict__ terms, const int32_t *__restrict__ frozen,
-            int32_t *__restrict__ match_out)
+            int32_t *__restrict__ match_out, int matcher)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const FrameView F = frame_view(o, slot);
-
-    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 8); i += blockDim.x)
-        reinterpret_cast<double *>(&sm.M)[i] = reinterpret_cast<const double *>(&m)[i];
-    for (int i = threadIdx.x; i < 3 * F.n_pts; i += blockDim.x) sm.cloud[i] = F.cloud[i];
-    __syncthreads();
-    if (threadIdx.x < HPE_NSPH) sm.rad[threadIdx.x] = sm.M.rad[threadIdx.x];
+    stage_model(sm.fs, m);
+    stage_frame(sm.fs, F);
     __syncthreads();
 
     LanePoints P;
-    load_lane_points(F, lane, P);
+    load_lane_points(sm.fs.cloudf, F.n_pts, lane, P);
     const WarpScratch ws = warp_scratch(sm.ws, warp, HPE_GROUP);
 
     const int64_t total_warps = (int64_t)gridDim.x * COST_WARPS;
@@ -83,9 +82,9 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
 
     for (int64_t p0 = lo; p0 < hi; p0 += HPE_GROUP) {
         int cnt = (int)min((int64_t)HPE_GROUP, hi - p0);
-        group_fk(sm.M, [&](int g) { return theta + (p0 + g) * HPE_NDOF; }, cnt, ws, lane);
+        group_fk(sm.fs.M, [&](int g) { return theta + (p0 + g) * HPE_NDOF; }, cnt, ws, lane);
         for (int g = 0; g < cnt; ++g) {
-            double depth = depth_lanes(sm.rad, F, ws, g, lane);
+            double depth = depth_and_stage(sm.fs.rad, F, ws, P, g, lane);
             int idx[HPE_PPL];
             if (frozen) {
 #pragma unroll
@@ -93,8 +92,10 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
                     int k = lane + 32 * q;
                     idx[q] = k < F.n_pts ? frozen[k] : 0;
                 }
+            } else if (matcher == 1) {
+                match_sweep_direct(ws, sm.fs.cloudf, F.n_pts, lane, idx);
             } else {
-                match_sweep(ws.sph4 + g * HPE_NSPH, P, F.n_pts, lane, idx);
+                match_sweep(ws, P, sm.fs.cloudf, F.n_pts, lane, idx);
             }
             if (match_out) {
 #pragma unroll
@@ -103,9 +104,9 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
                     if (k < F.n_pts) match_out[(p0 + g) * F.n_pts + k] = idx[q];
                 }
             }
-            double align = align_lanes(sm.rad, ws, g, sm.cloud, F.n_pts, lane, idx);
+            double align = align_lanes(sm.fs.rad, ws, g, sm.fs.cloud, F.n_pts, lane, idx);
             double colli = 0.0;
-            if (WITH_COLLI) colli = warp_sum(collision_lane(sm.rad, ws.sphd + (size_t)g * HPE_NSPH * 3, lane));
+            if (WITH_COLLI) colli = warp_sum(collision_lane(sm.fs.rad, ws.sphd + (size_t)g * HPE_NSPH * 3, lane));
             if (lane == 0) {
                 if (cost) cost[p0 + g] = WITH_COLLI ? align + depth + colli : align + depth;
                 if (terms) {
@@ -115,7 +116,6 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
                 }
             }
         }
-        __syncwarp();
     }
 }
 
@@ -194,11 +194,11 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
     int64_t want = (groups + COST_WARPS - 1) / COST_WARPS;
     int blocks = (int)(want < 2LL * sms ? want : 2LL * sms);
     if (with_colli)
-        cost_kernel<true><<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev,
-                                                                              terms_dev, frozen_match_dev, match_out_dev);
+        cost_kernel<true><<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev, terms_dev,
+                                                                              frozen_match_dev, match_out_dev, g_hpe_matcher);
     else
-        cost_kernel<false><<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev,
-                                                                               terms_dev, frozen_match_dev, match_out_dev);
+        cost_kernel<false><<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev, terms_dev,
+                                                                               frozen_match_dev, match_out_dev, g_hpe_matcher);
     return cudaGetLastError();
 }
 

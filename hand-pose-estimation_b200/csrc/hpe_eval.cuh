@@ -2,59 +2,126 @@
 // (src/costfunc.cpp:31-127) for a group of up to HPE_GROUP poses against one frame.
 //
 // Work split inside a warp:
-//   phase 1  lanes = (pose, digit): forward kinematics in FP64 -> sphere centres in shared
-//            memory (float4 for the matcher, double for the FP64 terms)
-//   phase 2  per pose, lanes = spheres: projection + depth-map / distance-transform gathers
-//   phase 3  per pose, lanes = points (8 per lane, registers): 48-sphere float32 sweep with
-//            OpenCV's operation order, then the FP64 alignment sum
+//   phase 1  lanes = (pose, digit): forward kinematics in FP64 -> FP64 sphere centres in shared memory
+//   phase 2  per pose, lanes = spheres: projection + depth-map / distance-transform gathers; the same
+//            lanes stage the pose's float32 centres for the matcher
+//   phase 3  per pose, lanes = points (8 per lane, registers): nearest-centre search in FP32, then the
+//            FP64 alignment sum
 //   phase 4  (cal_cost2 only) lanes = sphere pairs: self-collision
 // The model (DevModel) and the radii are read from shared memory: lanes index them with
 // different digits/spheres, which would serialise on the constant bank.
+//
+// The nearest-centre search (compute_correspondences, src/costfunc.cpp:306-343) must return the
+// index cv::BFMatcher returns: first minimum over j of sqrtf(d_j), d_j = ((t0^2 + t1^2) + t2^2) in
+// float32, t = p - c_j.  Doing that directly costs 8 FP32-pipe + 5 ALU-pipe instructions per
+// (point, sphere) pair.  match_sweep() gets the same index with ~5.5:
+//   sweep A  s_j = |c'_j|^2 - 2 p'.c'_j (3 FFMA, coordinates recentred on the cloud centroid) for
+//            all 48 spheres, reduced to the minimum per block of 4 spheres, keeping the best
+//            block, its value M1 and the runner-up block value M2;
+//   certify  s_j + |p'|^2 equals the exact squared distance D_j up to E_j <= u(104|p'|^2 + 13|s_j|),
+//            u = 2^-24 (forward error of the 3 FFMAs plus the rounding of p', -2c', |c'|^2), and the
+//            reference's d_j, sqrtf(d_j) order two spheres like D_j once D differs by > 24u D.
+//            Hence if M2 - M1 > tau = u(260|p'|^2 + 52|M1|) no sphere outside the best block can be
+//            the reference's answer;
+//   sweep B  the reference's exact arithmetic on the 4 spheres of the best block (first minimum,
+//            runner-up tracked to detect sqrtf ties);
+//   fallback if the certificate fails or sqrtf ties inside the block, the point is redone with the
+//            exact restatement over all 48 spheres (match_point_exact).
 #pragma once
 #include "hpe_device.cuh"
 
-// per-warp shared-memory scratch for a group of poses (sized by the launch: slots * 1920 B)
+#define HPE_BLK 4                        // spheres per sweep-A block
+#define HPE_NBLK (HPE_NSPH / HPE_BLK)    // 12 blocks
+
+// per-warp shared-memory scratch
 struct WarpScratch {
-    float4 *sph4;   // [slot][48]    (x,-y,-z,0): the float32 centres cv::BFMatcher sees
-    double *sphd;   // [slot][48][3] un-negated FP64 centres
+    double *sphd;   // [slot][48][3] un-negated FP64 centres of the group's poses
+    float4 *cf;     // [48] (x,-y,-z,0): the float32 centres cv::BFMatcher sees, pose being matched
+    float4 *ex;     // [48] (-2c'x, -2c'y, -2c'z, |c'|^2), c' = cf - q, pose being matched
 };
-#define HPE_WS_BYTES_PER_SLOT (HPE_NSPH * 16 + HPE_NSPH * 24)
+#define HPE_WS_BYTES(slots) ((slots) * HPE_NSPH * 24 + 2 * HPE_NSPH * 16)
 
 __device__ __forceinline__ WarpScratch warp_scratch(unsigned char *base, int warp, int slots)
 {
-    // layout: all float4 blocks first (16-byte aligned), then the doubles
     WarpScratch w;
-    unsigned char *p = base + (size_t)warp * slots * HPE_WS_BYTES_PER_SLOT;
-    w.sph4 = reinterpret_cast<float4 *>(p);
-    w.sphd = reinterpret_cast<double *>(p + (size_t)slots * HPE_NSPH * 16);
+    unsigned char *p = base + (size_t)warp * HPE_WS_BYTES(slots);
+    w.cf = reinterpret_cast<float4 *>(p);
+    w.ex = w.cf + HPE_NSPH;
+    w.sphd = reinterpret_cast<double *>(p + 2 * HPE_NSPH * 16);
     return w;
 }
 
-// the lane's 8 observed points, float32 (conv_to<fmat>, src/costfunc.cpp:322)
-struct LanePoints {
-    float x[HPE_PPL], y[HPE_PPL], z[HPE_PPL];
+// model + frame data every CTA stages once
+struct __align__(16) FrameSmem {
+    DevModel M;
+    double rad[HPE_NSPH];
+    double cloud[3 * HPE_MAXPTS];    // FP64 cloud, SoA with stride n_pts (X | -Y | -Z)
+    float cloudf[3 * HPE_MAXPTS];    // its float32 conversion, SoA with stride HPE_MAXPTS
 };
 
-__device__ __forceinline__ void load_lane_points(const FrameView &F, int lane, LanePoints &P)
+// all threads of the CTA; caller syncs afterwards
+__device__ __forceinline__ void stage_model(FrameSmem &fs, const DevModel &m)
 {
-#pragma unroll
-    for (int m = 0; m < HPE_PPL; ++m) {
-        int k = lane + 32 * m;
-        bool ok = k < F.n_pts;
-        P.x[m] = ok ? (float)F.cloud[k] : 0.f;
-        P.y[m] = ok ? (float)F.cloud[F.n_pts + k] : 0.f;
-        P.z[m] = ok ? (float)F.cloud[2 * F.n_pts + k] : 0.f;
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 8); i += blockDim.x)
+        reinterpret_cast<double *>(&fs.M)[i] = reinterpret_cast<const double *>(&m)[i];
+    if (threadIdx.x < HPE_NSPH) fs.rad[threadIdx.x] = m.rad[threadIdx.x];
+}
+
+__device__ __forceinline__ void stage_frame(FrameSmem &fs, const FrameView &F)
+{
+    for (int i = threadIdx.x; i < 3 * HPE_MAXPTS; i += blockDim.x) {
+        int c = i / HPE_MAXPTS, k = i - c * HPE_MAXPTS;
+        double v = k < F.n_pts ? F.cloud[c * F.n_pts + k] : 0.0;
+        if (k < F.n_pts) fs.cloud[c * F.n_pts + k] = v;
+        fs.cloudf[i] = (float)v;
     }
 }
 
-// Exact restatement of the matcher for ONE point (slow path, used when the fast sweep
-// cannot prove its winner): first minimum of sqrtf(d) over the 48 spheres.
-static __device__ __noinline__ int match_point_exact(const float4 *sph, float px, float py, float pz)
+// the lane's 8 observed points: float32 coordinates recentred on q (the cloud centroid) and
+// the certificate scale 260 u |p'|^2
+struct LanePoints {
+    float x[HPE_PPL], y[HPE_PPL], z[HPE_PPL], tau0[HPE_PPL];
+    float qx, qy, qz;
+};
+
+// cloudf_s: shared-memory float32 copy of the cloud (conv_to<fmat>, src/costfunc.cpp:322), SoA
+// with stride HPE_MAXPTS.  Must be called by all 32 lanes.
+__device__ __forceinline__ void load_lane_points(const float *cloudf_s, int n_pts, int lane, LanePoints &P)
+{
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+    for (int m = 0; m < HPE_PPL; ++m) {
+        int k = lane + 32 * m;
+        bool ok = k < n_pts;
+        P.x[m] = ok ? cloudf_s[k] : 0.f;
+        P.y[m] = ok ? cloudf_s[HPE_MAXPTS + k] : 0.f;
+        P.z[m] = ok ? cloudf_s[2 * HPE_MAXPTS + k] : 0.f;
+        sx += P.x[m]; sy += P.y[m]; sz += P.z[m];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    P.qx = sx / (float)n_pts; P.qy = sy / (float)n_pts; P.qz = sz / (float)n_pts;
+#pragma unroll
+    for (int m = 0; m < HPE_PPL; ++m) {
+        P.x[m] = __fsub_rn(P.x[m], P.qx);
+        P.y[m] = __fsub_rn(P.y[m], P.qy);
+        P.z[m] = __fsub_rn(P.z[m], P.qz);
+        float pp = P.x[m] * P.x[m] + P.y[m] * P.y[m] + P.z[m] * P.z[m];
+        P.tau0[m] = 1.56e-5f * pp;      // 260 * 2^-24 = 1.5497e-5, rounded up
+    }
+}
+
+// Exact restatement of the matcher for ONE point: first minimum of sqrtf(d) over the 48 spheres.
+static __device__ __noinline__ int match_point_exact(const float4 *cf, float px, float py, float pz)
 {
     float best = __int_as_float(0x7f800000);
     int bi = 0;
     for (int j = 0; j < HPE_NSPH; ++j) {
-        float4 c = sph[j];
+        float4 c = cf[j];
         float t0 = __fsub_rn(px, c.x), t1 = __fsub_rn(py, c.y), t2 = __fsub_rn(pz, c.z);
         float d = __fmul_rn(t0, t0);
         d = __fadd_rn(d, __fmul_rn(t1, t1));
@@ -65,26 +132,33 @@ static __device__ __noinline__ int match_point_exact(const float4 *sph, float px
     return bi;
 }
 
-// phase 3a: nearest-centre index for the lane's 8 points (compute_correspondences,
-// src/costfunc.cpp:306-343).  Fast sweep compares squared distances and tracks the
-// runner-up; sqrtf can only merge values that are within a few ulp, so whenever
-// sqrtf(best) == sqrtf(second) the point is re-done with the exact restatement.
-__device__ __forceinline__ void match_sweep(const float4 *sph, const LanePoints &P, int n_pts, int lane,
-                                            int idx[HPE_PPL])
+__device__ __forceinline__ float fmin3(float a, float b, float c)
 {
-    float b1[HPE_PPL], b2[HPE_PPL];
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// Direct form over all 48 spheres (the reference's arithmetic on every pair): kept as the
+// cross-check of match_sweep (hpe_set_matcher(1)).
+__device__ __forceinline__ void match_sweep_direct(const WarpScratch &ws, const float *cloudf_s, int n_pts,
+                                                   int lane, int idx[HPE_PPL])
+{
+    float px[HPE_PPL], py[HPE_PPL], pz[HPE_PPL], b1[HPE_PPL], b2[HPE_PPL];
 #pragma unroll
     for (int m = 0; m < HPE_PPL; ++m) {
+        int k = min(lane + 32 * m, HPE_MAXPTS - 1);
+        px[m] = cloudf_s[k]; py[m] = cloudf_s[HPE_MAXPTS + k]; pz[m] = cloudf_s[2 * HPE_MAXPTS + k];
         b1[m] = __int_as_float(0x7f800000);
         b2[m] = __int_as_float(0x7f800000);
         idx[m] = 0;
     }
 #pragma unroll 4
     for (int j = 0; j < HPE_NSPH; ++j) {
-        float4 c = sph[j];
+        float4 c = ws.cf[j];
 #pragma unroll
         for (int m = 0; m < HPE_PPL; ++m) {
-            float t0 = __fsub_rn(P.x[m], c.x), t1 = __fsub_rn(P.y[m], c.y), t2 = __fsub_rn(P.z[m], c.z);
+            float t0 = __fsub_rn(px[m], c.x), t1 = __fsub_rn(py[m], c.y), t2 = __fsub_rn(pz[m], c.z);
             float d = __fmul_rn(t0, t0);
             d = __fadd_rn(d, __fmul_rn(t1, t1));
             d = __fadd_rn(d, __fmul_rn(t2, t2));
@@ -93,8 +167,63 @@ __device__ __forceinline__ void match_sweep(const float4 *sph, const LanePoints 
         }
     }
 #pragma unroll
+    for (int m = 0; m < HPE_PPL; ++m)
+        if (lane + 32 * m < n_pts && __fsqrt_rn(b1[m]) == __fsqrt_rn(b2[m]))
+            idx[m] = match_point_exact(ws.cf, px[m], py[m], pz[m]);
+}
+
+// phase 3a (see the header comment).  ws.cf / ws.ex must hold the pose being matched.
+__device__ __forceinline__ void match_sweep(const WarpScratch &ws, const LanePoints &P, const float *cloudf_s,
+                                            int n_pts, int lane, int idx[HPE_PPL])
+{
+    const float INF = __int_as_float(0x7f800000);
+    float M1[HPE_PPL], M2[HPE_PPL];
+    int g1[HPE_PPL];
+#pragma unroll
+    for (int m = 0; m < HPE_PPL; ++m) { M1[m] = INF; M2[m] = INF; g1[m] = 0; }
+
+    // ---- sweep A ----
+#pragma unroll 2
+    for (int g = 0; g < HPE_NBLK; ++g) {
+        const float4 e0 = ws.ex[g * HPE_BLK + 0], e1 = ws.ex[g * HPE_BLK + 1];
+        const float4 e2 = ws.ex[g * HPE_BLK + 2], e3 = ws.ex[g * HPE_BLK + 3];
+#pragma unroll
+        for (int m = 0; m < HPE_PPL; ++m) {
+            float s0 = fmaf(P.z[m], e0.z, fmaf(P.y[m], e0.y, fmaf(P.x[m], e0.x, e0.w)));
+            float s1 = fmaf(P.z[m], e1.z, fmaf(P.y[m], e1.y, fmaf(P.x[m], e1.x, e1.w)));
+            float s2 = fmaf(P.z[m], e2.z, fmaf(P.y[m], e2.y, fmaf(P.x[m], e2.x, e2.w)));
+            float s3 = fmaf(P.z[m], e3.z, fmaf(P.y[m], e3.y, fmaf(P.x[m], e3.x, e3.w)));
+            float gm = fmin3(fminf(s0, s1), s2, s3);
+            M2[m] = fminf(M2[m], fmaxf(M1[m], gm));
+            bool better = gm < M1[m];
+            M1[m] = fminf(M1[m], gm);
+            g1[m] = better ? g : g1[m];
+        }
+    }
+
+    // ---- certificate + sweep B ----
+#pragma unroll
     for (int m = 0; m < HPE_PPL; ++m) {
-        if (lane + 32 * m < n_pts && __fsqrt_rn(b1[m]) == __fsqrt_rn(b2[m])) idx[m] = match_point_exact(sph, P.x[m], P.y[m], P.z[m]);
+        int k = min(lane + 32 * m, HPE_MAXPTS - 1);
+        const float px = cloudf_s[k], py = cloudf_s[HPE_MAXPTS + k], pz = cloudf_s[2 * HPE_MAXPTS + k];
+        const float tau = fmaf(3.2e-6f, fabsf(M1[m]), P.tau0[m]);       // 52 * 2^-24 = 3.0994e-6
+        bool slow = !(M2[m] - M1[m] > tau);                             // also catches NaN
+        float b1 = INF, b2 = INF;
+        int bi = 0;
+        const float4 *blk = ws.cf + g1[m] * HPE_BLK;
+#pragma unroll
+        for (int i = 0; i < HPE_BLK; ++i) {
+            float4 c = blk[i];
+            float t0 = __fsub_rn(px, c.x), t1 = __fsub_rn(py, c.y), t2 = __fsub_rn(pz, c.z);
+            float d = __fmul_rn(t0, t0);
+            d = __fadd_rn(d, __fmul_rn(t1, t1));
+            d = __fadd_rn(d, __fmul_rn(t2, t2));
+            b2 = fminf(b2, fmaxf(b1, d));
+            if (d < b1) { b1 = d; bi = i; }
+        }
+        slow = slow || (__fsqrt_rn(b1) == __fsqrt_rn(b2));
+        idx[m] = g1[m] * HPE_BLK + bi;
+        if (slow && lane + 32 * m < n_pts) idx[m] = match_point_exact(ws.cf, px, py, pz);
     }
 }
 
@@ -142,6 +271,7 @@ template <class ThetaAt>
 __device__ __forceinline__ void group_fk(const DevModel &M, ThetaAt theta, int n, const WarpScratch &ws, int lane)
 {
     int g = lane / 5, d = lane - 5 * g;
+    __syncwarp();
     if (g < n) {
         double J[5][3], S[10][3];
         fk_digit(M, d, theta(g), J);
@@ -154,22 +284,35 @@ __device__ __forceinline__ void group_fk(const DevModel &M, ThetaAt theta, int n
                 sd[0] = S[i][0];
                 sd[1] = S[i][1];
                 sd[2] = S[i][2];
-                ws.sph4[g * HPE_NSPH + first + i] =
-                    make_float4((float)S[i][0], (float)(-S[i][1]), (float)(-S[i][2]), 0.f);
             }
         }
     }
     __syncwarp();
 }
 
-// phase 2: depth_penalty (src/costfunc.cpp:227-304) of pose g, lanes = spheres.  Valid on all lanes.
-__device__ __forceinline__ double depth_lanes(const double *rad_s, const FrameView &F, const WarpScratch &ws,
-                                              int g, int lane)
+// phase 2: depth_penalty (src/costfunc.cpp:227-304) of pose g, lanes = spheres; the same lanes
+// stage the pose's float32 centres (cf) and sweep-A operands (ex).  Result valid on all lanes.
+__device__ __forceinline__ double depth_and_stage(const double *rad_s, const FrameView &F, const WarpScratch &ws,
+                                                  const LanePoints &P, int g, int lane)
 {
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
-    double dv = depth_term(F, sd[lane * 3], sd[lane * 3 + 1], sd[lane * 3 + 2], rad_s[lane]);
-    if (lane < HPE_NSPH - 32)
-        dv += depth_term(F, sd[(lane + 32) * 3], sd[(lane + 32) * 3 + 1], sd[(lane + 32) * 3 + 2], rad_s[lane + 32]);
+    double dv = 0.0;
+    __syncwarp();      // previous pose's matcher is done with cf/ex
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int j = lane + 32 * h;
+        if (j < HPE_NSPH) {
+            double x = sd[j * 3], y = sd[j * 3 + 1], z = sd[j * 3 + 2];
+            dv += depth_term(F, x, y, z, rad_s[j]);
+            float4 c = make_float4((float)x, (float)(-y), (float)(-z), 0.f);   // conv_to<fmat>, negated frame
+            // c' = cf - q exactly (FP64), then one rounding each for -2c' and |c'|^2
+            double cx = (double)c.x - (double)P.qx, cy = (double)c.y - (double)P.qy, cz = (double)c.z - (double)P.qz;
+            ws.cf[j] = c;
+            ws.ex[j] = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz),
+                                   (float)(cx * cx + cy * cy + cz * cz));
+        }
+    }
+    __syncwarp();
     return warp_sum(dv);
 }
 

@@ -57,6 +57,7 @@ struct PsoDev {           // constants of one pso_evolve call, passed by value
 };
 
 int hpe_set_error(int code, const char *fmt, ...);
+extern int g_hpe_matcher;   // hpe_set_matcher(): 0 = certified two-sweep search, 1 = direct form
 #define HPE_CUDA(call)                                                                           \
     do {                                                                                         \
         cudaError_t e_ = (call);                                                                 \

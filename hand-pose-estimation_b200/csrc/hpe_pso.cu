@@ -12,9 +12,7 @@ constexpr int PSO_WARPS = 8;
 constexpr int PSO_NK = 3;            // informants drawn per particle, src/PSO.cpp:769
 
 struct __align__(16) PsoSmemHead {
-    DevModel M;
-    double rad[HPE_NSPH];
-    double cloud[3 * HPE_MAXPTS];
+    FrameSmem fs;
     double gbest[HPE_NDOF];
     double x0[HPE_NDOF];
     double gbest_cost;
@@ -25,7 +23,7 @@ struct __align__(16) PsoSmemHead {
     //              double fx[num_p]; int informant[num_p]; int R[num_p][3];
 };
 
-__host__ __device__ inline size_t pso_ws_bytes(int gsz) { return (size_t)PSO_WARPS * gsz * HPE_WS_BYTES_PER_SLOT; }
+__host__ __device__ inline size_t pso_ws_bytes(int gsz) { return (size_t)PSO_WARPS * HPE_WS_BYTES(gsz); }
 __host__ __device__ inline size_t pso_smem_bytes(int num_p, int gsz)
 {
     return sizeof(PsoSmemHead) + pso_ws_bytes(gsz) + (size_t)num_p * (HPE_NDOF * 8 + 8 + 8 + 4 + PSO_NK * 4) + 16;
@@ -62,10 +60,8 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
     double *pb = pbest_scratch + (size_t)blockIdx.x * num_p * D;
     const double C2 = C1;
 
-    for (int i = tid; i < (int)(sizeof(DevModel) / 8); i += nthr)
-        reinterpret_cast<double *>(&sm.M)[i] = reinterpret_cast<const double *>(&m)[i];
+    stage_model(sm.fs, m);
     __syncthreads();
-    if (tid < HPE_NSPH) sm.rad[tid] = sm.M.rad[tid];
 
     const int n_frames = chain ? count_swarms : 1;
     for (int fr = 0; fr < n_frames; ++fr) {
@@ -74,14 +70,14 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
         const FrameView F = frame_view(o, slot);
         const uint64_t seed = seeds ? seeds[b] : 1000ull;
         __syncthreads();
-        for (int i = tid; i < 3 * F.n_pts; i += nthr) sm.cloud[i] = F.cloud[i];
+        stage_frame(sm.fs, F);
         if (tid < D) {
             // chain mode: x0 = bestp of the previous frame (src/testmodel.cpp:138)
             sm.x0[tid] = (chain && fr > 0) ? sm.gbest[tid] : x0_in[(size_t)b * D + tid];
         }
         __syncthreads();
         LanePoints P;
-        load_lane_points(F, lane, P);
+        load_lane_points(sm.fs.cloudf, F.n_pts, lane, P);
         const bool frame_ok = o.meta[slot].ok != 0;
 
         // generate_particles: x0 + randn % std, v = 0 (src/PSO.cpp:56-74, :726)
@@ -103,12 +99,12 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
             for (int p0 = warp * gsz; p0 < num_p; p0 += per_round) {
                 int cnt = min(gsz, num_p - p0);
                 const WarpScratch ws = warp_scratch(ws_base, warp, gsz);
-                group_fk(sm.M, [&](int g) { return x + (size_t)(p0 + g) * D; }, cnt, ws, lane);
+                group_fk(sm.fs.M, [&](int g) { return x + (size_t)(p0 + g) * D; }, cnt, ws, lane);
                 for (int g = 0; g < cnt; ++g) {
-                    double depth = depth_lanes(sm.rad, F, ws, g, lane);
+                    double depth = depth_and_stage(sm.fs.rad, F, ws, P, g, lane);
                     int idx[HPE_PPL];
-                    match_sweep(ws.sph4 + g * HPE_NSPH, P, F.n_pts, lane, idx);
-                    double align = align_lanes(sm.rad, ws, g, sm.cloud, F.n_pts, lane, idx);
+                    match_sweep(ws, P, sm.fs.cloudf, F.n_pts, lane, idx);
+                    double align = align_lanes(sm.fs.rad, ws, g, sm.fs.cloud, F.n_pts, lane, idx);
                     if (lane == 0) fx[p0 + g] = align + depth;
                 }
                 __syncwarp();

@@ -146,6 +146,12 @@ int hpe_render_dev(const hpe_model *m, const double *theta_dev, int64_t n, doubl
 /* host convenience: theta host n*26 -> depth_mm host n*240*320 */
 int hpe_render(const hpe_model *m, const double *theta, int64_t n, double focal, float *depth_mm);
 
+/* ---- diagnostics ---- */
+/* Nearest-centre search used by the cost kernels launched through hpe_cost_batch*,
+ * hpe_correspondences: 0 (default) = certified two-sweep search, 1 = the reference's arithmetic
+ * on all 48 spheres.  Both return cv::BFMatcher's indices; 1 exists to cross-check 0. */
+int hpe_set_matcher(int mode);
+
 /* ---- measurement ---- */
 /* FP32 (non-tensor) FFMA peak of the current device in TFLOP/s, measured with a
  * register-only FFMA kernel; the denominator of the cost kernel's roofline (the

@@ -188,3 +188,50 @@ def test_errors_are_reported(hpe, D):
         hpe.handmodel(tb_spheres=[3, 2, 2, 2])
     with pytest.raises(hpe.HpeError):
         hpe.observedmodel(capacity=1, num_samples=300)
+
+
+def test_certified_matcher_equals_direct_form(hpe, orc, omodel, frame0, D):
+    """the two-sweep search (default) and the reference's arithmetic on all 48 spheres give the
+    same indices, on random poses, near-optimal poses and poses far from the cloud"""
+    truth, depth, oobs = frame0
+    rng = np.random.default_rng(8)
+    th = np.concatenate([truth + rng.normal(size=(3000, 26)) * D.STD,
+                         truth + rng.normal(size=(3000, 26)) * D.STD * 0.05,
+                         truth + rng.normal(size=(500, 26)) * D.STD * 4.0])
+    hand, obs = hpe.handmodel(), hpe.observedmodel(capacity=1)
+    obs.upload(depth[None])
+    cf = hpe.costfunc(hand, obs)
+    lib = hpe.lib()
+    try:
+        assert lib.hpe_set_matcher(1) == 0
+        m_direct = cf.compute_correspondences(th)
+    finally:
+        lib.hpe_set_matcher(0)
+    m_fast = cf.compute_correspondences(th)
+    assert np.array_equal(m_direct, m_fast)
+    for i in (0, 1, 3000, 3001, 6000, 6499):
+        S, _ = orc.fk(omodel, th[i])
+        assert np.array_equal(m_fast[i], orc.correspondences(oobs.cloud, S))
+
+
+def test_matcher_on_exact_ties(hpe, orc, omodel, D):
+    """a cloud made of sphere centres and of midpoints between neighbouring spheres: exact and
+    near ties, where only the first-minimum / sqrtf semantics decide"""
+    rng = np.random.default_rng(9)
+    truth = synth_pose(D, rng)
+    depth = orc.render_depth(omodel, truth)
+    oobs = orc.Observation(depth)
+    S, _ = orc.fk(omodel, truth)
+    pts = [S[j] for j in range(48)] + [(S[j] + S[j + 1]) / 2 for j in range(47)]
+    pts += [S[j] + rng.normal(size=3) * 1e-7 for j in range(48)]
+    pts += [(S[j] + S[(j + 10) % 48]) / 2 for j in range(48)]
+    cloud = np.array(pts)[:250]
+    cloud = np.concatenate([cloud, oobs.cloud[: 250 - len(cloud)]])
+    hand, obs = hpe.handmodel(), hpe.observedmodel(capacity=1)
+    obs.set(0, depth, oobs.dt.astype(np.float32), cloud, oobs.scale)
+    cf = hpe.costfunc(hand, obs)
+    th = np.concatenate([truth[None], truth + rng.normal(size=(200, 26)) * 1e-6])
+    m = cf.compute_correspondences(th)
+    for i in range(len(th)):
+        Si, _ = orc.fk(omodel, th[i])
+        assert np.array_equal(m[i], orc.correspondences(cloud, Si)), i
