@@ -99,6 +99,13 @@ int hpe_set_matcher(int mode)
     return HPE_OK;
 }
 
+int hpe_debug_fallback_points(unsigned long long *count, int reset)
+{
+    if (!count) return hpe_set_error(HPE_ERR_ARG, "hpe_debug_fallback_points: NULL output");
+    *count = hpe_fallbacks_cost(reset) + hpe_fallbacks_pso(reset);
+    return HPE_OK;
+}
+
 int hpe_device_count(void)
 {
     int n = 0;

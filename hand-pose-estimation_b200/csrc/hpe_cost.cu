@@ -58,11 +58,11 @@ struct __align__(16) CostSmem {
     __align__(16) unsigned char ws[COST_WARPS * HPE_WS_BYTES(HPE_GROUP)];
 };
 
-template <bool WITH_COLLI>
+template <bool WITH_COLLI, int MATCHER>
 __global__ void __launch_bounds__(COST_WARPS * 32, 2)
 cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, int64_t n,
             double *__restrict__ cost, double *__restrict__ terms, const int32_t *__restrict__ frozen,
-            int32_t *__restrict__ match_out, int matcher)
+            int32_t *__restrict__ match_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
@@ -85,26 +85,27 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
         group_fk(sm.fs.M, [&](int g) { return theta + (p0 + g) * HPE_NDOF; }, cnt, ws, lane);
         for (int g = 0; g < cnt; ++g) {
             double depth = depth_and_stage(sm.fs.rad, F, ws, P, g, lane);
-            int idx[HPE_PPL];
+            unsigned long long packed;
             if (frozen) {
+                int idx[HPE_PPL];
 #pragma unroll
                 for (int q = 0; q < HPE_PPL; ++q) {
                     int k = lane + 32 * q;
                     idx[q] = k < F.n_pts ? frozen[k] : 0;
                 }
-            } else if (matcher == 1) {
-                match_sweep_direct(ws, sm.fs.cloudf, F.n_pts, lane, idx);
+                packed = pack_indices(idx);
+            } else if (MATCHER == 1) {
+                packed = match_sweep_direct(ws, sm.fs.cloudf, F.n_pts, lane);
             } else {
-                match_sweep(ws, P, sm.fs.cloudf, F.n_pts, lane, idx);
+                packed = match_sweep(ws, P, sm.fs.cloudf, F.n_pts, lane);
             }
             if (match_out) {
-#pragma unroll
                 for (int q = 0; q < HPE_PPL; ++q) {
                     int k = lane + 32 * q;
-                    if (k < F.n_pts) match_out[(p0 + g) * F.n_pts + k] = idx[q];
+                    if (k < F.n_pts) match_out[(p0 + g) * F.n_pts + k] = (int)((packed >> (8 * q)) & 255ull);
                 }
             }
-            double align = align_lanes(sm.fs.rad, ws, g, sm.fs.cloud, F.n_pts, lane, idx);
+            double align = align_lanes(sm.fs.rad, ws, g, sm.fs.cloud, F.n_pts, lane, packed);
             double colli = 0.0;
             if (WITH_COLLI) colli = warp_sum(collision_lane(sm.fs.rad, ws.sphd + (size_t)g * HPE_NSPH * 3, lane));
             if (lane == 0) {
@@ -167,6 +168,8 @@ __global__ void __launch_bounds__(256) render_kernel(DevModel m, const double *_
 
 }  // namespace
 
+HPE_DEFINE_FALLBACK_GETTER(hpe_fallbacks_cost)
+
 cudaError_t hpe_launch_fk(const DevModel &m, const double *theta_dev, int64_t n, double *spheres_dev,
                           double *joints_dev, cudaStream_t st)
 {
@@ -187,18 +190,25 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(cost_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
-        cudaFuncSetAttribute(cost_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
     }
     int64_t groups = (n + HPE_GROUP - 1) / HPE_GROUP;
     int64_t want = (groups + COST_WARPS - 1) / COST_WARPS;
     int blocks = (int)(want < 2LL * sms ? want : 2LL * sms);
-    if (with_colli)
-        cost_kernel<true><<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev, terms_dev,
-                                                                              frozen_match_dev, match_out_dev, g_hpe_matcher);
-    else
-        cost_kernel<false><<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev, terms_dev,
-                                                                               frozen_match_dev, match_out_dev, g_hpe_matcher);
+    static bool attr = false;
+    if (!attr) {
+        const int smem = (int)sizeof(CostSmem);
+        cudaFuncSetAttribute(cost_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(cost_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(cost_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(cost_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr = true;
+    }
+    auto launch = [&](auto kern) {
+        kern<<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev, terms_dev,
+                                                                 frozen_match_dev, match_out_dev);
+    };
+    if (g_hpe_matcher == 1) launch(with_colli ? cost_kernel<true, 1> : cost_kernel<false, 1>);
+    else launch(with_colli ? cost_kernel<true, 0> : cost_kernel<false, 0>);
     return cudaGetLastError();
 }
 

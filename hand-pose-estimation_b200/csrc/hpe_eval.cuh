@@ -14,7 +14,7 @@
 // The nearest-centre search (compute_correspondences, src/costfunc.cpp:306-343) must return the
 // index cv::BFMatcher returns: first minimum over j of sqrtf(d_j), d_j = ((t0^2 + t1^2) + t2^2) in
 // float32, t = p - c_j.  Doing that directly costs 8 FP32-pipe + 5 ALU-pipe instructions per
-// (point, sphere) pair.  match_sweep() gets the same index with ~5.5:
+// (point, sphere) pair.  match_sweep() gets the same index with ~5.7:
 //   sweep A  s_j = |c'_j|^2 - 2 p'.c'_j (3 FFMA, coordinates recentred on the cloud centroid) for
 //            all 48 spheres, reduced to the minimum per block of 4 spheres, keeping the best
 //            block, its value M1 and the runner-up block value M2;
@@ -23,12 +23,26 @@
 //            reference's d_j, sqrtf(d_j) order two spheres like D_j once D differs by > 24u D.
 //            Hence if M2 - M1 > tau = u(260|p'|^2 + 52|M1|) no sphere outside the best block can be
 //            the reference's answer;
-//   sweep B  the reference's exact arithmetic on the 4 spheres of the best block (first minimum,
-//            runner-up tracked to detect sqrtf ties);
-//   fallback if the certificate fails or sqrtf ties inside the block, the point is redone with the
-//            exact restatement over all 48 spheres (match_point_exact).
+//   sweep B  the 4 spheres of the best block once more (same FFMAs, bit-identical s): winner index
+//            and the runner-up r inside the block; the certificate becomes min(M2, r) - M1 > tau, i.e.
+//            EVERY other sphere is provably farther in the reference's own arithmetic (ties and
+//            sqrtf merges included, they need differences below 24u D);
+//   fallback if the certificate fails the point is redone with the exact restatement of the
+//            reference's arithmetic over all 48 spheres (match_point_exact).
 #pragma once
 #include "hpe_device.cuh"
+
+// diagnostics: points sent to the exact fallback / points matched (hpe_debug_counters)
+// (one copy per translation unit; the host getters below are instantiated next to the kernels)
+static __device__ unsigned long long g_hpe_fallback_points;
+#define HPE_DEFINE_FALLBACK_GETTER(name)                                                          \
+    unsigned long long name(int reset)                                                            \
+    {                                                                                             \
+        unsigned long long v = 0, z = 0;                                                          \
+        cudaMemcpyFromSymbol(&v, g_hpe_fallback_points, sizeof v);                                \
+        if (reset) cudaMemcpyToSymbol(g_hpe_fallback_points, &z, sizeof z);                       \
+        return v;                                                                                 \
+    }
 
 #define HPE_BLK 4                        // spheres per sweep-A block
 #define HPE_NBLK (HPE_NSPH / HPE_BLK)    // 12 blocks
@@ -132,6 +146,34 @@ static __device__ __noinline__ int match_point_exact(const float4 *cf, float px,
     return bi;
 }
 
+// The same for one point with the whole warp: lane handles spheres lane and lane+32, then a
+// lexicographic (sqrtf(d), index) minimum over the warp = first minimum.  All 32 lanes call it.
+static __device__ __noinline__ int match_point_exact_warp(const float4 *cf, float px, float py, float pz, int lane)
+{
+    float w = __int_as_float(0x7f800000);
+    int bi = lane;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int j = lane + 32 * h;
+        if (j < HPE_NSPH) {
+            float4 c = cf[j];
+            float t0 = __fsub_rn(px, c.x), t1 = __fsub_rn(py, c.y), t2 = __fsub_rn(pz, c.z);
+            float d = __fmul_rn(t0, t0);
+            d = __fadd_rn(d, __fmul_rn(t1, t1));
+            d = __fadd_rn(d, __fmul_rn(t2, t2));
+            float wj = __fsqrt_rn(d);
+            if (wj < w) { w = wj; bi = j; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ow = __shfl_xor_sync(0xffffffffu, w, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ow < w || (ow == w && oi < bi)) { w = ow; bi = oi; }
+    }
+    return bi;
+}
+
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 {
     float d;
@@ -139,11 +181,14 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
     return d;
 }
 
+__device__ __forceinline__ unsigned long long pack_indices(const int idx[HPE_PPL]);
+
 // Direct form over all 48 spheres (the reference's arithmetic on every pair): kept as the
 // cross-check of match_sweep (hpe_set_matcher(1)).
-__device__ __forceinline__ void match_sweep_direct(const WarpScratch &ws, const float *cloudf_s, int n_pts,
-                                                   int lane, int idx[HPE_PPL])
+__device__ __forceinline__ unsigned long long match_sweep_direct(const WarpScratch &ws, const float *cloudf_s,
+                                                                 int n_pts, int lane)
 {
+    int idx[HPE_PPL];
     float px[HPE_PPL], py[HPE_PPL], pz[HPE_PPL], b1[HPE_PPL], b2[HPE_PPL];
 #pragma unroll
     for (int m = 0; m < HPE_PPL; ++m) {
@@ -170,11 +215,13 @@ __device__ __forceinline__ void match_sweep_direct(const WarpScratch &ws, const 
     for (int m = 0; m < HPE_PPL; ++m)
         if (lane + 32 * m < n_pts && __fsqrt_rn(b1[m]) == __fsqrt_rn(b2[m]))
             idx[m] = match_point_exact(ws.cf, px[m], py[m], pz[m]);
+    return pack_indices(idx);
 }
 
 // phase 3a (see the header comment).  ws.cf / ws.ex must hold the pose being matched.
-__device__ __forceinline__ void match_sweep(const WarpScratch &ws, const LanePoints &P, const float *cloudf_s,
-                                            int n_pts, int lane, int idx[HPE_PPL])
+// Returns the 8 indices packed 8 bits each (point m of the lane in bits [8m, 8m+8)).
+__device__ __forceinline__ unsigned long long match_sweep(const WarpScratch &ws, const LanePoints &P,
+                                                          const float *cloudf_s, int n_pts, int lane)
 {
     const float INF = __int_as_float(0x7f800000);
     float M1[HPE_PPL], M2[HPE_PPL];
@@ -182,7 +229,7 @@ __device__ __forceinline__ void match_sweep(const WarpScratch &ws, const LanePoi
 #pragma unroll
     for (int m = 0; m < HPE_PPL; ++m) { M1[m] = INF; M2[m] = INF; g1[m] = 0; }
 
-    // ---- sweep A ----
+    // ---- sweep A: block minima of s_j over all 48 spheres ----
 #pragma unroll 2
     for (int g = 0; g < HPE_NBLK; ++g) {
         const float4 e0 = ws.ex[g * HPE_BLK + 0], e1 = ws.ex[g * HPE_BLK + 1];
@@ -201,44 +248,66 @@ __device__ __forceinline__ void match_sweep(const WarpScratch &ws, const LanePoi
         }
     }
 
-    // ---- certificate + sweep B ----
+    // ---- sweep B: the 4 spheres of the best block again (bit-identical s), winner + runner-up,
+    //      certificate against every other sphere ----
+    unsigned long long packed = 0ull;
+    unsigned slow = 0u;
 #pragma unroll
     for (int m = 0; m < HPE_PPL; ++m) {
-        int k = min(lane + 32 * m, HPE_MAXPTS - 1);
-        const float px = cloudf_s[k], py = cloudf_s[HPE_MAXPTS + k], pz = cloudf_s[2 * HPE_MAXPTS + k];
-        const float tau = fmaf(3.2e-6f, fabsf(M1[m]), P.tau0[m]);       // 52 * 2^-24 = 3.0994e-6
-        bool slow = !(M2[m] - M1[m] > tau);                             // also catches NaN
-        float b1 = INF, b2 = INF;
-        int bi = 0;
-        const float4 *blk = ws.cf + g1[m] * HPE_BLK;
-#pragma unroll
-        for (int i = 0; i < HPE_BLK; ++i) {
-            float4 c = blk[i];
-            float t0 = __fsub_rn(px, c.x), t1 = __fsub_rn(py, c.y), t2 = __fsub_rn(pz, c.z);
-            float d = __fmul_rn(t0, t0);
-            d = __fadd_rn(d, __fmul_rn(t1, t1));
-            d = __fadd_rn(d, __fmul_rn(t2, t2));
-            b2 = fminf(b2, fmaxf(b1, d));
-            if (d < b1) { b1 = d; bi = i; }
-        }
-        slow = slow || (__fsqrt_rn(b1) == __fsqrt_rn(b2));
-        idx[m] = g1[m] * HPE_BLK + bi;
-        if (slow && lane + 32 * m < n_pts) idx[m] = match_point_exact(ws.cf, px, py, pz);
+        const float4 *blk = ws.ex + g1[m] * HPE_BLK;
+        const float4 e0 = blk[0], e1 = blk[1], e2 = blk[2], e3 = blk[3];
+        float s0 = fmaf(P.z[m], e0.z, fmaf(P.y[m], e0.y, fmaf(P.x[m], e0.x, e0.w)));
+        float s1 = fmaf(P.z[m], e1.z, fmaf(P.y[m], e1.y, fmaf(P.x[m], e1.x, e1.w)));
+        float s2 = fmaf(P.z[m], e2.z, fmaf(P.y[m], e2.y, fmaf(P.x[m], e2.x, e2.w)));
+        float s3 = fmaf(P.z[m], e3.z, fmaf(P.y[m], e3.y, fmaf(P.x[m], e3.x, e3.w)));
+        float lo01 = fminf(s0, s1), hi01 = fmaxf(s0, s1), lo23 = fminf(s2, s3), hi23 = fmaxf(s2, s3);
+        float r = fmin3(fmaxf(lo01, lo23), hi01, hi23);                   // runner-up inside the block
+        const float tau = fmaf(3.2e-6f, fabsf(M1[m]), P.tau0[m]);         // 52 * 2^-24 = 3.0994e-6
+        bool cert = fminf(M2[m], r) - M1[m] > tau;                        // false on NaN
+        int i = s1 < s0 ? 1 : 0, j = s3 < s2 ? 3 : 2;
+        int bi = lo23 < lo01 ? j : i;
+        packed |= (unsigned long long)(g1[m] * HPE_BLK + bi) << (8 * m);
+        slow |= (cert ? 0u : 1u) << m;
     }
+    // ---- fallback: the reference's arithmetic on all 48 spheres, one flagged point at a time with
+    //      the whole warp on it (lanes = spheres) ----
+    if (__any_sync(0xffffffffu, slow != 0u)) {
+        for (int m = 0; m < HPE_PPL; ++m) {
+            unsigned todo = __ballot_sync(0xffffffffu, ((slow >> m) & 1u) && lane + 32 * m < n_pts);
+            if (todo && lane == 0) atomicAdd(&g_hpe_fallback_points, (unsigned long long)__popc(todo));
+            while (todo) {
+                int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                int k = src + 32 * m;
+                int e = match_point_exact_warp(ws.cf, cloudf_s[k], cloudf_s[HPE_MAXPTS + k],
+                                               cloudf_s[2 * HPE_MAXPTS + k], lane);
+                if (lane == src) packed = (packed & ~(0xffull << (8 * m))) | ((unsigned long long)e << (8 * m));
+            }
+        }
+    }
+    return packed;
+}
+
+__device__ __forceinline__ unsigned long long pack_indices(const int idx[HPE_PPL])
+{
+    unsigned long long packed = 0ull;
+#pragma unroll
+    for (int m = 0; m < HPE_PPL; ++m) packed |= (unsigned long long)(idx[m] & 255) << (8 * m);
+    return packed;
 }
 
 // phase 3b: align_models (src/costfunc.cpp:346-377) for the lane's points, FP64.
 // cloud_s: shared-memory SoA copy of the frame's cloud (X | -Y | -Z), stride n_pts.
 __device__ __forceinline__ double align_lane(const double *rad_s, const double *sphd,
                                              const double *cloud_s, int n_pts, int lane,
-                                             const int idx[HPE_PPL])
+                                             unsigned long long packed)
 {
     double acc = 0.0;
-#pragma unroll
+#pragma unroll 2
     for (int m = 0; m < HPE_PPL; ++m) {
         int k = lane + 32 * m;
         if (k < n_pts) {
-            int j = idx[m];
+            int j = (int)((packed >> (8 * m)) & 255ull);
             // negated-frame centre = (cx, -cy, -cz)
             double a = cloud_s[k] - sphd[j * 3 + 0];
             double b = cloud_s[n_pts + k] + sphd[j * 3 + 1];
@@ -298,7 +367,7 @@ __device__ __forceinline__ double depth_and_stage(const double *rad_s, const Fra
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
     double dv = 0.0;
     __syncwarp();      // previous pose's matcher is done with cf/ex
-#pragma unroll
+#pragma unroll 1
     for (int h = 0; h < 2; ++h) {
         int j = lane + 32 * h;
         if (j < HPE_NSPH) {
@@ -318,8 +387,8 @@ __device__ __forceinline__ double depth_and_stage(const double *rad_s, const Fra
 
 // phase 3b reduced over the warp and scaled by lambda = |M|/|P| (src/costfunc.cpp:372-373)
 __device__ __forceinline__ double align_lanes(const double *rad_s, const WarpScratch &ws, int g,
-                                              const double *cloud_s, int n_pts, int lane, const int idx[HPE_PPL])
+                                              const double *cloud_s, int n_pts, int lane, unsigned long long packed)
 {
-    double a = align_lane(rad_s, ws.sphd + (size_t)g * HPE_NSPH * 3, cloud_s, n_pts, lane, idx);
+    double a = align_lane(rad_s, ws.sphd + (size_t)g * HPE_NSPH * 3, cloud_s, n_pts, lane, packed);
     return __dmul_rn(warp_sum(a), (double)HPE_NSPH / (double)n_pts);
 }

@@ -80,3 +80,5 @@ cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p,
 cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_t n, double focal,
                               float *depth_dev, cudaStream_t st);
 size_t hpe_observe_scratch_bytes(int count);
+unsigned long long hpe_fallbacks_cost(int reset);
+unsigned long long hpe_fallbacks_pso(int reset);

@@ -63,9 +63,8 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
     stage_model(sm.fs, m);
     __syncthreads();
 
-    const int n_frames = chain ? count_swarms : 1;
-    for (int fr = 0; fr < n_frames; ++fr) {
-        const int b = chain ? fr : blockIdx.x;        // swarm index
+    // independent swarms: CTA-strided; chain mode: one CTA walks the sequence
+    for (int b = chain ? 0 : (int)blockIdx.x; b < count_swarms; b += chain ? 1 : (int)gridDim.x) {
         const int slot = first + b;
         const FrameView F = frame_view(o, slot);
         const uint64_t seed = seeds ? seeds[b] : 1000ull;
@@ -73,7 +72,7 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
         stage_frame(sm.fs, F);
         if (tid < D) {
             // chain mode: x0 = bestp of the previous frame (src/testmodel.cpp:138)
-            sm.x0[tid] = (chain && fr > 0) ? sm.gbest[tid] : x0_in[(size_t)b * D + tid];
+            sm.x0[tid] = (chain && b > 0) ? sm.gbest[tid] : x0_in[(size_t)b * D + tid];
         }
         __syncthreads();
         LanePoints P;
@@ -102,9 +101,8 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
                 group_fk(sm.fs.M, [&](int g) { return x + (size_t)(p0 + g) * D; }, cnt, ws, lane);
                 for (int g = 0; g < cnt; ++g) {
                     double depth = depth_and_stage(sm.fs.rad, F, ws, P, g, lane);
-                    int idx[HPE_PPL];
-                    match_sweep(ws, P, sm.fs.cloudf, F.n_pts, lane, idx);
-                    double align = align_lanes(sm.fs.rad, ws, g, sm.fs.cloud, F.n_pts, lane, idx);
+                    unsigned long long packed = match_sweep(ws, P, sm.fs.cloudf, F.n_pts, lane);
+                    double align = align_lanes(sm.fs.rad, ws, g, sm.fs.cloud, F.n_pts, lane, packed);
                     if (lane == 0) fx[p0 + g] = align + depth;
                 }
                 __syncwarp();
@@ -197,6 +195,8 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
 
 }  // namespace
 
+HPE_DEFINE_FALLBACK_GETTER(hpe_fallbacks_pso)
+
 cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
                            int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
                            double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st)
@@ -215,17 +215,33 @@ cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p,
         if (e != cudaSuccess) return e;
         attr_set = smem;
     }
-    int blocks = chain ? 1 : count;
-    double *scratch = nullptr;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int resident = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pso_kernel, PSO_WARPS * 32, smem);
+    if (resident < 1) resident = 1;
+    int blocks = chain ? 1 : (count < resident * sms ? count : resident * sms);
+    // velocity + pbest of the resident swarms: grow-only scratch (L2-resident, 27 KB per swarm)
+    static double *scratch = nullptr;
+    static size_t scratch_bytes = 0;
     size_t per = (size_t)p.num_p * HPE_NDOF * sizeof(double);
-    cudaError_t e = cudaMallocAsync(&scratch, 2 * per * blocks, st);
-    if (e != cudaSuccess) return e;
+    if (2 * per * blocks > scratch_bytes) {
+        if (scratch) cudaFree(scratch);
+        scratch = nullptr; scratch_bytes = 0;
+        cudaError_t e = cudaMalloc(&scratch, 2 * per * blocks);
+        if (e != cudaSuccess) return e;
+        scratch_bytes = 2 * per * blocks;
+    }
+    cudaError_t e;
     const double W1 = 1. / (2 * log(2.0));       // src/PSO.cpp:772
     const double C1 = 0.5 + log(2.0);            // src/PSO.cpp:773-774
     pso_kernel<<<blocks, PSO_WARPS * 32, smem, st>>>(m, o, p, x0_dev, first, count, seeds_dev, scratch,
                                                      scratch + (size_t)p.num_p * HPE_NDOF * blocks, bestp_dev,
                                                      best_cost_dev, trace_dev, chain, gsz, W1, C1);
     e = cudaGetLastError();
-    cudaFreeAsync(scratch, st);
     return e;
 }

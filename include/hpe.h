@@ -151,6 +151,8 @@ int hpe_render(const hpe_model *m, const double *theta, int64_t n, double focal,
  * hpe_correspondences: 0 (default) = certified two-sweep search, 1 = the reference's arithmetic
  * on all 48 spheres.  Both return cv::BFMatcher's indices; 1 exists to cross-check 0. */
 int hpe_set_matcher(int mode);
+/* number of points the certified search handed to its exact fallback since the last reset */
+int hpe_debug_fallback_points(unsigned long long *count, int reset);
 
 /* ---- measurement ---- */
 /* FP32 (non-tensor) FFMA peak of the current device in TFLOP/s, measured with a
