@@ -20,7 +20,190 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float *out, int iters, f
     if (s == 123.456f) out[0] = s;     // never true; keeps the chains alive
 }
 
+// pattern 1: every FFMA has three different register sources and no operand is shared by
+// neighbouring instructions: r[k] = r[k] * x[k] + y[k]
+__global__ void __launch_bounds__(256) ffma_3reg_kernel(float *out, int iters, const float *in)
+{
+    float r[8], x[8], y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { r[k] = in[threadIdx.x + k]; x[k] = in[64 + threadIdx.x + k]; y[k] = in[128 + threadIdx.x + k]; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = fmaf(r[k], x[k], y[k]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = fmaf(r[k], x[(k + 1) & 7], y[(k + 3) & 7]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += r[k];
+    if (s == 123.456f) out[0] = s;
+}
+
+// pattern 2: the sweep-A shape: 4 points x 4 spheres, s = p.z*e.z + (p.y*e.y + (p.x*e.x + e.w)), block min
+__global__ void __launch_bounds__(256) ffma_sweep_kernel(float *out, int iters, const float4 *in)
+{
+    float4 p[4], e[4];
+    float m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { p[k] = in[threadIdx.x + k]; m[k] = 1e30f; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e[j] = in[256 + ((i * 4 + j) & 63)];
+        float s[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[k][j] = fmaf(p[k].x, e[j].x, e[j].w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[k][j] = fmaf(p[k].y, e[j].y, s[k][j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[k][j] = fmaf(p[k].z, e[j].z, s[k][j]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[k] = fminf(m[k], fminf(fminf(s[k][0], s[k][1]), fminf(s[k][2], s[k][3])));
+    }
+    float t = m[0] + m[1] + m[2] + m[3];
+    if (t == 123.456f) out[0] = t;
+}
+
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+// pattern 3: packed FFMA2 chains with shared operands (its peak)
+__global__ void __launch_bounds__(256) ffma2_peak_kernel(unsigned long long *out, int iters, unsigned long long a,
+                                                         unsigned long long b)
+{
+    unsigned long long r[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) r[k] = out[(threadIdx.x + k) & 255];
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r[k] = ffma2(r[k], a, b);
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s ^= r[k];
+    if (s == 0x123456789abcdefull) out[0] = s;
+}
+
+// pattern 4: the sweep-A shape on FFMA2: 4 points (coordinates duplicated into both halves) x 2
+// sphere pairs from shared memory, 24 FFMA2 + the block-minimum bookkeeping per iteration
+__global__ void __launch_bounds__(256) ffma2_sweep_kernel(float *out, int iters, const float4 *in)
+{
+    __shared__ ulonglong2 sph[64 * 4];      // per sphere pair: (x0x1, y0y1), (z0z1, w0w1)
+    for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) sph[i] = reinterpret_cast<const ulonglong2 *>(in)[i];
+    __syncthreads();
+    unsigned long long px[4], py[4], pz[4];
+    float M1[4], M2[4];
+    int g1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float4 p = in[512 + threadIdx.x + k];
+        unsigned ux = __float_as_uint(p.x), uy = __float_as_uint(p.y), uz = __float_as_uint(p.z);
+        px[k] = ((unsigned long long)ux << 32) | ux;
+        py[k] = ((unsigned long long)uy << 32) | uy;
+        pz[k] = ((unsigned long long)uz << 32) | uz;
+        M1[k] = 1e30f; M2[k] = 1e30f; g1[k] = 0;
+    }
+    for (int i = 0; i < iters; ++i) {
+        const ulonglong2 *blk = sph + (i & 31) * 4;
+        ulonglong2 a0 = blk[0], a1 = blk[1], b0 = blk[2], b1 = blk[3];   // pair A: (xy)(zw), pair B
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned long long sa = ffma2(pz[k], a1.x, ffma2(py[k], a0.y, ffma2(px[k], a0.x, a1.y)));
+            unsigned long long sb = ffma2(pz[k], b1.x, ffma2(py[k], b0.y, ffma2(px[k], b0.x, b1.y)));
+            float gm;
+            asm("min.f32 %0, %1, %2, %3;" : "=f"(gm) : "f"(fminf(lo32(sa), hi32(sa))), "f"(lo32(sb)), "f"(hi32(sb)));
+            M2[k] = fminf(M2[k], fmaxf(M1[k], gm));
+            bool better = gm < M1[k];
+            M1[k] = fminf(M1[k], gm);
+            g1[k] = better ? i : g1[k];
+        }
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t += M1[k] + M2[k] + (float)g1[k];
+    if (t == 123.456f) out[0] = t;
+}
+
 }  // namespace
+
+// out[2]: FFMA2 peak in TFLOP/s; out[3]: sweep-A shape on FFMA2, (point,sphere) pairs per second / 1e12
+extern "C" int hpe_measure_fp32x2(double out[2])
+{
+    int dev = 0, sms = 0;
+    HPE_CUDA(cudaGetDevice(&dev));
+    HPE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float *d = nullptr;
+    HPE_CUDA(cudaMalloc(&d, 1024 * 16));
+    HPE_CUDA(cudaMemset(d, 0, 1024 * 16));
+    cudaEvent_t e0, e1;
+    HPE_CUDA(cudaEventCreate(&e0));
+    HPE_CUDA(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256;
+    for (int which = 0; which < 2; ++which) {
+        double best = 0.0;
+        const int iters = 1 << 12;
+        for (int rep = 0; rep < 5; ++rep) {
+            HPE_CUDA(cudaEventRecord(e0, 0));
+            if (which == 0) ffma2_peak_kernel<<<blocks, threads>>>((unsigned long long *)d, iters, 0x3f8000003f800000ull, 0ull);
+            else ffma2_sweep_kernel<<<blocks, threads>>>(d, iters, (const float4 *)d);
+            HPE_CUDA(cudaEventRecord(e1, 0));
+            HPE_CUDA(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            HPE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            double units = (which == 0 ? 4.0 * 16.0 : 16.0) * iters * (double)blocks * threads;   // flop | pairs
+            double v = units / (ms * 1e-3) * 1e-12;
+            if (rep > 0 && v > best) best = v;
+        }
+        out[which] = best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return HPE_OK;
+}
+
+// out[0]: 3-register FFMA pattern, TFLOP/s; out[1]: sweep-shaped pattern, TFLOP/s counting its FFMAs only
+extern "C" int hpe_measure_fp32_patterns(double out[2])
+{
+    int dev = 0, sms = 0;
+    HPE_CUDA(cudaGetDevice(&dev));
+    HPE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float *d = nullptr;
+    HPE_CUDA(cudaMalloc(&d, 4096 * 16));
+    HPE_CUDA(cudaMemset(d, 0, 4096 * 16));
+    cudaEvent_t e0, e1;
+    HPE_CUDA(cudaEventCreate(&e0));
+    HPE_CUDA(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256;
+    for (int which = 0; which < 2; ++which) {
+        double best = 0.0;
+        const int iters = which == 0 ? (1 << 13) : (1 << 12);
+        for (int rep = 0; rep < 5; ++rep) {
+            HPE_CUDA(cudaEventRecord(e0, 0));
+            if (which == 0) ffma_3reg_kernel<<<blocks, threads>>>(d, iters, d + 16);
+            else ffma_sweep_kernel<<<blocks, threads>>>(d, iters, (const float4 *)(d + 64));
+            HPE_CUDA(cudaEventRecord(e1, 0));
+            HPE_CUDA(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            HPE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            double ffma = (which == 0 ? 16.0 : 48.0) * iters * (double)blocks * threads;
+            double tf = 2.0 * ffma / (ms * 1e-3) * 1e-12;
+            if (rep > 0 && tf > best) best = tf;
+        }
+        out[which] = best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return HPE_OK;
+}
 
 extern "C" int hpe_measure_fp32_peak(double *tflops, double *sm_mhz_est)
 {

@@ -5,6 +5,9 @@
 
 namespace {
 
+#ifndef HPE_STAGGER
+#define HPE_STAGGER 1
+#endif
 constexpr int COST_WARPS = 8;
 }  // namespace
 
@@ -59,7 +62,7 @@ struct __align__(16) CostSmem {
 };
 
 template <bool WITH_COLLI, int MATCHER>
-__global__ void __launch_bounds__(COST_WARPS * 32, 2)
+__global__ void __launch_bounds__(COST_WARPS * 32, HPE_MINBLOCKS)
 cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, int64_t n,
             double *__restrict__ cost, double *__restrict__ terms, const int32_t *__restrict__ frozen,
             int32_t *__restrict__ match_out)
@@ -67,45 +70,29 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const FrameView F = frame_view(o, slot);
     stage_model(sm.fs, m);
-    stage_frame(sm.fs, F);
-    __syncthreads();
-
-    LanePoints P;
-    load_lane_points(sm.fs.cloudf, F.n_pts, lane, P);
+    stage_frame(sm.fs, frame_view(o, slot));     // ends synchronised
     const WarpScratch ws = warp_scratch(sm.ws, warp, HPE_GROUP);
+    const int n_pts = sm.fs.n_pts;
 
     const int64_t total_warps = (int64_t)gridDim.x * COST_WARPS;
     const int64_t gw = (int64_t)blockIdx.x * COST_WARPS + warp;
     const int64_t lo = n * gw / total_warps, hi = n * (gw + 1) / total_warps;
 
-    for (int64_t p0 = lo; p0 < hi; p0 += HPE_GROUP) {
-        int cnt = (int)min((int64_t)HPE_GROUP, hi - p0);
+#if HPE_STAGGER
+    // warps of an SM start with first groups of different sizes so that their FP64 / gather phases
+    // do not line up in time
+    int first_cnt = 1 + (int)(gw % HPE_GROUP);
+#else
+    int first_cnt = HPE_GROUP;
+#endif
+    for (int64_t p0 = lo; p0 < hi;) {
+        int cnt = (int)min((int64_t)(p0 == lo ? first_cnt : HPE_GROUP), hi - p0);
         group_fk(sm.fs.M, [&](int g) { return theta + (p0 + g) * HPE_NDOF; }, cnt, ws, lane);
         for (int g = 0; g < cnt; ++g) {
-            double depth = depth_and_stage(sm.fs.rad, F, ws, P, g, lane);
-            unsigned long long packed;
-            if (frozen) {
-                int idx[HPE_PPL];
-#pragma unroll
-                for (int q = 0; q < HPE_PPL; ++q) {
-                    int k = lane + 32 * q;
-                    idx[q] = k < F.n_pts ? frozen[k] : 0;
-                }
-                packed = pack_indices(idx);
-            } else if (MATCHER == 1) {
-                packed = match_sweep_direct(ws, sm.fs.cloudf, F.n_pts, lane);
-            } else {
-                packed = match_sweep(ws, P, sm.fs.cloudf, F.n_pts, lane);
-            }
-            if (match_out) {
-                for (int q = 0; q < HPE_PPL; ++q) {
-                    int k = lane + 32 * q;
-                    if (k < F.n_pts) match_out[(p0 + g) * F.n_pts + k] = (int)((packed >> (8 * q)) & 255ull);
-                }
-            }
-            double align = align_lanes(sm.fs.rad, ws, g, sm.fs.cloud, F.n_pts, lane, packed);
+            double depth = depth_and_stage(sm.fs, ws, g, lane);
+            double align = match_align<MATCHER>(sm.fs, ws, g, lane, frozen,
+                                                match_out ? match_out + (p0 + g) * n_pts : nullptr);
             double colli = 0.0;
             if (WITH_COLLI) colli = warp_sum(collision_lane(sm.fs.rad, ws.sphd + (size_t)g * HPE_NSPH * 3, lane));
             if (lane == 0) {
@@ -117,6 +104,7 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
                 }
             }
         }
+        p0 += cnt;
     }
 }
 
@@ -193,7 +181,7 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
     }
     int64_t groups = (n + HPE_GROUP - 1) / HPE_GROUP;
     int64_t want = (groups + COST_WARPS - 1) / COST_WARPS;
-    int blocks = (int)(want < 2LL * sms ? want : 2LL * sms);
+    int blocks = (int)(want < (long long)HPE_MINBLOCKS * sms ? want : (long long)HPE_MINBLOCKS * sms);
     static bool attr = false;
     if (!attr) {
         const int smem = (int)sizeof(CostSmem);

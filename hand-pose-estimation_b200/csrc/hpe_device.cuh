@@ -15,7 +15,8 @@
 #define HPE_NJOINT 21
 #define HPE_W 320
 #define HPE_H 240
-#define HPE_GROUP 6          // poses evaluated together by one warp (6 poses x 5 digits = 30 FK lanes)
+#define HPE_GROUP 5          // poses evaluated together by one warp (5 poses x 5 digits = 25 FK lanes);
+                             // 6 would fill 30 lanes but its scratch leaves room for 2 CTAs per SM, not 3
 #define HPE_MAXPTS 256       // 8 points per lane
 #define HPE_PPL 8
 
@@ -183,7 +184,8 @@ __device__ __forceinline__ int digit_first_sphere(int d) { return d == 0 ? 0 : 8
 // ---------------------------------------------------------------------------------------
 // depth term of one sphere (src/costfunc.cpp:251-300), un-negated centre (x,y,z), radius r
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double depth_term(const FrameView &F, double x, double y, double z, double r)
+template <class FrameT>
+__device__ __forceinline__ double depth_term(const FrameT &F, double x, double y, double z, double r)
 {
     // K*c without FMA contraction: row0 = f*x + cx*z, row1 = f*y + cy*z, row2 = z
     double pu = __ddiv_rn(__dadd_rn(__dmul_rn(F.focal, x), __dmul_rn(F.cx, z)), z);

@@ -5,35 +5,35 @@
 //   phase 1  lanes = (pose, digit): forward kinematics in FP64 -> FP64 sphere centres in shared memory
 //   phase 2  per pose, lanes = spheres: projection + depth-map / distance-transform gathers; the same
 //            lanes stage the pose's float32 centres for the matcher
-//   phase 3  per pose, lanes = points (8 per lane, registers): nearest-centre search in FP32, then the
-//            FP64 alignment sum
+//   phase 3  per pose, lanes = points (two passes of 4 points per lane): nearest-centre search in
+//            FP32, then the FP64 alignment sum of those points
 //   phase 4  (cal_cost2 only) lanes = sphere pairs: self-collision
-// The model (DevModel) and the radii are read from shared memory: lanes index them with
-// different digits/spheres, which would serialise on the constant bank.
+// Everything a warp needs between phases lives in shared memory (model, frame scalars, cloud,
+// recentred points), so the kernels stay under 85 registers and 3 CTAs of 8 warps fit per SM: the
+// FP64 / gather phases of some warps hide under the FP32 sweeps of the others.
 //
 // The nearest-centre search (compute_correspondences, src/costfunc.cpp:306-343) must return the
 // index cv::BFMatcher returns: first minimum over j of sqrtf(d_j), d_j = ((t0^2 + t1^2) + t2^2) in
 // float32, t = p - c_j.  Doing that directly costs 8 FP32-pipe + 5 ALU-pipe instructions per
-// (point, sphere) pair.  match_sweep() gets the same index with ~5.7:
-//   sweep A  s_j = |c'_j|^2 - 2 p'.c'_j (3 FFMA, coordinates recentred on the cloud centroid) for
+// (point, sphere) pair.  match_pass() gets the same index with ~5.5:
+//   sweep A  s_j = |c'_j|^2 - 2 p'.c'_j (3 FFMA, coordinates recentred on the cloud centroid q) for
 //            all 48 spheres, reduced to the minimum per block of 4 spheres, keeping the best
 //            block, its value M1 and the runner-up block value M2;
+//   sweep B  the 4 spheres of the best block once more (same FFMAs, bit-identical s): winner index
+//            and the runner-up r inside the block;
 //   certify  s_j + |p'|^2 equals the exact squared distance D_j up to E_j <= u(104|p'|^2 + 13|s_j|),
 //            u = 2^-24 (forward error of the 3 FFMAs plus the rounding of p', -2c', |c'|^2), and the
-//            reference's d_j, sqrtf(d_j) order two spheres like D_j once D differs by > 24u D.
-//            Hence if M2 - M1 > tau = u(260|p'|^2 + 52|M1|) no sphere outside the best block can be
-//            the reference's answer;
-//   sweep B  the 4 spheres of the best block once more (same FFMAs, bit-identical s): winner index
-//            and the runner-up r inside the block; the certificate becomes min(M2, r) - M1 > tau, i.e.
-//            EVERY other sphere is provably farther in the reference's own arithmetic (ties and
-//            sqrtf merges included, they need differences below 24u D);
-//   fallback if the certificate fails the point is redone with the exact restatement of the
-//            reference's arithmetic over all 48 spheres (match_point_exact).
+//            reference's d_j / sqrtf(d_j) order two spheres like D_j once D differs by more than 24u D
+//            (ties and sqrtf merges need smaller differences).  Hence if
+//            min(M2, r) - M1 > tau = u(260|p'|^2 + 52|M1|) EVERY other sphere is provably farther in
+//            the reference's own arithmetic and the winner is the reference's answer;
+//   fallback otherwise (2-5 points in 10,000) the point is redone with the exact restatement of the
+//            reference's arithmetic over all 48 spheres, the whole warp on one point.
 #pragma once
 #include "hpe_device.cuh"
 
-// diagnostics: points sent to the exact fallback / points matched (hpe_debug_counters)
-// (one copy per translation unit; the host getters below are instantiated next to the kernels)
+// diagnostics: points sent to the exact fallback (hpe_debug_fallback_points); one copy per
+// translation unit, the host getters are instantiated next to the kernels
 static __device__ unsigned long long g_hpe_fallback_points;
 #define HPE_DEFINE_FALLBACK_GETTER(name)                                                          \
     unsigned long long name(int reset)                                                            \
@@ -44,8 +44,15 @@ static __device__ unsigned long long g_hpe_fallback_points;
         return v;                                                                                 \
     }
 
+#ifndef HPE_SWEEP_STAGED
+#define HPE_SWEEP_STAGED 1
+#endif
+#ifndef HPE_MINBLOCKS
+#define HPE_MINBLOCKS 3                  // CTAs of 8 warps per SM the kernels are compiled for
+#endif
 #define HPE_BLK 4                        // spheres per sweep-A block
 #define HPE_NBLK (HPE_NSPH / HPE_BLK)    // 12 blocks
+#define HPE_PASS 4                       // points per lane and pass (2 passes cover 8 x 32 = 256 points)
 
 // per-warp shared-memory scratch
 struct WarpScratch {
@@ -67,10 +74,14 @@ __device__ __forceinline__ WarpScratch warp_scratch(unsigned char *base, int war
 
 // model + frame data every CTA stages once
 struct __align__(16) FrameSmem {
+    float4 pre[HPE_MAXPTS];          // (x', y', z', 260u|p'|^2): float32 points recentred on q
     DevModel M;
     double rad[HPE_NSPH];
-    double cloud[3 * HPE_MAXPTS];    // FP64 cloud, SoA with stride n_pts (X | -Y | -Z)
-    float cloudf[3 * HPE_MAXPTS];    // its float32 conversion, SoA with stride HPE_MAXPTS
+    double cloud[3 * HPE_MAXPTS];    // FP64 cloud, SoA with stride HPE_MAXPTS (X | -Y | -Z)
+    double scale, dt_max, focal, cx, cy, lambda;
+    const float *depth_mm, *dt_px;
+    float qx, qy, qz;
+    int n_pts;
 };
 
 // all threads of the CTA; caller syncs afterwards
@@ -81,73 +92,45 @@ __device__ __forceinline__ void stage_model(FrameSmem &fs, const DevModel &m)
     if (threadIdx.x < HPE_NSPH) fs.rad[threadIdx.x] = m.rad[threadIdx.x];
 }
 
+// all threads of the CTA (blockDim >= 32); contains __syncthreads, ends synchronised
 __device__ __forceinline__ void stage_frame(FrameSmem &fs, const FrameView &F)
 {
+    __syncthreads();
     for (int i = threadIdx.x; i < 3 * HPE_MAXPTS; i += blockDim.x) {
         int c = i / HPE_MAXPTS, k = i - c * HPE_MAXPTS;
-        double v = k < F.n_pts ? F.cloud[c * F.n_pts + k] : 0.0;
-        if (k < F.n_pts) fs.cloud[c * F.n_pts + k] = v;
-        fs.cloudf[i] = (float)v;
+        fs.cloud[i] = k < F.n_pts ? F.cloud[c * F.n_pts + k] : 0.0;
     }
+    if (threadIdx.x == 0) {
+        fs.scale = F.scale; fs.dt_max = F.dt_max; fs.focal = F.focal; fs.cx = F.cx; fs.cy = F.cy;
+        fs.lambda = (double)HPE_NSPH / (double)F.n_pts;       // |M|/|P|, src/costfunc.cpp:372
+        fs.depth_mm = F.depth_mm; fs.dt_px = F.dt_px; fs.n_pts = F.n_pts;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {     // centroid of the float32 cloud (any float origin is valid)
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int k = threadIdx.x; k < F.n_pts; k += 32) {
+            sx += (float)fs.cloud[k]; sy += (float)fs.cloud[HPE_MAXPTS + k]; sz += (float)fs.cloud[2 * HPE_MAXPTS + k];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+            sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        }
+        if (threadIdx.x == 0) { fs.qx = sx / (float)F.n_pts; fs.qy = sy / (float)F.n_pts; fs.qz = sz / (float)F.n_pts; }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < HPE_MAXPTS; k += blockDim.x) {
+        // conv_to<fmat> (src/costfunc.cpp:322), then p' = fl(pf - q)
+        float x = __fsub_rn((float)fs.cloud[k], fs.qx), y = __fsub_rn((float)fs.cloud[HPE_MAXPTS + k], fs.qy),
+              z = __fsub_rn((float)fs.cloud[2 * HPE_MAXPTS + k], fs.qz);
+        float pp = x * x + y * y + z * z;
+        fs.pre[k] = make_float4(x, y, z, 1.56e-5f * pp);      // 260 * 2^-24 = 1.5497e-5, rounded up
+    }
+    __syncthreads();
 }
 
-// the lane's 8 observed points: float32 coordinates recentred on q (the cloud centroid) and
-// the certificate scale 260 u |p'|^2
-struct LanePoints {
-    float x[HPE_PPL], y[HPE_PPL], z[HPE_PPL], tau0[HPE_PPL];
-    float qx, qy, qz;
-};
-
-// cloudf_s: shared-memory float32 copy of the cloud (conv_to<fmat>, src/costfunc.cpp:322), SoA
-// with stride HPE_MAXPTS.  Must be called by all 32 lanes.
-__device__ __forceinline__ void load_lane_points(const float *cloudf_s, int n_pts, int lane, LanePoints &P)
-{
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-#pragma unroll
-    for (int m = 0; m < HPE_PPL; ++m) {
-        int k = lane + 32 * m;
-        bool ok = k < n_pts;
-        P.x[m] = ok ? cloudf_s[k] : 0.f;
-        P.y[m] = ok ? cloudf_s[HPE_MAXPTS + k] : 0.f;
-        P.z[m] = ok ? cloudf_s[2 * HPE_MAXPTS + k] : 0.f;
-        sx += P.x[m]; sy += P.y[m]; sz += P.z[m];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, o);
-        sy += __shfl_xor_sync(0xffffffffu, sy, o);
-        sz += __shfl_xor_sync(0xffffffffu, sz, o);
-    }
-    P.qx = sx / (float)n_pts; P.qy = sy / (float)n_pts; P.qz = sz / (float)n_pts;
-#pragma unroll
-    for (int m = 0; m < HPE_PPL; ++m) {
-        P.x[m] = __fsub_rn(P.x[m], P.qx);
-        P.y[m] = __fsub_rn(P.y[m], P.qy);
-        P.z[m] = __fsub_rn(P.z[m], P.qz);
-        float pp = P.x[m] * P.x[m] + P.y[m] * P.y[m] + P.z[m] * P.z[m];
-        P.tau0[m] = 1.56e-5f * pp;      // 260 * 2^-24 = 1.5497e-5, rounded up
-    }
-}
-
-// Exact restatement of the matcher for ONE point: first minimum of sqrtf(d) over the 48 spheres.
-static __device__ __noinline__ int match_point_exact(const float4 *cf, float px, float py, float pz)
-{
-    float best = __int_as_float(0x7f800000);
-    int bi = 0;
-    for (int j = 0; j < HPE_NSPH; ++j) {
-        float4 c = cf[j];
-        float t0 = __fsub_rn(px, c.x), t1 = __fsub_rn(py, c.y), t2 = __fsub_rn(pz, c.z);
-        float d = __fmul_rn(t0, t0);
-        d = __fadd_rn(d, __fmul_rn(t1, t1));
-        d = __fadd_rn(d, __fmul_rn(t2, t2));
-        float w = __fsqrt_rn(d);
-        if (w < best) { best = w; bi = j; }
-    }
-    return bi;
-}
-
-// The same for one point with the whole warp: lane handles spheres lane and lane+32, then a
-// lexicographic (sqrtf(d), index) minimum over the warp = first minimum.  All 32 lanes call it.
+// Exact restatement of the matcher for one point with the whole warp: lane handles spheres lane
+// and lane+32, then a lexicographic (sqrtf(d), index) minimum over the warp = first minimum.
 static __device__ __noinline__ int match_point_exact_warp(const float4 *cf, float px, float py, float pz, int lane)
 {
     float w = __int_as_float(0x7f800000);
@@ -181,143 +164,162 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
     return d;
 }
 
-__device__ __forceinline__ unsigned long long pack_indices(const int idx[HPE_PPL]);
-
-// Direct form over all 48 spheres (the reference's arithmetic on every pair): kept as the
-// cross-check of match_sweep (hpe_set_matcher(1)).
-__device__ __forceinline__ unsigned long long match_sweep_direct(const WarpScratch &ws, const float *cloudf_s,
-                                                                 int n_pts, int lane)
+__device__ __forceinline__ float expanded(const float4 &p, const float4 &e)
 {
-    int idx[HPE_PPL];
-    float px[HPE_PPL], py[HPE_PPL], pz[HPE_PPL], b1[HPE_PPL], b2[HPE_PPL];
+    return fmaf(p.z, e.z, fmaf(p.y, e.y, fmaf(p.x, e.x, e.w)));
+}
+
+// the reference's arithmetic on every pair, 4 points of the lane (cross-check: hpe_set_matcher(1))
+__device__ __forceinline__ void match_pass_direct(const FrameSmem &fs, const WarpScratch &ws, int k0, int lane,
+                                                  int idx[HPE_PASS])
+{
+    const float INF = __int_as_float(0x7f800000);
+    float px[HPE_PASS], py[HPE_PASS], pz[HPE_PASS], b1[HPE_PASS];
 #pragma unroll
-    for (int m = 0; m < HPE_PPL; ++m) {
-        int k = min(lane + 32 * m, HPE_MAXPTS - 1);
-        px[m] = cloudf_s[k]; py[m] = cloudf_s[HPE_MAXPTS + k]; pz[m] = cloudf_s[2 * HPE_MAXPTS + k];
-        b1[m] = __int_as_float(0x7f800000);
-        b2[m] = __int_as_float(0x7f800000);
+    for (int m = 0; m < HPE_PASS; ++m) {
+        int k = k0 + 32 * m;
+        px[m] = (float)fs.cloud[k]; py[m] = (float)fs.cloud[HPE_MAXPTS + k]; pz[m] = (float)fs.cloud[2 * HPE_MAXPTS + k];
+        b1[m] = INF;
         idx[m] = 0;
     }
-#pragma unroll 4
+#pragma unroll 2
     for (int j = 0; j < HPE_NSPH; ++j) {
         float4 c = ws.cf[j];
 #pragma unroll
-        for (int m = 0; m < HPE_PPL; ++m) {
+        for (int m = 0; m < HPE_PASS; ++m) {
             float t0 = __fsub_rn(px[m], c.x), t1 = __fsub_rn(py[m], c.y), t2 = __fsub_rn(pz[m], c.z);
             float d = __fmul_rn(t0, t0);
             d = __fadd_rn(d, __fmul_rn(t1, t1));
             d = __fadd_rn(d, __fmul_rn(t2, t2));
-            b2[m] = fminf(b2[m], fmaxf(b1[m], d));
-            if (d < b1[m]) { b1[m] = d; idx[m] = j; }
+            float w = __fsqrt_rn(d);
+            if (w < b1[m]) { b1[m] = w; idx[m] = j; }
         }
     }
-#pragma unroll
-    for (int m = 0; m < HPE_PPL; ++m)
-        if (lane + 32 * m < n_pts && __fsqrt_rn(b1[m]) == __fsqrt_rn(b2[m]))
-            idx[m] = match_point_exact(ws.cf, px[m], py[m], pz[m]);
-    return pack_indices(idx);
 }
 
-// phase 3a (see the header comment).  ws.cf / ws.ex must hold the pose being matched.
-// Returns the 8 indices packed 8 bits each (point m of the lane in bits [8m, 8m+8)).
-__device__ __forceinline__ unsigned long long match_sweep(const WarpScratch &ws, const LanePoints &P,
-                                                          const float *cloudf_s, int n_pts, int lane)
+// phase 3a for 4 points of the lane, k = k0 + 32 m (see the header comment).  ws.cf / ws.ex must
+// hold the pose being matched.
+__device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratch &ws, int k0, int lane,
+                                           int idx[HPE_PASS])
 {
     const float INF = __int_as_float(0x7f800000);
-    float M1[HPE_PPL], M2[HPE_PPL];
-    int g1[HPE_PPL];
+    float4 p[HPE_PASS];
+    float M1[HPE_PASS], M2[HPE_PASS];
+    int g1[HPE_PASS];
 #pragma unroll
-    for (int m = 0; m < HPE_PPL; ++m) { M1[m] = INF; M2[m] = INF; g1[m] = 0; }
-
+    for (int m = 0; m < HPE_PASS; ++m) {
+        p[m] = fs.pre[k0 + 32 * m];
+        M1[m] = INF; M2[m] = INF; g1[m] = 0;
+    }
     // ---- sweep A: block minima of s_j over all 48 spheres ----
-#pragma unroll 2
+#pragma unroll 3
     for (int g = 0; g < HPE_NBLK; ++g) {
-        const float4 e0 = ws.ex[g * HPE_BLK + 0], e1 = ws.ex[g * HPE_BLK + 1];
-        const float4 e2 = ws.ex[g * HPE_BLK + 2], e3 = ws.ex[g * HPE_BLK + 3];
+        float4 e[HPE_BLK];
 #pragma unroll
-        for (int m = 0; m < HPE_PPL; ++m) {
-            float s0 = fmaf(P.z[m], e0.z, fmaf(P.y[m], e0.y, fmaf(P.x[m], e0.x, e0.w)));
-            float s1 = fmaf(P.z[m], e1.z, fmaf(P.y[m], e1.y, fmaf(P.x[m], e1.x, e1.w)));
-            float s2 = fmaf(P.z[m], e2.z, fmaf(P.y[m], e2.y, fmaf(P.x[m], e2.x, e2.w)));
-            float s3 = fmaf(P.z[m], e3.z, fmaf(P.y[m], e3.y, fmaf(P.x[m], e3.x, e3.w)));
-            float gm = fmin3(fminf(s0, s1), s2, s3);
+        for (int j = 0; j < HPE_BLK; ++j) e[j] = ws.ex[g * HPE_BLK + j];
+#if HPE_SWEEP_STAGED
+        // 16 independent accumulators, one coordinate at a time: consecutive FFMAs share the sphere
+        // operands (operand-reuse cache) and nothing waits on a 4-cycle dependency
+        float s[HPE_PASS][HPE_BLK];
+#pragma unroll
+        for (int j = 0; j < HPE_BLK; ++j)
+#pragma unroll
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].x, e[j].x, e[j].w);
+#pragma unroll
+        for (int j = 0; j < HPE_BLK; ++j)
+#pragma unroll
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].y, e[j].y, s[m][j]);
+#pragma unroll
+        for (int j = 0; j < HPE_BLK; ++j)
+#pragma unroll
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].z, e[j].z, s[m][j]);
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) {
+            float gm = fmin3(fminf(s[m][0], s[m][1]), s[m][2], s[m][3]);
+#else
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) {
+            float gm = fmin3(fminf(expanded(p[m], e[0]), expanded(p[m], e[1])), expanded(p[m], e[2]), expanded(p[m], e[3]));
+#endif
             M2[m] = fminf(M2[m], fmaxf(M1[m], gm));
             bool better = gm < M1[m];
             M1[m] = fminf(M1[m], gm);
             g1[m] = better ? g : g1[m];
         }
     }
-
-    // ---- sweep B: the 4 spheres of the best block again (bit-identical s), winner + runner-up,
-    //      certificate against every other sphere ----
-    unsigned long long packed = 0ull;
+    // ---- sweep B + certificate ----
     unsigned slow = 0u;
 #pragma unroll
-    for (int m = 0; m < HPE_PPL; ++m) {
+    for (int m = 0; m < HPE_PASS; ++m) {
         const float4 *blk = ws.ex + g1[m] * HPE_BLK;
-        const float4 e0 = blk[0], e1 = blk[1], e2 = blk[2], e3 = blk[3];
-        float s0 = fmaf(P.z[m], e0.z, fmaf(P.y[m], e0.y, fmaf(P.x[m], e0.x, e0.w)));
-        float s1 = fmaf(P.z[m], e1.z, fmaf(P.y[m], e1.y, fmaf(P.x[m], e1.x, e1.w)));
-        float s2 = fmaf(P.z[m], e2.z, fmaf(P.y[m], e2.y, fmaf(P.x[m], e2.x, e2.w)));
-        float s3 = fmaf(P.z[m], e3.z, fmaf(P.y[m], e3.y, fmaf(P.x[m], e3.x, e3.w)));
+        float s0 = expanded(p[m], blk[0]), s1 = expanded(p[m], blk[1]);
+        float s2 = expanded(p[m], blk[2]), s3 = expanded(p[m], blk[3]);
         float lo01 = fminf(s0, s1), hi01 = fmaxf(s0, s1), lo23 = fminf(s2, s3), hi23 = fmaxf(s2, s3);
         float r = fmin3(fmaxf(lo01, lo23), hi01, hi23);                   // runner-up inside the block
-        const float tau = fmaf(3.2e-6f, fabsf(M1[m]), P.tau0[m]);         // 52 * 2^-24 = 3.0994e-6
+        const float tau = fmaf(3.2e-6f, fabsf(M1[m]), p[m].w);            // 52 * 2^-24 = 3.0994e-6
         bool cert = fminf(M2[m], r) - M1[m] > tau;                        // false on NaN
         int i = s1 < s0 ? 1 : 0, j = s3 < s2 ? 3 : 2;
-        int bi = lo23 < lo01 ? j : i;
-        packed |= (unsigned long long)(g1[m] * HPE_BLK + bi) << (8 * m);
+        idx[m] = g1[m] * HPE_BLK + (lo23 < lo01 ? j : i);
         slow |= (cert ? 0u : 1u) << m;
     }
-    // ---- fallback: the reference's arithmetic on all 48 spheres, one flagged point at a time with
-    //      the whole warp on it (lanes = spheres) ----
+    // ---- fallback ----
     if (__any_sync(0xffffffffu, slow != 0u)) {
-        for (int m = 0; m < HPE_PPL; ++m) {
-            unsigned todo = __ballot_sync(0xffffffffu, ((slow >> m) & 1u) && lane + 32 * m < n_pts);
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) {
+            unsigned todo = __ballot_sync(0xffffffffu, ((slow >> m) & 1u) && k0 + 32 * m < fs.n_pts);
             if (todo && lane == 0) atomicAdd(&g_hpe_fallback_points, (unsigned long long)__popc(todo));
             while (todo) {
                 int src = __ffs(todo) - 1;
                 todo &= todo - 1;
-                int k = src + 32 * m;
-                int e = match_point_exact_warp(ws.cf, cloudf_s[k], cloudf_s[HPE_MAXPTS + k],
-                                               cloudf_s[2 * HPE_MAXPTS + k], lane);
-                if (lane == src) packed = (packed & ~(0xffull << (8 * m))) | ((unsigned long long)e << (8 * m));
+                int k = k0 - lane + src + 32 * m;
+                int e = match_point_exact_warp(ws.cf, (float)fs.cloud[k], (float)fs.cloud[HPE_MAXPTS + k],
+                                               (float)fs.cloud[2 * HPE_MAXPTS + k], lane);
+                if (lane == src) idx[m] = e;
             }
         }
     }
-    return packed;
 }
 
-__device__ __forceinline__ unsigned long long pack_indices(const int idx[HPE_PPL])
+// phase 3 of pose g: both passes; returns the warp-reduced align_models value
+// (src/costfunc.cpp:346-377), valid on all lanes.  frozen: optional fixed correspondences
+// (n_pts ints); match_row: optional output row (n_pts ints).
+template <int MATCHER>
+__device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScratch &ws, int g, int lane,
+                                              const int32_t *frozen, int32_t *match_row)
 {
-    unsigned long long packed = 0ull;
-#pragma unroll
-    for (int m = 0; m < HPE_PPL; ++m) packed |= (unsigned long long)(idx[m] & 255) << (8 * m);
-    return packed;
-}
-
-// phase 3b: align_models (src/costfunc.cpp:346-377) for the lane's points, FP64.
-// cloud_s: shared-memory SoA copy of the frame's cloud (X | -Y | -Z), stride n_pts.
-__device__ __forceinline__ double align_lane(const double *rad_s, const double *sphd,
-                                             const double *cloud_s, int n_pts, int lane,
-                                             unsigned long long packed)
-{
+    const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
+    const int n_pts = fs.n_pts;
     double acc = 0.0;
-#pragma unroll 2
-    for (int m = 0; m < HPE_PPL; ++m) {
-        int k = lane + 32 * m;
-        if (k < n_pts) {
-            int j = (int)((packed >> (8 * m)) & 255ull);
-            // negated-frame centre = (cx, -cy, -cz)
-            double a = cloud_s[k] - sphd[j * 3 + 0];
-            double b = cloud_s[n_pts + k] + sphd[j * 3 + 1];
-            double e = cloud_s[2 * n_pts + k] + sphd[j * 3 + 2];
-            double nor = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e)));
-            double df = fabs(nor - rad_s[j]);
-            acc += __dmul_rn(df, df);
+#pragma unroll 1
+    for (int pass = 0; pass < HPE_PPL / HPE_PASS; ++pass) {
+        const int k0 = lane + 32 * HPE_PASS * pass;
+        int idx[HPE_PASS];
+        if (frozen) {
+#pragma unroll
+            for (int m = 0; m < HPE_PASS; ++m) idx[m] = k0 + 32 * m < n_pts ? frozen[k0 + 32 * m] : 0;
+        } else if (MATCHER == 1) {
+            match_pass_direct(fs, ws, k0, lane, idx);
+        } else {
+            match_pass(fs, ws, k0, lane, idx);
+        }
+        // align_models for these 4 points, FP64, the reference's operation order
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) {
+            int k = k0 + 32 * m;
+            if (k < n_pts) {
+                int j = idx[m];
+                if (match_row) match_row[k] = j;
+                // negated-frame centre = (cx, -cy, -cz)
+                double a = fs.cloud[k] - sd[j * 3 + 0];
+                double b = fs.cloud[HPE_MAXPTS + k] + sd[j * 3 + 1];
+                double e = fs.cloud[2 * HPE_MAXPTS + k] + sd[j * 3 + 2];
+                double nor = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e)));
+                double df = fabs(nor - fs.rad[j]);
+                acc += __dmul_rn(df, df);
+            }
         }
     }
-    return acc;
+    return __dmul_rn(warp_sum(acc), fs.lambda);
 }
 
 // phase 4: self_collision_penalty (src/costfunc.cpp:130-197): 4 adjacent digit pairs x 36
@@ -361,21 +363,20 @@ __device__ __forceinline__ void group_fk(const DevModel &M, ThetaAt theta, int n
 
 // phase 2: depth_penalty (src/costfunc.cpp:227-304) of pose g, lanes = spheres; the same lanes
 // stage the pose's float32 centres (cf) and sweep-A operands (ex).  Result valid on all lanes.
-__device__ __forceinline__ double depth_and_stage(const double *rad_s, const FrameView &F, const WarpScratch &ws,
-                                                  const LanePoints &P, int g, int lane)
+__device__ __forceinline__ double depth_and_stage(const FrameSmem &fs, const WarpScratch &ws, int g, int lane)
 {
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
     double dv = 0.0;
     __syncwarp();      // previous pose's matcher is done with cf/ex
-#pragma unroll 1
+#pragma unroll
     for (int h = 0; h < 2; ++h) {
         int j = lane + 32 * h;
         if (j < HPE_NSPH) {
             double x = sd[j * 3], y = sd[j * 3 + 1], z = sd[j * 3 + 2];
-            dv += depth_term(F, x, y, z, rad_s[j]);
+            dv += depth_term(fs, x, y, z, fs.rad[j]);
             float4 c = make_float4((float)x, (float)(-y), (float)(-z), 0.f);   // conv_to<fmat>, negated frame
             // c' = cf - q exactly (FP64), then one rounding each for -2c' and |c'|^2
-            double cx = (double)c.x - (double)P.qx, cy = (double)c.y - (double)P.qy, cz = (double)c.z - (double)P.qz;
+            double cx = (double)c.x - (double)fs.qx, cy = (double)c.y - (double)fs.qy, cz = (double)c.z - (double)fs.qz;
             ws.cf[j] = c;
             ws.ex[j] = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz),
                                    (float)(cx * cx + cy * cy + cz * cz));
@@ -383,12 +384,4 @@ __device__ __forceinline__ double depth_and_stage(const double *rad_s, const Fra
     }
     __syncwarp();
     return warp_sum(dv);
-}
-
-// phase 3b reduced over the warp and scaled by lambda = |M|/|P| (src/costfunc.cpp:372-373)
-__device__ __forceinline__ double align_lanes(const double *rad_s, const WarpScratch &ws, int g,
-                                              const double *cloud_s, int n_pts, int lane, unsigned long long packed)
-{
-    double a = align_lane(rad_s, ws.sphd + (size_t)g * HPE_NSPH * 3, cloud_s, n_pts, lane, packed);
-    return __dmul_rn(warp_sum(a), (double)HPE_NSPH / (double)n_pts);
 }

@@ -19,14 +19,14 @@ struct __align__(16) PsoSmemHead {
     int count;
     int fmin_id;
     int pad;
-    // followed by: warp scratch [PSO_WARPS][gsz] slots; double x[num_p][26]; double pcost[num_p];
+    // followed by: warp scratch [PSO_WARPS][gsz] slots; double pcost[num_p];
     //              double fx[num_p]; int informant[num_p]; int R[num_p][3];
 };
 
 __host__ __device__ inline size_t pso_ws_bytes(int gsz) { return (size_t)PSO_WARPS * HPE_WS_BYTES(gsz); }
 __host__ __device__ inline size_t pso_smem_bytes(int num_p, int gsz)
 {
-    return sizeof(PsoSmemHead) + pso_ws_bytes(gsz) + (size_t)num_p * (HPE_NDOF * 8 + 8 + 8 + 4 + PSO_NK * 4) + 16;
+    return sizeof(PsoSmemHead) + pso_ws_bytes(gsz) + (size_t)num_p * (8 + 8 + 4 + PSO_NK * 4) + 16;
 }
 
 // lexicographic (cost, index) minimum over the warp; valid on all lanes
@@ -40,9 +40,9 @@ __device__ __forceinline__ void warp_argmin(double &c, int &i)
     }
 }
 
-__global__ void __launch_bounds__(PSO_WARPS * 32, 2)
+__global__ void __launch_bounds__(PSO_WARPS * 32, HPE_MINBLOCKS)
 pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, int first, int count_swarms,
-           const uint64_t *__restrict__ seeds, double *__restrict__ vel_scratch, double *__restrict__ pbest_scratch,
+           const uint64_t *__restrict__ seeds, double *__restrict__ state_scratch,
            double *__restrict__ bestp_out, double *__restrict__ best_cost_out, double *__restrict__ trace_out,
            int chain, int gsz, double W1, double C1)
 {
@@ -50,14 +50,16 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
     PsoSmemHead &sm = *reinterpret_cast<PsoSmemHead *>(smem_raw);
     const int num_p = prm.num_p, D = HPE_NDOF;
     unsigned char *ws_base = smem_raw + sizeof(PsoSmemHead);
-    double *x = reinterpret_cast<double *>(ws_base + pso_ws_bytes(gsz));
-    double *pcost = x + (size_t)num_p * D;
+    double *pcost = reinterpret_cast<double *>(ws_base + pso_ws_bytes(gsz));
     double *fx = pcost + num_p;
     int *informant = reinterpret_cast<int *>(fx + num_p);
     int *R = informant + num_p;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
-    double *v = vel_scratch + (size_t)blockIdx.x * num_p * D;
-    double *pb = pbest_scratch + (size_t)blockIdx.x * num_p * D;
+    // positions, velocities and personal bests of this CTA's swarm: global scratch (81 B per
+    // particle and array, L2-resident); only the costs and the topology live in shared memory
+    double *x = state_scratch + (size_t)blockIdx.x * 3 * num_p * D;
+    double *v = x + (size_t)num_p * D;
+    double *pb = v + (size_t)num_p * D;
     const double C2 = C1;
 
     stage_model(sm.fs, m);
@@ -66,17 +68,13 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
     // independent swarms: CTA-strided; chain mode: one CTA walks the sequence
     for (int b = chain ? 0 : (int)blockIdx.x; b < count_swarms; b += chain ? 1 : (int)gridDim.x) {
         const int slot = first + b;
-        const FrameView F = frame_view(o, slot);
         const uint64_t seed = seeds ? seeds[b] : 1000ull;
-        __syncthreads();
-        stage_frame(sm.fs, F);
+        stage_frame(sm.fs, frame_view(o, slot));     // ends synchronised
         if (tid < D) {
             // chain mode: x0 = bestp of the previous frame (src/testmodel.cpp:138)
             sm.x0[tid] = (chain && b > 0) ? sm.gbest[tid] : x0_in[(size_t)b * D + tid];
         }
         __syncthreads();
-        LanePoints P;
-        load_lane_points(sm.fs.cloudf, F.n_pts, lane, P);
         const bool frame_ok = o.meta[slot].ok != 0;
 
         // generate_particles: x0 + randn % std, v = 0 (src/PSO.cpp:56-74, :726)
@@ -100,9 +98,8 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
                 const WarpScratch ws = warp_scratch(ws_base, warp, gsz);
                 group_fk(sm.fs.M, [&](int g) { return x + (size_t)(p0 + g) * D; }, cnt, ws, lane);
                 for (int g = 0; g < cnt; ++g) {
-                    double depth = depth_and_stage(sm.fs.rad, F, ws, P, g, lane);
-                    unsigned long long packed = match_sweep(ws, P, sm.fs.cloudf, F.n_pts, lane);
-                    double align = align_lanes(sm.fs.rad, ws, g, sm.fs.cloud, F.n_pts, lane, packed);
+                    double depth = depth_and_stage(sm.fs, ws, g, lane);
+                    double align = match_align<0>(sm.fs, ws, g, lane, nullptr, nullptr);
                     if (lane == 0) fx[p0 + g] = align + depth;
                 }
                 __syncwarp();
@@ -229,18 +226,17 @@ cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p,
     static double *scratch = nullptr;
     static size_t scratch_bytes = 0;
     size_t per = (size_t)p.num_p * HPE_NDOF * sizeof(double);
-    if (2 * per * blocks > scratch_bytes) {
+    if (3 * per * blocks > scratch_bytes) {
         if (scratch) cudaFree(scratch);
         scratch = nullptr; scratch_bytes = 0;
-        cudaError_t e = cudaMalloc(&scratch, 2 * per * blocks);
+        cudaError_t e = cudaMalloc(&scratch, 3 * per * blocks);
         if (e != cudaSuccess) return e;
-        scratch_bytes = 2 * per * blocks;
+        scratch_bytes = 3 * per * blocks;
     }
     cudaError_t e;
     const double W1 = 1. / (2 * log(2.0));       // src/PSO.cpp:772
     const double C1 = 0.5 + log(2.0);            // src/PSO.cpp:773-774
-    pso_kernel<<<blocks, PSO_WARPS * 32, smem, st>>>(m, o, p, x0_dev, first, count, seeds_dev, scratch,
-                                                     scratch + (size_t)p.num_p * HPE_NDOF * blocks, bestp_dev,
+    pso_kernel<<<blocks, PSO_WARPS * 32, smem, st>>>(m, o, p, x0_dev, first, count, seeds_dev, scratch, bestp_dev,
                                                      best_cost_dev, trace_dev, chain, gsz, W1, C1);
     e = cudaGetLastError();
     return e;

@@ -17,7 +17,8 @@ class HpeError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(os.path.dirname(_HERE), "libhpe_b200.so")
+    # HPE_B200_LIB selects another build of the same library (kernel tuning experiments)
+    return os.environ.get("HPE_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libhpe_b200.so")
 
 
 class PsoParams(C.Structure):
