@@ -1,0 +1,299 @@
+// hpe_swarm.cu -- PSO::pso_evolve (src/PSO.cpp:717-886) for ONE large swarm whose particles are
+// block-partitioned over GPUs (BASELINE config "multi-restart swarm").  A rank owns particles
+// [lo,hi); per generation it needs every particle's (pcost, pbest) row because informants are
+// drawn over the whole swarm (src/PSO.cpp:790-812), so the caller all-gathers the 27-double rows
+// between hpe_swarm_step / hpe_swarm_reduce (NCCL over NVLink in bench.py, gloo in the CPU tests of
+// the host logic).  All arithmetic is keyed by the GLOBAL particle index (Philox counters), so the
+// sharded run is bit-identical to the single-GPU run and to the one-CTA kernel of hpe_pso.cu.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "hpe_internal.h"
+
+namespace {
+
+constexpr int NK = 3;                 // informants drawn per particle, src/PSO.cpp:769
+constexpr int ROW = 1 + HPE_NDOF;     // table row: pcost, pbest[26]
+
+struct SwarmCtl {                     // device-resident control block
+    double gbest_cost;
+    double gbest[HPE_NDOF];
+    int count;
+    int iter;                         // evaluations done so far (1 after init)
+    unsigned long long best_key;      // scratch of the argmin reduction
+    int best_idx;
+};
+
+__device__ __forceinline__ unsigned long long cost_bits(double c)
+{
+    // costs are >= 0 (or NaN/inf): the IEEE bit pattern of a non-negative double orders like the value;
+    // NaN maps above +inf so that it never wins a minimum
+    return c == c ? (unsigned long long)__double_as_longlong(c) : 0xfff8000000000000ull;
+}
+
+// generate_particles for the owned rows (src/PSO.cpp:56-74): x0 + randn % std, v = 0
+__global__ void swarm_generate(PsoDev prm, const double *x0, uint64_t seed, int lo, int hi, double *x, double *v)
+{
+    int it = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = (hi - lo) * (HPE_NDOF / 2);
+    if (it >= n) return;
+    int li = it / (HPE_NDOF / 2), dp = it - li * (HPE_NDOF / 2);
+    double z[2];
+    normal2(seed, (uint32_t)dp, (uint32_t)(lo + li), 0u, z);
+    x[li * HPE_NDOF + 2 * dp] = __dadd_rn(x0[2 * dp], __dmul_rn(z[0], prm.std[2 * dp]));
+    x[li * HPE_NDOF + 2 * dp + 1] = __dadd_rn(x0[2 * dp + 1], __dmul_rn(z[1], prm.std[2 * dp + 1]));
+    v[li * HPE_NDOF + 2 * dp] = 0.0;
+    v[li * HPE_NDOF + 2 * dp + 1] = 0.0;
+}
+
+// pbest bookkeeping of the owned rows after an evaluation (src/PSO.cpp:753, 855-860)
+__global__ void swarm_pbest(int lo, int hi, const double *x, const double *fx, double *table, const SwarmCtl *ctl)
+{
+    // blockDim.x is a multiple of ROW, so a row never straddles two CTAs
+    int it = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = it < (hi - lo) * ROW;
+    int li = live ? it / ROW : 0, c = live ? it - li * ROW : 0;
+    double *row = table + (size_t)(lo + li) * ROW;
+    // every thread of a row evaluates `take` on the old pcost before thread c == 0 overwrites it
+    bool take = live && (ctl->iter == 0 || fx[li] < row[0]);
+    double val = !live ? 0.0 : (c == 0 ? fx[li] : x[li * HPE_NDOF + c - 1]);
+    __syncthreads();
+    if (take) row[c] = val;
+}
+
+// global first minimum of pcost + gbest/count bookkeeping (src/PSO.cpp:755-760, 864-876)
+__global__ void swarm_argmin_partial(int num_p, const double *table, SwarmCtl *ctl)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long key = ~0ull;
+    if (i < num_p) key = cost_bits(table[(size_t)i * ROW]);
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+        if (ok < key) key = ok;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMin(&ctl->best_key, key);
+}
+
+__global__ void swarm_argmin_index(int num_p, const double *table, SwarmCtl *ctl)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < num_p && cost_bits(table[(size_t)i * ROW]) == ctl->best_key) atomicMin(&ctl->best_idx, i);
+}
+
+__global__ void swarm_gbest(const double *table, SwarmCtl *ctl, double *trace)
+{
+    __shared__ int improved;
+    if (threadIdx.x == 0) {
+        int id = ctl->best_idx;
+        double fmin = table[(size_t)id * ROW];
+        improved = fmin < ctl->gbest_cost;
+        if (improved) {
+            ctl->gbest_cost = fmin;
+            ctl->count = ctl->iter == 0 ? 100 : 0;
+        } else if (ctl->iter > 0) {
+            ctl->count += 1;
+        }
+        ctl->iter += 1;
+        if (trace && ctl->iter >= 2) trace[ctl->iter - 2] = ctl->gbest_cost;
+    }
+    __syncthreads();
+    if (improved && threadIdx.x < HPE_NDOF) ctl->gbest[threadIdx.x] = table[(size_t)ctl->best_idx * ROW + 1 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) { ctl->best_key = ~0ull; ctl->best_idx = 0x7fffffff; }
+}
+
+// topology (src/PSO.cpp:790-803): R[s][k] = floor(U (num_p-1) + 0.5), redrawn only when count > 0
+__global__ void swarm_topology(int num_p, uint64_t seed, const SwarmCtl *ctl, int *R)
+{
+    if (ctl->count <= 0) return;
+    int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= num_p * NK) return;
+    int s = it / NK, k = it - s * NK;
+    double u[2];
+    uniform2(seed, (uint32_t)(k >> 1), (uint32_t)s, (uint32_t)ctl->iter, 3u, u);
+    R[it] = (int)floor(__dadd_rn(__dmul_rn(u[k & 1], (double)(num_p - 1)), 0.5));
+}
+
+// informant(i) = first minimum of pcost over {s : L(s,i) = 1}, L = eye + links (src/PSO.cpp:810-812),
+// as two scatter passes over the num_p*(NK+1) links: minimum cost, then lowest index attaining it
+__global__ void swarm_inf_init(int num_p, const double *table, unsigned long long *key, int *inf)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_p) return;
+    key[i] = cost_bits(table[(size_t)i * ROW]);
+    inf[i] = 0x7fffffff;
+}
+
+__global__ void swarm_inf_cost(int num_p, const double *table, const int *R, unsigned long long *key)
+{
+    int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= num_p * NK) return;
+    atomicMin(&key[R[it]], cost_bits(table[(size_t)(it / NK) * ROW]));
+}
+
+__global__ void swarm_inf_index(int num_p, const double *table, const int *R, const unsigned long long *key, int *inf)
+{
+    int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= num_p * (NK + 1)) return;
+    int s = it / (NK + 1), k = it - s * (NK + 1);
+    int r = k == NK ? s : R[s * NK + k];
+    if (cost_bits(table[(size_t)s * ROW]) == key[r]) atomicMin(&inf[r], s);
+}
+
+// velocity, position, check_constraints for the owned rows (src/PSO.cpp:824-840, 358-377)
+__global__ void swarm_update(PsoDev prm, uint64_t seed, int lo, int hi, const double *table, const int *inf,
+                             const SwarmCtl *ctl, double *x, double *v, double W1, double C1)
+{
+    int it = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = (hi - lo) * (HPE_NDOF / 2);
+    if (it >= n) return;
+    int li = it / (HPE_NDOF / 2), dp = it - li * (HPE_NDOF / 2);
+    int i = lo + li, informant = inf[i];
+    const uint32_t gen = (uint32_t)ctl->iter;
+    const double *pb = table + (size_t)i * ROW + 1, *pbi = table + (size_t)informant * ROW + 1;
+    double rp[2], rg[2];
+    uniform2(seed, (uint32_t)dp, (uint32_t)i, gen, 1u, rp);
+    uniform2(seed, (uint32_t)dp, (uint32_t)i, gen, 2u, rg);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        int d = 2 * dp + e, at = li * HPE_NDOF + d;
+        double xi = x[at];
+        double nv = __dadd_rn(__dmul_rn(v[at], W1), __dmul_rn(__dmul_rn(rp[e], C1), __dadd_rn(pb[d], -xi)));
+        if (informant != i) nv = __dadd_rn(nv, __dmul_rn(__dmul_rn(rg[e], C1), __dadd_rn(pbi[d], -xi)));
+        double nx = __dadd_rn(xi, nv);
+        if (nx < prm.lb[d] || nx > prm.ub[d]) { nx = prm.lb[d]; nv = 0.0; }   // upper violation -> LOWER bound (:372)
+        x[at] = nx;
+        v[at] = nv;
+    }
+}
+
+inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+}  // namespace
+
+struct hpe_swarm {
+    const hpe_model *m;
+    const hpe_obs *o;
+    int slot, num_p, lo, hi;
+    PsoDev prm;
+    uint64_t seed;
+    double W1, C1;
+    double *x0, *x, *v, *fx, *table, *trace;
+    int *R, *inf;
+    unsigned long long *key;
+    SwarmCtl *ctl;
+};
+
+extern "C" {
+
+int hpe_swarm_destroy(hpe_swarm *s)
+{
+    if (!s) return HPE_OK;
+    cudaFree(s->x0); cudaFree(s->x); cudaFree(s->v); cudaFree(s->fx); cudaFree(s->table); cudaFree(s->trace);
+    cudaFree(s->R); cudaFree(s->inf); cudaFree(s->key); cudaFree(s->ctl);
+    delete s;
+    return HPE_OK;
+}
+
+int hpe_swarm_create(const hpe_model *m, const hpe_obs *o, int slot, const hpe_pso_params *p, int num_particles,
+                     int lo, int hi, const double x0[HPE_NDOF], uint64_t seed, hpe_swarm **out)
+{
+    if (!m || !o || !p || !x0 || !out || num_particles < 1 || lo < 0 || hi > num_particles || lo > hi || p->maxiter < 1)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_create: bad argument");
+    if (slot < 0 || slot >= o->v.capacity) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_create: slot out of range");
+    hpe_swarm *s = new (std::nothrow) hpe_swarm();
+    if (!s) return hpe_set_error(HPE_ERR_ARG, "out of host memory");
+    s->m = m; s->o = o; s->slot = slot; s->num_p = num_particles; s->lo = lo; s->hi = hi; s->seed = seed;
+    memcpy(s->prm.lb, p->lb, sizeof s->prm.lb);
+    memcpy(s->prm.ub, p->ub, sizeof s->prm.ub);
+    memcpy(s->prm.std, p->std, sizeof s->prm.std);
+    s->prm.maxiter = p->maxiter;
+    s->prm.num_p = num_particles;
+    s->W1 = 1. / (2 * log(2.0));      // src/PSO.cpp:772
+    s->C1 = 0.5 + log(2.0);           // src/PSO.cpp:773-774
+    const size_t own = (size_t)(hi - lo > 0 ? hi - lo : 1), np = (size_t)num_particles;
+    const int tl = p->maxiter > 1 ? p->maxiter - 1 : 1;
+    cudaError_t e = cudaMalloc(&s->x0, sizeof(double) * HPE_NDOF);
+    if (e == cudaSuccess) e = cudaMalloc(&s->x, sizeof(double) * own * HPE_NDOF);
+    if (e == cudaSuccess) e = cudaMalloc(&s->v, sizeof(double) * own * HPE_NDOF);
+    if (e == cudaSuccess) e = cudaMalloc(&s->fx, sizeof(double) * own);
+    if (e == cudaSuccess) e = cudaMalloc(&s->table, sizeof(double) * np * ROW);
+    if (e == cudaSuccess) e = cudaMalloc(&s->trace, sizeof(double) * tl);
+    if (e == cudaSuccess) e = cudaMalloc(&s->R, sizeof(int) * np * NK);
+    if (e == cudaSuccess) e = cudaMalloc(&s->inf, sizeof(int) * np);
+    if (e == cudaSuccess) e = cudaMalloc(&s->key, sizeof(unsigned long long) * np);
+    if (e == cudaSuccess) e = cudaMalloc(&s->ctl, sizeof(SwarmCtl));
+    if (e == cudaSuccess) e = cudaMemcpy(s->x0, x0, sizeof(double) * HPE_NDOF, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(s->table, 0, sizeof(double) * np * ROW);
+    if (e != cudaSuccess) {
+        hpe_swarm_destroy(s);
+        return hpe_set_error(HPE_ERR_CUDA, "hpe_swarm_create: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return HPE_OK;
+}
+
+double *hpe_swarm_table(hpe_swarm *s) { return s ? s->table : nullptr; }
+
+int hpe_swarm_init(hpe_swarm *s, void *stream)
+{
+    if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_init: NULL swarm");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int own = s->hi - s->lo;
+    SwarmCtl c;
+    memset(&c, 0, sizeof c);
+    c.gbest_cost = 1e100; c.count = 100; c.iter = 0; c.best_key = ~0ull; c.best_idx = 0x7fffffff;
+    HPE_CUDA(cudaMemcpyAsync(s->ctl, &c, sizeof c, cudaMemcpyHostToDevice, st));
+    if (own > 0) {
+        swarm_generate<<<nblk((long long)own * (HPE_NDOF / 2), 256), 256, 0, st>>>(s->prm, s->x0, s->seed, s->lo, s->hi, s->x, s->v);
+        HPE_CUDA(hpe_launch_cost(s->m->dm, s->o->v, s->slot, s->x, own, false, s->fx, nullptr, nullptr, nullptr, st));
+        swarm_pbest<<<nblk((long long)own * ROW, 27 * 8), 27 * 8, 0, st>>>(s->lo, s->hi, s->x, s->fx, s->table, s->ctl);
+    }
+    HPE_CUDA(cudaGetLastError());
+    return HPE_OK;
+}
+
+int hpe_swarm_reduce(hpe_swarm *s, void *stream)
+{
+    if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_reduce: NULL swarm");
+    cudaStream_t st = (cudaStream_t)stream;
+    swarm_argmin_partial<<<nblk(s->num_p, 256), 256, 0, st>>>(s->num_p, s->table, s->ctl);
+    swarm_argmin_index<<<nblk(s->num_p, 256), 256, 0, st>>>(s->num_p, s->table, s->ctl);
+    swarm_gbest<<<1, 32, 0, st>>>(s->table, s->ctl, s->trace);
+    HPE_CUDA(cudaGetLastError());
+    return HPE_OK;
+}
+
+int hpe_swarm_step(hpe_swarm *s, void *stream)
+{
+    if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_step: NULL swarm");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int own = s->hi - s->lo, np = s->num_p;
+    swarm_topology<<<nblk((long long)np * NK, 256), 256, 0, st>>>(np, s->seed, s->ctl, s->R);
+    swarm_inf_init<<<nblk(np, 256), 256, 0, st>>>(np, s->table, s->key, s->inf);
+    swarm_inf_cost<<<nblk((long long)np * NK, 256), 256, 0, st>>>(np, s->table, s->R, s->key);
+    swarm_inf_index<<<nblk((long long)np * (NK + 1), 256), 256, 0, st>>>(np, s->table, s->R, s->key, s->inf);
+    if (own > 0) {
+        swarm_update<<<nblk((long long)own * (HPE_NDOF / 2), 256), 256, 0, st>>>(s->prm, s->seed, s->lo, s->hi, s->table, s->inf,
+                                                                               s->ctl, s->x, s->v, s->W1, s->C1);
+        HPE_CUDA(hpe_launch_cost(s->m->dm, s->o->v, s->slot, s->x, own, false, s->fx, nullptr, nullptr, nullptr, st));
+        swarm_pbest<<<nblk((long long)own * ROW, 27 * 8), 27 * 8, 0, st>>>(s->lo, s->hi, s->x, s->fx, s->table, s->ctl);
+    }
+    HPE_CUDA(cudaGetLastError());
+    return HPE_OK;
+}
+
+int hpe_swarm_best(hpe_swarm *s, double bestp[HPE_NDOF], double *best_cost, double *trace)
+{
+    if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_best: NULL swarm");
+    SwarmCtl c;
+    HPE_CUDA(cudaMemcpy(&c, s->ctl, sizeof c, cudaMemcpyDeviceToHost));
+    if (bestp) memcpy(bestp, c.gbest, sizeof c.gbest);
+    if (best_cost) *best_cost = c.gbest_cost;
+    if (trace && s->prm.maxiter > 1)
+        HPE_CUDA(cudaMemcpy(trace, s->trace, sizeof(double) * (s->prm.maxiter - 1), cudaMemcpyDeviceToHost));
+    return HPE_OK;
+}
+
+}  // extern "C"

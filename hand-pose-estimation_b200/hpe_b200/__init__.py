@@ -13,8 +13,8 @@ There is no CPU fallback: importing works anywhere, every compute call needs the
 and a GPU and raises HpeError otherwise.
 """
 from . import defaults
-from .binding import (HpeError, lib, library_path, device_count, handmodel, observedmodel, costfunc, PSO,
+from .binding import (HpeError, lib, library_path, device_count, handmodel, observedmodel, costfunc, PSO, Swarm,
                       PsoParams, render_frames)
 
 __all__ = ["defaults", "HpeError", "lib", "library_path", "device_count", "handmodel", "observedmodel",
-           "costfunc", "PSO", "PsoParams", "render_frames"]
+           "costfunc", "PSO", "Swarm", "PsoParams", "render_frames"]

@@ -298,6 +298,50 @@ class PSO:
         return poses, costs
 
 
+class Swarm:
+    """One large swarm (pso_evolve semantics) whose particles [lo,hi) live on this GPU.  Drive it as
+        init(); exchange(); reduce(); for _ in range(maxiter-1): step(); exchange(); reduce()
+    where exchange() makes every rank's table complete (all-gather of the owned rows; a no-op
+    when lo,hi cover the whole swarm)."""
+    ROW = 27
+
+    def __init__(self, optfunc, params, num_particles, lo, hi, x0, seed=1000, slot=0):
+        self._h = C.c_void_p()
+        self.num_particles, self.lo, self.hi = int(num_particles), int(lo), int(hi)
+        self.maxiter = params.maxiter
+        x0 = _f64(x0).reshape(26)
+        self._keep = (optfunc, params)
+        _check(lib().hpe_swarm_create(optfunc.hand._h, optfunc.observation._h, int(slot), C.byref(params),
+                                      self.num_particles, self.lo, self.hi, _p(x0), C.c_uint64(seed),
+                                      C.byref(self._h)))
+        lib().hpe_swarm_table.restype = C.c_void_p
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.hpe_swarm_destroy(self._h)
+            self._h = None
+
+    def table_ptr(self):
+        """device pointer of the [num_particles][27] float64 table (pcost, pbest)"""
+        return lib().hpe_swarm_table(self._h)
+
+    def init(self, stream=None):
+        _check(lib().hpe_swarm_init(self._h, C.c_void_p(stream or 0)))
+
+    def step(self, stream=None):
+        _check(lib().hpe_swarm_step(self._h, C.c_void_p(stream or 0)))
+
+    def reduce(self, stream=None):
+        _check(lib().hpe_swarm_reduce(self._h, C.c_void_p(stream or 0)))
+
+    def best(self):
+        bestp = np.empty(26)
+        cost = C.c_double()
+        trace = np.empty(max(self.maxiter - 1, 1))
+        _check(lib().hpe_swarm_best(self._h, _p(bestp), C.byref(cost), _p(trace)))
+        return bestp, cost.value, trace[:self.maxiter - 1]
+
+
 def measure_fp32_peak():
     """(TFLOP/s, implied SM MHz) of a register-only FFMA kernel on the current device."""
     tf, mhz = C.c_double(), C.c_double()

@@ -44,6 +44,7 @@ typedef enum {
 
 typedef struct hpe_model hpe_model; /* handmodel + 4 fingermodel + thumbmodel geometry */
 typedef struct hpe_obs hpe_obs;     /* a batch of observedmodel states (frames) on the device */
+typedef struct hpe_swarm hpe_swarm; /* one large swarm stepped generation by generation */
 
 /* PSO::set_pso_params (src/PSO.cpp:38-54).  w,c1,c2,minstep,minfunc are accepted
  * for signature fidelity and ignored, exactly as pso_evolve ignores them
@@ -137,6 +138,26 @@ int hpe_pso_evolve(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p
 int hpe_track_sequence(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p,
                        int num_particles, const double x0[HPE_NDOF], int first, int n_frames,
                        uint64_t seed, double *poses, double *costs);
+
+/* ---- one large swarm, particles [lo,hi) of num_particles owned by this GPU ---- */
+/* State lives on the device; the caller (one process per GPU) exchanges the
+ * pbest table between generations (all-gather of hpe_swarm_table rows). */
+int hpe_swarm_create(const hpe_model *m, const hpe_obs *o, int slot, const hpe_pso_params *p,
+                     int num_particles, int lo, int hi, const double x0[HPE_NDOF], uint64_t seed,
+                     hpe_swarm **out);
+int hpe_swarm_destroy(hpe_swarm *s);
+/* device pointer to the global table [num_particles][27] doubles = (pcost, pbest[26]);
+ * rows [lo,hi) are written by this GPU, the others must be filled by the exchange. */
+double *hpe_swarm_table(hpe_swarm *s);
+/* generation 0: generate_particles + evaluation of the owned rows (src/PSO.cpp:745-763) */
+int hpe_swarm_init(hpe_swarm *s, void *stream);
+/* after the exchange: global argmin / count bookkeeping (src/PSO.cpp:864-876) */
+int hpe_swarm_reduce(hpe_swarm *s, void *stream);
+/* one generation for the owned rows: topology, informants, velocity, clamp, evaluation,
+ * pbest (src/PSO.cpp:781-861).  Requires a complete table. */
+int hpe_swarm_step(hpe_swarm *s, void *stream);
+/* host copies of gbest (and of bcost_evo, maxiter-1 values, may be NULL) after the last hpe_swarm_reduce */
+int hpe_swarm_best(hpe_swarm *s, double bestp[HPE_NDOF], double *best_cost, double *trace);
 
 /* ---- synthetic frames (also the overlay of src/costfunc.cpp:439-473) ---- */
 /* ray-cast the sphere model at n poses into depth frames (mm, 0 = background).

@@ -1,0 +1,94 @@
+"""GPU: the CUDA path against the committed golden file (tests/golden/golden_v1.npz, produced by
+tests/golden/make_golden.py from the CPU oracle), and size-independent properties at the full
+BASELINE sizes where the oracle would take too long."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(HERE, "golden", "golden_v1.npz"))
+
+
+def golden_frame(g):
+    fr = np.zeros((240, 320), dtype=np.float32)
+    fr[g["frame_y"], g["frame_x"]] = g["frame_mm"]
+    return fr
+
+
+def test_cuda_path_reproduces_golden(hpe, golden, D):
+    g = golden
+    hand, obs = hpe.handmodel(), hpe.observedmodel(capacity=1)
+    obs.upload(golden_frame(g)[None])
+    o = obs.get(0)
+    assert o["n_hand"] == int(g["n_hand"]) and np.array_equal(o["cloud"], g["cloud"])
+    assert abs(o["scale"] - float(g["scale"])) <= 1e-13 * float(g["scale"])
+    assert o["dt_max"] == np.float32(g["dt_max"]) and np.array_equal(o["dt"][::16], g["dt_rows"])
+    assert abs(o["dt"].astype(np.float64).sum() - float(g["dt_sum"])) < 1e-6
+    S, J = hand.build_hand_models(g["poses"])
+    assert np.abs(S - g["spheres"]).max() < 1e-11 and np.abs(J - g["joints"]).max() < 1e-11
+    cf = hpe.costfunc(hand, obs)
+    a, d, c = cf.cal_cost_batch(g["poses"], with_collision=True)
+    assert np.allclose(a, g["align"], rtol=1e-9) and np.allclose(d, g["depth_term"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(c, g["colli"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(cf.compute_correspondences(g["poses"]), g["match"].astype(np.int32))
+    pso = hpe.PSO()
+    pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, int(g["pso_maxiter"]), 1e-8, 1e-8)
+    bp, best, tr = pso.pso_evolve_batch(cf, g["pso_x0"][None], int(g["pso_num_p"]), seeds=[int(g["pso_seed"])])
+    assert np.allclose(tr[0], g["pso_trace"], rtol=1e-8) and np.abs(bp[0] - g["pso_bestp"]).max() < 1e-7
+
+
+def test_full_size_cost_batch_properties(hpe, orc, omodel, golden, D):
+    """configs[1] at its real size (65,536 poses): spot-check against the oracle, and properties that
+    do not need it: batch-split invariance, permutation equivariance, translation of the cloud."""
+    g = golden
+    truth = g["truth"]
+    rng = np.random.default_rng(2)
+    n = 65536
+    th = truth + rng.normal(size=(n, 26)) * D.STD
+    hand, obs = hpe.handmodel(), hpe.observedmodel(capacity=1)
+    fr = golden_frame(g)
+    obs.upload(fr[None])
+    cf = hpe.costfunc(hand, obs)
+    a, d, _ = cf.cal_cost_batch(th)
+    assert np.isfinite(a).all() and np.isfinite(d).all() and (a >= 0).all() and (d >= 0).all()
+    pick = rng.choice(n, 2048, replace=False)
+    ao, do, _ = orc.cost_batch(omodel, orc.Observation(fr), th[pick], collision=False)
+    rel = np.abs((a[pick] + d[pick]) - (ao + do)) / (ao + do)
+    assert rel.max() < 1e-9                                    # north star asks for 1e-4
+    # a pose's cost does not depend on the batch it is evaluated in, nor on its position in it
+    a2, d2, _ = cf.cal_cost_batch(th[1000:1777])
+    assert np.array_equal(a2, a[1000:1777]) and np.array_equal(d2, d[1000:1777])
+    perm = rng.permutation(n)
+    a3, d3, _ = cf.cal_cost_batch(th[perm])
+    assert np.array_equal(a3, a[perm]) and np.array_equal(d3, d[perm])
+
+
+def test_full_size_swarm_batch_properties(hpe, golden, D):
+    """many independent 64 x 30 swarms: a swarm's result does not depend on the batch around it;
+    the trace is non-increasing and ends at the reported best cost"""
+    g = golden
+    rng = np.random.default_rng(6)
+    n_fr = 600
+    truths = np.clip(D.X0 + rng.normal(size=(n_fr, 26)) * D.STD * 0.5, D.LB, D.UB)
+    hand = hpe.handmodel()
+    frames = hpe.render_frames(hand, truths)
+    obs = hpe.observedmodel(capacity=n_fr)
+    obs.upload(frames)
+    cf = hpe.costfunc(hand, obs)
+    pso = hpe.PSO()
+    pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, 30, 1e-8, 1e-8)
+    x0 = truths + rng.normal(size=truths.shape) * D.STD * 0.3
+    bp, best, tr = pso.pso_evolve_batch(cf, x0, 64)
+    assert np.all(np.diff(tr, axis=1) <= 0) and np.array_equal(tr[:, -1], best)
+    a, d, _ = cf.cal_cost_batch(bp[17:18], slot=17)
+    assert abs(a[0] + d[0] - best[17]) <= 1e-12 * best[17]       # gbest_pos scores gbest_cost
+    bp2, best2, _ = pso.pso_evolve_batch(cf, x0[100:110], 64, first=100)
+    assert np.array_equal(bp2, bp[100:110]) and np.array_equal(best2, best[100:110])
+    x0_cost = np.array([cf.cal_cost(x0[k], slot=k) for k in range(0, n_fr, 50)])
+    assert np.all(best[::50] < x0_cost)
