@@ -50,9 +50,11 @@ def pose_sets(D, truth, n_sets, seed):
 
 
 class ClockSampler:
-    """nvidia-smi sampling (every 100 ms) of SM clock and throttle reasons during the timed region"""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi sampling (every 50 ms) of SM clock and throttle reasons; started before the warm-up
+    (nvidia-smi needs a moment to come up) and reduced to the samples inside the timed window"""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.path = index, None, None
@@ -62,12 +64,14 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0, t1: time.time() bounds of the timed region"""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -76,25 +80,26 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 6:
+            if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, val in zip(names, f[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.path)
-        if sm:
-            out["sm_mhz"] = float(np.median(sm))
-            out["sm_max_mhz"] = float(max(mx))
-        out["reasons"] = sorted(reasons)
-        out["samples"] = len(sm)
+        inside = [r for r in rows if t0 is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+        use = inside or rows
+        if use:
+            out["sm_mhz"] = float(np.median([r[1] for r in use]))
+            out["sm_max_mhz"] = float(max(r[2] for r in use))
+            out["reasons"] = sorted({nm for r in use for nm in r[3]})
+        out["samples"] = len(use)
+        out["window"] = "timed region" if inside else "whole run (timed region shorter than the sampling period)"
         return out
 
 
@@ -111,18 +116,26 @@ def cpu_baseline(n_pts, seconds=12.0, reference_arm=False, steps=0, warmup=0):
     th = pose_sets(D, truth, 1, 2)[0]
     cores = orc.num_threads()
     if reference_arm:
-        for _ in range(warmup):
-            orc.cost_batch(om, obs, th, collision=False)
+        # each step scores a bounded sample of the 65,536 poses, sized so that warmup + steps take
+        # about a minute on this host whatever K and W are
         t0 = time.perf_counter()
-        for _ in range(steps):
-            orc.cost_batch(om, obs, th, collision=False)
+        orc.cost_batch(om, obs, th[:4096], collision=False)
+        rate = 4096 / (time.perf_counter() - t0)
+        per_step = int(min(N_POSES, max(256, rate * 60.0 / max(steps + warmup, 1))))
+        for _ in range(warmup):
+            orc.cost_batch(om, obs, th[:per_step], collision=False)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            off = (k * per_step) % (N_POSES - per_step + 1)
+            orc.cost_batch(om, obs, th[off:off + per_step], collision=False)
         dt = time.perf_counter() - t0
-        return {"value": steps * N_POSES / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{steps} steps x {N_POSES} poses (the full workload), oracle port, OpenMP"}, dt
+        return {"value": steps * per_step / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{steps} steps x {per_step} of the workload's {N_POSES} poses, oracle port, OpenMP, "
+                          f"{cores} threads"}, dt
     t0 = time.perf_counter()
     orc.cost_batch(om, obs, th[:4096], collision=False)
     rate = 4096 / (time.perf_counter() - t0)
-    n = int(min(max(rate * seconds, 4096), 8 * N_POSES))
+    n = int(min(max(rate * seconds, 4096), 256 * N_POSES))
     reps, rem = divmod(n, N_POSES)
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -159,8 +172,8 @@ def workload_config(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--npts", type=int, default=256)
     ap.add_argument("--no-extras", action="store_true", help="skip the 250-point and frames/s side measurements")
@@ -215,19 +228,21 @@ def main():
     peak_tf, mhz = hpe_b200.binding.measure_fp32_peak()
 
     # ---- device-resident throughput ----
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         step_dev(i)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
     e0.record()
     for i in range(args.steps):
         step_dev(i)
     e1.record()
     barrier()
+    t_wall1 = time.time()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, t_wall1)
     ms_step = ms_total / args.steps
     value = world * N_POSES / (ms_step * 1e-3)
 
@@ -303,6 +318,32 @@ def main():
         extras["pso_evals_per_sec"] = world * n_fr * 64 * 30 / dt
         extras["pso_batch"] = f"{n_fr} frames x 64 particles x 30 generations per GPU, host x0 in, best pose out"
         extras["pso_median_final_cost"] = float(np.median(best))
+        # configs[3]: one swarm of 16,384 particles x 30 generations, particles sharded over the ranks,
+        # (pcost, pbest) rows all-gathered once per generation (NCCL over NVLink when N > 1)
+        from hpe_b200 import sharding
+        NP_BIG, GEN = 16384, 30
+        pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, GEN, 1e-8, 1e-8)
+        truth0 = synth_truth(D, np.random.default_rng(4))            # every rank fits the same frame
+        frame0 = hpe_b200.render_frames(hand, truth0[None])
+        obs0 = hpe_b200.observedmodel(capacity=1, num_samples=250)
+        obs0.upload(frame0)
+        cf0 = hpe_b200.costfunc(hand, obs0)
+        x00 = truth0 + np.random.default_rng(44).normal(size=26) * D.STD * 0.3
+        lo, hi = sharding.shard_range(NP_BIG, rank, world)
+        times = []
+        for rep in range(3):
+            sw = hpe_b200.Swarm(cf0, pso.params, NP_BIG, lo, hi, x00, seed=4)
+            barrier()
+            e0.record()
+            bp, bc, _ = sharding.run_sharded_swarm(sw, NP_BIG, stream)
+            e1.record()
+            barrier()
+            times.append(max_over_ranks(e0.elapsed_time(e1)))
+        extras["swarm16k_ms"] = min(times[1:])
+        extras["swarm16k_evals_per_sec"] = NP_BIG * GEN / (min(times[1:]) * 1e-3)
+        extras["swarm16k_best_cost"] = bc
+        extras["swarm16k"] = (f"{NP_BIG} particles x {GEN} generations on one frame, {world} rank(s), "
+                              "27-double rows all-gathered per generation; strong scaling")
 
     if rank == 0:
         flop = flops_per_eval(args.npts)
