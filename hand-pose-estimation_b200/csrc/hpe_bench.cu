@@ -205,6 +205,35 @@ extern "C" int hpe_measure_fp32_patterns(double out[2])
     return HPE_OK;
 }
 
+namespace {
+__global__ void div10_selftest_kernel(unsigned long long *mismatches)
+{
+    unsigned long long bad = 0;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32);
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        float mm = __uint_as_float((unsigned)b);
+        if (!(fabsf(mm) <= 3.4e38f)) continue;                       // skip NaN/inf
+        double ref = __ddiv_rn((double)mm, 10.0), got = div10_exact(mm);
+        if (ref != got) bad++;                                      // (-0.0 and +0.0 compare equal; zero takes another branch)
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+
+// sweeps every finite float through div10_exact (hpe_device.cuh) against the IEEE division
+extern "C" int hpe_selftest_div10(unsigned long long *mismatches)
+{
+    if (!mismatches) return hpe_set_error(HPE_ERR_ARG, "hpe_selftest_div10: NULL output");
+    unsigned long long *d = nullptr;
+    HPE_CUDA(cudaMalloc(&d, 8));
+    HPE_CUDA(cudaMemset(d, 0, 8));
+    div10_selftest_kernel<<<148 * 16, 256>>>(d);
+    HPE_CUDA(cudaGetLastError());
+    HPE_CUDA(cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return HPE_OK;
+}
+
 extern "C" int hpe_measure_fp32_peak(double *tflops, double *sm_mhz_est)
 {
     if (!tflops) return hpe_set_error(HPE_ERR_ARG, "hpe_measure_fp32_peak: NULL output");

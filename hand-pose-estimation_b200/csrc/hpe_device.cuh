@@ -184,20 +184,44 @@ __device__ __forceinline__ int digit_first_sphere(int d) { return d == 0 ? 0 : 8
 // ---------------------------------------------------------------------------------------
 // depth term of one sphere (src/costfunc.cpp:251-300), un-negated centre (x,y,z), radius r
 // ---------------------------------------------------------------------------------------
+// RN(mm / 10.0) for a float mm without the division: q0 = mm*0.1, one FMA residual correction.
+// Equal to __ddiv_rn((double)mm, 10.0) for EVERY finite float (hpe_selftest_div10 sweeps all 2^32
+// bit patterns on the device; tests/test_gpu_parity.py asserts zero mismatches).
+__device__ __forceinline__ double div10_exact(float mm)
+{
+    double a = (double)mm;
+    double q = __dmul_rn(a, 0.1);
+    double r = __fma_rn(-q, 10.0, a);
+    return __fma_rn(r, 0.1, q);
+}
+
+// floor(RN(a / z)) given rz = RN(1/z): q = a*rz is within 2 ulp of a/z, so the two floors can differ
+// only when a/z lies within 2^-51 |a/z| of an integer; anything closer than 1e-6 to an integer (and
+// NaN/inf) takes the IEEE division instead.
+__device__ __forceinline__ double floor_div(double a, double z, double rz)
+{
+    double q = __dmul_rn(a, rz);
+    double f = floor(q);
+    double frac = q - f;
+    if (!(frac > 1e-6 && frac < 1.0 - 1e-6) || !(fabs(q) < 1e9)) f = floor(__ddiv_rn(a, z));
+    return f;
+}
+
 template <class FrameT>
 __device__ __forceinline__ double depth_term(const FrameT &F, double x, double y, double z, double r)
 {
-    // K*c without FMA contraction: row0 = f*x + cx*z, row1 = f*y + cy*z, row2 = z
-    double pu = __ddiv_rn(__dadd_rn(__dmul_rn(F.focal, x), __dmul_rn(F.cx, z)), z);
-    double pv = __ddiv_rn(__dadd_rn(__dmul_rn(F.focal, y), __dmul_rn(F.cy, z)), z);
-    double dx = floor(pu), dy = floor(pv);
+    // K*c without FMA contraction: row0 = f*x + cx*z, row1 = f*y + cy*z, row2 = z; then the
+    // reference's floor(row / z) (src/costfunc.cpp:251-255)
+    const double rz = __drcp_rn(z);
+    double dx = floor_div(__dadd_rn(__dmul_rn(F.focal, x), __dmul_rn(F.cx, z)), z, rz);
+    double dy = floor_div(__dadd_rn(__dmul_rn(F.focal, y), __dmul_rn(F.cy, z)), z, rz);
     bool inside = dx >= 0.0 && dx < (double)HPE_W && dy >= 0.0 && dy < (double)HPE_H;
     double v;
     if (inside) {
         int at = (int)dy * HPE_W + (int)dx;
-        double d_jc = __ddiv_rn((double)__ldg(F.depth_mm + at), 10.0);
-        if (d_jc != 0.0) {
-            v = fmax(0.0, d_jc - z);
+        float mm = __ldg(F.depth_mm + at);
+        if (mm != 0.0f) {
+            v = fmax(0.0, div10_exact(mm) - z);       // depthmp is the file value / 10 (src/observedmodel.cpp:300-303)
         } else {
             v = __dadd_rn(__dmul_rn((double)__ldg(F.dt_px + at), F.scale), r);
         }

@@ -175,11 +175,19 @@ int hpe_set_matcher(int mode);
 /* number of points the certified search handed to its exact fallback since the last reset */
 int hpe_debug_fallback_points(unsigned long long *count, int reset);
 
+/* device self-test: the division-free mm/10 of the depth term against the IEEE division over every
+ * finite float; *mismatches must come back 0 */
+int hpe_selftest_div10(unsigned long long *mismatches);
+
 /* ---- measurement ---- */
 /* FP32 (non-tensor) FFMA peak of the current device in TFLOP/s, measured with a
  * register-only FFMA kernel; the denominator of the cost kernel's roofline (the
  * driver-written MEASURED_PEAKS.json carries only HBM and bf16-tensor figures). */
 int hpe_measure_fp32_peak(double *tflops, double *sm_mhz_est);
+/* issue-behaviour probes quoted in DESIGN.md: out[0] 3-register FFMA pattern, out[1] sweep-shaped scalar loop (TFLOP/s) */
+int hpe_measure_fp32_patterns(double out[2]);
+/* out[0] FFMA2 peak (TFLOP/s), out[1] sweep-shaped FFMA2 loop (1e12 point-sphere pairs/s) */
+int hpe_measure_fp32x2(double out[2]);
 
 #ifdef __cplusplus
 }
