@@ -99,6 +99,13 @@ int hpe_set_matcher(int mode)
     return HPE_OK;
 }
 
+int hpe_set_chamfer(int mode)
+{
+    if (mode != 0 && mode != 1) return hpe_set_error(HPE_ERR_ARG, "chamfer mode must be 0 or 1");
+    g_hpe_chamfer = mode;
+    return HPE_OK;
+}
+
 int hpe_debug_fallback_points(unsigned long long *count, int reset)
 {
     if (!count) return hpe_set_error(HPE_ERR_ARG, "hpe_debug_fallback_points: NULL output");
@@ -209,6 +216,7 @@ int hpe_obs_create(int capacity, int num_samples, double focal, hpe_obs **out)
     if (e == cudaSuccess) e = cudaMalloc(&v.dt_px, sizeof(float) * npix * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&v.cloud, sizeof(double) * 3 * num_samples * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&v.meta, sizeof(FrameMeta) * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&v.wf_halo, sizeof(unsigned) * 2 * HPE_W * capacity);
     if (e == cudaSuccess) e = cudaMemset(v.meta, 0, sizeof(FrameMeta) * capacity);
     if (e != cudaSuccess) {
         hpe_obs_destroy(o);
@@ -221,7 +229,7 @@ int hpe_obs_create(int capacity, int num_samples, double focal, hpe_obs **out)
 int hpe_obs_destroy(hpe_obs *o)
 {
     if (!o) return HPE_OK;
-    cudaFree(o->v.depth_mm); cudaFree(o->v.dt_px); cudaFree(o->v.cloud); cudaFree(o->v.meta);
+    cudaFree(o->v.depth_mm); cudaFree(o->v.dt_px); cudaFree(o->v.cloud); cudaFree(o->v.meta); cudaFree(o->v.wf_halo);
     delete o;
     return HPE_OK;
 }

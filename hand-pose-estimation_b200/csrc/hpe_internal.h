@@ -20,6 +20,7 @@ struct ObsView {
     float     *dt_px;     // [capacity][240][320]
     double    *cloud;     // [capacity][3][n_pts]
     FrameMeta *meta;      // [capacity]
+    unsigned  *wf_halo;   // [capacity][2][320] scratch of the wavefront chamfer (band halo rows)
     double focal, cx, cy;
     int n_pts;
     int capacity;
@@ -57,6 +58,7 @@ struct PsoDev {           // constants of one pso_evolve call, passed by value
 };
 
 int hpe_set_error(int code, const char *fmt, ...);
+extern int g_hpe_chamfer;   // hpe_set_chamfer(): 0 = wavefront two-pass, 1 = row-search closed form
 extern int g_hpe_matcher;   // hpe_set_matcher(): 0 = certified two-sweep search, 1 = direct form
 #define HPE_CUDA(call)                                                                           \
     do {                                                                                         \

@@ -200,6 +200,145 @@ __global__ void __launch_bounds__(OBS_THREADS) chamfer_kernel(ObsView o, int fir
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// The same transform as OpenCV runs it: forward and backward raster pass with the 5x5 mask,
+// parallelised as a skewed wavefront.  Pixel (i,j) of the forward pass needs (i-1, j-2..j+2),
+// (i-2, j-1), (i-2, j+1), (i, j-1): with lane r on row i0+r and column t - 3r at step t all of
+// them are final.  One warp walks a frame in bands of 32 rows; the band lives in shared memory
+// (row pitch 324 words -> the 32 lanes hit 32 different banks); the forward result of the whole
+// frame is parked in the dt_px output buffer (as uint32) and overwritten by the backward pass.
+// ---------------------------------------------------------------------------------------
+constexpr int WF_PITCH = HPE_W + 4;
+constexpr int WF_ROWS = 34;                       // 32 band rows + 2 halo rows
+constexpr unsigned WF_MAX = 0x7fffffffu >> 2;     // OpenCV's DIST_MAX
+constexpr unsigned WF_A = 65536u, WF_B = 91750u, WF_C = 143976u;
+constexpr int WF_SMEM_PER_WARP = WF_ROWS * WF_PITCH * 4 + 32 * 10 * 4;
+constexpr int WF_WARPS = 4;
+
+__global__ void __launch_bounds__(WF_WARPS * 32) chamfer_wavefront_kernel(ObsView o, int first, int count)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = blockIdx.x * WF_WARPS + warp;
+    if (fr >= count) return;
+    const int slot = first + fr;
+    if (!o.meta[slot].ok) return;
+    unsigned *S = reinterpret_cast<unsigned *>(smem_raw + (size_t)warp * WF_SMEM_PER_WARP);
+    unsigned *mask = S + WF_ROWS * WF_PITCH;                     // [32][10] bit rows: 1 = hand pixel
+    const float *__restrict__ depth = o.depth_mm + (size_t)slot * NPIX;
+    unsigned *tmp = reinterpret_cast<unsigned *>(o.dt_px + (size_t)slot * NPIX);
+    float *out = o.dt_px + (size_t)slot * NPIX;
+    const int NB = (HPE_H + 31) / 32;
+
+    // ---------------- forward pass, bands top to bottom ----------------
+    for (int b = 0; b < NB; ++b) {
+        const int i0 = b * 32;
+        // halo columns and halo rows
+        for (int rr = lane; rr < WF_ROWS; rr += 32) {
+            S[rr * WF_PITCH + 0] = WF_MAX; S[rr * WF_PITCH + 1] = WF_MAX;
+            S[rr * WF_PITCH + HPE_W + 2] = WF_MAX; S[rr * WF_PITCH + HPE_W + 3] = WF_MAX;
+        }
+        for (int hr = 0; hr < 2; ++hr) {
+            int gi = i0 - 2 + hr;
+            for (int c = lane; c < HPE_W; c += 32) S[hr * WF_PITCH + 2 + c] = gi >= 0 ? tmp[gi * HPE_W + c] : WF_MAX;
+        }
+        for (int rr = 0; rr < 32; ++rr) {
+            int gi = i0 + rr;
+            for (int c = 0; c < HPE_W / 32; ++c) {
+                bool hand = gi < HPE_H && depth[gi * HPE_W + c * 32 + lane] != 0.0f;
+                unsigned bits = __ballot_sync(0xffffffffu, hand);
+                if (lane == 0) mask[rr * 10 + c] = bits;
+            }
+        }
+        __syncwarp();
+        const bool live = i0 + lane < HPE_H;
+        unsigned *row = S + (lane + 2) * WF_PITCH + 2;           // my row, column 0
+        for (int t = 0; t < HPE_W + 3 * 31; ++t) {
+            int j = t - 3 * lane;
+            if (live && j >= 0 && j < HPE_W) {
+                unsigned v = 0;
+                if (!((mask[lane * 10 + (j >> 5)] >> (j & 31)) & 1u)) {
+                    const unsigned *p = row + j;
+                    v = p[-2 * WF_PITCH - 1] + WF_C;
+                    v = min(v, p[-2 * WF_PITCH + 1] + WF_C);
+                    v = min(v, p[-WF_PITCH - 2] + WF_C);
+                    v = min(v, p[-WF_PITCH - 1] + WF_B);
+                    v = min(v, p[-WF_PITCH] + WF_A);
+                    v = min(v, p[-WF_PITCH + 1] + WF_B);
+                    v = min(v, p[-WF_PITCH + 2] + WF_C);
+                    v = min(v, p[-1] + WF_A);
+                }
+                row[j] = v;
+            }
+            __syncwarp();
+        }
+        for (int rr = 0; rr < 32 && i0 + rr < HPE_H; ++rr)
+            for (int c = lane; c < HPE_W; c += 32) tmp[(i0 + rr) * HPE_W + c] = S[(rr + 2) * WF_PITCH + 2 + c];
+        __syncwarp();
+    }
+    __threadfence_block();
+    // ---------------- backward pass, bands bottom to top ----------------
+    float vmax = 0.f;
+    for (int b = NB - 1; b >= 0; --b) {
+        const int i0 = b * 32;
+        const int rows = min(32, HPE_H - i0);
+        // smem row rr (0..31) = image row i0 + rr; rows 32,33 = halo below (i0+32, i0+33)
+        for (int rr = lane; rr < WF_ROWS; rr += 32) {
+            S[rr * WF_PITCH + 0] = WF_MAX; S[rr * WF_PITCH + 1] = WF_MAX;
+            S[rr * WF_PITCH + HPE_W + 2] = WF_MAX; S[rr * WF_PITCH + HPE_W + 3] = WF_MAX;
+        }
+        for (int rr = 0; rr < WF_ROWS; ++rr) {
+            int gi = i0 + rr;
+            // rows below this band already hold final FLOAT values: convert back to Q16 exactly
+            // (a final value is k * 2^-16 with k < 2^25; k survives the float only when k < 2^24,
+            // so the backward pass keeps its own exact copy instead, see `fin` below)
+            for (int c = lane; c < HPE_W; c += 32)
+                S[rr * WF_PITCH + 2 + c] = (gi < HPE_H && rr < rows) ? tmp[gi * HPE_W + c] : WF_MAX;
+        }
+        __syncwarp();
+        // halo rows below: exact Q16 values of the previous (lower) band, kept in global scratch rows
+        if (b < NB - 1) {
+            for (int hr = 0; hr < 2; ++hr)
+                for (int c = lane; c < HPE_W; c += 32)
+                    S[(rows + hr) * WF_PITCH + 2 + c] = o.wf_halo[((size_t)slot * 2 + hr) * HPE_W + c];
+        }
+        __syncwarp();
+        const bool live = lane < rows;
+        unsigned *row = S + (rows - 1 - lane) * WF_PITCH + 2;    // lane 0 = bottom row of the band
+        for (int t = 0; t < HPE_W + 3 * 31; ++t) {
+            int j = HPE_W - 1 - (t - 3 * lane);
+            if (live && j >= 0 && j < HPE_W) {
+                unsigned *p = row + j;
+                unsigned v = p[0];
+                v = min(v, p[2 * WF_PITCH + 1] + WF_C);
+                v = min(v, p[2 * WF_PITCH - 1] + WF_C);
+                v = min(v, p[WF_PITCH + 2] + WF_C);
+                v = min(v, p[WF_PITCH + 1] + WF_B);
+                v = min(v, p[WF_PITCH] + WF_A);
+                v = min(v, p[WF_PITCH - 1] + WF_B);
+                v = min(v, p[WF_PITCH - 2] + WF_C);
+                v = min(v, p[1] + WF_A);
+                p[0] = v;
+            }
+            __syncwarp();
+        }
+        // the two top rows of this band are the halo of the band above
+        for (int hr = 0; hr < 2; ++hr)
+            for (int c = lane; c < HPE_W; c += 32)
+                o.wf_halo[((size_t)slot * 2 + hr) * HPE_W + c] = S[hr * WF_PITCH + 2 + c];
+        for (int rr = 0; rr < rows; ++rr)
+            for (int c = lane; c < HPE_W; c += 32) {
+                unsigned v = min(S[rr * WF_PITCH + 2 + c], WF_MAX);
+                float f = __uint2float_rn(v) * (1.f / 65536.f);   // OpenCV: (float)(t0 * scale)
+                out[(i0 + rr) * HPE_W + c] = f;
+                vmax = fmaxf(vmax, f);
+            }
+        __syncwarp();
+    }
+    for (int d = 16; d > 0; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    if (lane == 0) o.meta[slot].dt_max = (double)vmax;
+}
+
 // disttrans.max() for a slot whose distance transform was injected by the caller
 __global__ void __launch_bounds__(1024) dtmax_kernel(ObsView o, int slot)
 {
@@ -221,6 +360,7 @@ __global__ void __launch_bounds__(1024) dtmax_kernel(ObsView o, int slot)
 }  // namespace
 
 size_t hpe_observe_scratch_bytes(int) { return 0; }
+int g_hpe_chamfer = 0;   // 0 = wavefront two-pass (default), 1 = row-search closed form (cross-check)
 
 cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *, cudaStream_t st)
 {
@@ -232,7 +372,18 @@ cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *, c
         attr = true;
     }
     cloud_kernel<<<count, OBS_THREADS, 0, st>>>(o, first);
-    chamfer_kernel<<<count, OBS_THREADS, smem, st>>>(o, first);
+    if (g_hpe_chamfer == 1) {
+        chamfer_kernel<<<count, OBS_THREADS, smem, st>>>(o, first);
+    } else {
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaFuncSetAttribute(chamfer_wavefront_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 WF_WARPS * WF_SMEM_PER_WARP);
+            attr2 = true;
+        }
+        chamfer_wavefront_kernel<<<(count + WF_WARPS - 1) / WF_WARPS, WF_WARPS * 32, WF_WARPS * WF_SMEM_PER_WARP, st>>>(
+            o, first, count);
+    }
     return cudaGetLastError();
 }
 

@@ -172,6 +172,9 @@ int hpe_render(const hpe_model *m, const double *theta, int64_t n, double focal,
  * hpe_correspondences: 0 (default) = certified two-sweep search, 1 = the reference's arithmetic
  * on all 48 spheres.  Both return cv::BFMatcher's indices; 1 exists to cross-check 0. */
 int hpe_set_matcher(int mode);
+/* distance transform used by hpe_obs_upload*: 0 (default) = OpenCV's two raster passes run as a
+ * skewed wavefront, 1 = closed-form row search.  Bit-identical results; 1 exists to cross-check 0. */
+int hpe_set_chamfer(int mode);
 /* number of points the certified search handed to its exact fallback since the last reset */
 int hpe_debug_fallback_points(unsigned long long *count, int reset);
 
