@@ -308,7 +308,7 @@ def main():
         pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, 30, 1e-8, 1e-8)
         x0 = truths + rng.normal(size=truths.shape) * D.STD * 0.3
         cfb = hpe_b200.costfunc(hand, obsb)
-        pso.pso_evolve_batch(cfb, x0[:64], 64, want_trace=False)
+        pso.pso_evolve_batch(cfb, x0, 64, want_trace=False)      # warm-up at full size (workspace growth)
         barrier()
         t0 = time.perf_counter()
         bestp, best, _ = pso.pso_evolve_batch(cfb, x0, 64, want_trace=False)

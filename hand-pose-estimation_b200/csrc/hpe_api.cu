@@ -342,16 +342,36 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
     char *base = (char *)g_ws.p;
     double *d_th = (double *)base, *d_tm = (double *)(base + b_th);
     int32_t *d_fr = (int32_t *)(base + b_th + b_tm), *d_mo = (int32_t *)(base + b_th + b_tm + b_fr);
-    HPE_CUDA(cudaMemcpyAsync(d_th, theta, sizeof(double) * n * HPE_NDOF, cudaMemcpyHostToDevice, 0));
     if (frozen) HPE_CUDA(cudaMemcpyAsync(d_fr, frozen, sizeof(int32_t) * np, cudaMemcpyHostToDevice, 0));
-    HPE_CUDA(hpe_launch_cost(m->dm, o->v, slot, d_th, n, colli != nullptr, nullptr, d_tm, frozen ? d_fr : nullptr,
-                             match_out ? d_mo : nullptr, 0));
-    // the kernel writes the terms as three arrays: copy each straight into the caller's buffer
-    if (align) HPE_CUDA(cudaMemcpyAsync(align, d_tm, sizeof(double) * n, cudaMemcpyDeviceToHost, 0));
-    if (depth) HPE_CUDA(cudaMemcpyAsync(depth, d_tm + n, sizeof(double) * n, cudaMemcpyDeviceToHost, 0));
-    if (colli) HPE_CUDA(cudaMemcpyAsync(colli, d_tm + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, 0));
-    if (match_out) HPE_CUDA(cudaMemcpyAsync(match_out, d_mo, sizeof(int32_t) * n * np, cudaMemcpyDeviceToHost, 0));
-    HPE_CUDA(cudaStreamSynchronize(0));
+    // Chunks of poses ping-pong over two streams: the host->device copy of one chunk (the poses are
+    // 208 B each, PCIe is the slowest stage of a large batch) runs under the kernel of the other.
+    // The kernel writes the terms as three arrays that are copied straight into the caller's buffers.
+    static cudaStream_t pipe[2] = {nullptr, nullptr};
+    static cudaEvent_t ready = nullptr;
+    if (!pipe[0]) {
+        HPE_CUDA(cudaStreamCreateWithFlags(&pipe[0], cudaStreamNonBlocking));
+        HPE_CUDA(cudaStreamCreateWithFlags(&pipe[1], cudaStreamNonBlocking));
+        HPE_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    }
+    HPE_CUDA(cudaEventRecord(ready, 0));          // prior default-stream work (frozen copy, observation kernels)
+    const int64_t chunk = n > 16384 ? 8192 : n;
+    int k = 0;
+    for (int64_t c0 = 0; c0 < n; c0 += chunk, ++k) {
+        const int64_t cn = n - c0 < chunk ? n - c0 : chunk;
+        cudaStream_t st = pipe[k & 1];
+        if (k < 2) HPE_CUDA(cudaStreamWaitEvent(st, ready, 0));
+        HPE_CUDA(cudaMemcpyAsync(d_th + c0 * HPE_NDOF, theta + c0 * HPE_NDOF, sizeof(double) * cn * HPE_NDOF,
+                                 cudaMemcpyHostToDevice, st));
+        HPE_CUDA(hpe_launch_cost(m->dm, o->v, slot, d_th + c0 * HPE_NDOF, cn, colli != nullptr, nullptr, d_tm + c0,
+                                 frozen ? d_fr : nullptr, match_out ? d_mo + c0 * np : nullptr, st, n));
+        if (align) HPE_CUDA(cudaMemcpyAsync(align + c0, d_tm + c0, sizeof(double) * cn, cudaMemcpyDeviceToHost, st));
+        if (depth) HPE_CUDA(cudaMemcpyAsync(depth + c0, d_tm + n + c0, sizeof(double) * cn, cudaMemcpyDeviceToHost, st));
+        if (colli) HPE_CUDA(cudaMemcpyAsync(colli + c0, d_tm + 2 * n + c0, sizeof(double) * cn, cudaMemcpyDeviceToHost, st));
+        if (match_out)
+            HPE_CUDA(cudaMemcpyAsync(match_out + c0 * np, d_mo + c0 * np, sizeof(int32_t) * cn * np, cudaMemcpyDeviceToHost, st));
+    }
+    HPE_CUDA(cudaStreamSynchronize(pipe[0]));
+    HPE_CUDA(cudaStreamSynchronize(pipe[1]));
     return HPE_OK;
 }
 

@@ -64,8 +64,8 @@ struct __align__(16) CostSmem {
 template <bool WITH_COLLI, int MATCHER>
 __global__ void __launch_bounds__(COST_WARPS * 32, HPE_MINBLOCKS)
 cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, int64_t n,
-            double *__restrict__ cost, double *__restrict__ terms, const int32_t *__restrict__ frozen,
-            int32_t *__restrict__ match_out)
+            double *__restrict__ cost, double *__restrict__ terms, int64_t tstride,
+            const int32_t *__restrict__ frozen, int32_t *__restrict__ match_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
@@ -98,9 +98,9 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
             if (lane == 0) {
                 if (cost) cost[p0 + g] = WITH_COLLI ? align + depth + colli : align + depth;
                 if (terms) {
-                    terms[p0 + g] = align;           // SoA: align[n] | depth[n] | colli[n]
-                    terms[n + p0 + g] = depth;
-                    terms[2 * n + p0 + g] = colli;
+                    terms[p0 + g] = align;           // SoA: align | depth | colli, tstride apart
+                    terms[tstride + p0 + g] = depth;
+                    terms[2 * tstride + p0 + g] = colli;
                 }
             }
         }
@@ -170,9 +170,11 @@ cudaError_t hpe_launch_fk(const DevModel &m, const double *theta_dev, int64_t n,
 
 cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const double *theta_dev,
                             int64_t n, bool with_colli, double *cost_dev, double *terms_dev,
-                            const int32_t *frozen_match_dev, int32_t *match_out_dev, cudaStream_t st)
+                            const int32_t *frozen_match_dev, int32_t *match_out_dev, cudaStream_t st,
+                            int64_t terms_stride)
 {
     if (n <= 0) return cudaSuccess;
+    if (terms_stride <= 0) terms_stride = n;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -193,7 +195,7 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
     }
     auto launch = [&](auto kern) {
         kern<<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev, terms_dev,
-                                                                 frozen_match_dev, match_out_dev);
+                                                                 terms_stride, frozen_match_dev, match_out_dev);
     };
     if (g_hpe_matcher == 1) launch(with_colli ? cost_kernel<true, 1> : cost_kernel<false, 1>);
     else launch(with_colli ? cost_kernel<true, 0> : cost_kernel<false, 0>);

@@ -213,7 +213,7 @@ constexpr int WF_ROWS = 34;                       // 32 band rows + 2 halo rows
 constexpr unsigned WF_MAX = 0x7fffffffu >> 2;     // OpenCV's DIST_MAX
 constexpr unsigned WF_A = 65536u, WF_B = 91750u, WF_C = 143976u;
 constexpr int WF_SMEM_PER_WARP = WF_ROWS * WF_PITCH * 4 + 32 * 10 * 4;
-constexpr int WF_WARPS = 4;
+constexpr int WF_WARPS = 5;                       // 5 x 45,344 B = 226,720 B of the 227 KB a CTA may use
 
 __global__ void __launch_bounds__(WF_WARPS * 32) chamfer_wavefront_kernel(ObsView o, int first, int count)
 {
@@ -253,22 +253,19 @@ __global__ void __launch_bounds__(WF_WARPS * 32) chamfer_wavefront_kernel(ObsVie
         __syncwarp();
         const bool live = i0 + lane < HPE_H;
         unsigned *row = S + (lane + 2) * WF_PITCH + 2;           // my row, column 0
+        unsigned mbits = mask[lane * 10];
         for (int t = 0; t < HPE_W + 3 * 31; ++t) {
             int j = t - 3 * lane;
             if (live && j >= 0 && j < HPE_W) {
-                unsigned v = 0;
-                if (!((mask[lane * 10 + (j >> 5)] >> (j & 31)) & 1u)) {
-                    const unsigned *p = row + j;
-                    v = p[-2 * WF_PITCH - 1] + WF_C;
-                    v = min(v, p[-2 * WF_PITCH + 1] + WF_C);
-                    v = min(v, p[-WF_PITCH - 2] + WF_C);
-                    v = min(v, p[-WF_PITCH - 1] + WF_B);
-                    v = min(v, p[-WF_PITCH] + WF_A);
-                    v = min(v, p[-WF_PITCH + 1] + WF_B);
-                    v = min(v, p[-WF_PITCH + 2] + WF_C);
-                    v = min(v, p[-1] + WF_A);
-                }
-                row[j] = v;
+                // all eight neighbours are final: load them together, reduce as a tree
+                const unsigned *p = row + j;
+                unsigned a0 = p[-2 * WF_PITCH - 1], a1 = p[-2 * WF_PITCH + 1], a2 = p[-WF_PITCH - 2], a3 = p[-WF_PITCH - 1];
+                unsigned a4 = p[-WF_PITCH], a5 = p[-WF_PITCH + 1], a6 = p[-WF_PITCH + 2], a7 = p[-1];
+                unsigned m01 = min(a0, a1), m26 = min(a2, a6), m35 = min(a3, a5), m47 = min(a4, a7);
+                unsigned v = min(min(min(m01, m26) + WF_C, m35 + WF_B), m47 + WF_A);
+                bool hand = (mbits >> (j & 31)) & 1u;
+                row[j] = hand ? 0u : v;
+                if ((j & 31) == 31) mbits = mask[lane * 10 + min((j >> 5) + 1, 9)];
             }
             __syncwarp();
         }
@@ -309,16 +306,10 @@ __global__ void __launch_bounds__(WF_WARPS * 32) chamfer_wavefront_kernel(ObsVie
             int j = HPE_W - 1 - (t - 3 * lane);
             if (live && j >= 0 && j < HPE_W) {
                 unsigned *p = row + j;
-                unsigned v = p[0];
-                v = min(v, p[2 * WF_PITCH + 1] + WF_C);
-                v = min(v, p[2 * WF_PITCH - 1] + WF_C);
-                v = min(v, p[WF_PITCH + 2] + WF_C);
-                v = min(v, p[WF_PITCH + 1] + WF_B);
-                v = min(v, p[WF_PITCH] + WF_A);
-                v = min(v, p[WF_PITCH - 1] + WF_B);
-                v = min(v, p[WF_PITCH - 2] + WF_C);
-                v = min(v, p[1] + WF_A);
-                p[0] = v;
+                unsigned a0 = p[2 * WF_PITCH + 1], a1 = p[2 * WF_PITCH - 1], a2 = p[WF_PITCH + 2], a3 = p[WF_PITCH + 1];
+                unsigned a4 = p[WF_PITCH], a5 = p[WF_PITCH - 1], a6 = p[WF_PITCH - 2], a7 = p[1], own = p[0];
+                unsigned m01 = min(a0, a1), m26 = min(a2, a6), m35 = min(a3, a5), m47 = min(a4, a7);
+                p[0] = min(own, min(min(min(m01, m26) + WF_C, m35 + WF_B), m47 + WF_A));
             }
             __syncwarp();
         }

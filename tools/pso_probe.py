@@ -19,7 +19,7 @@ pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, maxiter, 1e-8, 1
 x0 = truths + rng.normal(size=truths.shape) * D.STD * 0.3
 cf = hpe_b200.costfunc(hand, obs)
 pso.pso_evolve_batch(cf, x0[:8], num_p, want_trace=False)
-for rep in range(3):
+for rep in range(int(os.environ.get("REPS", "3"))):
     t0 = time.perf_counter()
     bestp, best, _ = pso.pso_evolve_batch(cf, x0, num_p, want_trace=False)
     dt = time.perf_counter() - t0
