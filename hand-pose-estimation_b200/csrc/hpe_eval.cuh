@@ -47,6 +47,9 @@ static __device__ unsigned long long g_hpe_fallback_points;
 #ifndef HPE_SWEEP_STAGED
 #define HPE_SWEEP_STAGED 1
 #endif
+#ifndef HPE_PACKED_INDEX
+#define HPE_PACKED_INDEX 0   // 1: block index packed in the minimum's low mantissa bits (measured: no gain)
+#endif
 #ifndef HPE_MINBLOCKS
 #define HPE_MINBLOCKS 3                  // CTAs of 8 warps per SM the kernels are compiled for
 #endif
@@ -211,6 +214,42 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
         p[m] = fs.pre[k0 + 32 * m];
         M1[m] = INF; M2[m] = INF; g1[m] = 0;
     }
+#if HPE_PACKED_INDEX
+    // ---- sweep A, two blocks per step; the block index rides in the 4 low mantissa bits of the block
+    //      minimum (a perturbation below 32u|s|, paid for in tau), so best / runner-up tracking is
+    //      5.5 instead of 7 ALU instructions per (point, block) ----
+#pragma unroll 2
+    for (int g = 0; g < HPE_NBLK; g += 2) {
+        float4 e[2 * HPE_BLK];
+#pragma unroll
+        for (int j = 0; j < 2 * HPE_BLK; ++j) e[j] = ws.ex[g * HPE_BLK + j];
+        float s[HPE_PASS][2 * HPE_BLK];
+#pragma unroll
+        for (int j = 0; j < 2 * HPE_BLK; ++j)
+#pragma unroll
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].x, e[j].x, e[j].w);
+#pragma unroll
+        for (int j = 0; j < 2 * HPE_BLK; ++j)
+#pragma unroll
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].y, e[j].y, s[m][j]);
+#pragma unroll
+        for (int j = 0; j < 2 * HPE_BLK; ++j)
+#pragma unroll
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].z, e[j].z, s[m][j]);
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) {
+            float ga = fmin3(fminf(s[m][0], s[m][1]), s[m][2], s[m][3]);
+            float gb = fmin3(fminf(s[m][4], s[m][5]), s[m][6], s[m][7]);
+            ga = __uint_as_float((__float_as_uint(ga) & 0xfffffff0u) | (unsigned)g);
+            gb = __uint_as_float((__float_as_uint(gb) & 0xfffffff0u) | (unsigned)(g + 1));
+            float lo = fminf(ga, gb), hi = fmaxf(ga, gb);
+            M2[m] = fmin3(M2[m], hi, fmaxf(M1[m], lo));
+            M1[m] = fminf(M1[m], lo);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < HPE_PASS; ++m) g1[m] = (int)(__float_as_uint(M1[m]) & 15u);
+#else
     // ---- sweep A: block minima of s_j over all 48 spheres ----
 #pragma unroll 3
     for (int g = 0; g < HPE_NBLK; ++g) {
@@ -247,6 +286,7 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
             g1[m] = better ? g : g1[m];
         }
     }
+#endif
     // ---- sweep B + certificate ----
     unsigned slow = 0u;
 #pragma unroll
@@ -256,8 +296,15 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
         float s2 = expanded(p[m], blk[2]), s3 = expanded(p[m], blk[3]);
         float lo01 = fminf(s0, s1), hi01 = fmaxf(s0, s1), lo23 = fminf(s2, s3), hi23 = fmaxf(s2, s3);
         float r = fmin3(fmaxf(lo01, lo23), hi01, hi23);                   // runner-up inside the block
+#if HPE_PACKED_INDEX
+        // exact minimum of the best block; M2 carries an index in its low bits: |M2 - true| < 32u|M2|
+        const float m1 = fminf(lo01, lo23);
+        const float tau = fmaf(7.2e-6f, fabsf(m1), p[m].w);               // (52 + 2*32) * 2^-24 = 6.9e-6
+        bool cert = fminf(M2[m], r) - m1 > tau;                           // false on NaN
+#else
         const float tau = fmaf(3.2e-6f, fabsf(M1[m]), p[m].w);            // 52 * 2^-24 = 3.0994e-6
         bool cert = fminf(M2[m], r) - M1[m] > tau;                        // false on NaN
+#endif
         int i = s1 < s0 ? 1 : 0, j = s3 < s2 ? 3 : 2;
         idx[m] = g1[m] * HPE_BLK + (lo23 < lo01 ? j : i);
         slow |= (cert ? 0u : 1u) << m;
