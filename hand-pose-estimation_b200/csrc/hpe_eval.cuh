@@ -61,9 +61,12 @@ static __device__ unsigned long long g_hpe_fallback_points;
 struct WarpScratch {
     double *sphd;   // [slot][48][3] un-negated FP64 centres of the group's poses
     float4 *cf;     // [48] (x,-y,-z,0): the float32 centres cv::BFMatcher sees, pose being matched
-    float4 *ex;     // [48] (-2c'x, -2c'y, -2c'z, |c'|^2), c' = cf - q, pose being matched
+    float4 *ex;     // [12][5] (-2c'x, -2c'y, -2c'z, |c'|^2), c' = cf - q, pose being matched; blocks of 4 spheres
+                    // are 80 B apart (one pad entry) so that sweep B's per-lane block reads spread over the banks
 };
-#define HPE_WS_BYTES(slots) ((slots) * HPE_NSPH * 24 + 2 * HPE_NSPH * 16)
+#define HPE_EX_PITCH (HPE_BLK + 1)
+#define HPE_EX_AT(j) (((j) / HPE_BLK) * HPE_EX_PITCH + ((j) % HPE_BLK))
+#define HPE_WS_BYTES(slots) ((slots) * HPE_NSPH * 24 + HPE_NSPH * 16 + HPE_NBLK * HPE_EX_PITCH * 16)
 
 __device__ __forceinline__ WarpScratch warp_scratch(unsigned char *base, int warp, int slots)
 {
@@ -71,7 +74,7 @@ __device__ __forceinline__ WarpScratch warp_scratch(unsigned char *base, int war
     unsigned char *p = base + (size_t)warp * HPE_WS_BYTES(slots);
     w.cf = reinterpret_cast<float4 *>(p);
     w.ex = w.cf + HPE_NSPH;
-    w.sphd = reinterpret_cast<double *>(p + 2 * HPE_NSPH * 16);
+    w.sphd = reinterpret_cast<double *>(p + HPE_NSPH * 16 + HPE_NBLK * HPE_EX_PITCH * 16);
     return w;
 }
 
@@ -222,7 +225,7 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
     for (int g = 0; g < HPE_NBLK; g += 2) {
         float4 e[2 * HPE_BLK];
 #pragma unroll
-        for (int j = 0; j < 2 * HPE_BLK; ++j) e[j] = ws.ex[g * HPE_BLK + j];
+        for (int j = 0; j < 2 * HPE_BLK; ++j) e[j] = ws.ex[HPE_EX_AT(g * HPE_BLK + j)];
         float s[HPE_PASS][2 * HPE_BLK];
 #pragma unroll
         for (int j = 0; j < 2 * HPE_BLK; ++j)
@@ -255,7 +258,7 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
     for (int g = 0; g < HPE_NBLK; ++g) {
         float4 e[HPE_BLK];
 #pragma unroll
-        for (int j = 0; j < HPE_BLK; ++j) e[j] = ws.ex[g * HPE_BLK + j];
+        for (int j = 0; j < HPE_BLK; ++j) e[j] = ws.ex[g * HPE_EX_PITCH + j];
 #if HPE_SWEEP_STAGED
         // 16 independent accumulators, one coordinate at a time: consecutive FFMAs share the sphere
         // operands (operand-reuse cache) and nothing waits on a 4-cycle dependency
@@ -291,7 +294,7 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
     unsigned slow = 0u;
 #pragma unroll
     for (int m = 0; m < HPE_PASS; ++m) {
-        const float4 *blk = ws.ex + g1[m] * HPE_BLK;
+        const float4 *blk = ws.ex + g1[m] * HPE_EX_PITCH;
         float s0 = expanded(p[m], blk[0]), s1 = expanded(p[m], blk[1]);
         float s2 = expanded(p[m], blk[2]), s3 = expanded(p[m], blk[3]);
         float lo01 = fminf(s0, s1), hi01 = fmaxf(s0, s1), lo23 = fminf(s2, s3), hi23 = fmaxf(s2, s3);
@@ -425,7 +428,7 @@ __device__ __forceinline__ double depth_and_stage(const FrameSmem &fs, const War
             // c' = cf - q exactly (FP64), then one rounding each for -2c' and |c'|^2
             double cx = (double)c.x - (double)fs.qx, cy = (double)c.y - (double)fs.qy, cz = (double)c.z - (double)fs.qz;
             ws.cf[j] = c;
-            ws.ex[j] = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz),
+            ws.ex[HPE_EX_AT(j)] = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz),
                                    (float)(cx * cx + cy * cy + cz * cz));
         }
     }
