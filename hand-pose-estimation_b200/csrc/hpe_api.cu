@@ -99,6 +99,14 @@ int hpe_set_matcher(int mode)
     return HPE_OK;
 }
 
+int g_hpe_pso_path = 0;
+int hpe_set_pso_path(int mode)
+{
+    if (mode < 0 || mode > 2) return hpe_set_error(HPE_ERR_ARG, "pso path must be 0, 1 or 2");
+    g_hpe_pso_path = mode;
+    return HPE_OK;
+}
+
 int hpe_set_chamfer(int mode)
 {
     if (mode != 0 && mode != 1) return hpe_set_error(HPE_ERR_ARG, "chamfer mode must be 0 or 1");
@@ -109,7 +117,7 @@ int hpe_set_chamfer(int mode)
 int hpe_debug_fallback_points(unsigned long long *count, int reset)
 {
     if (!count) return hpe_set_error(HPE_ERR_ARG, "hpe_debug_fallback_points: NULL output");
-    *count = hpe_fallbacks_cost(reset) + hpe_fallbacks_pso(reset);
+    *count = hpe_fallbacks_cost(reset) + hpe_fallbacks_pso(reset) + hpe_fallbacks_pso_cluster(reset);
     return HPE_OK;
 }
 
@@ -418,8 +426,13 @@ static int pso_host(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *
            *d_tr = (double *)(base + b_x0 + b_sd + b_bp + b_bc);
     HPE_CUDA(cudaMemcpyAsync(d_x0, x0, sizeof(double) * n_x0 * HPE_NDOF, cudaMemcpyHostToDevice, 0));
     if (seeds) HPE_CUDA(cudaMemcpyAsync(d_sd, seeds, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, 0));
-    cudaError_t e = hpe_launch_pso(m->dm, o->v, make_pso(p, num_particles), d_x0, first, count, seeds ? d_sd : nullptr,
-                                   d_bp, d_bc, trace ? d_tr : nullptr, chain, 0);
+    // few swarms (or a sequence): one swarm per 8-CTA cluster; many swarms: one per CTA
+    const bool use_cluster = g_hpe_pso_path == 2 || (g_hpe_pso_path == 0 && (chain || count <= 36));
+    cudaError_t e = use_cluster
+        ? hpe_launch_pso_cluster(m->dm, o->v, make_pso(p, num_particles), d_x0, first, count, seeds ? d_sd : nullptr,
+                                 d_bp, d_bc, trace ? d_tr : nullptr, chain, 0)
+        : hpe_launch_pso(m->dm, o->v, make_pso(p, num_particles), d_x0, first, count, seeds ? d_sd : nullptr,
+                         d_bp, d_bc, trace ? d_tr : nullptr, chain, 0);
     if (e != cudaSuccess)
         return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
                              "pso launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));

@@ -80,8 +80,14 @@ cudaError_t hpe_launch_dtmax(const ObsView &o, int slot, cudaStream_t st);
 cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
                            int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
                            double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st);
+// the same for one swarm per 8-CTA cluster (latency path: sequences, small batches)
+cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
+                                   int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
+                                   double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st);
 cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_t n, double focal,
                               float *depth_dev, cudaStream_t st);
 size_t hpe_observe_scratch_bytes(int count);
 unsigned long long hpe_fallbacks_cost(int reset);
 unsigned long long hpe_fallbacks_pso(int reset);
+unsigned long long hpe_fallbacks_pso_cluster(int reset);
+extern int g_hpe_pso_path;   // hpe_set_pso_path(): 0 = automatic, 1 = one CTA per swarm, 2 = one cluster per swarm

@@ -172,6 +172,10 @@ int hpe_render(const hpe_model *m, const double *theta, int64_t n, double focal,
  * hpe_correspondences: 0 (default) = certified two-sweep search, 1 = the reference's arithmetic
  * on all 48 spheres.  Both return cv::BFMatcher's indices; 1 exists to cross-check 0. */
 int hpe_set_matcher(int mode);
+/* kernel behind hpe_pso_evolve / hpe_track_sequence: 0 (default) = automatic (one 8-CTA cluster per swarm
+ * for sequences and batches of <= 36 swarms, one CTA per swarm otherwise), 1 = always one CTA per swarm,
+ * 2 = always one cluster per swarm.  Results are bit-identical. */
+int hpe_set_pso_path(int mode);
 /* distance transform used by hpe_obs_upload*: 0 (default) = OpenCV's two raster passes run as a
  * skewed wavefront, 1 = closed-form row search.  Bit-identical results; 1 exists to cross-check 0. */
 int hpe_set_chamfer(int mode);

@@ -90,3 +90,32 @@ def test_sharded_swarm_is_bit_identical(hpe, D, setup):
         for bp, bc, tr in res:
             assert np.array_equal(bp, ref[0]) and bc == ref[1] and np.array_equal(tr, ref[2])
     assert ref[2][-1] <= ref[2][0]
+
+
+def test_cluster_kernel_is_bit_identical_to_one_cta_kernel(hpe, orc, omodel, D):
+    """one swarm per 8-CTA cluster (latency path) == one swarm per CTA (throughput path), for batches,
+    odd particle counts and chained sequences"""
+    rng = np.random.default_rng(52)
+    n_fr = 5
+    truths = [synth_pose(D, rng) for _ in range(n_fr)]
+    frames = np.stack([orc.render_depth(omodel, t) for t in truths])
+    x0 = np.stack([t + rng.normal(size=26) * D.STD * 0.3 for t in truths])
+    hand, obs = hpe.handmodel(), hpe.observedmodel(capacity=n_fr)
+    obs.upload(frames)
+    cf = hpe.costfunc(hand, obs)
+    lib = hpe.lib()
+    for num_p, maxiter in ((64, 10), (37, 6), (130, 4)):
+        pso = hpe.PSO()
+        pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, maxiter, 1e-8, 1e-8)
+        res = {}
+        for path in (1, 2):
+            assert lib.hpe_set_pso_path(path) == 0
+            try:
+                res[path] = (pso.pso_evolve_batch(cf, x0, num_p, seeds=[7, 8, 9, 10, 11]),
+                             pso.track_sequence(cf, x0[0], num_p, n_fr, seed=1000))
+            finally:
+                lib.hpe_set_pso_path(0)
+        (b1, c1, t1), (p1, k1) = res[1]
+        (b2, c2, t2), (p2, k2) = res[2]
+        assert np.array_equal(b1, b2) and np.array_equal(c1, c2) and np.array_equal(t1, t2)
+        assert np.array_equal(p1, p2) and np.array_equal(k1, k2)
