@@ -344,6 +344,32 @@ def main():
         extras["swarm16k_best_cost"] = bc
         extras["swarm16k"] = (f"{NP_BIG} particles x {GEN} generations on one frame, {world} rank(s), "
                               "27-double rows all-gathered per generation; strong scaling")
+        # configs[2]: sequential tracking, one 1,000-frame sequence per rank, frame k+1 starts from frame
+        # k's best pose (one swarm per 8-CTA cluster); frames preprocessed up front
+        n_seq = 1000
+        rng = np.random.default_rng(3 + rank)
+        pose = synth_truth(D, rng)
+        walk = np.empty((n_seq, 26))
+        for k in range(n_seq):
+            pose = np.clip(pose + rng.uniform(-1, 1, size=26) * np.r_[[2.0] * 3, [0.2] * 3, [2.0] * 20], D.LB, D.UB)
+            walk[k] = pose
+        seq_dev = torch.empty(n_seq, D.H, D.W, dtype=torch.float32, device="cuda")
+        walk_dev = torch.from_numpy(walk).cuda()
+        hpe_b200.binding.render_dev(hand, walk_dev.data_ptr(), n_seq, seq_dev.data_ptr())
+        torch.cuda.synchronize()
+        obss = hpe_b200.observedmodel(capacity=n_seq, num_samples=250)
+        obss.upload_dev(seq_dev.data_ptr(), 0, n_seq)
+        cfs = hpe_b200.costfunc(hand, obss)
+        xs0 = walk[0] + rng.normal(size=26) * D.STD * 0.3
+        pso.track_sequence(cfs, xs0, 64, 16)
+        barrier()
+        t0 = time.perf_counter()
+        poses, costs = pso.track_sequence(cfs, xs0, 64, n_seq)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        extras["track_frames_per_sec"] = world * n_seq / dt
+        extras["track"] = (f"{n_seq}-frame synthetic sequence per GPU, 64 particles x 30 generations per frame, temporal "
+                           f"init; median final cost {float(np.median(costs)):.3f}")
 
     if rank == 0:
         flop = flops_per_eval(args.npts)

@@ -109,6 +109,68 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
 }
 
 // ---------------------------------------------------------------------------------------
+// One generation of a large swarm for the particles [lo, lo+own) owned by this GPU, fused:
+// velocity/position update with the reference's clamp (src/PSO.cpp:824-840, 358-377), evaluation
+// (cal_cost) and the pbest row update (:855-860) -- the warp that evaluates a particle also moves it
+// and writes its (pcost, pbest) row.  sw.update = 0 for generation 0 (x already generated).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(COST_WARPS * 32, HPE_MINBLOCKS)
+swarm_step_kernel(DevModel m, ObsView o, int slot, SwarmStepArgs sw)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    stage_model(sm.fs, m);
+    stage_frame(sm.fs, frame_view(o, slot));     // ends synchronised
+    const WarpScratch ws = warp_scratch(sm.ws, warp, HPE_GROUP);
+    constexpr int D = HPE_NDOF, ROW = HPE_NDOF + 1;
+    const int64_t n = sw.own;
+    const int64_t total_warps = (int64_t)gridDim.x * COST_WARPS;
+    const int64_t gw = (int64_t)blockIdx.x * COST_WARPS + warp;
+    const int64_t lo = n * gw / total_warps, hi = n * (gw + 1) / total_warps;
+    const int iter = sw.ctl->iter;               // evaluations done so far = generation of this update
+    const double *table = sw.table_in;   // rows of the previous generation (complete on every rank)
+
+    for (int64_t p0 = lo; p0 < hi; p0 += HPE_GROUP) {
+        int cnt = (int)min((int64_t)HPE_GROUP, hi - p0);
+        if (sw.update) {
+            for (int it = lane; it < cnt * (D / 2); it += 32) {
+                int g = it / (D / 2), dp = it - g * (D / 2);
+                int li = (int)(p0 + g), i = sw.lo + li, informant = sw.inf[i];
+                const double *pb = table + (size_t)i * ROW + 1, *pbi = table + (size_t)informant * ROW + 1;
+                double rp[2], rg[2];
+                uniform2(sw.seed, (uint32_t)dp, (uint32_t)i, (uint32_t)iter, 1u, rp);
+                uniform2(sw.seed, (uint32_t)dp, (uint32_t)i, (uint32_t)iter, 2u, rg);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    int d = 2 * dp + e, at = li * D + d;
+                    double xi = sw.x[at];
+                    double nv = __dadd_rn(__dmul_rn(sw.v[at], sw.W1), __dmul_rn(__dmul_rn(rp[e], sw.C1), __dadd_rn(pb[d], -xi)));
+                    if (informant != i) nv = __dadd_rn(nv, __dmul_rn(__dmul_rn(rg[e], sw.C1), __dadd_rn(pbi[d], -xi)));
+                    double nx = __dadd_rn(xi, nv);
+                    if (nx < sw.prm.lb[d] || nx > sw.prm.ub[d]) { nx = sw.prm.lb[d]; nv = 0.0; }   // :372
+                    sw.x[at] = nx;
+                    sw.v[at] = nv;
+                }
+            }
+            __syncwarp();
+        }
+        group_fk(sm.fs.M, [&](int g) { return sw.x + (p0 + g) * D; }, cnt, ws, lane);
+        for (int g = 0; g < cnt; ++g) {
+            double depth = depth_and_stage(sm.fs, ws, g, lane);
+            double align = match_align<0>(sm.fs, ws, g, lane, nullptr, nullptr);
+            double fx = align + depth;
+            // pbest row of this particle goes to the other table: informants must keep seeing the previous
+            // generation's rows while other warps of this launch are still updating their particles
+            const double *row = table + (size_t)(sw.lo + p0 + g) * ROW;
+            double *row_out = sw.table_out + (size_t)(sw.lo + p0 + g) * ROW;
+            bool take = iter == 0 || fx < row[0];
+            if (lane < ROW) row_out[lane] = take ? (lane == 0 ? fx : sw.x[(p0 + g) * D + lane - 1]) : row[lane];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Synthetic frames: ray-cast the 48 spheres at pose theta[f] into frame f.  One CTA per
 // frame; FP64 so that the frame equals the oracle's renderer up to FK rounding.
 // ---------------------------------------------------------------------------------------
@@ -199,6 +261,27 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
     };
     if (g_hpe_matcher == 1) launch(with_colli ? cost_kernel<true, 1> : cost_kernel<false, 1>);
     else launch(with_colli ? cost_kernel<true, 0> : cost_kernel<false, 0>);
+    return cudaGetLastError();
+}
+
+cudaError_t hpe_launch_swarm_step(const DevModel &m, const ObsView &o, int slot, const SwarmStepArgs &a, cudaStream_t st)
+{
+    if (a.own <= 0) return cudaSuccess;
+    static int sms = 0;
+    static bool attr = false;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (!attr) {
+        cudaFuncSetAttribute(swarm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
+        attr = true;
+    }
+    int64_t groups = ((int64_t)a.own + HPE_GROUP - 1) / HPE_GROUP;
+    int64_t want = (groups + COST_WARPS - 1) / COST_WARPS;
+    int blocks = (int)(want < (long long)HPE_MINBLOCKS * sms ? want : (long long)HPE_MINBLOCKS * sms);
+    swarm_step_kernel<<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, a);
     return cudaGetLastError();
 }
 

@@ -57,6 +57,27 @@ struct PsoDev {           // constants of one pso_evolve call, passed by value
     int num_p;
 };
 
+// device-resident control block of a large swarm (hpe_swarm.cu)
+struct SwarmCtl {
+    double gbest_cost;
+    double gbest[HPE_NDOF];
+    int count;
+    int iter;                         // evaluations done so far (1 after init)
+};
+
+// arguments of the fused update + evaluate + pbest kernel (swarm_step_kernel, hpe_cost.cu)
+struct SwarmStepArgs {
+    PsoDev prm;
+    uint64_t seed;
+    const double *table_in;           // [num_p][27] rows of the previous generation
+    double *table_out;                // rows of this generation (owned rows written here)
+    const int *inf;                   // informant of every particle
+    const SwarmCtl *ctl;
+    double *x, *v;                    // owned positions / velocities [own][26]
+    double W1, C1;
+    int lo, own, update;
+};
+
 int hpe_set_error(int code, const char *fmt, ...);
 extern int g_hpe_chamfer;   // hpe_set_chamfer(): 0 = wavefront two-pass, 1 = row-search closed form
 extern int g_hpe_matcher;   // hpe_set_matcher(): 0 = certified two-sweep search, 1 = direct form
@@ -87,6 +108,7 @@ cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const Ps
 cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_t n, double focal,
                               float *depth_dev, cudaStream_t st);
 size_t hpe_observe_scratch_bytes(int count);
+cudaError_t hpe_launch_swarm_step(const DevModel &m, const ObsView &o, int slot, const SwarmStepArgs &a, cudaStream_t st);
 unsigned long long hpe_fallbacks_cost(int reset);
 unsigned long long hpe_fallbacks_pso(int reset);
 unsigned long long hpe_fallbacks_pso_cluster(int reset);

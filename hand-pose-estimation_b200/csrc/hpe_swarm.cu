@@ -5,6 +5,13 @@
 // between hpe_swarm_step / hpe_swarm_reduce (NCCL over NVLink in bench.py, gloo in the CPU tests of
 // the host logic).  All arithmetic is keyed by the GLOBAL particle index (Philox counters), so the
 // sharded run is bit-identical to the single-GPU run and to the one-CTA kernel of hpe_pso.cu.
+//
+// Launches per generation: links (topology redraw + key init), two scatter-min passes for the
+// informants, ONE fused kernel that moves, evaluates and writes the pbest rows of the owned particles
+// (swarm_step_kernel, hpe_cost.cu), and after the exchange one single-CTA argmin + gbest/count update.
+// The rows are double buffered: a generation reads table[cur] and writes table[cur ^ 1], because an
+// informant's row must stay that of the previous generation while other warps of the same launch
+// already finish theirs.  Nothing synchronises with the host inside a generation.
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -15,15 +22,6 @@ namespace {
 
 constexpr int NK = 3;                 // informants drawn per particle, src/PSO.cpp:769
 constexpr int ROW = 1 + HPE_NDOF;     // table row: pcost, pbest[26]
-
-struct SwarmCtl {                     // device-resident control block
-    double gbest_cost;
-    double gbest[HPE_NDOF];
-    int count;
-    int iter;                         // evaluations done so far (1 after init)
-    unsigned long long best_key;      // scratch of the argmin reduction
-    int best_idx;
-};
 
 __device__ __forceinline__ unsigned long long cost_bits(double c)
 {
@@ -47,84 +45,73 @@ __global__ void swarm_generate(PsoDev prm, const double *x0, uint64_t seed, int 
     v[li * HPE_NDOF + 2 * dp + 1] = 0.0;
 }
 
-// pbest bookkeeping of the owned rows after an evaluation (src/PSO.cpp:753, 855-860)
-__global__ void swarm_pbest(int lo, int hi, const double *x, const double *fx, double *table, const SwarmCtl *ctl)
+// global first minimum of pcost + gbest/count bookkeeping (src/PSO.cpp:755-760, 864-876), one CTA
+__global__ void __launch_bounds__(1024) swarm_reduce_kernel(int num_p, const double *table, SwarmCtl *ctl, double *trace)
 {
-    // blockDim.x is a multiple of ROW, so a row never straddles two CTAs
-    int it = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = it < (hi - lo) * ROW;
-    int li = live ? it / ROW : 0, c = live ? it - li * ROW : 0;
-    double *row = table + (size_t)(lo + li) * ROW;
-    // every thread of a row evaluates `take` on the old pcost before thread c == 0 overwrites it
-    bool take = live && (ctl->iter == 0 || fx[li] < row[0]);
-    double val = !live ? 0.0 : (c == 0 ? fx[li] : x[li * HPE_NDOF + c - 1]);
-    __syncthreads();
-    if (take) row[c] = val;
-}
-
-// global first minimum of pcost + gbest/count bookkeeping (src/PSO.cpp:755-760, 864-876)
-__global__ void swarm_argmin_partial(int num_p, const double *table, SwarmCtl *ctl)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ unsigned long long skey[32];
+    __shared__ int sidx[32];
+    __shared__ int improved, winner;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long key = ~0ull;
-    if (i < num_p) key = cost_bits(table[(size_t)i * ROW]);
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < num_p; i += blockDim.x) {
+        unsigned long long k = cost_bits(table[(size_t)i * ROW]);
+        if (k < key) { key = k; idx = i; }            // ascending i: the lowest index of a tie stays
+    }
     for (int o = 16; o > 0; o >>= 1) {
         unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
-        if (ok < key) key = ok;
+        int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; }
     }
-    if ((threadIdx.x & 31) == 0) atomicMin(&ctl->best_key, key);
-}
-
-__global__ void swarm_argmin_index(int num_p, const double *table, SwarmCtl *ctl)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < num_p && cost_bits(table[(size_t)i * ROW]) == ctl->best_key) atomicMin(&ctl->best_idx, i);
-}
-
-__global__ void swarm_gbest(const double *table, SwarmCtl *ctl, double *trace)
-{
-    __shared__ int improved;
-    if (threadIdx.x == 0) {
-        int id = ctl->best_idx;
-        double fmin = table[(size_t)id * ROW];
-        improved = fmin < ctl->gbest_cost;
-        if (improved) {
-            ctl->gbest_cost = fmin;
-            ctl->count = ctl->iter == 0 ? 100 : 0;
-        } else if (ctl->iter > 0) {
-            ctl->count += 1;
+    if (lane == 0) { skey[warp] = key; sidx[warp] = idx; }
+    __syncthreads();
+    if (warp == 0) {
+        key = skey[lane]; idx = sidx[lane];
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+            int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; }
         }
-        ctl->iter += 1;
-        if (trace && ctl->iter >= 2) trace[ctl->iter - 2] = ctl->gbest_cost;
+        if (lane == 0) {
+            if (idx == 0x7fffffff) idx = 0;
+            double fmin = table[(size_t)idx * ROW];
+            improved = fmin < ctl->gbest_cost;
+            winner = idx;
+            if (improved) {
+                ctl->gbest_cost = fmin;
+                ctl->count = ctl->iter == 0 ? 100 : 0;
+            } else if (ctl->iter > 0) {
+                ctl->count += 1;
+            }
+            ctl->iter += 1;
+            if (trace && ctl->iter >= 2) trace[ctl->iter - 2] = ctl->gbest_cost;
+        }
     }
     __syncthreads();
-    if (improved && threadIdx.x < HPE_NDOF) ctl->gbest[threadIdx.x] = table[(size_t)ctl->best_idx * ROW + 1 + threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0) { ctl->best_key = ~0ull; ctl->best_idx = 0x7fffffff; }
+    // gbest_pos = particles.col(fmin_id): that particle has just improved, so its position is its pbest
+    if (improved && threadIdx.x < HPE_NDOF) ctl->gbest[threadIdx.x] = table[(size_t)winner * ROW + 1 + threadIdx.x];
 }
 
-// topology (src/PSO.cpp:790-803): R[s][k] = floor(U (num_p-1) + 0.5), redrawn only when count > 0
-__global__ void swarm_topology(int num_p, uint64_t seed, const SwarmCtl *ctl, int *R)
+// topology (src/PSO.cpp:790-803): R[s][k] = floor(U (num_p-1) + 0.5), redrawn only when count > 0;
+// and the start values of the informant search: key[i] = own cost (L = eye), inf[i] = unset
+__global__ void swarm_links(int num_p, uint64_t seed, const SwarmCtl *ctl, const double *table, int *R,
+                            unsigned long long *key, int *inf)
 {
-    if (ctl->count <= 0) return;
     int it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= num_p * NK) return;
-    int s = it / NK, k = it - s * NK;
-    double u[2];
-    uniform2(seed, (uint32_t)(k >> 1), (uint32_t)s, (uint32_t)ctl->iter, 3u, u);
-    R[it] = (int)floor(__dadd_rn(__dmul_rn(u[k & 1], (double)(num_p - 1)), 0.5));
+    if (it < num_p) {
+        key[it] = cost_bits(table[(size_t)it * ROW]);
+        inf[it] = 0x7fffffff;
+    }
+    if (ctl->count > 0 && it < num_p * NK) {
+        int s = it / NK, k = it - s * NK;
+        double u[2];
+        uniform2(seed, (uint32_t)(k >> 1), (uint32_t)s, (uint32_t)ctl->iter, 3u, u);
+        R[it] = (int)floor(__dadd_rn(__dmul_rn(u[k & 1], (double)(num_p - 1)), 0.5));
+    }
 }
 
-// informant(i) = first minimum of pcost over {s : L(s,i) = 1}, L = eye + links (src/PSO.cpp:810-812),
-// as two scatter passes over the num_p*(NK+1) links: minimum cost, then lowest index attaining it
-__global__ void swarm_inf_init(int num_p, const double *table, unsigned long long *key, int *inf)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= num_p) return;
-    key[i] = cost_bits(table[(size_t)i * ROW]);
-    inf[i] = 0x7fffffff;
-}
-
+// informant(i) = first minimum of pcost over {s : L(s,i) = 1} (src/PSO.cpp:810-812), as two scatter
+// passes over the num_p*(NK+1) links: minimum cost, then lowest index attaining it
 __global__ void swarm_inf_cost(int num_p, const double *table, const int *R, unsigned long long *key)
 {
     int it = blockIdx.x * blockDim.x + threadIdx.x;
@@ -141,33 +128,6 @@ __global__ void swarm_inf_index(int num_p, const double *table, const int *R, co
     if (cost_bits(table[(size_t)s * ROW]) == key[r]) atomicMin(&inf[r], s);
 }
 
-// velocity, position, check_constraints for the owned rows (src/PSO.cpp:824-840, 358-377)
-__global__ void swarm_update(PsoDev prm, uint64_t seed, int lo, int hi, const double *table, const int *inf,
-                             const SwarmCtl *ctl, double *x, double *v, double W1, double C1)
-{
-    int it = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = (hi - lo) * (HPE_NDOF / 2);
-    if (it >= n) return;
-    int li = it / (HPE_NDOF / 2), dp = it - li * (HPE_NDOF / 2);
-    int i = lo + li, informant = inf[i];
-    const uint32_t gen = (uint32_t)ctl->iter;
-    const double *pb = table + (size_t)i * ROW + 1, *pbi = table + (size_t)informant * ROW + 1;
-    double rp[2], rg[2];
-    uniform2(seed, (uint32_t)dp, (uint32_t)i, gen, 1u, rp);
-    uniform2(seed, (uint32_t)dp, (uint32_t)i, gen, 2u, rg);
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        int d = 2 * dp + e, at = li * HPE_NDOF + d;
-        double xi = x[at];
-        double nv = __dadd_rn(__dmul_rn(v[at], W1), __dmul_rn(__dmul_rn(rp[e], C1), __dadd_rn(pb[d], -xi)));
-        if (informant != i) nv = __dadd_rn(nv, __dmul_rn(__dmul_rn(rg[e], C1), __dadd_rn(pbi[d], -xi)));
-        double nx = __dadd_rn(xi, nv);
-        if (nx < prm.lb[d] || nx > prm.ub[d]) { nx = prm.lb[d]; nv = 0.0; }   // upper violation -> LOWER bound (:372)
-        x[at] = nx;
-        v[at] = nv;
-    }
-}
-
 inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace
@@ -175,22 +135,30 @@ inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 struct hpe_swarm {
     const hpe_model *m;
     const hpe_obs *o;
-    int slot, num_p, lo, hi;
+    int slot, num_p, lo, hi, cur;
     PsoDev prm;
     uint64_t seed;
     double W1, C1;
-    double *x0, *x, *v, *fx, *table, *trace;
+    double *x0, *x, *v, *table[2], *trace;
     int *R, *inf;
     unsigned long long *key;
     SwarmCtl *ctl;
 };
+
+static SwarmStepArgs step_args(const hpe_swarm *s, int update, const double *in, double *out)
+{
+    SwarmStepArgs a;
+    a.prm = s->prm; a.seed = s->seed; a.table_in = in; a.table_out = out; a.inf = s->inf; a.ctl = s->ctl;
+    a.x = s->x; a.v = s->v; a.W1 = s->W1; a.C1 = s->C1; a.lo = s->lo; a.own = s->hi - s->lo; a.update = update;
+    return a;
+}
 
 extern "C" {
 
 int hpe_swarm_destroy(hpe_swarm *s)
 {
     if (!s) return HPE_OK;
-    cudaFree(s->x0); cudaFree(s->x); cudaFree(s->v); cudaFree(s->fx); cudaFree(s->table); cudaFree(s->trace);
+    cudaFree(s->x0); cudaFree(s->x); cudaFree(s->v); cudaFree(s->table[0]); cudaFree(s->table[1]); cudaFree(s->trace);
     cudaFree(s->R); cudaFree(s->inf); cudaFree(s->key); cudaFree(s->ctl);
     delete s;
     return HPE_OK;
@@ -204,7 +172,7 @@ int hpe_swarm_create(const hpe_model *m, const hpe_obs *o, int slot, const hpe_p
     if (slot < 0 || slot >= o->v.capacity) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_create: slot out of range");
     hpe_swarm *s = new (std::nothrow) hpe_swarm();
     if (!s) return hpe_set_error(HPE_ERR_ARG, "out of host memory");
-    s->m = m; s->o = o; s->slot = slot; s->num_p = num_particles; s->lo = lo; s->hi = hi; s->seed = seed;
+    s->m = m; s->o = o; s->slot = slot; s->num_p = num_particles; s->lo = lo; s->hi = hi; s->seed = seed; s->cur = 0;
     memcpy(s->prm.lb, p->lb, sizeof s->prm.lb);
     memcpy(s->prm.ub, p->ub, sizeof s->prm.ub);
     memcpy(s->prm.std, p->std, sizeof s->prm.std);
@@ -217,15 +185,16 @@ int hpe_swarm_create(const hpe_model *m, const hpe_obs *o, int slot, const hpe_p
     cudaError_t e = cudaMalloc(&s->x0, sizeof(double) * HPE_NDOF);
     if (e == cudaSuccess) e = cudaMalloc(&s->x, sizeof(double) * own * HPE_NDOF);
     if (e == cudaSuccess) e = cudaMalloc(&s->v, sizeof(double) * own * HPE_NDOF);
-    if (e == cudaSuccess) e = cudaMalloc(&s->fx, sizeof(double) * own);
-    if (e == cudaSuccess) e = cudaMalloc(&s->table, sizeof(double) * np * ROW);
+    if (e == cudaSuccess) e = cudaMalloc(&s->table[0], sizeof(double) * np * ROW);
+    if (e == cudaSuccess) e = cudaMalloc(&s->table[1], sizeof(double) * np * ROW);
     if (e == cudaSuccess) e = cudaMalloc(&s->trace, sizeof(double) * tl);
     if (e == cudaSuccess) e = cudaMalloc(&s->R, sizeof(int) * np * NK);
     if (e == cudaSuccess) e = cudaMalloc(&s->inf, sizeof(int) * np);
     if (e == cudaSuccess) e = cudaMalloc(&s->key, sizeof(unsigned long long) * np);
     if (e == cudaSuccess) e = cudaMalloc(&s->ctl, sizeof(SwarmCtl));
     if (e == cudaSuccess) e = cudaMemcpy(s->x0, x0, sizeof(double) * HPE_NDOF, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(s->table, 0, sizeof(double) * np * ROW);
+    if (e == cudaSuccess) e = cudaMemset(s->table[0], 0, sizeof(double) * np * ROW);
+    if (e == cudaSuccess) e = cudaMemset(s->table[1], 0, sizeof(double) * np * ROW);
     if (e != cudaSuccess) {
         hpe_swarm_destroy(s);
         return hpe_set_error(HPE_ERR_CUDA, "hpe_swarm_create: %s", cudaGetErrorString(e));
@@ -234,7 +203,8 @@ int hpe_swarm_create(const hpe_model *m, const hpe_obs *o, int slot, const hpe_p
     return HPE_OK;
 }
 
-double *hpe_swarm_table(hpe_swarm *s) { return s ? s->table : nullptr; }
+// the table the last hpe_swarm_init / hpe_swarm_step wrote its owned rows into (it alternates)
+double *hpe_swarm_table(hpe_swarm *s) { return s ? s->table[s->cur] : nullptr; }
 
 int hpe_swarm_init(hpe_swarm *s, void *stream)
 {
@@ -243,12 +213,12 @@ int hpe_swarm_init(hpe_swarm *s, void *stream)
     const int own = s->hi - s->lo;
     SwarmCtl c;
     memset(&c, 0, sizeof c);
-    c.gbest_cost = 1e100; c.count = 100; c.iter = 0; c.best_key = ~0ull; c.best_idx = 0x7fffffff;
+    c.gbest_cost = 1e100; c.count = 100; c.iter = 0;
     HPE_CUDA(cudaMemcpyAsync(s->ctl, &c, sizeof c, cudaMemcpyHostToDevice, st));
+    s->cur = 0;
     if (own > 0) {
         swarm_generate<<<nblk((long long)own * (HPE_NDOF / 2), 256), 256, 0, st>>>(s->prm, s->x0, s->seed, s->lo, s->hi, s->x, s->v);
-        HPE_CUDA(hpe_launch_cost(s->m->dm, s->o->v, s->slot, s->x, own, false, s->fx, nullptr, nullptr, nullptr, st));
-        swarm_pbest<<<nblk((long long)own * ROW, 27 * 8), 27 * 8, 0, st>>>(s->lo, s->hi, s->x, s->fx, s->table, s->ctl);
+        HPE_CUDA(hpe_launch_swarm_step(s->m->dm, s->o->v, s->slot, step_args(s, 0, s->table[0], s->table[0]), st));
     }
     HPE_CUDA(cudaGetLastError());
     return HPE_OK;
@@ -257,10 +227,7 @@ int hpe_swarm_init(hpe_swarm *s, void *stream)
 int hpe_swarm_reduce(hpe_swarm *s, void *stream)
 {
     if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_reduce: NULL swarm");
-    cudaStream_t st = (cudaStream_t)stream;
-    swarm_argmin_partial<<<nblk(s->num_p, 256), 256, 0, st>>>(s->num_p, s->table, s->ctl);
-    swarm_argmin_index<<<nblk(s->num_p, 256), 256, 0, st>>>(s->num_p, s->table, s->ctl);
-    swarm_gbest<<<1, 32, 0, st>>>(s->table, s->ctl, s->trace);
+    swarm_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(s->num_p, s->table[s->cur], s->ctl, s->trace);
     HPE_CUDA(cudaGetLastError());
     return HPE_OK;
 }
@@ -269,17 +236,14 @@ int hpe_swarm_step(hpe_swarm *s, void *stream)
 {
     if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_step: NULL swarm");
     cudaStream_t st = (cudaStream_t)stream;
-    const int own = s->hi - s->lo, np = s->num_p;
-    swarm_topology<<<nblk((long long)np * NK, 256), 256, 0, st>>>(np, s->seed, s->ctl, s->R);
-    swarm_inf_init<<<nblk(np, 256), 256, 0, st>>>(np, s->table, s->key, s->inf);
-    swarm_inf_cost<<<nblk((long long)np * NK, 256), 256, 0, st>>>(np, s->table, s->R, s->key);
-    swarm_inf_index<<<nblk((long long)np * (NK + 1), 256), 256, 0, st>>>(np, s->table, s->R, s->key, s->inf);
-    if (own > 0) {
-        swarm_update<<<nblk((long long)own * (HPE_NDOF / 2), 256), 256, 0, st>>>(s->prm, s->seed, s->lo, s->hi, s->table, s->inf,
-                                                                               s->ctl, s->x, s->v, s->W1, s->C1);
-        HPE_CUDA(hpe_launch_cost(s->m->dm, s->o->v, s->slot, s->x, own, false, s->fx, nullptr, nullptr, nullptr, st));
-        swarm_pbest<<<nblk((long long)own * ROW, 27 * 8), 27 * 8, 0, st>>>(s->lo, s->hi, s->x, s->fx, s->table, s->ctl);
-    }
+    const int np = s->num_p;
+    const double *in = s->table[s->cur];
+    double *out = s->table[s->cur ^ 1];
+    swarm_links<<<nblk((long long)np * NK, 256), 256, 0, st>>>(np, s->seed, s->ctl, in, s->R, s->key, s->inf);
+    swarm_inf_cost<<<nblk((long long)np * NK, 256), 256, 0, st>>>(np, in, s->R, s->key);
+    swarm_inf_index<<<nblk((long long)np * (NK + 1), 256), 256, 0, st>>>(np, in, s->R, s->key, s->inf);
+    HPE_CUDA(hpe_launch_swarm_step(s->m->dm, s->o->v, s->slot, step_args(s, 1, in, out), st));
+    s->cur ^= 1;
     HPE_CUDA(cudaGetLastError());
     return HPE_OK;
 }

@@ -77,12 +77,20 @@ def tensor_from_device_pointer(ptr, n, dtype="<f8"):
 
 def run_sharded_swarm(swarm, n_rows, stream=None):
     """drive one hpe_b200.Swarm shard to completion, exchanging the table with the other ranks"""
-    table = tensor_from_device_pointer(swarm.table_ptr(), n_rows * swarm.ROW).view(n_rows, swarm.ROW)
+    views = {}
+
+    def table():
+        # the rows are double buffered inside the library: the current table alternates every generation
+        ptr = swarm.table_ptr()
+        if ptr not in views:
+            views[ptr] = tensor_from_device_pointer(ptr, n_rows * swarm.ROW).view(n_rows, swarm.ROW)
+        return views[ptr]
+
     swarm.init(stream)
-    allgather_rows(table, n_rows)
+    allgather_rows(table(), n_rows)
     swarm.reduce(stream)
     for _ in range(swarm.maxiter - 1):
         swarm.step(stream)
-        allgather_rows(table, n_rows)
+        allgather_rows(table(), n_rows)
         swarm.reduce(stream)
     return swarm.best()

@@ -147,7 +147,8 @@ int hpe_swarm_create(const hpe_model *m, const hpe_obs *o, int slot, const hpe_p
                      hpe_swarm **out);
 int hpe_swarm_destroy(hpe_swarm *s);
 /* device pointer to the global table [num_particles][27] doubles = (pcost, pbest[26]);
- * rows [lo,hi) are written by this GPU, the others must be filled by the exchange. */
+ * rows [lo,hi) are written by this GPU, the others must be filled by the exchange.  The rows are
+ * double buffered: call this again after every hpe_swarm_init / hpe_swarm_step, the pointer alternates. */
 double *hpe_swarm_table(hpe_swarm *s);
 /* generation 0: generate_particles + evaluation of the owned rows (src/PSO.cpp:745-763) */
 int hpe_swarm_init(hpe_swarm *s, void *stream);
