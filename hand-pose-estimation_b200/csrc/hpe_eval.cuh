@@ -80,7 +80,7 @@ __device__ __forceinline__ WarpScratch warp_scratch(unsigned char *base, int war
 
 // model + frame data every CTA stages once
 struct __align__(16) FrameSmem {
-    float4 pre[HPE_MAXPTS];          // (x', y', z', 260u|p'|^2): float32 points recentred on q
+    float4 pre[HPE_MAXPTS];          // (260u|p'|^2, x', y', z'): float32 points recentred on q
     DevModel M;
     double rad[HPE_NSPH];
     double cloud[3 * HPE_MAXPTS];    // FP64 cloud, SoA with stride HPE_MAXPTS (X | -Y | -Z)
@@ -130,7 +130,8 @@ __device__ __forceinline__ void stage_frame(FrameSmem &fs, const FrameView &F)
         float x = __fsub_rn((float)fs.cloud[k], fs.qx), y = __fsub_rn((float)fs.cloud[HPE_MAXPTS + k], fs.qy),
               z = __fsub_rn((float)fs.cloud[2 * HPE_MAXPTS + k], fs.qz);
         float pp = x * x + y * y + z * z;
-        fs.pre[k] = make_float4(x, y, z, 1.56e-5f * pp);      // 260 * 2^-24 = 1.5497e-5, rounded up
+        fs.pre[k] = make_float4(1.56e-5f * pp, x, y, z);      // (260 * 2^-24 |p'|^2 rounded up, x', y', z'): the coordinates sit in
+                                                              // register banks 1,2,3, the sphere operands they meet in 0,1,2
     }
     __syncthreads();
 }
@@ -172,7 +173,7 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
 
 __device__ __forceinline__ float expanded(const float4 &p, const float4 &e)
 {
-    return fmaf(p.z, e.z, fmaf(p.y, e.y, fmaf(p.x, e.x, e.w)));
+    return fmaf(p.w, e.z, fmaf(p.z, e.y, fmaf(p.y, e.x, e.w)));
 }
 
 // the reference's arithmetic on every pair, 4 points of the lane (cross-check: hpe_set_matcher(1))
@@ -230,15 +231,15 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
 #pragma unroll
         for (int j = 0; j < 2 * HPE_BLK; ++j)
 #pragma unroll
-            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].x, e[j].x, e[j].w);
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].y, e[j].x, e[j].w);
 #pragma unroll
         for (int j = 0; j < 2 * HPE_BLK; ++j)
 #pragma unroll
-            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].y, e[j].y, s[m][j]);
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].z, e[j].y, s[m][j]);
 #pragma unroll
         for (int j = 0; j < 2 * HPE_BLK; ++j)
 #pragma unroll
-            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].z, e[j].z, s[m][j]);
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].w, e[j].z, s[m][j]);
 #pragma unroll
         for (int m = 0; m < HPE_PASS; ++m) {
             float ga = fmin3(fminf(s[m][0], s[m][1]), s[m][2], s[m][3]);
@@ -266,15 +267,15 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
 #pragma unroll
         for (int j = 0; j < HPE_BLK; ++j)
 #pragma unroll
-            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].x, e[j].x, e[j].w);
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].y, e[j].x, e[j].w);
 #pragma unroll
         for (int j = 0; j < HPE_BLK; ++j)
 #pragma unroll
-            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].y, e[j].y, s[m][j]);
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].z, e[j].y, s[m][j]);
 #pragma unroll
         for (int j = 0; j < HPE_BLK; ++j)
 #pragma unroll
-            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].z, e[j].z, s[m][j]);
+            for (int m = 0; m < HPE_PASS; ++m) s[m][j] = fmaf(p[m].w, e[j].z, s[m][j]);
 #pragma unroll
         for (int m = 0; m < HPE_PASS; ++m) {
             float gm = fmin3(fminf(s[m][0], s[m][1]), s[m][2], s[m][3]);
@@ -302,10 +303,10 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
 #if HPE_PACKED_INDEX
         // exact minimum of the best block; M2 carries an index in its low bits: |M2 - true| < 32u|M2|
         const float m1 = fminf(lo01, lo23);
-        const float tau = fmaf(7.2e-6f, fabsf(m1), p[m].w);               // (52 + 2*32) * 2^-24 = 6.9e-6
+        const float tau = fmaf(7.2e-6f, fabsf(m1), p[m].x);               // (52 + 2*32) * 2^-24 = 6.9e-6
         bool cert = fminf(M2[m], r) - m1 > tau;                           // false on NaN
 #else
-        const float tau = fmaf(3.2e-6f, fabsf(M1[m]), p[m].w);            // 52 * 2^-24 = 3.0994e-6
+        const float tau = fmaf(3.2e-6f, fabsf(M1[m]), p[m].x);            // 52 * 2^-24 = 3.0994e-6
         bool cert = fminf(M2[m], r) - M1[m] > tau;                        // false on NaN
 #endif
         int i = s1 < s0 ? 1 : 0, j = s3 < s2 ? 3 : 2;
