@@ -128,6 +128,50 @@ __global__ void swarm_inf_index(int num_p, const double *table, const int *R, co
     if (cost_bits(table[(size_t)s * ROW]) == key[r]) atomicMin(&inf[r], s);
 }
 
+// ---- device-initiated exchange over NVLink peer memory (instead of the caller's all-gather) ----
+// Every rank maps the other ranks' tables (CUDA IPC).  After its step kernel a rank stores its owned rows
+// straight into every peer's table and then raises its flag in every peer's flag array; the peers' reduce
+// kernel waits on those flags.  Generation g reads buffer g%2 and writes (g+1)%2, and a rank starts
+// generation g+1 only after it has seen every peer's flag for generation g, i.e. after every peer has
+// finished reading buffer g%2 -- so the stores of generation g+1 into that buffer cannot race.
+constexpr int MAX_PEERS = 16;
+struct PeerPtrs {
+    double *table[MAX_PEERS];          // peer table being written this generation (NULL for self)
+    volatile unsigned *flags[MAX_PEERS];
+};
+
+__global__ void swarm_push_rows(PeerPtrs peers, int world, const double *table, int lo, int hi)
+{
+    const size_t n = (size_t)(hi - lo) * ROW, off = (size_t)lo * ROW;
+    for (int p = 0; p < world; ++p) {
+        double *dst = peers.table[p];
+        if (!dst) continue;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+            dst[off + i] = table[off + i];
+    }
+}
+
+// runs after swarm_push_rows in stream order: publish "my rows of generation `gen` are in your table"
+__global__ void swarm_signal(PeerPtrs peers, int world, int rank, unsigned gen)
+{
+    __threadfence_system();
+    if (threadIdx.x < world && peers.flags[threadIdx.x]) peers.flags[threadIdx.x][rank] = gen;
+    __threadfence_system();
+}
+
+// first kernel after the exchange point: wait until every peer has delivered generation `gen`
+__global__ void swarm_wait(volatile unsigned *flags, int world, int rank, unsigned gen, SwarmCtl *ctl)
+{
+    if (threadIdx.x < world && threadIdx.x != rank) {
+        long long spins = 0;
+        while (flags[threadIdx.x] < gen) {
+            if (++spins > (1ll << 31)) { ctl->count = -12345; break; }   // bounded: a lost peer must not hang the GPU
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
 inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace
@@ -143,7 +187,33 @@ struct hpe_swarm {
     int *R, *inf;
     unsigned long long *key;
     SwarmCtl *ctl;
+    // peer exchange
+    void *shared_base;                 // one allocation: table[0] | table[1] | flags
+    unsigned *flags;
+    int world, rank;
+    unsigned gen;                      // generations pushed so far
+    void *peer_base[MAX_PEERS];
 };
+
+static size_t table_bytes(int num_p) { return ((sizeof(double) * (size_t)num_p * ROW + 255) / 256) * 256; }
+
+// after the owned rows of table[cur] are complete: hand them to the peers and raise the flags
+static cudaError_t push_to_peers(hpe_swarm *s, cudaStream_t st)
+{
+    if (s->world <= 1) return cudaSuccess;
+    PeerPtrs pp;
+    memset(&pp, 0, sizeof pp);
+    for (int p = 0; p < s->world; ++p) {
+        if (p == s->rank) continue;
+        char *base = (char *)s->peer_base[p];
+        pp.table[p] = (double *)(base + (size_t)s->cur * table_bytes(s->num_p));
+        pp.flags[p] = (volatile unsigned *)(base + 2 * table_bytes(s->num_p));
+    }
+    s->gen += 1;
+    if (s->hi > s->lo) swarm_push_rows<<<64, 256, 0, st>>>(pp, s->world, s->table[s->cur], s->lo, s->hi);
+    swarm_signal<<<1, 32, 0, st>>>(pp, s->world, s->rank, s->gen);
+    return cudaGetLastError();
+}
 
 static SwarmStepArgs step_args(const hpe_swarm *s, int update, const double *in, double *out)
 {
@@ -158,7 +228,9 @@ extern "C" {
 int hpe_swarm_destroy(hpe_swarm *s)
 {
     if (!s) return HPE_OK;
-    cudaFree(s->x0); cudaFree(s->x); cudaFree(s->v); cudaFree(s->table[0]); cudaFree(s->table[1]); cudaFree(s->trace);
+    for (int p = 0; p < MAX_PEERS; ++p)
+        if (s->peer_base[p]) cudaIpcCloseMemHandle(s->peer_base[p]);
+    cudaFree(s->x0); cudaFree(s->x); cudaFree(s->v); cudaFree(s->shared_base); cudaFree(s->trace);
     cudaFree(s->R); cudaFree(s->inf); cudaFree(s->key); cudaFree(s->ctl);
     delete s;
     return HPE_OK;
@@ -185,16 +257,23 @@ int hpe_swarm_create(const hpe_model *m, const hpe_obs *o, int slot, const hpe_p
     cudaError_t e = cudaMalloc(&s->x0, sizeof(double) * HPE_NDOF);
     if (e == cudaSuccess) e = cudaMalloc(&s->x, sizeof(double) * own * HPE_NDOF);
     if (e == cudaSuccess) e = cudaMalloc(&s->v, sizeof(double) * own * HPE_NDOF);
-    if (e == cudaSuccess) e = cudaMalloc(&s->table[0], sizeof(double) * np * ROW);
-    if (e == cudaSuccess) e = cudaMalloc(&s->table[1], sizeof(double) * np * ROW);
+    // both row buffers and the peer flags in one allocation, so that one IPC handle exposes them
+    const size_t tb = table_bytes(num_particles);
+    if (e == cudaSuccess) e = cudaMalloc(&s->shared_base, 2 * tb + sizeof(unsigned) * MAX_PEERS);
+    if (e == cudaSuccess) e = cudaMemset(s->shared_base, 0, 2 * tb + sizeof(unsigned) * MAX_PEERS);
+    if (e == cudaSuccess) {
+        s->table[0] = (double *)s->shared_base;
+        s->table[1] = (double *)((char *)s->shared_base + tb);
+        s->flags = (unsigned *)((char *)s->shared_base + 2 * tb);
+    }
+    s->world = 1; s->rank = 0; s->gen = 0;
     if (e == cudaSuccess) e = cudaMalloc(&s->trace, sizeof(double) * tl);
     if (e == cudaSuccess) e = cudaMalloc(&s->R, sizeof(int) * np * NK);
     if (e == cudaSuccess) e = cudaMalloc(&s->inf, sizeof(int) * np);
     if (e == cudaSuccess) e = cudaMalloc(&s->key, sizeof(unsigned long long) * np);
     if (e == cudaSuccess) e = cudaMalloc(&s->ctl, sizeof(SwarmCtl));
     if (e == cudaSuccess) e = cudaMemcpy(s->x0, x0, sizeof(double) * HPE_NDOF, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(s->table[0], 0, sizeof(double) * np * ROW);
-    if (e == cudaSuccess) e = cudaMemset(s->table[1], 0, sizeof(double) * np * ROW);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the cleared flags must be in place before a peer can attach
     if (e != cudaSuccess) {
         hpe_swarm_destroy(s);
         return hpe_set_error(HPE_ERR_CUDA, "hpe_swarm_create: %s", cudaGetErrorString(e));
@@ -220,6 +299,7 @@ int hpe_swarm_init(hpe_swarm *s, void *stream)
         swarm_generate<<<nblk((long long)own * (HPE_NDOF / 2), 256), 256, 0, st>>>(s->prm, s->x0, s->seed, s->lo, s->hi, s->x, s->v);
         HPE_CUDA(hpe_launch_swarm_step(s->m->dm, s->o->v, s->slot, step_args(s, 0, s->table[0], s->table[0]), st));
     }
+    HPE_CUDA(push_to_peers(s, st));
     HPE_CUDA(cudaGetLastError());
     return HPE_OK;
 }
@@ -227,6 +307,7 @@ int hpe_swarm_init(hpe_swarm *s, void *stream)
 int hpe_swarm_reduce(hpe_swarm *s, void *stream)
 {
     if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_reduce: NULL swarm");
+    if (s->world > 1) swarm_wait<<<1, 32, 0, (cudaStream_t)stream>>>(s->flags, s->world, s->rank, s->gen, s->ctl);
     swarm_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(s->num_p, s->table[s->cur], s->ctl, s->trace);
     HPE_CUDA(cudaGetLastError());
     return HPE_OK;
@@ -244,7 +325,34 @@ int hpe_swarm_step(hpe_swarm *s, void *stream)
     swarm_inf_index<<<nblk((long long)np * (NK + 1), 256), 256, 0, st>>>(np, in, s->R, s->key, s->inf);
     HPE_CUDA(hpe_launch_swarm_step(s->m->dm, s->o->v, s->slot, step_args(s, 1, in, out), st));
     s->cur ^= 1;
+    HPE_CUDA(push_to_peers(s, st));
     HPE_CUDA(cudaGetLastError());
+    return HPE_OK;
+}
+
+// ---- peer exchange setup: each rank publishes one 64-byte CUDA IPC handle, then maps the others ----
+int hpe_swarm_ipc_handle(hpe_swarm *s, unsigned char handle[64])
+{
+    if (!s || !handle) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_ipc_handle: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    HPE_CUDA(cudaIpcGetMemHandle(&h, s->shared_base));
+    memcpy(handle, &h, 64);
+    return HPE_OK;
+}
+
+int hpe_swarm_attach_peers(hpe_swarm *s, const unsigned char *handles, int world, int rank)
+{
+    if (!s || !handles || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_attach_peers: bad argument (at most %d ranks)", MAX_PEERS);
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)p * 64, 64);
+        HPE_CUDA(cudaIpcOpenMemHandle(&s->peer_base[p], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    s->world = world;
+    s->rank = rank;
     return HPE_OK;
 }
 

@@ -321,6 +321,19 @@ class Swarm:
             _LIB.hpe_swarm_destroy(self._h)
             self._h = None
 
+    def ipc_handle(self):
+        """64-byte CUDA IPC handle of this rank's table (to be gathered over any host transport)"""
+        buf = (C.c_ubyte * 64)()
+        _check(lib().hpe_swarm_ipc_handle(self._h, buf))
+        return bytes(buf)
+
+    def attach_peers(self, handles, rank):
+        """handles: list of `world` 64-byte handles (own entry ignored).  Afterwards init/step push the owned
+        rows into the peers' tables over NVLink and reduce waits for theirs: no all-gather needed."""
+        blob = b"".join(handles)
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _check(lib().hpe_swarm_attach_peers(self._h, arr, len(handles), int(rank)))
+
     def table_ptr(self):
         """device pointer of the [num_particles][27] float64 table (pcost, pbest)"""
         return lib().hpe_swarm_table(self._h)

@@ -75,6 +75,28 @@ def tensor_from_device_pointer(ptr, n, dtype="<f8"):
     return torch.as_tensor(_Arr(), device="cuda")
 
 
+def attach_swarm_peers(swarm):
+    """exchange the CUDA IPC handles of the ranks' tables (host side, once) and map the peers"""
+    w = world()
+    if w == 1:
+        return
+    handles = [None] * w
+    dist.all_gather_object(handles, swarm.ipc_handle())
+    swarm.attach_peers(handles, rank())
+    dist.barrier()
+
+
+def run_sharded_swarm_p2p(swarm, stream=None):
+    """drive one shard whose peers are attached: the rows travel by direct NVLink stores issued from the
+    step kernels and the ranks meet on device-side flags; the host only enqueues launches"""
+    swarm.init(stream)
+    swarm.reduce(stream)
+    for _ in range(swarm.maxiter - 1):
+        swarm.step(stream)
+        swarm.reduce(stream)
+    return swarm.best()
+
+
 def run_sharded_swarm(swarm, n_rows, stream=None):
     """drive one hpe_b200.Swarm shard to completion, exchanging the table with the other ranks"""
     views = {}

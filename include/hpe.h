@@ -157,6 +157,14 @@ int hpe_swarm_reduce(hpe_swarm *s, void *stream);
 /* one generation for the owned rows: topology, informants, velocity, clamp, evaluation,
  * pbest (src/PSO.cpp:781-861).  Requires a complete table. */
 int hpe_swarm_step(hpe_swarm *s, void *stream);
+/* Device-initiated exchange instead of the caller's all-gather (one process per GPU on one NVLink
+ * node): every rank publishes the 64-byte CUDA IPC handle of its table, gathers all `world` handles (any
+ * host transport) and attaches.  From then on hpe_swarm_init / hpe_swarm_step store the owned rows
+ * directly into every peer's table over NVLink and raise a flag there, hpe_swarm_reduce waits on the
+ * flags on the device; the caller issues init, reduce, (step, reduce) x (maxiter-1) with no exchange and
+ * no host synchronisation in between.  Results are bit-identical to the all-gather path. */
+int hpe_swarm_ipc_handle(hpe_swarm *s, unsigned char handle[64]);
+int hpe_swarm_attach_peers(hpe_swarm *s, const unsigned char *handles /* world*64 */, int world, int rank);
 /* host copies of gbest (and of bcost_evo, maxiter-1 values, may be NULL) after the last hpe_swarm_reduce */
 int hpe_swarm_best(hpe_swarm *s, double bestp[HPE_NDOF], double *best_cost, double *trace);
 
