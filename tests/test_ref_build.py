@@ -1,0 +1,161 @@
+"""CPU: the oracle restatement (oracle/hpe_oracle.c) against THE REFERENCE'S OWN CODE.
+
+oracle/_ref/libhpe_ref.so is the reference's src/{fingermodel,thumbmodel,handmodel,costfunc,
+observedmodel,PSO}.cpp compiled unmodified from /root/reference (oracle/Makefile) against the stand-in
+Armadillo/OpenCV headers of oracle/shim/ -- the image has neither library.  The reference's logic runs
+as written; what the stand-ins restate (BFMatcher, distanceTransform, Armadillo's summation order) is
+pinned separately against cv2 in tests/test_oracle_pins.py.  The reference's RNG calls are fed the
+counter-based streams of DESIGN.md "RNG" through a hook, so PSO::pso_evolve itself can be compared.
+
+The .so is built where /root/reference exists and ships with the snapshot; tests that need it skip
+when it is absent, the committed fixtures (tests/golden/golden_ref_v1.npz, written from it by
+tests/golden/make_golden_ref.py) are always checked."""
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def gref():
+    return np.load(os.path.join(HERE, "golden", "golden_ref_v1.npz"))
+
+
+@pytest.fixture(scope="module")
+def R(orc):
+    import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    r = ref.Reference(threads=1)
+    yield r
+    r.close()
+
+
+# ---------------------------------------------------------------- fixtures written by the reference
+def test_oracle_reproduces_reference_fixtures(orc, omodel, gref, D):
+    """runs everywhere (also on the GPU box): the oracle against values the reference code produced"""
+    g = gref
+    depth = orc.render_depth(omodel, g["truth"])
+    obs = orc.Observation(depth)
+    assert np.array_equal(obs.cloud, g["cloud"]) and obs.scale == float(g["scale"])
+    assert obs.dt_max == float(g["dt_max"]) and np.array_equal(obs.dt[::16].astype(np.float32), g["dt_rows"])
+    assert obs.dt.sum() == float(g["dt_sum"]) and obs.depth.sum() == float(g["depth_cm_sum"])
+    S, J = orc.fk(omodel, g["poses"])
+    assert np.array_equal(S, g["spheres"]) and np.array_equal(J, g["joints"])          # bit-exact
+    a, d, c = orc.cost_batch(omodel, obs, g["poses"])
+    assert np.array_equal(a, g["align"]) and np.array_equal(d, g["depth_term"]) and np.array_equal(c, g["colli"])
+    assert np.array_equal(a + d, g["cal_cost"]) and np.array_equal(a + d + c, g["cal_cost2"])
+    for i in range(len(g["poses"])):
+        assert np.array_equal(orc.correspondences(obs.cloud, S[i]), g["match"][i].astype(np.int32))
+    tot, _, _ = orc.cal_cost2(omodel, obs, g["poses"][2], match=g["match"][3].astype(np.int32))
+    assert tot == float(g["frozen_cost"])
+    for tag in ("pso", "pso64"):
+        prm = orc.pso_params(maxiter=int(g[tag + "_maxiter"]))
+        bestp, best, _, _, _ = orc.pso_evolve(omodel, obs, prm, g["pso_x0"], int(g[tag + "_num_p"]), int(g[tag + "_seed"]))
+        assert np.array_equal(bestp, g[tag + "_bestp"]) and best == float(g[tag + "_best"])
+
+
+def test_oracle_golden_equals_reference_golden(gref):
+    """the oracle-made fixture file and the reference-made one agree field by field"""
+    a = np.load(os.path.join(HERE, "golden", "golden_v1.npz"))
+    shared = [k for k in gref.files if k in a.files]
+    assert len(shared) >= 18
+    for k in shared:
+        assert np.array_equal(a[k], gref[k]), k
+
+
+# ---------------------------------------------------------------- live comparison with the reference build
+def test_fk_bit_exact(orc, omodel, R, D):
+    rng = np.random.default_rng(11)
+    S, J = R.fk(D.X0)
+    # SURVEY B.4 sanity values
+    assert np.allclose(S[0], [2.155593, -2.404259, -31.112313], atol=1e-6)
+    assert np.allclose(S[47], [-7.823058, 4.986993, -25.010879], atol=1e-6)
+    assert np.allclose(J[4], [2.754023, -5.852627, 21.259828], atol=1e-6)
+    for k in range(300):
+        th = D.X0 + rng.normal(size=26) * D.STD * (3.0 if k % 3 == 0 else 1.0)
+        So, Jo = orc.fk(omodel, th)
+        Sr, Jr = R.fk(th)
+        assert np.array_equal(So, Sr) and np.array_equal(Jo, Jr)
+
+
+def test_observation_bit_exact(orc, omodel, R, D):
+    """load_data + depth_to_ptncloud + dist_transform through next_frame, three frames in a row
+    (the frame is swapped under the live costfunc like src/testmodel.cpp:124)"""
+    rng = np.random.default_rng(12)
+    for k in range(3):
+        truth = np.clip(D.X0 + rng.normal(size=26) * D.STD * 0.6, D.LB, D.UB)
+        depth = orc.render_depth(omodel, truth)
+        if k == 2:
+            depth[:, :40] = 0; depth[200:, :] = 0          # cropped hand
+        oo = orc.Observation(depth)
+        assert R.load_depth(depth) == oo.n_pts == 250
+        cloud, dcm, dt = R.observation()
+        assert np.array_equal(cloud, oo.cloud) and np.array_equal(dcm, oo.depth) and np.array_equal(dt, oo.dt)
+        assert R.scale == oo.scale
+        th = truth + rng.normal(size=26) * D.STD * 0.5
+        assert R.cal_cost(th) == orc.cal_cost(omodel, oo, th)
+
+
+def test_cost_terms_bit_exact(orc, omodel, R, D):
+    rng = np.random.default_rng(13)
+    truth = np.clip(D.X0 + rng.normal(size=26) * D.STD * 0.5, D.LB, D.UB)
+    depth = orc.render_depth(omodel, truth)
+    oo = orc.Observation(depth)
+    R.load_depth(depth)
+    th = np.concatenate([truth[None], truth + rng.normal(size=(150, 26)) * D.STD,
+                         truth + rng.normal(size=(50, 26)) * D.STD * 4.0,        # far away, out-of-image spheres
+                         truth + rng.normal(size=(50, 26)) * D.STD * 0.05])
+    a, d, c = orc.cost_batch(omodel, oo, th)
+    for i in range(len(th)):
+        t, m = R.cost_terms(th[i])
+        _, _, mo = orc.cal_cost2(omodel, oo, th[i])
+        assert np.array_equal(m, mo)
+        assert t[0] == a[i] and t[1] == d[i] and t[2] == c[i]
+        assert R.cal_cost(th[i]) == a[i] + d[i]
+    # frozen correspondences
+    _, m5 = R.cal_cost2(th[5])
+    v, _ = R.cal_cost2(th[6], match=m5)
+    vo, _, _ = orc.cal_cost2(omodel, oo, th[6], match=m5)
+    assert v == vo
+
+
+@pytest.mark.parametrize("num_p,maxiter,seed", [(16, 6, 1000), (64, 30, 1000), (33, 9, 77)])
+def test_pso_evolve_on_replayed_streams(orc, omodel, R, D, num_p, maxiter, seed):
+    """PSO::pso_evolve as written (informants, clamp to the LOWER bound, count/topology rule) ends at
+    exactly the oracle's pose when both draw the same counter-based streams"""
+    import ref
+    rng = np.random.default_rng(14 + num_p)
+    truth = np.clip(D.X0 + rng.normal(size=26) * D.STD * 0.5, D.LB, D.UB)
+    depth = orc.render_depth(omodel, truth)
+    oo = orc.Observation(depth)
+    R.load_depth(depth)
+    x0 = truth + rng.normal(size=26) * D.STD * 0.3
+    R.set_pso_params(maxiter=maxiter)
+    hook = ref.PhiloxReplay(seed)
+    hook.num_p = num_p
+    hook.install()
+    try:
+        b = R.pso_evolve(x0, num_p)
+    finally:
+        ref.PhiloxReplay.uninstall()
+    assert hook.seeds_seen == [1000] and hook.gen == maxiter - 1     # arma_rng::set_seed(1000), src/PSO.cpp:722
+    bo, co, _, _, _ = orc.pso_evolve(omodel, oo, orc.pso_params(maxiter=maxiter), x0, num_p, seed)
+    assert np.array_equal(b, bo) and R.cal_cost(b) == co
+
+
+def test_shim_primitives_against_numpy():
+    """the stand-in headers themselves: matcher and chamfer transform equal the oracle's restatements
+    (which tests/test_oracle_pins.py pins bit-for-bit against cv2)"""
+    import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    # exercised through test_observation_bit_exact / test_cost_terms_bit_exact: this test only records
+    # that the library exports the entry points the other tests use
+    L = ref.lib()
+    for n in ("ref_create", "ref_load_frame", "ref_fk", "ref_cal_cost", "ref_cal_cost2", "ref_cost_terms",
+              "ref_cost_batch", "ref_set_pso_params", "ref_pso_evolve", "ref_pso_optimise",
+              "ref_refine_init_pose", "ref_gnd_truth_err", "ref_dim_restore", "ref_set_rng"):
+        assert hasattr(L, n)
