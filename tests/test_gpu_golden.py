@@ -92,3 +92,32 @@ def test_full_size_swarm_batch_properties(hpe, golden, D):
     assert np.array_equal(bp2, bp[100:110]) and np.array_equal(best2, best[100:110])
     x0_cost = np.array([cf.cal_cost(x0[k], slot=k) for k in range(0, n_fr, 50)])
     assert np.all(best[::50] < x0_cost)
+
+
+def test_cuda_path_reproduces_reference_fixtures(hpe, D):
+    """tests/golden/golden_ref_v1.npz was written by the REFERENCE'S OWN CODE (oracle/_ref, see
+    tests/golden/make_golden_ref.py): forward kinematics, observation, the three energy terms, the
+    correspondences and two PSO::pso_evolve runs on the replayed random streams"""
+    g = np.load(os.path.join(HERE, "golden", "golden_ref_v1.npz"))
+    g1 = np.load(os.path.join(HERE, "golden", "golden_v1.npz"))
+    hand, obs = hpe.handmodel(), hpe.observedmodel(capacity=1)
+    obs.upload(golden_frame(g1)[None])
+    o = obs.get(0)
+    assert np.array_equal(o["cloud"], g["cloud"])                                   # bit-exact
+    assert abs(o["scale"] - float(g["scale"])) <= 1e-13 * float(g["scale"])
+    assert o["dt_max"] == np.float32(g["dt_max"]) and np.array_equal(o["dt"][::16], g["dt_rows"])
+    S, J = hand.build_hand_models(g["poses"])
+    assert np.abs(S - g["spheres"]).max() < 1e-11 and np.abs(J - g["joints"]).max() < 1e-11
+    cf = hpe.costfunc(hand, obs)
+    a, d, c = cf.cal_cost_batch(g["poses"], with_collision=True)
+    assert np.allclose(a + d, g["cal_cost"], rtol=1e-9) and np.allclose(a + d + c, g["cal_cost2"], rtol=1e-9)
+    assert np.allclose(a, g["align"], rtol=1e-9) and np.allclose(d, g["depth_term"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(cf.compute_correspondences(g["poses"]), g["match"].astype(np.int32))
+    pso = hpe.PSO()
+    for tag in ("pso", "pso64"):
+        pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, int(g[tag + "_maxiter"]), 1e-8, 1e-8)
+        bp, best, _ = pso.pso_evolve_batch(cf, g["pso_x0"][None], int(g[tag + "_num_p"]), seeds=[int(g[tag + "_seed"])])
+        assert np.abs(bp[0] - g[tag + "_bestp"]).max() < 1e-7 and abs(best[0] - float(g[tag + "_best"])) <= 1e-8 * best[0]
+        # 1 mm joint criterion of the north star, on the reference's final pose
+        _, Jg = hand.build_hand_models(np.stack([bp[0], g[tag + "_bestp"]]))
+        assert np.abs(Jg[0] - Jg[1]).max() * 10.0 < 1e-3
