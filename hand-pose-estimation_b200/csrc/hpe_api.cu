@@ -117,7 +117,8 @@ int hpe_set_chamfer(int mode)
 int hpe_debug_fallback_points(unsigned long long *count, int reset)
 {
     if (!count) return hpe_set_error(HPE_ERR_ARG, "hpe_debug_fallback_points: NULL output");
-    *count = hpe_fallbacks_cost(reset) + hpe_fallbacks_pso(reset) + hpe_fallbacks_pso_cluster(reset);
+    *count = hpe_fallbacks_cost(reset) + hpe_fallbacks_pso(reset) + hpe_fallbacks_pso_cluster(reset) +
+             hpe_fallbacks_refine(reset);
     return HPE_OK;
 }
 
@@ -457,6 +458,66 @@ int hpe_track_sequence(const hpe_model *m, const hpe_obs *o, const hpe_pso_param
     if (n_frames < 0) return hpe_set_error(HPE_ERR_ARG, "hpe_track_sequence: bad frame count");
     std::vector<uint64_t> seeds((size_t)(n_frames > 0 ? n_frames : 1), seed);
     return pso_host(m, o, p, num_particles, x0, 1, first, n_frames, seeds.data(), poses, costs, nullptr, 1);
+}
+
+// PSO::refine_init_pose for `count` frames (hpe_refine.cu)
+int hpe_refine_init_pose(const hpe_model *m, const hpe_obs *o, double *x0, int first, int count, int *evals)
+{
+    if (!m || !x0) return hpe_set_error(HPE_ERR_ARG, "hpe_refine_init_pose: bad argument");
+    if (int rc = check_slot(o, first, count)) return rc;
+    if (count == 0) return HPE_OK;
+    if (int rc = check_filled(o, first, count)) return rc;
+    size_t b_x = align_up(sizeof(double) * count * HPE_NDOF), b_e = align_up(sizeof(int) * count);
+    HPE_CUDA(g_ws.reserve(b_x + b_e));
+    double *d_x = (double *)g_ws.p;
+    int *d_e = (int *)((char *)g_ws.p + b_x);
+    HPE_CUDA(cudaMemcpyAsync(d_x, x0, sizeof(double) * count * HPE_NDOF, cudaMemcpyHostToDevice, 0));
+    HPE_CUDA(hpe_launch_refine(m->dm, o->v, first, count, d_x, d_e, 0));
+    HPE_CUDA(cudaMemcpyAsync(x0, d_x, sizeof(double) * count * HPE_NDOF, cudaMemcpyDeviceToHost, 0));
+    if (evals) HPE_CUDA(cudaMemcpyAsync(evals, d_e, sizeof(int) * count, cudaMemcpyDeviceToHost, 0));
+    HPE_CUDA(cudaStreamSynchronize(0));
+    return HPE_OK;
+}
+
+// the complete per-frame loop of test_full (src/testmodel.cpp:117-138): refine_init_pose, pso_evolve,
+// x0 = bestp.  Everything is queued on one stream (two launches and one 208-byte copy per frame), the
+// host synchronises once at the end.
+int hpe_track_sequence_refined(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                               const double x0[HPE_NDOF], int first, int n_frames, uint64_t seed, double *poses,
+                               double *costs, double *refined)
+{
+    if (!m || !p || !x0 || !poses || num_particles < 1 || p->maxiter < 1 || n_frames < 0)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_track_sequence_refined: bad argument");
+    if (int rc = check_slot(o, first, n_frames)) return rc;
+    if (n_frames == 0) return HPE_OK;
+    if (int rc = check_filled(o, first, n_frames)) return rc;
+    const size_t row = sizeof(double) * HPE_NDOF;
+    size_t b_x = align_up(row * n_frames), b_bp = b_x, b_bc = align_up(sizeof(double) * n_frames),
+           b_sd = align_up(sizeof(uint64_t) * n_frames);
+    HPE_CUDA(g_ws.reserve(b_x + b_bp + b_bc + b_sd));
+    char *base = (char *)g_ws.p;
+    double *d_x = (double *)base, *d_bp = (double *)(base + b_x), *d_bc = (double *)(base + b_x + b_bp);
+    uint64_t *d_sd = (uint64_t *)(base + b_x + b_bp + b_bc);
+    std::vector<uint64_t> seeds((size_t)n_frames, seed);
+    HPE_CUDA(cudaMemcpyAsync(d_sd, seeds.data(), sizeof(uint64_t) * n_frames, cudaMemcpyHostToDevice, 0));
+    HPE_CUDA(cudaMemcpyAsync(d_x, x0, row, cudaMemcpyHostToDevice, 0));
+    const PsoDev prm = make_pso(p, num_particles);
+    for (int k = 0; k < n_frames; ++k) {
+        double *xk = d_x + (size_t)k * HPE_NDOF, *bk = d_bp + (size_t)k * HPE_NDOF;
+        if (k > 0) HPE_CUDA(cudaMemcpyAsync(xk, bk - HPE_NDOF, row, cudaMemcpyDeviceToDevice, 0));
+        HPE_CUDA(hpe_launch_refine(m->dm, o->v, first + k, 1, xk, nullptr, 0));
+        cudaError_t e = g_hpe_pso_path == 1
+            ? hpe_launch_pso(m->dm, o->v, prm, xk, first + k, 1, d_sd + k, bk, d_bc + k, nullptr, 0, 0)
+            : hpe_launch_pso_cluster(m->dm, o->v, prm, xk, first + k, 1, d_sd + k, bk, d_bc + k, nullptr, 0, 0);
+        if (e != cudaSuccess)
+            return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
+                                 "pso launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));
+    }
+    HPE_CUDA(cudaMemcpyAsync(poses, d_bp, row * n_frames, cudaMemcpyDeviceToHost, 0));
+    if (costs) HPE_CUDA(cudaMemcpyAsync(costs, d_bc, sizeof(double) * n_frames, cudaMemcpyDeviceToHost, 0));
+    if (refined) HPE_CUDA(cudaMemcpyAsync(refined, d_x, row * n_frames, cudaMemcpyDeviceToHost, 0));
+    HPE_CUDA(cudaStreamSynchronize(0));
+    return HPE_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -105,6 +105,10 @@ cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p,
 cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
                                    int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
                                    double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st);
+// PSO::refine_init_pose for frames [first, first+count): x_dev count*26 in place, evals_dev count or NULL
+cudaError_t hpe_launch_refine(const DevModel &m, const ObsView &o, int first, int count, double *x_dev, int *evals_dev,
+                              cudaStream_t st);
+unsigned long long hpe_fallbacks_refine(int reset);
 cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_t n, double focal,
                               float *depth_dev, cudaStream_t st);
 size_t hpe_observe_scratch_bytes(int count);

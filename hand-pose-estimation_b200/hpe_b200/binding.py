@@ -297,6 +297,30 @@ class PSO:
                                         _p(poses), _p(costs)))
         return poses, costs
 
+    def refine_init_pose(self, x0, optfunc, slot=0):
+        """PSO::refine_init_pose(x0, optfunc) (src/PSO.cpp:216-266); returns the refined pose (the
+        reference updates x0 in place)."""
+        return self.refine_init_pose_batch(np.asarray(x0, dtype=np.float64).reshape(1, 26), optfunc, first=slot)[0][0]
+
+    def refine_init_pose_batch(self, x0, optfunc, first=0):
+        """x0[b] refined against frame first+b; returns (poses, number of cal_cost2 evaluations)"""
+        x = _f64(x0).reshape(-1, 26).copy()
+        ev = np.zeros(x.shape[0], dtype=np.int32)
+        _check(lib().hpe_refine_init_pose(optfunc.hand._h, optfunc.observation._h, _p(x), int(first), int(x.shape[0]),
+                                          _p(ev, C.c_int)))
+        return x, ev
+
+    def track_sequence_refined(self, optfunc, x0, num_particles, n_frames, seed=1000, first=0):
+        """the loop of test_full as written (src/testmodel.cpp:117-138): refine_init_pose, pso_evolve,
+        x0 = bestp; returns (bestp per frame, gbest cost per frame, refined start pose per frame)"""
+        x0 = _f64(x0).reshape(26)
+        poses, refined = np.empty((n_frames, 26)), np.empty((n_frames, 26))
+        costs = np.empty(n_frames)
+        _check(lib().hpe_track_sequence_refined(optfunc.hand._h, optfunc.observation._h, C.byref(self.params),
+                                                int(num_particles), _p(x0), int(first), int(n_frames),
+                                                C.c_uint64(seed), _p(poses), _p(costs), _p(refined)))
+        return poses, costs, refined
+
 
 class Swarm:
     """One large swarm (pso_evolve semantics) whose particles [lo,hi) live on this GPU.  Drive it as

@@ -139,6 +139,19 @@ int hpe_track_sequence(const hpe_model *m, const hpe_obs *o, const hpe_pso_param
                        int num_particles, const double x0[HPE_NDOF], int first, int n_frames,
                        uint64_t seed, double *poses, double *costs);
 
+/* PSO::refine_init_pose (src/PSO.cpp:216-266) with cal_grad (:183-214) and goldstein (:438-480) for
+ * `count` frames: x0 (host, count*26) is refined in place against frame slot first+b -- gradient
+ * descent with a Goldstein line search on theta[0:3], then on theta[3:6], every evaluation a
+ * cal_cost2 (frozen correspondences for the probes and the line search).  evals (may be NULL)
+ * receives the number of cal_cost2 evaluations the reference's sequential loop would have made. */
+int hpe_refine_init_pose(const hpe_model *m, const hpe_obs *o, double *x0, int first, int count, int *evals);
+/* the tracking loop of test_full as written (src/testmodel.cpp:117-138): per frame
+ * refine_init_pose(x0), pso_evolve(x0) -> bestp, x0 = bestp.  poses: n_frames*26 (bestp), costs:
+ * n_frames (gbest_cost), refined (may be NULL): n_frames*26, the pose each swarm started from. */
+int hpe_track_sequence_refined(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p,
+                               int num_particles, const double x0[HPE_NDOF], int first, int n_frames,
+                               uint64_t seed, double *poses, double *costs, double *refined);
+
 /* ---- one large swarm, particles [lo,hi) of num_particles owned by this GPU ---- */
 /* State lives on the device; the caller (one process per GPU) exchanges the
  * pbest table between generations (all-gather of hpe_swarm_table rows). */

@@ -238,6 +238,19 @@ public:
         check(hpe_track_sequence(optfunc.hand->c_handle(), optfunc.observation->c_handle(), &p_, num_particles, x0.data(),
                                  first, n_frames, seed, poses, costs));
     }
+    // void refine_init_pose(x0, optfunc), src/PSO.cpp:216-266: x0 is updated in place
+    void refine_init_pose(vec &x0, costfunc &optfunc, int slot = 0)
+    {
+        if (x0.size() != HPE_NDOF) throw error(HPE_ERR_ARG, "refine_init_pose: x0 must have 26 entries");
+        check(hpe_refine_init_pose(optfunc.hand->c_handle(), optfunc.observation->c_handle(), x0.data(), slot, 1, nullptr));
+    }
+    // the loop of test_full as written: refine_init_pose, pso_evolve, x0 = bestp (src/testmodel.cpp:117-138)
+    void track_sequence_refined(costfunc &optfunc, const vec &x0, int num_particles, int first, int n_frames,
+                                double *poses, double *costs, double *refined = nullptr, unsigned long long seed = 1000)
+    {
+        check(hpe_track_sequence_refined(optfunc.hand->c_handle(), optfunc.observation->c_handle(), &p_, num_particles,
+                                         x0.data(), first, n_frames, seed, poses, costs, refined));
+    }
     const hpe_pso_params &params() const { return p_; }
 
 private:

@@ -791,6 +791,140 @@ int orc_pso_evolve(const orc_model *m, const orc_obs *o, const orc_pso_params *p
 }
 
 /* ------------------------------------------------------------------ */
+/* PSO::refine_init_pose and its helpers            */
+/* ------------------------------------------------------------------ */
+
+/* op_dot::direct_dot_arma: two partial dot products over even / odd elements */
+static double arma_dot(const double *a, const double *b, int n)
+{
+    double v1 = 0, v2 = 0;
+    int i, j;
+    for (i = 0, j = 1; j < n; i += 2, j += 2) { v1 += a[i] * b[i]; v2 += a[j] * b[j]; }
+    if (i < n) v1 += a[i] * b[i];
+    return v1 + v2;
+}
+
+/* PSO::cal_grad, src/PSO.cpp:183-214: central differences (eps = 1e-5) of cal_cost2 with FROZEN
+ * correspondences over the selected parameters, zero elsewhere */
+void orc_cal_grad(const orc_model *m, const orc_obs *o, const double theta[ORC_NDOF],
+                  const int sel[ORC_NDOF], int32_t *match, double grad[ORC_NDOF])
+{
+    for (int i = 0; i < ORC_NDOF; ++i) {
+        grad[i] = 0.0;
+        if (!sel[i]) continue;
+        const double eps = 1e-5;
+        double xph[ORC_NDOF], xmh[ORC_NDOF];
+        memcpy(xph, theta, sizeof xph);
+        memcpy(xmh, theta, sizeof xmh);
+        xph[i] += eps;
+        xmh[i] -= eps;
+        double f_xph = orc_cal_cost2(m, o, xph, match, 0, 0);
+        double f_xmh = orc_cal_cost2(m, o, xmh, match, 0, 0);
+        grad[i] = (f_xph - f_xmh) / (2 * eps);
+    }
+}
+
+/* PSO::goldstein, src/PSO.cpp:438-480: bracketing line search on the Armijo / Goldstein pair;
+ * returns the iteration count, *tk = accepted step or 0 */
+int orc_goldstein(const orc_model *m, const orc_obs *o, const double theta[ORC_NDOF],
+                  const double g_k[ORC_NDOF], int32_t *match, double f_k, double *tk, int maxiter)
+{
+    double a = 0, b = 1e100, alpha = 0.5;
+    const double t = 2, c = 0.25;
+    double p_k[ORC_NDOF];
+    for (int i = 0; i < ORC_NDOF; ++i) p_k[i] = -1 * g_k[i];
+    int iter = 0;
+    while (iter < maxiter) {
+        iter += 1;
+        double theta1[ORC_NDOF];
+        for (int i = 0; i < ORC_NDOF; ++i) theta1[i] = theta[i] + alpha * p_k[i];
+        double f_k1 = orc_cal_cost2(m, o, theta1, match, 0, 0);
+        double armijo = f_k + c * alpha * arma_dot(g_k, p_k, ORC_NDOF);
+        double goldstein = f_k + (1 - c) * alpha * arma_dot(g_k, p_k, ORC_NDOF);
+        if (f_k1 <= armijo) {
+            if (f_k1 >= goldstein) {
+                *tk = alpha;
+                return iter;
+            }
+            a = alpha;
+            {
+                /* std::min(t*alpha, 0.5*(alpha+b)): the first argument unless the second is smaller */
+                double x = t * alpha, y = 0.5 * (alpha + b);
+                alpha = y < x ? y : x;
+            }
+        } else {
+            b = alpha;
+            alpha = 0.5 * (a + alpha);
+        }
+    }
+    *tk = 0;
+    return iter;
+}
+
+/* PSO::refine_init_pose, src/PSO.cpp:216-266: gradient descent on theta[0:3] (rotation), then on
+ * theta[3:6] (position); each group: up to 15 iterations of (cal_cost2 with fresh correspondences,
+ * numerical gradient on the frozen ones, Goldstein step), stopping after the first failed line
+ * search or when |grad| <= 1e-6.  evals (optional) counts cal_cost2 calls. */
+void orc_refine_init_pose(const orc_model *m, const orc_obs *o, double x0[ORC_NDOF], int *evals)
+{
+    const int len = 2;
+    const int start_idx[7] = {0, 3, 6, 10, 14, 18, 22};
+    const int end_idx[7] = {2, 5, 9, 13, 17, 21, 25};
+    int32_t *match = (int32_t *)malloc(sizeof(int32_t) * (o->n_pts > 0 ? o->n_pts : 1));
+    int n_evals = 0;
+    for (int i = 0; i < len; ++i) {
+        const double eps = 1e-6;
+        double tol = 1;
+        int cnt = 0, iter = 0;
+        const int maxiter = 15;
+        while (tol > eps && iter < maxiter && cnt < 1) {
+            int sel[ORC_NDOF] = {0};
+            for (int d = start_idx[i]; d <= end_idx[i]; ++d) sel[d] = 1;
+            double grad[ORC_NDOF];
+            double f_k = orc_cal_cost2(m, o, x0, match, 1, 0);
+            orc_cal_grad(m, o, x0, sel, match, grad);
+            double tk = 0;
+            int ls = orc_goldstein(m, o, x0, grad, match, f_k, &tk, 30);
+            n_evals += 1 + 2 * (end_idx[i] - start_idx[i] + 1) + ls;
+            if (tk == 0) cnt += 1;
+            for (int d = 0; d < ORC_NDOF; ++d) x0[d] = x0[d] - tk * grad[d];
+            double sq[ORC_NDOF];
+            for (int d = 0; d < ORC_NDOF; ++d) sq[d] = grad[d] * grad[d];
+            tol = sqrt(arma_accumulate(sq, ORC_NDOF));
+            iter += 1;
+        }
+    }
+    if (evals) *evals = n_evals;
+    free(match);
+}
+
+/* PSO::dim_restore, src/PSO.cpp:160-180: 22 -> 26 parameters with DIP = 2/3 PIP */
+void orc_dim_restore(const double in[22], double out[ORC_NDOF])
+{
+    for (int i = 0; i <= 9; ++i) out[i] = in[i];
+    for (int f = 0; f < 4; ++f) {
+        for (int k = 0; k < 3; ++k) out[10 + 4 * f + k] = in[10 + 3 * f + k];
+        out[13 + 4 * f] = 2. / 3 * in[12 + 3 * f];
+    }
+}
+
+/* costfunc::gnd_truth_err, src/costfunc.cpp:476-507: joints (21 x 3, cm, as build_hand_model left
+ * them) x 10 -> mm, y and z negated; gt_row = one joint.txt row (63 values: x,y,z per joint, mm);
+ * sum of the distances of the wrist and the five finger tips (rows 0,4,8,12,16,20) */
+double orc_gnd_truth_err(const double joints[ORC_NJOINT * 3], const double gt_row[63])
+{
+    static const int sj[6] = {0, 4, 8, 12, 16, 20};
+    double dist[6];
+    for (int q = 0; q < 6; ++q) {
+        int j = sj[q];
+        double hx = joints[j * 3] * 10.0, hy = joints[j * 3 + 1] * 10.0 * -1, hz = joints[j * 3 + 2] * 10.0 * -1;
+        double dx = gt_row[j * 3] - hx, dy = gt_row[j * 3 + 1] - hy, dz = gt_row[j * 3 + 2] - hz;
+        dist[q] = sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    return arma_accumulate(dist, 6);
+}
+
+/* ------------------------------------------------------------------ */
 /* Synthetic frames: ray-cast the 48 spheres.  Not a   */
 /* reference function.  Pixel (u,v) looks along ((u-160)/f,(v-120)/f,1).*/
 /* ------------------------------------------------------------------ */

@@ -115,6 +115,15 @@ int  orc_pso_evolve(const orc_model *m, const orc_obs *o, const orc_pso_params *
                     double bestp[ORC_NDOF], double *best_cost, double *trace,
                     double *final_particles, double *final_pcost);
 
+/* ---- initial-pose refinement, ground-truth error ---- */
+void orc_cal_grad(const orc_model *m, const orc_obs *o, const double theta[ORC_NDOF],
+                  const int sel[ORC_NDOF], int32_t *match, double grad[ORC_NDOF]);
+int  orc_goldstein(const orc_model *m, const orc_obs *o, const double theta[ORC_NDOF],
+                   const double g_k[ORC_NDOF], int32_t *match, double f_k, double *tk, int maxiter);
+void orc_refine_init_pose(const orc_model *m, const orc_obs *o, double x0[ORC_NDOF], int *evals);
+void orc_dim_restore(const double in[22], double out[ORC_NDOF]);
+double orc_gnd_truth_err(const double joints[ORC_NJOINT * 3], const double gt_row[63]);
+
 /* ---- synthetic data (test helper, not a reference function) ---- */
 void orc_render_depth(const double *spheres_unneg, const double *rad, double focal,
                       float *depth_mm /* H*W */);

@@ -235,3 +235,22 @@ def render_depth(model, theta, focal=D.FOCAL):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def refine_init_pose(model, obs, x0):
+    """PSO::refine_init_pose (src/PSO.cpp:216-266); returns (refined pose, number of cal_cost2 calls)"""
+    x = f64(x0).copy()
+    n = C.c_int()
+    lib().orc_refine_init_pose(C.byref(model), C.byref(obs.o), _p(x), C.byref(n))
+    return x, n.value
+
+
+def dim_restore(t22):
+    o = np.empty(26)
+    lib().orc_dim_restore(_p(f64(t22)), _p(o))
+    return o
+
+
+def gnd_truth_err(joints, gt_row):
+    lib().orc_gnd_truth_err.restype = C.c_double
+    return lib().orc_gnd_truth_err(_p(f64(joints)), _p(f64(gt_row)))
