@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-offline", action="store_true", help="skip the 262,144-frame offline batch extra")
     ap.add_argument("--npts", type=int, default=256)
     ap.add_argument("--no-extras", action="store_true", help="skip the 250-point and frames/s side measurements")
     args = ap.parse_args()
@@ -399,6 +400,63 @@ def main():
         extras["track_frames_per_sec"] = world * n_seq / dt
         extras["track"] = (f"{n_seq}-frame synthetic sequence per GPU, 64 particles x 30 generations per frame, temporal "
                            f"init; median final cost {float(np.median(costs)):.3f}")
+
+        # PSO::refine_init_pose for a batch of frames (one CTA per frame), and the complete
+        # per-frame loop of test_full (refine_init_pose -> pso_evolve -> x0 = bestp) on the head of the sequence
+        pso.refine_init_pose_batch(x0[:64], cfb)
+        barrier()
+        t0 = time.perf_counter()
+        _, ev = pso.refine_init_pose_batch(x0, cfb)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        extras["refine_frames_per_sec"] = world * n_fr / dt
+        extras["refine_evals_per_sec"] = world * float(ev.sum()) / dt
+        extras["refine"] = (f"{n_fr} frames per GPU, gradient descent + Goldstein search on rotation then position, "
+                            f"mean {float(ev.mean()):.0f} cal_cost2 evaluations per frame")
+        n_ref = 200
+        pso.track_sequence_refined(cfs, xs0, 64, 8)
+        barrier()
+        t0 = time.perf_counter()
+        _, costs_r, _ = pso.track_sequence_refined(cfs, xs0, 64, n_ref)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        extras["track_refined_frames_per_sec"] = world * n_ref / dt
+        extras["track_refined"] = (f"first {n_ref} frames of the sequence, refine_init_pose before every pso_evolve "
+                                   f"(src/testmodel.cpp:126-130); median final cost {float(np.median(costs_r)):.3f}")
+        # configs[4]: offline batch, 262,144 independent frames x (64 x 30), frames sharded over the ranks and
+        # streamed through the device in chunks: rendered on the device (nothing crosses PCIe but the poses),
+        # observed (cloud + distance transform) and fitted
+        if not args.no_offline:
+            N_OFF, CHUNK = 262144, 8192
+            lo, hi = sharding.shard_range(N_OFF, rank, world)
+            rng = np.random.default_rng(5)
+            truths_all = np.clip(D.X0 + rng.normal(size=(N_OFF, 26)) * D.STD * 0.5, D.LB, D.UB)[lo:hi]
+            x0_all = truths_all + np.random.default_rng(55 + rank).normal(size=truths_all.shape) * D.STD * 0.3
+            del frames_dev, seq_dev
+            torch.cuda.empty_cache()
+            fr_dev = torch.empty(CHUNK, D.H, D.W, dtype=torch.float32, device="cuda")
+            obsc = hpe_b200.observedmodel(capacity=CHUNK, num_samples=250)
+            cfc = hpe_b200.costfunc(hand, obsc)
+            best_all = np.empty(hi - lo)
+
+            def run_chunk(a, b):
+                th = torch.from_numpy(truths_all[a:b]).cuda()
+                hpe_b200.binding.render_dev(hand, th.data_ptr(), b - a, fr_dev.data_ptr())
+                obsc.upload_dev(fr_dev.data_ptr(), 0, b - a)
+                _, best_all[a:b], _ = pso.pso_evolve_batch(cfc, x0_all[a:b], 64, want_trace=False)
+
+            run_chunk(0, min(CHUNK, hi - lo))            # warm-up (workspace growth)
+            barrier()
+            t0 = time.perf_counter()
+            for a in range(0, hi - lo, CHUNK):
+                run_chunk(a, min(a + CHUNK, hi - lo))
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            extras["offline_frames_per_sec"] = N_OFF / dt
+            extras["offline_s"] = dt
+            extras["offline"] = (f"configs[4]: {N_OFF} frames over {world} rank(s) in chunks of {CHUNK}: device render + "
+                                 f"observation + 64 x 30 swarm each; strong scaling; median final cost "
+                                 f"{float(np.median(best_all)):.3f}")
 
     if rank == 0:
         flop = flops_per_eval(args.npts)

@@ -201,6 +201,27 @@ int hpe_fk_batch(const hpe_model *m, const double *theta, int64_t n, double *sph
     return HPE_OK;
 }
 
+// costfunc::gnd_truth_err for n (pose, joint.txt row) pairs
+int hpe_gnd_truth_err(const hpe_model *m, const double *theta, const double *gt_mm, int64_t n, double *err)
+{
+    if (!m || n < 0 || ((!theta || !gt_mm || !err) && n > 0)) return hpe_set_error(HPE_ERR_ARG, "hpe_gnd_truth_err: bad argument");
+    if (n == 0) return HPE_OK;
+    if (int rc = check_device()) return rc;
+    size_t b_th = align_up(sizeof(double) * n * HPE_NDOF), b_jt = align_up(sizeof(double) * n * HPE_NJOINT * 3),
+           b_gt = align_up(sizeof(double) * n * 63), b_er = align_up(sizeof(double) * n);
+    HPE_CUDA(g_ws.reserve(b_th + b_jt + b_gt + b_er));
+    char *base = (char *)g_ws.p;
+    double *d_th = (double *)base, *d_jt = (double *)(base + b_th), *d_gt = (double *)(base + b_th + b_jt),
+           *d_er = (double *)(base + b_th + b_jt + b_gt);
+    HPE_CUDA(cudaMemcpyAsync(d_th, theta, sizeof(double) * n * HPE_NDOF, cudaMemcpyHostToDevice, 0));
+    HPE_CUDA(cudaMemcpyAsync(d_gt, gt_mm, sizeof(double) * n * 63, cudaMemcpyHostToDevice, 0));
+    HPE_CUDA(hpe_launch_fk(m->dm, d_th, n, nullptr, d_jt, 0));
+    HPE_CUDA(hpe_launch_gt_err(d_jt, d_gt, n, d_er, 0));
+    HPE_CUDA(cudaMemcpyAsync(err, d_er, sizeof(double) * n, cudaMemcpyDeviceToHost, 0));
+    HPE_CUDA(cudaStreamSynchronize(0));
+    return HPE_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // observedmodel
 // ------------------------------------------------------------------------------------------

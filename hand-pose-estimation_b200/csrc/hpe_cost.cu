@@ -216,6 +216,29 @@ __global__ void __launch_bounds__(256) render_kernel(DevModel m, const double *_
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// costfunc::gnd_truth_err (src/costfunc.cpp:476-507): joints x 10 (cm -> mm), y and z negated,
+// distance to the ground-truth joints of joint.txt for the wrist and the five tips
+// (rows 0, 4, 8, 12, 16, 20), summed the way Armadillo sums a vector (two partial sums).
+// One thread per pose; joints [n][21][3] as fk_kernel wrote them, gt [n][63].
+// ---------------------------------------------------------------------------------------
+__global__ void gt_err_kernel(const double *__restrict__ joints, const double *__restrict__ gt, int64_t n,
+                              double *__restrict__ err)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *J = joints + i * HPE_NJOINT * 3, *G = gt + i * 63;
+    double d[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const int j = 4 * q;
+        double hx = __dmul_rn(J[j * 3], 10.0), hy = -__dmul_rn(J[j * 3 + 1], 10.0), hz = -__dmul_rn(J[j * 3 + 2], 10.0);
+        double dx = G[j * 3] - hx, dy = G[j * 3 + 1] - hy, dz = G[j * 3 + 2] - hz;
+        d[q] = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    }
+    err[i] = __dadd_rn(__dadd_rn(__dadd_rn(d[0], d[2]), d[4]), __dadd_rn(__dadd_rn(d[1], d[3]), d[5]));
+}
+
 }  // namespace
 
 HPE_DEFINE_FALLBACK_GETTER(hpe_fallbacks_cost)
@@ -227,6 +250,13 @@ cudaError_t hpe_launch_fk(const DevModel &m, const double *theta_dev, int64_t n,
     int64_t items = n * 5;
     int blocks = (int)((items + 159) / 160);
     fk_kernel<<<blocks, 160, 0, st>>>(m, theta_dev, n, spheres_dev, joints_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t hpe_launch_gt_err(const double *joints_dev, const double *gt_dev, int64_t n, double *err_dev, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    gt_err_kernel<<<(int)((n + 127) / 128), 128, 0, st>>>(joints_dev, gt_dev, n, err_dev);
     return cudaGetLastError();
 }
 

@@ -96,6 +96,7 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
                             int64_t n, bool with_colli, double *cost_dev, double *terms_dev,
                             const int32_t *frozen_match_dev, int32_t *match_out_dev, cudaStream_t st,
                             int64_t terms_stride = 0 /* distance between the three term arrays; 0 = n */);
+cudaError_t hpe_launch_gt_err(const double *joints_dev, const double *gt_dev, int64_t n, double *err_dev, cudaStream_t st);
 cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *scratch, cudaStream_t st);
 cudaError_t hpe_launch_dtmax(const ObsView &o, int slot, cudaStream_t st);
 cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,

@@ -78,6 +78,7 @@ class handmodel:
         _check(lib().hpe_model_create(_p(self._geo), _p(self._spacing), _p(self._cmc), _p(self._tb, C.c_int),
                                       _p(self._fg, C.c_int), _p(self._rad), C.byref(self._h)))
         self.hand_joints = np.zeros((21, 3))
+        self.last_theta = None
 
     def __del__(self):
         if getattr(self, "_h", None) and _LIB is not None:
@@ -104,6 +105,7 @@ class handmodel:
         (src/handmodel.cpp:259-298)."""
         S, J = self.build_hand_models(np.asarray(h_theta, dtype=np.float64).reshape(1, 26))
         self.hand_joints = J[0]
+        self.last_theta = np.asarray(h_theta, dtype=np.float64).reshape(26).copy()
         return S[0]
 
     def build_hand_models(self, thetas):
@@ -234,6 +236,24 @@ class costfunc:
         _check(lib().hpe_cost_batch_frozen(self.hand._h, self.observation._h, int(slot), _p(th), C.c_int64(n),
                                            _p(m, C.c_int32), _p(a), _p(d), _p(c)))
         return a, d, c
+
+    def gnd_truth_err(self, gnd_truth, frame, theta=None):
+        """costfunc::gnd_truth_err(gnd_truth, frame) (src/costfunc.cpp:476-507): gnd_truth = joint.txt
+        as an (n_frames, 63) array; uses the pose of the last build_hand_model call unless theta is given"""
+        th = self.hand.last_theta if theta is None else theta
+        if th is None:
+            raise HpeError(1, "gnd_truth_err: no pose (call build_hand_model first or pass theta)")
+        return self.gnd_truth_err_batch(np.asarray(th, dtype=np.float64).reshape(1, 26),
+                                        _f64(gnd_truth).reshape(-1, 63)[frame:frame + 1])[0]
+
+    def gnd_truth_err_batch(self, thetas, gt_rows):
+        th = _f64(thetas).reshape(-1, 26)
+        gt = _f64(gt_rows).reshape(-1, 63)
+        if gt.shape[0] != th.shape[0]:
+            raise HpeError(1, "gnd_truth_err_batch: one joint.txt row per pose")
+        err = np.empty(th.shape[0])
+        _check(lib().hpe_gnd_truth_err(self.hand._h, _p(th), _p(gt), C.c_int64(th.shape[0]), _p(err)))
+        return err
 
     def compute_correspondences(self, thetas, slot=0):
         th = _f64(thetas).reshape(-1, 26)

@@ -125,6 +125,12 @@ int hpe_cost_batch_frozen(const hpe_model *m, const hpe_obs *o, int slot, const 
 int hpe_correspondences(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
                         int32_t *match);
 
+/* costfunc::gnd_truth_err (src/costfunc.cpp:476-507) for n poses: the joints of theta[i] (x10 -> mm,
+ * y and z negated) against gt_mm[i] = one row of the data set's joint.txt (63 values, x y z of the 21
+ * joints, mm); err[i] = summed distance over the wrist and the five finger tips (joints 0,4,8,12,16,20).
+ * HOST pointers. */
+int hpe_gnd_truth_err(const hpe_model *m, const double *theta, const double *gt_mm, int64_t n, double *err);
+
 /* ---- PSO (src/PSO.h:56-68) -------------------------------------------- */
 /* PSO::pso_evolve (src/PSO.cpp:717-886) for `count` independent swarms, swarm b fitted to
  * frame slot first+b with initial pose x0[b].  seeds: count values or NULL (every swarm

@@ -190,6 +190,16 @@ public:
         check(hpe_correspondences(hand->c_handle(), observation->c_handle(), slot, theta.data(), 1, matchId.data()));
     }
 
+    // double gnd_truth_err(gnd_truth, frame), src/costfunc.cpp:476-507: gnd_truth = joint.txt, n_frames x 63
+    // row-major (mm); theta = the pose whose joints are compared (the reference reads hand_joints left by the
+    // last build_hand_model call)
+    double gnd_truth_err(const double *gnd_truth, int frame, const vec &theta)
+    {
+        double e = 0;
+        check(hpe_gnd_truth_err(hand->c_handle(), theta.data(), gnd_truth + (size_t)frame * 63, 1, &e));
+        return e;
+    }
+
     handmodel *hand;
     observedmodel *observation;
 };

@@ -97,3 +97,24 @@ def test_track_sequence_refined_matches_oracle(hpe, orc, omodel, D):
         _, Jo = orc.fk(omodel, bo)
         assert np.linalg.norm(Jg - Jo, axis=1).max() * 10.0 < 1.0, k
         cur = bo
+
+
+def test_gnd_truth_err_matches_reference_fixture_and_oracle(hpe, orc, omodel, D):
+    """costfunc::gnd_truth_err (src/costfunc.cpp:476-507), SURVEY 8(f) rank 2"""
+    g = np.load(os.path.join(HERE, "golden", "golden_ref_v1.npz"))
+    hand, obs = hpe.handmodel(), hpe.observedmodel(capacity=1)
+    cf = hpe.costfunc(hand, obs)
+    hand.build_hand_model(g["truth"])
+    for f in range(len(g["gt_rows"])):
+        e = cf.gnd_truth_err(g["gt_rows"], f)
+        assert abs(e - g["gt_err"][f]) <= 1e-12 * g["gt_err"][f]
+    rng = np.random.default_rng(41)
+    th = D.X0 + rng.normal(size=(500, 26)) * D.STD
+    gt = rng.normal(size=(500, 63)) * 50
+    e = cf.gnd_truth_err_batch(th, gt)
+    _, J = orc.fk(omodel, th)
+    eo = np.array([orc.gnd_truth_err(J[i], gt[i]) for i in range(500)])
+    assert np.allclose(e, eo, rtol=1e-12)
+    # a pose scored against its own joints (mm, y/z negated) has zero error
+    own = (J[:4] * 10.0 * np.array([1.0, -1.0, -1.0])).reshape(4, 63)
+    assert np.abs(cf.gnd_truth_err_batch(th[:4], own)).max() < 1e-9
