@@ -1,5 +1,7 @@
 // hpe_cost.cu -- batched handmodel::build_hand_model and costfunc::cal_cost/cal_cost2 kernels,
 // plus the sphere-model ray-caster used to synthesise Subject1-format frames.
+#include <cooperative_groups.h>
+
 #include "hpe_eval.cuh"
 #include "hpe_internal.h"
 
@@ -171,6 +173,240 @@ swarm_step_kernel(DevModel m, ObsView o, int slot, SwarmStepArgs sw)
 }
 
 // ---------------------------------------------------------------------------------------
+// The whole pso_evolve of one large sharded swarm in ONE cooperative launch per GPU (hpe_swarm_run):
+// every generation's topology draw, informant search, move + evaluate + pbest, the exchange of the
+// owned (pcost, pbest) rows with the other GPUs and the global argmin run inside this kernel.
+//   * exchange: the warp that finishes a particle stores its 27-double row into the local table AND
+//     straight into every peer's table over NVLink (CUDA IPC mappings); after a grid barrier one
+//     thread per peer raises this rank's generation flag in the peer's memory and waits for theirs.
+//     No NCCL call, no host involvement; compute and transfer overlap particle by particle.
+//   * rows are double buffered exactly like the stepwise path (hpe_swarm.cu), and a rank enters
+//     generation g+1 only after seeing every peer's flag of generation g, so stores into the buffer a
+//     peer still reads cannot happen.
+//   * 4 grid barriers per generation (informant cost pass | index pass | step | reduce).
+// Counters are keyed by the global particle index: the result is bit-identical to the stepwise
+// all-gather path, to any other sharding and to pso_kernel.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long run_cost_bits(double c)
+{
+    return c == c ? (unsigned long long)__double_as_longlong(c) : 0xfff8000000000000ull;
+}
+
+__global__ void __launch_bounds__(COST_WARPS * 32, HPE_MINBLOCKS)
+swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
+    __shared__ unsigned long long skey[COST_WARPS];
+    __shared__ int sidx[COST_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    stage_model(sm.fs, m);
+    stage_frame(sm.fs, frame_view(o, slot));     // ends synchronised
+    const WarpScratch ws = warp_scratch(sm.ws, warp, HPE_GROUP);
+    constexpr int D = HPE_NDOF, ROW = HPE_NDOF + 1, NK = 3;
+    const int num_p = a.num_p, own = a.hi - a.lo;
+    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + tid;
+    const int64_t total_warps = (int64_t)gridDim.x * COST_WARPS, gw = (int64_t)blockIdx.x * COST_WARPS + warp;
+    const int64_t plo = (int64_t)own * gw / total_warps, phi = (int64_t)own * (gw + 1) / total_warps;
+    SwarmCtl *ctl = a.ctl;
+    // optional phase timestamps (hpe_swarm_debug_times): 8 slots per generation, written by one thread
+#define RUN_STAMP(slot_) do { if (a.times && gtid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.times[g * 8 + (slot_)] = t_; } } while (0)
+
+    // generate_particles for the owned rows (src/PSO.cpp:56-74); informant search state cleared
+    for (int64_t it = gtid; it < (int64_t)own * (D / 2); it += gthreads) {
+        int li = (int)(it / (D / 2)), dp = (int)(it - (int64_t)li * (D / 2));
+        double z[2];
+        normal2(a.seed, (uint32_t)dp, (uint32_t)(a.lo + li), 0u, z);
+        a.x[li * D + 2 * dp] = __dadd_rn(a.x0[2 * dp], __dmul_rn(z[0], a.prm.std[2 * dp]));
+        a.x[li * D + 2 * dp + 1] = __dadd_rn(a.x0[2 * dp + 1], __dmul_rn(z[1], a.prm.std[2 * dp + 1]));
+        a.v[li * D + 2 * dp] = 0.0;
+        a.v[li * D + 2 * dp + 1] = 0.0;
+    }
+    for (int64_t i = gtid; i < num_p; i += gthreads) { a.key[i] = ~0ull; a.inf[i] = 0x7fffffff; }
+    if (gtid == 0) { ctl->gbest_cost = 1e100; ctl->count = 100; ctl->iter = 0; }
+    grid.sync();
+
+    int cur = 0;
+    for (int g = 0; g < a.maxiter; ++g) {
+        const double *table = a.table[cur];                 // rows of the previous generation, complete
+        double *out = g == 0 ? a.table[0] : a.table[cur ^ 1];
+        const int ob = g == 0 ? 0 : cur ^ 1;
+        const int iter = g;                                 // = ctl->iter: evaluations done so far
+        RUN_STAMP(0);
+        if (g > 0) {
+            // ---- topology (redrawn when count > 0, src/PSO.cpp:790-803) + informant cost pass (:810-812) ----
+            const bool redraw = ((volatile SwarmCtl *)ctl)->count > 0;
+            for (int64_t it = gtid; it < (int64_t)num_p * (NK + 1); it += gthreads) {
+                int s = (int)(it / (NK + 1)), k = (int)(it - (int64_t)s * (NK + 1));
+                int r = s;                                  // L = eye + links
+                if (k < NK) {
+                    if (redraw) {
+                        double u[2];
+                        uniform2(a.seed, (uint32_t)(k >> 1), (uint32_t)s, (uint32_t)iter, 3u, u);
+                        a.R[s * NK + k] = (int)floor(__dadd_rn(__dmul_rn(u[k & 1], (double)(num_p - 1)), 0.5));
+                    }
+                    r = a.R[s * NK + k];
+                }
+                atomicMin(&a.key[r], run_cost_bits(__ldcg(table + (size_t)s * ROW)));
+            }
+            grid.sync();
+            RUN_STAMP(1);
+            // ---- informant index pass: lowest index attaining the minimum ----
+            for (int64_t it = gtid; it < (int64_t)num_p * (NK + 1); it += gthreads) {
+                int s = (int)(it / (NK + 1)), k = (int)(it - (int64_t)s * (NK + 1));
+                int r = k < NK ? a.R[s * NK + k] : s;
+                if (run_cost_bits(__ldcg(table + (size_t)s * ROW)) == __ldcg(a.key + r)) atomicMin(&a.inf[r], s);
+            }
+            grid.sync();
+            RUN_STAMP(2);
+        }
+        // ---- move (g > 0), evaluate, pbest row -> local table and every peer's table ----
+        unsigned long long wkey = ~0ull;                     // first minimum of pcost over this warp's particles
+        int widx = 0x7fffffff;
+        for (int64_t p0 = plo; p0 < phi; p0 += HPE_GROUP) {
+            int cnt = (int)min((int64_t)HPE_GROUP, phi - p0);
+            if (g > 0) {
+                for (int it = lane; it < cnt * (D / 2); it += 32) {
+                    int gq = it / (D / 2), dp = it - gq * (D / 2);
+                    int li = (int)(p0 + gq), i = a.lo + li, informant = __ldcg(a.inf + i);
+                    const double *pb = table + (size_t)i * ROW + 1, *pbi = table + (size_t)informant * ROW + 1;
+                    double rp[2], rg[2];
+                    uniform2(a.seed, (uint32_t)dp, (uint32_t)i, (uint32_t)iter, 1u, rp);
+                    uniform2(a.seed, (uint32_t)dp, (uint32_t)i, (uint32_t)iter, 2u, rg);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        int d = 2 * dp + e, at = li * D + d;
+                        double xi = a.x[at];
+                        double nv = __dadd_rn(__dmul_rn(a.v[at], a.W1), __dmul_rn(__dmul_rn(rp[e], a.C1), __dadd_rn(__ldcg(pb + d), -xi)));
+                        if (informant != i) nv = __dadd_rn(nv, __dmul_rn(__dmul_rn(rg[e], a.C1), __dadd_rn(__ldcg(pbi + d), -xi)));
+                        double nx = __dadd_rn(xi, nv);
+                        if (nx < a.prm.lb[d] || nx > a.prm.ub[d]) { nx = a.prm.lb[d]; nv = 0.0; }   // :372
+                        a.x[at] = nx;
+                        a.v[at] = nv;
+                    }
+                }
+                __syncwarp();
+            }
+            group_fk(sm.fs.M, [&](int gq) { return a.x + (p0 + gq) * D; }, cnt, ws, lane);
+            for (int gq = 0; gq < cnt; ++gq) {
+                double depth = depth_and_stage(sm.fs, ws, gq, lane);
+                double align = match_align<0>(sm.fs, ws, gq, lane, nullptr, nullptr);
+                double fx = align + depth;
+                const size_t roff = (size_t)(a.lo + p0 + gq) * ROW;
+                const double *row = table + roff;
+                const double old_cost = g == 0 ? 0.0 : __ldcg(row);
+                bool take = g == 0 || fx < old_cost;
+                {
+                    unsigned long long kb = run_cost_bits(take ? fx : old_cost);
+                    if (kb < wkey) { wkey = kb; widx = (int)(a.lo + p0 + gq); }      // ascending index: ties keep the first
+                }
+                if (lane < ROW) {
+                    double val = take ? (lane == 0 ? fx : a.x[(p0 + gq) * D + lane - 1]) : __ldcg(row + lane);
+                    out[roff + lane] = val;
+                    for (int p = 0; p < a.world; ++p)
+                        if (a.peer_table[ob][p]) a.peer_table[ob][p][roff + lane] = val;      // NVLink store
+                }
+            }
+        }
+        // this CTA's minimum -> cta_key / cta_idx (the global argmin is then a reduction over CTAs and ranks)
+        if (lane == 0) { skey[warp] = wkey; sidx[warp] = widx; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long kk = skey[0];
+            int ii = sidx[0];
+            for (int w = 1; w < COST_WARPS; ++w)
+                if (skey[w] < kk || (skey[w] == kk && sidx[w] < ii)) { kk = skey[w]; ii = sidx[w]; }
+            a.cta_key[blockIdx.x] = kk;
+            a.cta_idx[blockIdx.x] = ii;
+        }
+        RUN_STAMP(3);
+        __threadfence_system();
+        grid.sync();
+        RUN_STAMP(4);
+        // informant search state for the next generation (nobody reads it any more in this one)
+        for (int64_t i = gtid; i < num_p; i += gthreads) { a.key[i] = ~0ull; a.inf[i] = 0x7fffffff; }
+        // ---- exchange point + global first minimum (src/PSO.cpp:755-760, 864-876): CTA 0 ----
+        if (blockIdx.x == 0) {
+            unsigned long long key = ~0ull;
+            int idx = 0x7fffffff;
+            for (int i = tid; i < (int)gridDim.x; i += COST_WARPS * 32) {
+                unsigned long long kk = __ldcg(a.cta_key + i);
+                int ii = __ldcg(a.cta_idx + i);
+                if (kk < key || (kk == key && ii < idx)) { key = kk; idx = ii; }
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, off);
+                int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+                if (ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; }
+            }
+            __syncthreads();                                  // skey / sidx of the step phase have been consumed
+            if (lane == 0) { skey[warp] = key; sidx[warp] = idx; }
+            __syncthreads();
+            const int par = g & 1;
+            const unsigned want = a.gen_base + (unsigned)g + 1u;
+            if (warp == 0) {
+                key = lane < COST_WARPS ? skey[lane] : ~0ull;
+                idx = lane < COST_WARPS ? sidx[lane] : 0x7fffffff;
+                for (int off = 16; off > 0; off >>= 1) {
+                    unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, off);
+                    int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+                    if (ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; }
+                }
+                // this rank's minimum goes to every peer next to the rows, then the flag: "generation g delivered"
+                if (lane < a.world && lane != a.rank) {
+                    SwarmMin *dst = a.peer_min[lane] + par * HPE_MAX_PEERS + a.rank;
+                    dst->key = key;
+                    dst->idx = idx;
+                    __threadfence_system();
+                    a.peer_flags[lane][a.rank] = want;
+                    __threadfence_system();
+                    long long spins = 0;
+                    while (a.my_flags[lane] < want) {
+                        if (++spins > (1ll << 28)) { ctl->count = -12345; break; }   // a lost peer must not hang the GPU
+                        __nanosleep(32);
+                    }
+                    __threadfence_system();
+                    const volatile SwarmMin *src = a.my_min + par * HPE_MAX_PEERS + lane;
+                    key = src->key;
+                    idx = src->idx;
+                } else if (lane >= a.world) {
+                    key = ~0ull;
+                    idx = 0x7fffffff;
+                }
+                RUN_STAMP(5);
+                for (int off = 16; off > 0; off >>= 1) {
+                    unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, off);
+                    int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+                    if (ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; }
+                }
+                if (idx == 0x7fffffff) idx = 0;
+                const double *vt = out;                       // the winner's row (remote rows arrived by NVLink stores)
+                const double fmin = __ldcg(vt + (size_t)idx * ROW);
+                const bool improved = fmin < ctl->gbest_cost;
+                if (improved && lane < D) ctl->gbest[lane] = __ldcg(vt + (size_t)idx * ROW + 1 + lane);
+                __syncwarp();
+                if (lane == 0) {
+                    if (improved) {
+                        ctl->gbest_cost = fmin;
+                        ctl->count = g == 0 ? 100 : 0;
+                    } else if (g > 0 && ctl->count != -12345) {
+                        ctl->count += 1;
+                    }
+                    ctl->iter = g + 1;
+                    if (a.trace && g >= 1) a.trace[g - 1] = ctl->gbest_cost;
+                }
+            }
+        }
+        RUN_STAMP(6);
+        grid.sync();
+        RUN_STAMP(7);
+        if (g > 0) cur ^= 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Synthetic frames: ray-cast the 48 spheres at pose theta[f] into frame f.  One CTA per
 // frame; FP64 so that the frame equals the oracle's renderer up to FK rounding.
 // ---------------------------------------------------------------------------------------
@@ -313,6 +549,30 @@ cudaError_t hpe_launch_swarm_step(const DevModel &m, const ObsView &o, int slot,
     int blocks = (int)(want < (long long)HPE_MINBLOCKS * sms ? want : (long long)HPE_MINBLOCKS * sms);
     swarm_step_kernel<<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, a);
     return cudaGetLastError();
+}
+
+cudaError_t hpe_launch_swarm_run(const DevModel &m, const ObsView &o, int slot, const SwarmRunArgs &a, cudaStream_t st)
+{
+    static int sms = 0, per_sm = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(swarm_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, swarm_run_kernel, COST_WARPS * 32, sizeof(CostSmem));
+        if (per_sm > HPE_MINBLOCKS) per_sm = HPE_MINBLOCKS;
+        if (per_sm < 1) per_sm = 1;
+    }
+    // all CTAs must be co-resident (grid barriers): one full wave, fewer when the shard is small
+    int64_t own = a.hi - a.lo;
+    int64_t want = (own + COST_WARPS - 1) / COST_WARPS;                 // one particle per warp is enough
+    int blocks = (int)(want < (int64_t)per_sm * sms ? want : (int64_t)per_sm * sms);
+    if (blocks < sms) blocks = sms;                                     // the scatter / reset phases want the whole chip
+    DevModel mm = m;
+    ObsView oo = o;
+    SwarmRunArgs aa = a;
+    void *args[] = {&mm, &oo, &slot, &aa};
+    return cudaLaunchCooperativeKernel((void *)swarm_run_kernel, dim3(blocks), dim3(COST_WARPS * 32), args, sizeof(CostSmem), st);
 }
 
 cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_t n, double focal,

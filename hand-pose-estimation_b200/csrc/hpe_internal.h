@@ -78,6 +78,36 @@ struct SwarmStepArgs {
     int lo, own, update;
 };
 
+// arguments of the one-launch sharded swarm (swarm_run_kernel, hpe_cost.cu)
+#define HPE_MAX_PEERS 16
+struct SwarmMin {                              // a rank's first minimum of pcost over its own rows
+    unsigned long long key;                    // IEEE bits of the cost (costs are >= 0)
+    int idx, pad;
+};
+struct SwarmRunArgs {
+    PsoDev prm;
+    uint64_t seed;
+    double W1, C1;
+    int num_p, lo, hi, maxiter;
+    double *table[2];                          // local row buffers [num_p][27]
+    double *x, *v;                             // owned positions / velocities
+    const double *x0;
+    int *R, *inf;
+    unsigned long long *key;
+    SwarmCtl *ctl;
+    double *trace;
+    double *peer_table[2][HPE_MAX_PEERS];      // the peers' row buffers (NULL for self / absent)
+    volatile unsigned *peer_flags[HPE_MAX_PEERS];   // the peers' flag arrays: [rank] is written by `rank`
+    volatile unsigned *my_flags;               // this rank's flag array (written by the peers)
+    SwarmMin *peer_min[HPE_MAX_PEERS];         // the peers' minimum boards [2][HPE_MAX_PEERS], entry [parity][rank] is ours
+    volatile SwarmMin *my_min;                 // this rank's board (written by the peers)
+    unsigned long long *cta_key;               // per-CTA minima of the step phase
+    int *cta_idx;
+    int world, rank;
+    unsigned gen_base;                         // flags are monotonic across runs
+    unsigned long long *times;                 // optional debug timestamps, 8 per generation (NULL: off)
+};
+
 int hpe_set_error(int code, const char *fmt, ...);
 extern int g_hpe_chamfer;   // hpe_set_chamfer(): 0 = wavefront two-pass, 1 = row-search closed form
 extern int g_hpe_matcher;   // hpe_set_matcher(): 0 = certified two-sweep search, 1 = direct form
@@ -114,6 +144,7 @@ cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_
                               float *depth_dev, cudaStream_t st);
 size_t hpe_observe_scratch_bytes(int count);
 cudaError_t hpe_launch_swarm_step(const DevModel &m, const ObsView &o, int slot, const SwarmStepArgs &a, cudaStream_t st);
+cudaError_t hpe_launch_swarm_run(const DevModel &m, const ObsView &o, int slot, const SwarmRunArgs &a, cudaStream_t st);
 unsigned long long hpe_fallbacks_cost(int reset);
 unsigned long long hpe_fallbacks_pso(int reset);
 unsigned long long hpe_fallbacks_pso_cluster(int reset);

@@ -134,7 +134,7 @@ __global__ void swarm_inf_index(int num_p, const double *table, const int *R, co
 // kernel waits on those flags.  Generation g reads buffer g%2 and writes (g+1)%2, and a rank starts
 // generation g+1 only after it has seen every peer's flag for generation g, i.e. after every peer has
 // finished reading buffer g%2 -- so the stores of generation g+1 into that buffer cannot race.
-constexpr int MAX_PEERS = 16;
+constexpr int MAX_PEERS = HPE_MAX_PEERS;
 struct PeerPtrs {
     double *table[MAX_PEERS];          // peer table being written this generation (NULL for self)
     volatile unsigned *flags[MAX_PEERS];
@@ -193,9 +193,14 @@ struct hpe_swarm {
     int world, rank;
     unsigned gen;                      // generations pushed so far
     void *peer_base[MAX_PEERS];
+    unsigned long long *cta_key;       // per-CTA minima of hpe_swarm_run
+    int *cta_idx;
+    unsigned long long *times;         // debug: phase timestamps of hpe_swarm_run (NULL until requested)
 };
 
 static size_t table_bytes(int num_p) { return ((sizeof(double) * (size_t)num_p * ROW + 255) / 256) * 256; }
+// one allocation exposed over CUDA IPC: table[0] | table[1] | flags[MAX_PEERS] (padded to 256 B) | min boards [2][MAX_PEERS]
+static size_t shared_bytes(int num_p) { return 2 * table_bytes(num_p) + 256 + sizeof(SwarmMin) * 2 * MAX_PEERS; }
 
 // after the owned rows of table[cur] are complete: hand them to the peers and raise the flags
 static cudaError_t push_to_peers(hpe_swarm *s, cudaStream_t st)
@@ -231,7 +236,7 @@ int hpe_swarm_destroy(hpe_swarm *s)
     for (int p = 0; p < MAX_PEERS; ++p)
         if (s->peer_base[p]) cudaIpcCloseMemHandle(s->peer_base[p]);
     cudaFree(s->x0); cudaFree(s->x); cudaFree(s->v); cudaFree(s->shared_base); cudaFree(s->trace);
-    cudaFree(s->R); cudaFree(s->inf); cudaFree(s->key); cudaFree(s->ctl);
+    cudaFree(s->R); cudaFree(s->inf); cudaFree(s->key); cudaFree(s->ctl); cudaFree(s->times); cudaFree(s->cta_key); cudaFree(s->cta_idx);
     delete s;
     return HPE_OK;
 }
@@ -259,8 +264,10 @@ int hpe_swarm_create(const hpe_model *m, const hpe_obs *o, int slot, const hpe_p
     if (e == cudaSuccess) e = cudaMalloc(&s->v, sizeof(double) * own * HPE_NDOF);
     // both row buffers and the peer flags in one allocation, so that one IPC handle exposes them
     const size_t tb = table_bytes(num_particles);
-    if (e == cudaSuccess) e = cudaMalloc(&s->shared_base, 2 * tb + sizeof(unsigned) * MAX_PEERS);
-    if (e == cudaSuccess) e = cudaMemset(s->shared_base, 0, 2 * tb + sizeof(unsigned) * MAX_PEERS);
+    if (e == cudaSuccess) e = cudaMalloc(&s->shared_base, shared_bytes(num_particles));
+    if (e == cudaSuccess) e = cudaMemset(s->shared_base, 0, shared_bytes(num_particles));
+    if (e == cudaSuccess) e = cudaMalloc(&s->cta_key, sizeof(unsigned long long) * 2048);
+    if (e == cudaSuccess) e = cudaMalloc(&s->cta_idx, sizeof(int) * 2048);
     if (e == cudaSuccess) {
         s->table[0] = (double *)s->shared_base;
         s->table[1] = (double *)((char *)s->shared_base + tb);
@@ -353,6 +360,52 @@ int hpe_swarm_attach_peers(hpe_swarm *s, const unsigned char *handles, int world
     }
     s->world = world;
     s->rank = rank;
+    return HPE_OK;
+}
+
+// the whole run (init + maxiter-1 generations, exchanges included) as one cooperative launch
+int hpe_swarm_run(hpe_swarm *s, void *stream)
+{
+    if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_run: NULL swarm");
+    SwarmRunArgs a;
+    memset(&a, 0, sizeof a);
+    a.prm = s->prm; a.seed = s->seed; a.W1 = s->W1; a.C1 = s->C1;
+    a.num_p = s->num_p; a.lo = s->lo; a.hi = s->hi; a.maxiter = s->prm.maxiter;
+    a.table[0] = s->table[0]; a.table[1] = s->table[1];
+    a.x = s->x; a.v = s->v; a.x0 = s->x0; a.R = s->R; a.inf = s->inf; a.key = s->key; a.ctl = s->ctl; a.trace = s->trace;
+    a.world = s->world; a.rank = s->rank; a.gen_base = s->gen; a.my_flags = s->flags;
+    const size_t tb = table_bytes(s->num_p);
+    a.my_min = (volatile SwarmMin *)((char *)s->shared_base + 2 * tb + 256);
+    a.cta_key = s->cta_key; a.cta_idx = s->cta_idx;
+    for (int p = 0; p < s->world && s->world > 1; ++p) {
+        if (p == s->rank) continue;
+        char *base = (char *)s->peer_base[p];
+        a.peer_table[0][p] = (double *)base;
+        a.peer_table[1][p] = (double *)(base + tb);
+        a.peer_flags[p] = (volatile unsigned *)(base + 2 * tb);
+        a.peer_min[p] = (SwarmMin *)(base + 2 * tb + 256);
+    }
+    a.times = s->times;
+    HPE_CUDA(hpe_launch_swarm_run(s->m->dm, s->o->v, s->slot, a, (cudaStream_t)stream));
+    s->gen += (unsigned)s->prm.maxiter;
+    // the last generation g = maxiter-1 wrote buffer (g == 0 ? 0 : 1 - (g-1)%2 ...): track it like the stepwise path
+    s->cur = s->prm.maxiter > 1 ? (s->prm.maxiter - 1) & 1 : 0;
+    return HPE_OK;
+}
+
+// diagnostics: globaltimer stamps (ns) of the phases of the last hpe_swarm_run, 8 per generation: start, after the
+// informant cost pass, after the index pass, end of this CTA's step work, after the step barrier, exchange done,
+// reduce done, after the closing barrier.  The first call only switches the recording on (out may be NULL).
+int hpe_swarm_debug_times(hpe_swarm *s, unsigned long long *out)
+{
+    if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_debug_times: NULL swarm");
+    const size_t n = (size_t)s->prm.maxiter * 8;
+    if (!s->times) {
+        HPE_CUDA(cudaMalloc(&s->times, sizeof(unsigned long long) * n));
+        HPE_CUDA(cudaMemset(s->times, 0, sizeof(unsigned long long) * n));
+        return HPE_OK;
+    }
+    if (out) HPE_CUDA(cudaMemcpy(out, s->times, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
     return HPE_OK;
 }
 

@@ -388,6 +388,16 @@ class Swarm:
     def step(self, stream=None):
         _check(lib().hpe_swarm_step(self._h, C.c_void_p(stream or 0)))
 
+    def run(self, stream=None):
+        """init + all generations + exchanges in one cooperative launch (peers attached when world > 1)"""
+        _check(lib().hpe_swarm_run(self._h, C.c_void_p(stream or 0)))
+
+    def debug_times(self):
+        """phase timestamps (ns) of the last run(), shape (maxiter, 8); the first call only enables recording"""
+        t = np.zeros((self.maxiter, 8), dtype=np.uint64)
+        _check(lib().hpe_swarm_debug_times(self._h, _p(t, C.c_uint64)))
+        return t
+
     def reduce(self, stream=None):
         _check(lib().hpe_swarm_reduce(self._h, C.c_void_p(stream or 0)))
 

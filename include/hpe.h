@@ -184,6 +184,15 @@ int hpe_swarm_step(hpe_swarm *s, void *stream);
  * no host synchronisation in between.  Results are bit-identical to the all-gather path. */
 int hpe_swarm_ipc_handle(hpe_swarm *s, unsigned char handle[64]);
 int hpe_swarm_attach_peers(hpe_swarm *s, const unsigned char *handles /* world*64 */, int world, int rank);
+/* The whole run -- hpe_swarm_init, then (hpe_swarm_step, exchange, hpe_swarm_reduce) x (maxiter-1) -- as ONE
+ * cooperative kernel launch per GPU: rows go to the peers by NVLink stores from the warp that produced
+ * them, ranks meet on device-side flags, 4 grid barriers per generation.  Peers must be attached when more
+ * than one rank takes part (hpe_swarm_attach_peers); every rank calls it once.  Bit-identical to the
+ * stepwise path.  Asynchronous on `stream`. */
+int hpe_swarm_run(hpe_swarm *s, void *stream);
+/* diagnostics: first call switches phase-timestamp recording on; later calls copy the stamps of the last
+ * hpe_swarm_run to out (maxiter*8 values, ns) */
+int hpe_swarm_debug_times(hpe_swarm *s, unsigned long long *out);
 /* host copies of gbest (and of bcost_evo, maxiter-1 values, may be NULL) after the last hpe_swarm_reduce */
 int hpe_swarm_best(hpe_swarm *s, double bestp[HPE_NDOF], double *best_cost, double *trace);
 

@@ -119,3 +119,22 @@ def test_cluster_kernel_is_bit_identical_to_one_cta_kernel(hpe, orc, omodel, D):
         (b2, c2, t2), (p2, k2) = res[2]
         assert np.array_equal(b1, b2) and np.array_equal(c1, c2) and np.array_equal(t1, t2)
         assert np.array_equal(p1, p2) and np.array_equal(k1, k2)
+
+
+def test_one_launch_swarm_is_bit_identical_to_stepwise(hpe, D, setup):
+    """hpe_swarm_run: the whole pso_evolve of a large swarm (topology, informants, move + evaluate,
+    global argmin) in one cooperative kernel launch == the stepwise launches, bit for bit"""
+    torch = pytest.importorskip("torch")
+    truth, depth, hand, obs, x0 = setup
+    pso = hpe.PSO()
+    cf = hpe.costfunc(hand, obs)
+    for num_p, maxiter, seed in ((1000, 8, 4), (64, 12, 77), (4099, 5, 9), (7, 3, 1)):
+        pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, maxiter, 1e-8, 1e-8)
+        (ref,) = _run_swarms(hpe, [hpe.Swarm(cf, pso.params, num_p, 0, num_p, x0, seed=seed)], torch)
+        sw = hpe.Swarm(cf, pso.params, num_p, 0, num_p, x0, seed=seed)
+        sw.run()
+        bp, bc, tr = sw.best()
+        assert np.array_equal(bp, ref[0]) and bc == ref[1] and np.array_equal(tr, ref[2]), (num_p, maxiter)
+        sw.run()                                       # a second run on the same handle starts afresh
+        bp2, bc2, tr2 = sw.best()
+        assert np.array_equal(bp2, ref[0]) and bc2 == ref[1] and np.array_equal(tr2, ref[2])

@@ -1,4 +1,5 @@
-"""Sharded 16k swarm, NCCL all-gather vs device-initiated peer exchange (run under torchrun on >= 2 GPUs)."""
+"""Sharded 16k swarm: NCCL all-gather vs stepwise peer exchange vs the one-launch kernel (hpe_swarm_run).
+Run under torchrun on >= 1 GPUs."""
 import os, sys, time
 import numpy as np
 import torch, torch.distributed as dist
@@ -26,23 +27,33 @@ def barrier():
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
 res = {}
-for mode in ("allgather", "p2p"):
+for mode in ("allgather", "p2p", "run"):
+    if mode == "p2p" and world == 1:
+        continue
     sw = hpe_b200.Swarm(cf, pso.params, NP, lo, hi, x0, seed=4)
-    if mode == "p2p":
+    if mode != "allgather":
         sharding.attach_swarm_peers(sw)
     ts = []
-    for rep in range(4):
+    for rep in range(5):
         barrier()
         e0.record()
-        out = sharding.run_sharded_swarm(sw, NP) if mode == "allgather" else sharding.run_sharded_swarm_p2p(sw)
+        if mode == "allgather":
+            out = sharding.run_sharded_swarm(sw, NP)
+        elif mode == "p2p":
+            out = sharding.run_sharded_swarm_p2p(sw)
+        else:
+            sw.run()
         e1.record()
         barrier()
+        if mode == "run":
+            out = sw.best()
         ts.append(sharding.max_over_ranks(e0.elapsed_time(e1), "cuda"))
     res[mode] = (min(ts[1:]), out)
     if rank == 0:
         print(f"{mode:10s} world={world} {NP} x {GEN}: {min(ts[1:]):.3f} ms  best cost {out[1]!r}", flush=True)
 if rank == 0:
-    a, b = res["allgather"][1], res["p2p"][1]
-    print("identical:", np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[2], b[2]))
+    a = res["allgather"][1]
+    for k, (_, b) in res.items():
+        print(k, "identical to allgather:", np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[2], b[2]))
 if world > 1:
     dist.destroy_process_group()
