@@ -1,5 +1,7 @@
 // hpe_api.cu -- the C ABI of include/hpe.h: handles, host<->device staging, launches.
 // No compute happens on the host and nothing here falls back to a CPU path.
+#include <ctime>
+#include <cstdlib>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -100,6 +102,16 @@ int hpe_set_matcher(int mode)
 }
 
 int g_hpe_pso_path = 0;
+int g_hpe_cost_pipeline = 0;   // 0 = chase kernel for large host batches, 1 = chunked launches only
+int g_hpe_cost_chunk = 0;      // poses per upload chunk of the chase path (0 = default)
+int hpe_set_cost_pipeline(int mode, int chunk_poses)
+{
+    if (mode < 0 || mode > 1 || chunk_poses < 0) return hpe_set_error(HPE_ERR_ARG, "hpe_set_cost_pipeline: bad argument");
+    g_hpe_cost_pipeline = mode;
+    g_hpe_cost_chunk = chunk_poses;
+    return HPE_OK;
+}
+
 int hpe_set_pso_path(int mode)
 {
     if (mode < 0 || mode > 2) return hpe_set_error(HPE_ERR_ARG, "pso path must be 0, 1 or 2");
@@ -368,39 +380,113 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
     const int np = o->v.n_pts;
     size_t b_th = align_up(sizeof(double) * n * HPE_NDOF), b_tm = align_up(sizeof(double) * n * 3),
            b_fr = align_up(sizeof(int32_t) * np), b_mo = match_out ? align_up(sizeof(int32_t) * n * np) : 0;
-    HPE_CUDA(g_ws.reserve(b_th + b_tm + b_fr + b_mo));
+    HPE_CUDA(g_ws.reserve(b_th + b_tm + b_fr + b_mo + 512));      // + arrival flags of the chase kernel
     char *base = (char *)g_ws.p;
     double *d_th = (double *)base, *d_tm = (double *)(base + b_th);
     int32_t *d_fr = (int32_t *)(base + b_th + b_tm), *d_mo = (int32_t *)(base + b_th + b_tm + b_fr);
     if (frozen) HPE_CUDA(cudaMemcpyAsync(d_fr, frozen, sizeof(int32_t) * np, cudaMemcpyHostToDevice, 0));
-    // Chunks of poses ping-pong over two streams: the host->device copy of one chunk (the poses are
-    // 208 B each, PCIe is the slowest stage of a large batch) runs under the kernel of the other.
-    // The kernel writes the terms as three arrays that are copied straight into the caller's buffers.
-    static cudaStream_t pipe[2] = {nullptr, nullptr};
-    static cudaEvent_t ready = nullptr;
+    // Three-stage pipeline over chunks of poses: an upload stream copies the chunks back to back (the poses
+    // are 208 B each; PCIe is the slowest stage of a large batch and 3.4 MB copies reach its full rate), a
+    // compute stream scores chunk i as soon as it has landed, a download stream returns the three term arrays
+    // -- the kernel writes them as separate arrays that go straight into the caller's buffers.
+    enum { MAX_CHUNKS = HPE_MAX_CHUNKS };
+    static cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};        // upload, compute, download
+    static cudaEvent_t ready = nullptr, up_done[MAX_CHUNKS], k_done[MAX_CHUNKS];
     if (!pipe[0]) {
-        HPE_CUDA(cudaStreamCreateWithFlags(&pipe[0], cudaStreamNonBlocking));
-        HPE_CUDA(cudaStreamCreateWithFlags(&pipe[1], cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i) HPE_CUDA(cudaStreamCreateWithFlags(&pipe[i], cudaStreamNonBlocking));
         HPE_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        for (int i = 0; i < MAX_CHUNKS; ++i) {
+            HPE_CUDA(cudaEventCreateWithFlags(&up_done[i], cudaEventDisableTiming));
+            HPE_CUDA(cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
+        }
     }
     HPE_CUDA(cudaEventRecord(ready, 0));          // prior default-stream work (frozen copy, observation kernels)
-    const int64_t chunk = n > 16384 ? 8192 : n;
+    HPE_CUDA(cudaStreamWaitEvent(pipe[0], ready, 0));
+    HPE_CUDA(cudaStreamWaitEvent(pipe[1], ready, 0));
+    int64_t chunk = n > 24576 ? 16384 : n;
+    if ((n + chunk - 1) / chunk > MAX_CHUNKS) chunk = (n + MAX_CHUNKS - 1) / MAX_CHUNKS;
+    if (n >= 32768 && g_hpe_cost_pipeline == 0) {
+        timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+        const double t_entry = ts0.tv_sec * 1e6 + ts0.tv_nsec * 1e-3;
+        // Large batch: ONE kernel launched before the upload chases the chunks as they land (cost_chase_kernel):
+        // no per-chunk launch, no lock-step of small launches; the flags are raised by 4-byte DMA copies queued
+        // behind each chunk on the upload stream.
+        static unsigned *ones = nullptr;              // pinned source of the flag copies
+        if (!ones) {
+            HPE_CUDA(cudaHostAlloc((void **)&ones, sizeof(unsigned) * MAX_CHUNKS, cudaHostAllocDefault));
+            for (int i = 0; i < MAX_CHUNKS; ++i) ones[i] = 1u;
+        }
+        // upload schedule: full-rate chunks first, then halving ones so that little is left to score when the
+        // last chunk lands (a fixed chunk size when hpe_set_cost_pipeline gave one)
+        ChaseChunks cks;
+        cks.count = 0;
+        {
+            const int64_t big = g_hpe_cost_chunk > 0 ? g_hpe_cost_chunk : 16384;
+            int64_t at = 0;
+            while (at < n && cks.count < MAX_CHUNKS - 1) {
+                int64_t left = n - at, take = big;
+                if (g_hpe_cost_chunk == 0 && left <= big) take = left > 4096 ? (left / 2 + 1023) / 1024 * 1024 : left;
+                if (take > left) take = left;
+                at += take;
+                cks.end[cks.count++] = at;
+            }
+            if (at < n) cks.end[cks.count++] = n;
+        }
+        const int nck = cks.count;
+        unsigned *d_flags = (unsigned *)(base + b_th + b_tm + b_fr + b_mo);
+        int *d_timeout = (int *)(d_flags + MAX_CHUNKS);
+        HPE_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(unsigned) * (MAX_CHUNKS + 1), pipe[1]));
+        HPE_CUDA(cudaEventRecord(k_done[0], pipe[1]));
+        HPE_CUDA(cudaStreamWaitEvent(pipe[0], k_done[0], 0));           // flags are cleared before any is raised
+        HPE_CUDA(hpe_launch_cost_chase(m->dm, o->v, slot, d_th, n, colli != nullptr, d_tm, n, frozen ? d_fr : nullptr,
+                                       match_out ? d_mo : nullptr, d_flags, cks, d_timeout, pipe[1]));
+        for (int c = 0; c < nck; ++c) {
+            const int64_t c0 = c ? cks.end[c - 1] : 0, cn = cks.end[c] - c0;
+            HPE_CUDA(cudaMemcpyAsync(d_th + c0 * HPE_NDOF, theta + c0 * HPE_NDOF, sizeof(double) * cn * HPE_NDOF,
+                                     cudaMemcpyHostToDevice, pipe[0]));
+            HPE_CUDA(cudaMemcpyAsync(d_flags + c, ones + c, sizeof(unsigned), cudaMemcpyHostToDevice, pipe[0]));
+        }
+        cudaStream_t st = pipe[1];
+        static int *timed_out_pin = nullptr;
+        if (!timed_out_pin) HPE_CUDA(cudaHostAlloc((void **)&timed_out_pin, sizeof(int), cudaHostAllocDefault));
+        if (align) HPE_CUDA(cudaMemcpyAsync(align, d_tm, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        if (depth) HPE_CUDA(cudaMemcpyAsync(depth, d_tm + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        if (colli) HPE_CUDA(cudaMemcpyAsync(colli, d_tm + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        if (match_out) HPE_CUDA(cudaMemcpyAsync(match_out, d_mo, sizeof(int32_t) * n * np, cudaMemcpyDeviceToHost, st));
+        HPE_CUDA(cudaMemcpyAsync(timed_out_pin, d_timeout, sizeof(int), cudaMemcpyDeviceToHost, st));
+        const bool dbg = getenv("HPE_DEBUG_PIPE") != nullptr;
+        auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+        const double t_q = dbg ? now() : 0;
+        HPE_CUDA(cudaStreamSynchronize(pipe[0]));
+        const double t_u = dbg ? now() : 0;
+        HPE_CUDA(cudaStreamSynchronize(pipe[1]));
+        if (dbg) fprintf(stderr, "chase: queued at +%.0f us, uploads done +%.0f us, all done +%.0f us\n", t_q - t_entry, t_u - t_entry, now() - t_entry);
+        if (*timed_out_pin) return hpe_set_error(HPE_ERR_CUDA, "hpe_cost_batch: the pose upload did not arrive (kernel gave up waiting)");
+        return HPE_OK;
+    }
     int k = 0;
     for (int64_t c0 = 0; c0 < n; c0 += chunk, ++k) {
         const int64_t cn = n - c0 < chunk ? n - c0 : chunk;
-        cudaStream_t st = pipe[k & 1];
-        if (k < 2) HPE_CUDA(cudaStreamWaitEvent(st, ready, 0));
         HPE_CUDA(cudaMemcpyAsync(d_th + c0 * HPE_NDOF, theta + c0 * HPE_NDOF, sizeof(double) * cn * HPE_NDOF,
-                                 cudaMemcpyHostToDevice, st));
+                                 cudaMemcpyHostToDevice, pipe[0]));
+        HPE_CUDA(cudaEventRecord(up_done[k], pipe[0]));
+    }
+    k = 0;
+    for (int64_t c0 = 0; c0 < n; c0 += chunk, ++k) {
+        const int64_t cn = n - c0 < chunk ? n - c0 : chunk;
+        HPE_CUDA(cudaStreamWaitEvent(pipe[1], up_done[k], 0));
         HPE_CUDA(hpe_launch_cost(m->dm, o->v, slot, d_th + c0 * HPE_NDOF, cn, colli != nullptr, nullptr, d_tm + c0,
-                                 frozen ? d_fr : nullptr, match_out ? d_mo + c0 * np : nullptr, st, n));
+                                 frozen ? d_fr : nullptr, match_out ? d_mo + c0 * np : nullptr, pipe[1], n));
+        HPE_CUDA(cudaEventRecord(k_done[k], pipe[1]));
+        cudaStream_t st = pipe[2];
+        HPE_CUDA(cudaStreamWaitEvent(st, k_done[k], 0));
         if (align) HPE_CUDA(cudaMemcpyAsync(align + c0, d_tm + c0, sizeof(double) * cn, cudaMemcpyDeviceToHost, st));
         if (depth) HPE_CUDA(cudaMemcpyAsync(depth + c0, d_tm + n + c0, sizeof(double) * cn, cudaMemcpyDeviceToHost, st));
         if (colli) HPE_CUDA(cudaMemcpyAsync(colli + c0, d_tm + 2 * n + c0, sizeof(double) * cn, cudaMemcpyDeviceToHost, st));
         if (match_out)
             HPE_CUDA(cudaMemcpyAsync(match_out + c0 * np, d_mo + c0 * np, sizeof(int32_t) * cn * np, cudaMemcpyDeviceToHost, st));
     }
-    HPE_CUDA(cudaStreamSynchronize(pipe[0]));
+    HPE_CUDA(cudaStreamSynchronize(pipe[2]));
     HPE_CUDA(cudaStreamSynchronize(pipe[1]));
     return HPE_OK;
 }

@@ -111,6 +111,68 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
 }
 
 // ---------------------------------------------------------------------------------------
+// cal_cost / cal_cost2 for a batch whose poses are STILL ARRIVING from the host: the kernel is
+// launched before the upload; the poses land chunk by chunk (DMA on another stream) and each chunk
+// raises arrived[c].  Warps take groups in order (group q = warp, warp + W, ...), wait for the chunk
+// of their group and score it, so the evaluation chases the copy instead of waiting for it and
+// every warp still walks several groups (no lock-step of the phases).  hpe_cost_batch uses it for
+// large host batches.
+// ---------------------------------------------------------------------------------------
+template <bool WITH_COLLI>
+__global__ void __launch_bounds__(COST_WARPS * 32, HPE_MINBLOCKS)
+cost_chase_kernel(DevModel m, ObsView o, int slot, const double *theta, int64_t n, double *__restrict__ terms,
+                  int64_t tstride, const int32_t *__restrict__ frozen, int32_t *__restrict__ match_out,
+                  const unsigned *arrived, ChaseChunks ck, int *timeout_flag)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    stage_model(sm.fs, m);
+    stage_frame(sm.fs, frame_view(o, slot));     // ends synchronised
+    const WarpScratch ws = warp_scratch(sm.ws, warp, HPE_GROUP);
+    const int n_pts = sm.fs.n_pts;
+    const int64_t total_warps = (int64_t)gridDim.x * COST_WARPS;
+    const int64_t gw = (int64_t)blockIdx.x * COST_WARPS + warp;
+    // groups of HPE_GROUP poses, except the last ~one-per-warp poses, which are taken one at a time so that the
+    // work left when the final chunk lands is spread over every warp of the grid
+    const int64_t tail = min(n, total_warps);
+    const int64_t g5 = (n - tail) / HPE_GROUP;
+    const int64_t groups = g5 + (n - g5 * HPE_GROUP);
+    int seen = -1;                                // chunks [0, seen] are known to have landed
+    for (int64_t q = gw; q < groups; q += total_warps) {
+        const int64_t p0 = q < g5 ? q * HPE_GROUP : g5 * HPE_GROUP + (q - g5);
+        const int cnt = q < g5 ? HPE_GROUP : 1;
+        int need = seen < 0 ? 0 : seen;
+        while (ck.end[need] < p0 + cnt) ++need;   // chunk holding the last pose of the group
+        if (need > seen) {
+            if (lane == 0) {
+                long long spins = 0;
+                const volatile unsigned *f = arrived + need;
+                while (*f == 0u) {
+                    if (++spins > (1ll << 26)) { *timeout_flag = 1; break; }   // a failed upload must not hang the GPU
+                    __nanosleep(200);
+                }
+                __threadfence_system();
+            }
+            __syncwarp();
+            seen = need;                          // chunks are uploaded in order on one stream
+        }
+        group_fk<true>(sm.fs.M, [&](int g) { return theta + (p0 + g) * HPE_NDOF; }, cnt, ws, lane);
+        for (int g = 0; g < cnt; ++g) {
+            double depth = depth_and_stage(sm.fs, ws, g, lane);
+            double align = match_align<0>(sm.fs, ws, g, lane, frozen, match_out ? match_out + (p0 + g) * n_pts : nullptr);
+            double colli = 0.0;
+            if (WITH_COLLI) colli = warp_sum(collision_lane(sm.fs.rad, ws.sphd + (size_t)g * HPE_NSPH * 3, lane));
+            if (lane == 0) {
+                terms[p0 + g] = align;
+                terms[tstride + p0 + g] = depth;
+                terms[2 * tstride + p0 + g] = colli;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // One generation of a large swarm for the particles [lo, lo+own) owned by this GPU, fused:
 // velocity/position update with the reference's clamp (src/PSO.cpp:824-840, 358-377), evaluation
 // (cal_cost) and the pbest row update (:855-860) -- the warp that evaluates a particle also moves it
@@ -486,6 +548,32 @@ cudaError_t hpe_launch_fk(const DevModel &m, const double *theta_dev, int64_t n,
     int64_t items = n * 5;
     int blocks = (int)((items + 159) / 160);
     fk_kernel<<<blocks, 160, 0, st>>>(m, theta_dev, n, spheres_dev, joints_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t hpe_launch_cost_chase(const DevModel &m, const ObsView &o, int slot, const double *theta_dev, int64_t n,
+                                  bool with_colli, double *terms_dev, int64_t terms_stride, const int32_t *frozen_dev,
+                                  int32_t *match_out_dev, const unsigned *arrived_dev, const ChaseChunks &chunks, int *timeout_dev,
+                                  cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(cost_chase_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
+        cudaFuncSetAttribute(cost_chase_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
+    }
+    int64_t groups = (n + HPE_GROUP - 1) / HPE_GROUP;
+    int64_t want = (groups + COST_WARPS - 1) / COST_WARPS;
+    int blocks = (int)(want < (long long)HPE_MINBLOCKS * sms ? want : (long long)HPE_MINBLOCKS * sms);
+    if (with_colli)
+        cost_chase_kernel<true><<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, terms_dev, terms_stride,
+                                                                                    frozen_dev, match_out_dev, arrived_dev, chunks, timeout_dev);
+    else
+        cost_chase_kernel<false><<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, terms_dev, terms_stride,
+                                                                                     frozen_dev, match_out_dev, arrived_dev, chunks, timeout_dev);
     return cudaGetLastError();
 }
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ void aff_planar(Aff &a, double c, double s, double L)
 }
 
 // Global pose T00 * Rz(t0+180) * Ry(t1) * Rx(t2)  (src/fingermodel.cpp:157-180, :289)
-__device__ __forceinline__ void aff_global(Aff &g, const double *th)
+__device__ __forceinline__ void aff_global(Aff &g, const double th[6])
 {
     double sz, cz, sy, cy, sx, cx;
     sincos(hpe_deg2rad(th[0] + 180.0), &sz, &cz);
@@ -84,11 +84,13 @@ __device__ __forceinline__ void aff_global(Aff &g, const double *th)
     g.tx = th[3]; g.ty = th[4]; g.tz = th[5];
 }
 
-// joints J[0..4] of digit d (0 = thumb) for pose th[26]
-__device__ __forceinline__ void fk_digit(const DevModel &M, int d, const double *th, double J[5][3])
+// joints J[0..4] of digit d (0 = thumb) from the six global parameters g6 = theta[0:6] and the digit's four
+// joint angles ang = theta[6+4d : 10+4d]
+__device__ __forceinline__ void fk_digit_vals(const DevModel &M, int d, const double g6[6], const double ang[4],
+                                              double J[5][3])
 {
     Aff cur;
-    aff_global(cur, th);
+    aff_global(cur, g6);
     // cur <- cur * base[d]   (general 3x4 product; base has r[2][*] = (0,0,1), t.z = 0)
     {
         const double *b = M.base[d];
@@ -108,7 +110,6 @@ __device__ __forceinline__ void fk_digit(const DevModel &M, int d, const double 
         J[0][1] = cur.r10 * bx + cur.r11 * by + cur.ty;
         J[0][2] = cur.r20 * bx + cur.r21 * by + cur.tz;
     }
-    const double *ang = th + 6 + 4 * d;
     const double *L = M.geo + 4 * d;
     double s1, c1, s2, c2;
     sincos(hpe_deg2rad(ang[0]), &s1, &c1);
@@ -147,6 +148,29 @@ __device__ __forceinline__ void fk_digit(const DevModel &M, int d, const double 
     J[4][0] = cur.tx + L[3] * (cur.r00 * c4 + cur.r01 * s4);
     J[4][1] = cur.ty + L[3] * (cur.r10 * c4 + cur.r11 * s4);
     J[4][2] = cur.tz + L[3] * (cur.r20 * c4 + cur.r21 * s4);
+}
+
+// joints J[0..4] of digit d (0 = thumb) for pose th[26]
+__device__ __forceinline__ void fk_digit(const DevModel &M, int d, const double *th, double J[5][3])
+{
+    double g6[6], a4[4];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) g6[i] = th[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a4[k] = th[6 + 4 * d + k];
+    fk_digit_vals(M, d, g6, a4, J);
+}
+
+// the same for a pose that may have been written while this kernel runs (chunks landing by DMA under a
+// persistent kernel): loads go to L2 (ld.global.cg), never through the non-coherent path
+__device__ __forceinline__ void fk_digit_cg(const DevModel &M, int d, const double *th, double J[5][3])
+{
+    double g6[6], a4[4];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) g6[i] = __ldcg(th + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a4[k] = __ldcg(th + 6 + 4 * d + k);
+    fk_digit_vals(M, d, g6, a4, J);
 }
 
 // Sphere centres of a digit from its joints (src/fingermodel.cpp:208-267,

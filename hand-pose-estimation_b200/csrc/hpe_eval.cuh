@@ -388,15 +388,17 @@ __device__ __forceinline__ double collision_lane(const double *rad_s, const doub
     return acc;
 }
 
-// phase 1 for up to HPE_GROUP poses; theta(g) returns a pointer to pose g's 26 doubles
-template <class ThetaAt>
+// phase 1 for up to HPE_GROUP poses; theta(g) returns a pointer to pose g's 26 doubles.  CG: read the
+// pose through L2 (poses that land by DMA while the kernel runs)
+template <bool CG = false, class ThetaAt>
 __device__ __forceinline__ void group_fk(const DevModel &M, ThetaAt theta, int n, const WarpScratch &ws, int lane)
 {
     int g = lane / 5, d = lane - 5 * g;
     __syncwarp();
     if (g < n) {
         double J[5][3], S[10][3];
-        fk_digit(M, d, theta(g), J);
+        if (CG) fk_digit_cg(M, d, theta(g), J);
+        else fk_digit(M, d, theta(g), J);
         int cnt = digit_spheres(d, J, S);
         int first = digit_first_sphere(d);
 #pragma unroll

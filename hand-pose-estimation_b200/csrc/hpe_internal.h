@@ -126,6 +126,16 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
                             int64_t n, bool with_colli, double *cost_dev, double *terms_dev,
                             const int32_t *frozen_match_dev, int32_t *match_out_dev, cudaStream_t st,
                             int64_t terms_stride = 0 /* distance between the three term arrays; 0 = n */);
+#define HPE_MAX_CHUNKS 64
+struct ChaseChunks {            // upload schedule of the chase kernel: chunk c holds poses [end[c-1], end[c])
+    int64_t end[HPE_MAX_CHUNKS];
+    int count;
+};
+// the same for poses that are still being uploaded chunk by chunk (arrived_dev[c] != 0 once chunk c has landed)
+cudaError_t hpe_launch_cost_chase(const DevModel &m, const ObsView &o, int slot, const double *theta_dev, int64_t n,
+                                  bool with_colli, double *terms_dev, int64_t terms_stride, const int32_t *frozen_dev,
+                                  int32_t *match_out_dev, const unsigned *arrived_dev, const ChaseChunks &chunks, int *timeout_dev,
+                                  cudaStream_t st);
 cudaError_t hpe_launch_gt_err(const double *joints_dev, const double *gt_dev, int64_t n, double *err_dev, cudaStream_t st);
 cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *scratch, cudaStream_t st);
 cudaError_t hpe_launch_dtmax(const ObsView &o, int slot, cudaStream_t st);

@@ -56,6 +56,11 @@ def _p(a, t=C.c_double):
     return None if a is None else a.ctypes.data_as(C.POINTER(t))
 
 
+def set_cost_pipeline(mode=0, chunk_poses=0):
+    """host path of hpe_cost_batch for >= 32,768 poses: 0 = chase kernel (default), 1 = one launch per chunk"""
+    _check(lib().hpe_set_cost_pipeline(int(mode), int(chunk_poses)))
+
+
 def device_count():
     return int(lib().hpe_device_count())
 

@@ -67,6 +67,15 @@ def test_full_size_cost_batch_properties(hpe, orc, omodel, golden, D):
     perm = rng.permutation(n)
     a3, d3, _ = cf.cal_cost_batch(th[perm])
     assert np.array_equal(a3, a[perm]) and np.array_equal(d3, d[perm])
+    # the two host pipelines for large batches (kernel chasing the upload / one launch per uploaded chunk)
+    # and odd upload chunk sizes return the same bits
+    try:
+        for mode, chunk in ((1, 0), (0, 5000), (0, 65536), (0, 1031)):
+            hpe.set_cost_pipeline(mode, chunk)
+            a4, d4, c4 = cf.cal_cost_batch(th[: n - 7], with_collision=True)
+            assert np.array_equal(a4, a[: n - 7]) and np.array_equal(d4, d[: n - 7]), (mode, chunk)
+    finally:
+        hpe.set_cost_pipeline(0, 0)
 
 
 def test_full_size_swarm_batch_properties(hpe, golden, D):
