@@ -121,7 +121,7 @@ int hpe_set_pso_path(int mode)
 
 int hpe_set_chamfer(int mode)
 {
-    if (mode != 0 && mode != 1) return hpe_set_error(HPE_ERR_ARG, "chamfer mode must be 0 or 1");
+    if (mode < 0 || mode > 2) return hpe_set_error(HPE_ERR_ARG, "chamfer mode must be 0, 1 or 2");
     g_hpe_chamfer = mode;
     return HPE_OK;
 }

@@ -330,6 +330,168 @@ __global__ void __launch_bounds__(WF_WARPS * 32) chamfer_wavefront_kernel(ObsVie
     if (lane == 0) o.meta[slot].dt_max = (double)vmax;
 }
 
+// ---------------------------------------------------------------------------------------
+// The same two raster passes, one ROW at a time with the whole row in flight (default path).
+// Forward pass, row i:  F(i,j) = min(U(i,j), F(i,j-1) + a)  where U gathers the seven mask
+// neighbours of rows i-1 and i-2, which are final.  Unrolled along the row this is
+//   F(i,j) = min_{k <= j} ( U(i,k) + (j-k) a ) = j a + prefix_min_k ( U(i,k) - k a ),
+// a prefix minimum -- so a warp owns a frame, a lane owns 10 consecutive columns, and a row costs a
+// short in-lane scan plus a 5-step shuffle scan instead of 320 dependent steps.  The backward pass
+// is the mirror image (suffix minimum, rows bottom-up).  The previous two rows live in registers;
+// nothing is staged in shared memory, so 16+ frames are in flight per SM and the kernel streams
+// 4 x 307 KB per frame (depth in, forward result out and back in, float result out).
+// Values that no feature pixel reaches stay at OpenCV's DIST_MAX-like sentinel (clamped to WF_MAX
+// per row); every such value is replaced by the backward pass when the frame has a hand pixel, so
+// the result is bit-identical to cv::distanceTransform (tests compare against cv2 and the oracle).
+// ---------------------------------------------------------------------------------------
+constexpr int SC_WARPS = 8;
+constexpr int SC_CPL = HPE_W / 32;               // 10 columns per lane
+
+// U(i,j) for the lane's 10 columns from the two previous rows (+2 / +1 halo columns on each side)
+__device__ __forceinline__ void sc_gather(const unsigned (&p1)[SC_CPL], const unsigned (&p2)[SC_CPL], unsigned l1a, unsigned l1b,
+                                          unsigned r1a, unsigned r1b, unsigned l2, unsigned r2, unsigned (&u)[SC_CPL])
+{
+    // e1[k] = row-1 value at local column k-2 (k = 0..13), e2[k] = row-2 value at local column k-1 (k = 0..11)
+    unsigned e1[SC_CPL + 4], e2[SC_CPL + 2];
+    e1[0] = l1a; e1[1] = l1b; e1[SC_CPL + 2] = r1a; e1[SC_CPL + 3] = r1b;
+    e2[0] = l2; e2[SC_CPL + 1] = r2;
+#pragma unroll
+    for (int k = 0; k < SC_CPL; ++k) { e1[k + 2] = p1[k]; e2[k + 1] = p2[k]; }
+#pragma unroll
+    for (int k = 0; k < SC_CPL; ++k) {
+        unsigned kn = min(min(e2[k], e2[k + 2]), min(e1[k], e1[k + 4])) + WF_C;     // knight moves
+        unsigned dg = min(e1[k + 1], e1[k + 3]) + WF_B;                              // diagonals
+        unsigned ax = e1[k + 2] + WF_A;                                              // axial
+        u[k] = min(min(kn, dg), ax);
+    }
+}
+
+__global__ void __launch_bounds__(SC_WARPS * 32) chamfer_scan_kernel(ObsView o, int first, int count)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = blockIdx.x * SC_WARPS + warp;
+    if (fr >= count) return;
+    const int slot = first + fr;
+    if (!o.meta[slot].ok) return;
+    const float *__restrict__ depth = o.depth_mm + (size_t)slot * NPIX;
+    unsigned *tmp = reinterpret_cast<unsigned *>(o.dt_px + (size_t)slot * NPIX);
+    float *out = o.dt_px + (size_t)slot * NPIX;
+    const int c0 = lane * SC_CPL;
+    const int A = (int)WF_A;
+
+    // ---------------- forward pass, rows top to bottom ----------------
+    unsigned p1[SC_CPL], p2[SC_CPL];
+#pragma unroll
+    for (int k = 0; k < SC_CPL; ++k) { p1[k] = WF_MAX; p2[k] = WF_MAX; }
+    float2 dn[SC_CPL / 2];
+#pragma unroll
+    for (int k = 0; k < SC_CPL / 2; ++k) dn[k] = __ldg(reinterpret_cast<const float2 *>(depth + c0) + k);
+    for (int i = 0; i < HPE_H; ++i) {
+        float2 dc[SC_CPL / 2];
+#pragma unroll
+        for (int k = 0; k < SC_CPL / 2; ++k) dc[k] = dn[k];
+        if (i + 1 < HPE_H) {
+#pragma unroll
+            for (int k = 0; k < SC_CPL / 2; ++k) dn[k] = __ldg(reinterpret_cast<const float2 *>(depth + (size_t)(i + 1) * HPE_W + c0) + k);
+        }
+        // halo columns of the two previous rows from the neighbouring lanes (image border: sentinel)
+        unsigned l1a = __shfl_up_sync(0xffffffffu, p1[SC_CPL - 2], 1), l1b = __shfl_up_sync(0xffffffffu, p1[SC_CPL - 1], 1);
+        unsigned r1a = __shfl_down_sync(0xffffffffu, p1[0], 1), r1b = __shfl_down_sync(0xffffffffu, p1[1], 1);
+        unsigned l2 = __shfl_up_sync(0xffffffffu, p2[SC_CPL - 1], 1), r2 = __shfl_down_sync(0xffffffffu, p2[0], 1);
+        if (lane == 0) { l1a = WF_MAX; l1b = WF_MAX; l2 = WF_MAX; }
+        if (lane == 31) { r1a = WF_MAX; r1b = WF_MAX; r2 = WF_MAX; }
+        unsigned u[SC_CPL];
+        sc_gather(p1, p2, l1a, l1b, r1a, r1b, l2, r2, u);
+#pragma unroll
+        for (int k = 0; k < SC_CPL / 2; ++k) {
+            if (dc[k].x != 0.0f) u[2 * k] = 0u;
+            if (dc[k].y != 0.0f) u[2 * k + 1] = 0u;
+        }
+        // in-lane scan with no carry, then the carry from the lanes to the left
+#pragma unroll
+        for (int k = 1; k < SC_CPL; ++k) u[k] = min(u[k], u[k - 1] + WF_A);
+        int s = (int)u[SC_CPL - 1] - SC_CPL * (lane + 1) * A;          // segment result in prefix-min coordinates
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s = min(s, t);
+        }
+        int carry = __shfl_up_sync(0xffffffffu, s, 1);                  // exclusive: minimum over the lanes to the left
+        if (lane > 0) {
+            carry += SC_CPL * lane * A;                                  // = F(i, c0 - 1)
+#pragma unroll
+            for (int k = 0; k < SC_CPL; ++k) u[k] = min(u[k], (unsigned)(carry + (k + 1) * A));
+        }
+#pragma unroll
+        for (int k = 0; k < SC_CPL; ++k) {
+            u[k] = min(u[k], WF_MAX);
+            p2[k] = p1[k];
+            p1[k] = u[k];
+        }
+        uint2 *dst = reinterpret_cast<uint2 *>(tmp + (size_t)i * HPE_W + c0);
+#pragma unroll
+        for (int k = 0; k < SC_CPL / 2; ++k) dst[k] = make_uint2(u[2 * k], u[2 * k + 1]);
+    }
+    // ---------------- backward pass, rows bottom to top, columns right to left ----------------
+    float vmax = 0.f;
+#pragma unroll
+    for (int k = 0; k < SC_CPL; ++k) { p1[k] = WF_MAX; p2[k] = WF_MAX; }
+    uint2 fn[SC_CPL / 2];
+    {
+        const uint2 *src = reinterpret_cast<const uint2 *>(tmp + (size_t)(HPE_H - 1) * HPE_W + c0);
+#pragma unroll
+        for (int k = 0; k < SC_CPL / 2; ++k) fn[k] = src[k];
+    }
+    for (int i = HPE_H - 1; i >= 0; --i) {
+        unsigned f[SC_CPL];
+#pragma unroll
+        for (int k = 0; k < SC_CPL / 2; ++k) { f[2 * k] = fn[k].x; f[2 * k + 1] = fn[k].y; }
+        if (i > 0) {
+            const uint2 *src = reinterpret_cast<const uint2 *>(tmp + (size_t)(i - 1) * HPE_W + c0);
+#pragma unroll
+            for (int k = 0; k < SC_CPL / 2; ++k) fn[k] = src[k];      // own columns only: never written by another lane
+        }
+        unsigned l1a = __shfl_up_sync(0xffffffffu, p1[SC_CPL - 2], 1), l1b = __shfl_up_sync(0xffffffffu, p1[SC_CPL - 1], 1);
+        unsigned r1a = __shfl_down_sync(0xffffffffu, p1[0], 1), r1b = __shfl_down_sync(0xffffffffu, p1[1], 1);
+        unsigned l2 = __shfl_up_sync(0xffffffffu, p2[SC_CPL - 1], 1), r2 = __shfl_down_sync(0xffffffffu, p2[0], 1);
+        if (lane == 0) { l1a = WF_MAX; l1b = WF_MAX; l2 = WF_MAX; }
+        if (lane == 31) { r1a = WF_MAX; r1b = WF_MAX; r2 = WF_MAX; }
+        unsigned u[SC_CPL];
+        sc_gather(p1, p2, l1a, l1b, r1a, r1b, l2, r2, u);              // the mask is symmetric: same gather on the rows below
+#pragma unroll
+        for (int k = 0; k < SC_CPL; ++k) u[k] = min(u[k], f[k]);
+        // suffix scan: B(i,j) = min(V(i,j), B(i,j+1) + a)
+#pragma unroll
+        for (int k = SC_CPL - 2; k >= 0; --k) u[k] = min(u[k], u[k + 1] + WF_A);
+        int s = (int)u[0] - SC_CPL * (32 - lane) * A;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_down_sync(0xffffffffu, s, d);
+            if (lane + d < 32) s = min(s, t);
+        }
+        int carry = __shfl_down_sync(0xffffffffu, s, 1);                // minimum over the lanes to the right
+        if (lane < 31) {
+            carry += SC_CPL * (31 - lane) * A;                           // = B(i, c0 + 10)
+#pragma unroll
+            for (int k = 0; k < SC_CPL; ++k) u[k] = min(u[k], (unsigned)(carry + (SC_CPL - k) * A));
+        }
+        float fo[SC_CPL];
+#pragma unroll
+        for (int k = 0; k < SC_CPL; ++k) {
+            u[k] = min(u[k], WF_MAX);
+            p2[k] = p1[k];
+            p1[k] = u[k];
+            fo[k] = __uint2float_rn(u[k]) * (1.f / 65536.f);            // OpenCV: (float)(t0 * scale)
+            vmax = fmaxf(vmax, fo[k]);
+        }
+        float2 *dst = reinterpret_cast<float2 *>(out + (size_t)i * HPE_W + c0);
+#pragma unroll
+        for (int k = 0; k < SC_CPL / 2; ++k) dst[k] = make_float2(fo[2 * k], fo[2 * k + 1]);
+    }
+    for (int d = 16; d > 0; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    if (lane == 0) o.meta[slot].dt_max = (double)vmax;
+}
+
 // disttrans.max() for a slot whose distance transform was injected by the caller
 __global__ void __launch_bounds__(1024) dtmax_kernel(ObsView o, int slot)
 {
@@ -351,7 +513,7 @@ __global__ void __launch_bounds__(1024) dtmax_kernel(ObsView o, int slot)
 }  // namespace
 
 size_t hpe_observe_scratch_bytes(int) { return 0; }
-int g_hpe_chamfer = 0;   // 0 = wavefront two-pass (default), 1 = row-search closed form (cross-check)
+int g_hpe_chamfer = 0;   // 0 = row-parallel two-pass (prefix-min scans, default), 1 = row-search closed form, 2 = skewed wavefront (cross-checks)
 
 cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *, cudaStream_t st)
 {
@@ -365,6 +527,8 @@ cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *, c
     cloud_kernel<<<count, OBS_THREADS, 0, st>>>(o, first);
     if (g_hpe_chamfer == 1) {
         chamfer_kernel<<<count, OBS_THREADS, smem, st>>>(o, first);
+    } else if (g_hpe_chamfer == 0) {
+        chamfer_scan_kernel<<<(count + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, st>>>(o, first, count);
     } else {
         static bool attr2 = false;
         if (!attr2) {

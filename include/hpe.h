@@ -217,8 +217,9 @@ int hpe_set_cost_pipeline(int mode, int chunk_poses);
  * for sequences and batches of <= 36 swarms, one CTA per swarm otherwise), 1 = always one CTA per swarm,
  * 2 = always one cluster per swarm.  Results are bit-identical. */
 int hpe_set_pso_path(int mode);
-/* distance transform used by hpe_obs_upload*: 0 (default) = OpenCV's two raster passes run as a
- * skewed wavefront, 1 = closed-form row search.  Bit-identical results; 1 exists to cross-check 0. */
+/* distance transform used by hpe_obs_upload*: 0 (default) = OpenCV's two raster passes, a row at a time with
+ * the in-row recurrence as a prefix-minimum scan; 1 = closed-form row search; 2 = the two passes as a skewed
+ * wavefront.  Bit-identical results; 1 and 2 exist to cross-check 0. */
 int hpe_set_chamfer(int mode);
 /* number of points the certified search handed to its exact fallback since the last reset */
 int hpe_debug_fallback_points(unsigned long long *count, int reset);

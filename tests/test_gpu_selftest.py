@@ -13,7 +13,8 @@ def test_div10_shortcut_is_the_ieee_division_for_every_float(hpe):
 
 
 def test_both_distance_transforms_equal_the_oracle(hpe, orc, omodel, D):
-    """default = OpenCV's two raster passes as a wavefront; mode 1 = closed-form row search"""
+    """default = OpenCV's two raster passes with prefix-minimum row scans; 1 = closed-form row search;
+    2 = the two passes as a skewed wavefront"""
     import numpy as np
     from conftest import synth_pose
     rng = np.random.default_rng(33)
@@ -22,7 +23,7 @@ def test_both_distance_transforms_equal_the_oracle(hpe, orc, omodel, D):
     frames[4, 200:240, 0:30] = 350.0; frames[4, 0:3, 317:320] = 220.0  # blobs touching the borders
     lib = hpe.lib()
     res = []
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         assert lib.hpe_set_chamfer(mode) == 0
         try:
             obs = hpe.observedmodel(capacity=5)
