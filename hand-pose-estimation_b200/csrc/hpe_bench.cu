@@ -234,6 +234,41 @@ extern "C" int hpe_selftest_div10(unsigned long long *mismatches)
     return HPE_OK;
 }
 
+namespace {
+// x / divisor the way cloud_kernel forms it: x = (column - 160) * Z with Z = mm / 10, for every float mm in
+// [1, 4096) mm and a spread of columns, against the IEEE division
+__global__ void div_const_selftest_kernel(double divisor, unsigned long long *mismatches)
+{
+    const double rf = __drcp_rn(divisor);
+    unsigned long long bad = 0;
+    const unsigned lo = 0x3f800000u, hi = 0x45800000u;      // 1.0f .. 4096.0f
+    for (unsigned long long b = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < hi;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        double Z = div10_exact(__uint_as_float((unsigned)b));
+#pragma unroll 1
+        for (int u = 0; u < 320; u += 21) {
+            double x = __dmul_rn((double)u - 160.0, Z);
+            if (__ddiv_rn(x, divisor) != div_const_exact(x, divisor, rf)) bad++;
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+
+// sweeps div_const_exact (hpe_device.cuh) against the IEEE division for the given divisor (the focal length)
+extern "C" int hpe_selftest_div_const(double divisor, unsigned long long *mismatches)
+{
+    if (!mismatches || !(divisor > 0)) return hpe_set_error(HPE_ERR_ARG, "hpe_selftest_div_const: bad argument");
+    unsigned long long *d = nullptr;
+    HPE_CUDA(cudaMalloc(&d, 8));
+    HPE_CUDA(cudaMemset(d, 0, 8));
+    div_const_selftest_kernel<<<148 * 16, 256>>>(divisor, d);
+    HPE_CUDA(cudaGetLastError());
+    HPE_CUDA(cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return HPE_OK;
+}
+
 extern "C" int hpe_measure_fp32_peak(double *tflops, double *sm_mhz_est)
 {
     if (!tflops) return hpe_set_error(HPE_ERR_ARG, "hpe_measure_fp32_peak: NULL output");

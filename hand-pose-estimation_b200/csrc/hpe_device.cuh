@@ -219,6 +219,16 @@ __device__ __forceinline__ double div10_exact(float mm)
     return __fma_rn(r, 0.1, q);
 }
 
+// RN(a / f) for a divisor f whose correctly rounded reciprocal rf = RN(1/f) is at hand (Markstein): q0 = RN(a rf)
+// is within one ulp of the quotient, r = a - q0 f is exact in one FMA, and q0 + r rf rounds to the IEEE
+// quotient.  hpe_selftest_div_const sweeps it against __ddiv_rn for the camera's focal length.
+__device__ __forceinline__ double div_const_exact(double a, double f, double rf)
+{
+    double q = __dmul_rn(a, rf);
+    double r = __fma_rn(-q, f, a);
+    return __fma_rn(r, rf, q);
+}
+
 // floor(RN(a / z)) given rz = RN(1/z): q = a*rz is within 2 ulp of a/z, so the two floors can differ
 // only when a/z lies within 2^-51 |a/z| of an integer; anything closer than 1e-6 to an integer (and
 // NaN/inf) takes the IEEE division instead.

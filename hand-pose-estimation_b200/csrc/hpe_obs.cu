@@ -9,7 +9,11 @@ namespace {
 
 constexpr int OBS_THREADS = 1024;
 constexpr int NPIX = HPE_W * HPE_H;            // 76,800
-constexpr int PIX_PER_WARP = NPIX / 32;        // 2,400 = 75 * 32
+
+// Chunks of 32 consecutive pixels are dealt to the warps round-robin (chunk c -> warp c % 32), so the ~12 % of
+// the image that is hand -- a compact blob of rows -- is spread over all 32 warps instead of keeping a few of
+// them busy with the FP64 work; raster-order ranks come from a prefix sum over the 2,400 chunk counts.
+constexpr int N_CHUNKS = NPIX / 32;            // 2,400
 
 __global__ void __launch_bounds__(OBS_THREADS) cloud_kernel(ObsView o, int first)
 {
@@ -17,29 +21,53 @@ __global__ void __launch_bounds__(OBS_THREADS) cloud_kernel(ObsView o, int first
     const float *__restrict__ depth = o.depth_mm + (size_t)slot * NPIX;
     double *__restrict__ cloud = o.cloud + (size_t)slot * 3 * o.n_pts;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int chunk_base[N_CHUNKS];        // count, then exclusive prefix = rank of the chunk's first hand pixel
+    __shared__ unsigned chunk_bits[N_CHUNKS];
     __shared__ int warp_tot[32];
-    __shared__ int warp_base[32];
     __shared__ double red_sum[32];
     __shared__ int red_cnt[32];
     __shared__ int n_total;
 
-    // pass 1: non-zero pixels per warp-owned contiguous span (raster order is preserved)
-    int cnt = 0;
-    for (int it = 0; it < PIX_PER_WARP / 32; ++it) {
-        int pix = warp * PIX_PER_WARP + it * 32 + lane;
-        unsigned b = __ballot_sync(0xffffffffu, depth[pix] != 0.0f);
-        cnt += __popc(b);
-    }
-    if (lane == 0) warp_tot[warp] = cnt;
-    __syncthreads();
-    if (warp == 0) {
-        int v = warp_tot[lane], s = v;
-        for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, s, d);
-            if (lane >= d) s += t;
+    // pass 1: hand-pixel bit masks and counts per chunk; 15 loads in flight per lane (the frame comes from HBM)
+    constexpr int P1_BATCH = 15;                // 75 chunks per warp = 5 batches
+    for (int c0 = warp; c0 < N_CHUNKS; c0 += 32 * P1_BATCH) {
+        float v[P1_BATCH];
+#pragma unroll
+        for (int k = 0; k < P1_BATCH; ++k) v[k] = __ldg(depth + (c0 + 32 * k) * 32 + lane);
+#pragma unroll
+        for (int k = 0; k < P1_BATCH; ++k) {
+            unsigned b = __ballot_sync(0xffffffffu, v[k] != 0.0f);
+            if (lane == 0) { chunk_bits[c0 + 32 * k] = b; chunk_base[c0 + 32 * k] = __popc(b); }
         }
-        warp_base[lane] = s - v;
-        if (lane == 31) n_total = s;
+    }
+    // 2 / dist of the scale estimate for the distances that occur (small integers): exact quotients, computed once
+    __shared__ double two_over[256];
+    if (threadIdx.x < 256) two_over[threadIdx.x] = threadIdx.x ? __ddiv_rn(2.0, (double)threadIdx.x) : 0.0;
+    __syncthreads();
+    // exclusive prefix sum over the chunk counts: thread t owns chunks 3t..3t+2 (800 threads), then a block scan
+    {
+        int a0 = 0, a1 = 0, a2 = 0;
+        const int c3 = threadIdx.x * 3;
+        if (c3 < N_CHUNKS) { a0 = chunk_base[c3]; a1 = chunk_base[c3 + 1]; a2 = chunk_base[c3 + 2]; }
+        int v = a0 + a1 + a2, sc = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, sc, d);
+            if (lane >= d) sc += t;
+        }
+        if (lane == 31) warp_tot[warp] = sc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane], ws = w;
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, ws, d);
+                if (lane >= d) ws += t;
+            }
+            warp_tot[lane] = ws - w;
+            if (lane == 31) n_total = ws;
+        }
+        __syncthreads();
+        const int base = warp_tot[warp] + sc - v;
+        if (c3 < N_CHUNKS) { chunk_base[c3] = base; chunk_base[c3 + 1] = base + a0; chunk_base[c3 + 2] = base + a0 + a1; }
     }
     __syncthreads();
     const int n = n_total;
@@ -53,32 +81,36 @@ __global__ void __launch_bounds__(OBS_THREADS) cloud_kernel(ObsView o, int first
     // :204-217  sample_f = n / num_samples (integer), idx = k * sample_f
     const int sample_f = n / o.n_pts;
     const double rad = 2.0;
+    const double rfocal = __drcp_rn(o.focal);
     double ssum = 0.0;
     int scnt = 0;
-    int run = warp_base[warp];
-    for (int it = 0; it < PIX_PER_WARP / 32; ++it) {
-        int pix = warp * PIX_PER_WARP + it * 32 + lane;
-        float mm = depth[pix];
-        bool nz = mm != 0.0f;
-        unsigned b = __ballot_sync(0xffffffffu, nz);
-        int rank = run + __popc(b & ((1u << lane) - 1u));
-        run += __popc(b);
+    for (int c = warp; c < N_CHUNKS; c += 32) {
+        const unsigned b = chunk_bits[c];
+        if (b == 0u) continue;                                                // warp-uniform
+        const bool nz = (b >> lane) & 1u;
         if (nz) {
+            const int pix = c * 32 + lane;
+            const int rank = chunk_base[c] + __popc(b & ((1u << lane) - 1u));
+            const float mm = __ldg(depth + pix);
             int v = pix / HPE_W, u = pix - v * HPE_W;
-            double Z = __ddiv_rn((double)mm, 10.0);                            // :300-303 mm -> cm
-            double X = __ddiv_rn(__dmul_rn((double)u - o.cx, Z), o.focal);     // :139-140
-            double Y = __ddiv_rn(__dmul_rn((double)v - o.cy, Z), o.focal);
+            // every quotient below is the IEEE division of the reference, obtained without a divide:
+            // mm/10 (div10_exact), x/focal (div_const_exact), floor(x/Z) (floor_div, exact fallback near integers)
+            double Z = div10_exact(mm);                                        // :300-303 mm -> cm
+            double X = div_const_exact(__dmul_rn((double)u - o.cx, Z), o.focal, rfocal);     // :139-140
             // scale estimate :171-202, K*(X,Y,Z) with row0 = f*X + cx*Z, no FMA contraction
-            double cu = floor(__ddiv_rn(__dadd_rn(__dmul_rn(o.focal, X), __dmul_rn(o.cx, Z)), Z));
-            double eu = floor(__ddiv_rn(__dadd_rn(__dmul_rn(o.focal, __dadd_rn(X, rad)), __dmul_rn(o.cx, Z)), Z));
+            const double rz = __drcp_rn(Z);
+            double cu = floor_div(__dadd_rn(__dmul_rn(o.focal, X), __dmul_rn(o.cx, Z)), Z, rz);
+            double eu = floor_div(__dadd_rn(__dmul_rn(o.focal, __dadd_rn(X, rad)), __dmul_rn(o.cx, Z)), Z, rz);
             double dist = fabs(eu - cu);   // the row-1 difference is identically zero
-            if (dist != 0.0) { ssum += __ddiv_rn(rad, dist); scnt++; }
+            if (dist != 0.0) { ssum += dist < 256.0 ? two_over[(int)dist] : __ddiv_rn(rad, dist); scnt++; }
             if (sample_f > 0) {
                 int k = rank / sample_f;
                 if (k * sample_f == rank && k < o.n_pts) {
+                    double Y = div_const_exact(__dmul_rn((double)v - o.cy, Z), o.focal, rfocal);
                     cloud[k] = X; cloud[o.n_pts + k] = -Y; cloud[2 * o.n_pts + k] = -Z;
                 }
             } else if (rank == 0) {
+                double Y = div_const_exact(__dmul_rn((double)v - o.cy, Z), o.focal, rfocal);
                 for (int k = 0; k < o.n_pts; ++k) {
                     cloud[k] = X; cloud[o.n_pts + k] = -Y; cloud[2 * o.n_pts + k] = -Z;
                 }

@@ -227,6 +227,9 @@ int hpe_debug_fallback_points(unsigned long long *count, int reset);
 /* device self-test: the division-free mm/10 of the depth term against the IEEE division over every
  * finite float; *mismatches must come back 0 */
 int hpe_selftest_div10(unsigned long long *mismatches);
+/* the same for the divide-free x / focal of the back-projection (src/observedmodel.cpp:139-143): x = (column -
+ * 160) * (mm / 10) for every float mm in [1, 4096) and a spread of columns; *mismatches must come back 0 */
+int hpe_selftest_div_const(double divisor, unsigned long long *mismatches);
 
 /* ---- measurement ---- */
 /* FP32 (non-tensor) FFMA peak of the current device in TFLOP/s, measured with a

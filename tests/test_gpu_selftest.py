@@ -12,6 +12,14 @@ def test_div10_shortcut_is_the_ieee_division_for_every_float(hpe):
     assert bad.value == 0
 
 
+def test_divide_free_back_projection_is_the_ieee_division(hpe, D):
+    lib = hpe.lib()
+    for f in (D.FOCAL, 241.42, 500.0, 3.0):
+        bad = C.c_ulonglong(123)
+        assert lib.hpe_selftest_div_const(C.c_double(f), C.byref(bad)) == 0
+        assert bad.value == 0, f
+
+
 def test_both_distance_transforms_equal_the_oracle(hpe, orc, omodel, D):
     """default = OpenCV's two raster passes with prefix-minimum row scans; 1 = closed-form row search;
     2 = the two passes as a skewed wavefront"""
