@@ -30,6 +30,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "hand-pose-estimation_b200"))
 
+# stdout carries exactly one JSON line: everything else that libraries print there (NCCL's version banner, ...)
+# is sent to stderr by pointing fd 1 at fd 2 and keeping the real stdout aside for emit()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "pso_cost_evals_per_sec"
 UNIT = "evals/s"
 N_POSES = 65536
@@ -187,7 +198,7 @@ def run_reference(args, rank):
             "gpu_launches": 0,
             "note": "kind=reference: the reference's own sources compiled against stand-in Armadillo/OpenCV headers "
                     "(oracle/_ref); kind=port: the oracle restatement; port_value is the port's rate either way"}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args):
@@ -501,7 +512,7 @@ def main():
                 "extras": extras}
         if world == 1:
             line["cpu_baseline"], _ = cpu_baseline(args.npts)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

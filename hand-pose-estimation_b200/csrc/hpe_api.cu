@@ -102,7 +102,7 @@ int hpe_set_matcher(int mode)
 }
 
 int g_hpe_pso_path = 0;
-int g_hpe_cost_pipeline = 0;   // 0 = chase kernel for large host batches, 1 = chunked launches only
+int g_hpe_cost_pipeline = 0;   // 0 = one launch per uploaded chunk (default), 1 = chase kernel for large host batches
 int g_hpe_cost_chunk = 0;      // poses per upload chunk of the chase path (0 = default)
 int hpe_set_cost_pipeline(int mode, int chunk_poses)
 {
@@ -405,7 +405,7 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
     HPE_CUDA(cudaStreamWaitEvent(pipe[1], ready, 0));
     int64_t chunk = n > 24576 ? 16384 : n;
     if ((n + chunk - 1) / chunk > MAX_CHUNKS) chunk = (n + MAX_CHUNKS - 1) / MAX_CHUNKS;
-    if (n >= 32768 && g_hpe_cost_pipeline == 0) {
+    if (n >= 32768 && g_hpe_cost_pipeline == 1) {
         timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
         const double t_entry = ts0.tv_sec * 1e6 + ts0.tv_nsec * 1e-3;
         // Large batch: ONE kernel launched before the upload chases the chunks as they land (cost_chase_kernel):

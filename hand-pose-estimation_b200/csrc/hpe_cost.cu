@@ -115,8 +115,8 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
 // launched before the upload; the poses land chunk by chunk (DMA on another stream) and each chunk
 // raises arrived[c].  Warps take groups in order (group q = warp, warp + W, ...), wait for the chunk
 // of their group and score it, so the evaluation chases the copy instead of waiting for it and
-// every warp still walks several groups (no lock-step of the phases).  hpe_cost_batch uses it for
-// large host batches.
+// every warp still walks several groups (no lock-step of the phases).  Opt-in (hpe_set_cost_pipeline(1, 0)):
+// it needs the copy engine and the SMs to run concurrently, which profilers and sanitizers prevent.
 // ---------------------------------------------------------------------------------------
 template <bool WITH_COLLI>
 __global__ void __launch_bounds__(COST_WARPS * 32, HPE_MINBLOCKS)
@@ -149,7 +149,7 @@ cost_chase_kernel(DevModel m, ObsView o, int slot, const double *theta, int64_t 
                 long long spins = 0;
                 const volatile unsigned *f = arrived + need;
                 while (*f == 0u) {
-                    if (++spins > (1ll << 26)) { *timeout_flag = 1; break; }   // a failed upload must not hang the GPU
+                    if (++spins > (1ll << 23)) { *timeout_flag = 1; break; }   // ~2 s: a failed / serialised upload must not hang the GPU
                     __nanosleep(200);
                 }
                 __threadfence_system();

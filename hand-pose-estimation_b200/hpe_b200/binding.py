@@ -57,7 +57,8 @@ def _p(a, t=C.c_double):
 
 
 def set_cost_pipeline(mode=0, chunk_poses=0):
-    """host path of hpe_cost_batch for >= 32,768 poses: 0 = chase kernel (default), 1 = one launch per chunk"""
+    """host path of hpe_cost_batch: 0 = one launch per uploaded chunk (default), 1 = chase kernel for >= 32,768
+    poses (needs concurrent copies and kernels: not under ncu / compute-sanitizer)"""
     _check(lib().hpe_set_cost_pipeline(int(mode), int(chunk_poses)))
 
 

@@ -209,9 +209,12 @@ int hpe_render(const hpe_model *m, const double *theta, int64_t n, double focal,
  * hpe_correspondences: 0 (default) = certified two-sweep search, 1 = the reference's arithmetic
  * on all 48 spheres.  Both return cv::BFMatcher's indices; 1 exists to cross-check 0. */
 int hpe_set_matcher(int mode);
-/* host path of hpe_cost_batch for batches of >= 32,768 poses: mode 0 (default) = one kernel launched before the
- * upload that scores the chunks as they land ("chase"), mode 1 = one launch per uploaded chunk; chunk_poses =
- * poses per upload chunk of mode 0 (0 = default 8192).  Results are identical. */
+/* host path of hpe_cost_batch: mode 0 (default) = upload / compute / download streams, one kernel launch per
+ * uploaded chunk of 16,384 poses; mode 1 (batches of >= 32,768 poses) = ONE kernel launched before the upload
+ * that scores the chunks as they land ("chase"; chunk_poses = poses per upload chunk, 0 = a decreasing
+ * schedule).  Mode 1 needs copies and kernels to run concurrently: under tools that serialise them (ncu,
+ * compute-sanitizer, CUDA_LAUNCH_BLOCKING=1) the kernel gives up after ~2 s and the call returns
+ * HPE_ERR_CUDA.  Results are identical. */
 int hpe_set_cost_pipeline(int mode, int chunk_poses);
 /* kernel behind hpe_pso_evolve / hpe_track_sequence: 0 (default) = automatic (one 8-CTA cluster per swarm
  * for sequences and batches of <= 36 swarms, one CTA per swarm otherwise), 1 = always one CTA per swarm,

@@ -70,7 +70,7 @@ def test_full_size_cost_batch_properties(hpe, orc, omodel, golden, D):
     # the two host pipelines for large batches (kernel chasing the upload / one launch per uploaded chunk)
     # and odd upload chunk sizes return the same bits
     try:
-        for mode, chunk in ((1, 0), (0, 5000), (0, 65536), (0, 1031)):
+        for mode, chunk in ((0, 0), (1, 0), (1, 5000), (1, 65536), (1, 1031)):
             hpe.set_cost_pipeline(mode, chunk)
             a4, d4, c4 = cf.cal_cost_batch(th[: n - 7], with_collision=True)
             assert np.array_equal(a4, a[: n - 7]) and np.array_equal(d4, d[: n - 7]), (mode, chunk)
