@@ -1,7 +1,7 @@
 /*
  * hpe_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
- * See hpe_oracle.h for the rules on who may call this and for the
- * "parity unpinned" statement.  Build: make -C oracle  (gcc -O2 -fopenmp
+ * See hpe_oracle.h for the rules on who may call this and for how it is
+ * pinned against the reference build (oracle/_ref).  Build: make -C oracle  (gcc -O2 -fopenmp
  * -ffp-contract=off: IEEE double/float, no FMA contraction, so that the
  * evaluation order written here is the arithmetic that runs).
  *

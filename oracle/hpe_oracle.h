@@ -7,13 +7,18 @@
  * cpu_baseline / --impl reference legs may build, link or call anything in
  * this directory; the product (libhpe_b200.so) never does.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
- * and cannot be compiled here (Armadillo, OpenCV C++ and GLUT are absent, no
- * network).  The pins that exist are substitutes, checked in tests/:
+ * PARITY: the reference ships no tests, golden vectors or fixtures and needs Armadillo +
+ * OpenCV C++, which the image lacks; oracle/_ref is therefore the reference's OWN hot-path
+ * sources compiled unmodified against minimal stand-in headers (oracle/shim/, see oracle/Makefile
+ * and oracle/ref_driver.cpp).  tests/test_ref_build.py and tests/test_oracle_refine.py hold this
+ * restatement bit-identical to that build (FK, observation, energy terms, correspondences,
+ * pso_evolve on replayed random streams, refine_init_pose, gnd_truth_err, dim_restore); what the
+ * stand-ins restate of the two libraries is pinned separately:
  *   - cv2.BFMatcher(NORM_L2)  == orc_correspondences       (bit-exact)
  *   - cv2.distanceTransform(DIST_L2, 5) with IPP off == orc_chamfer5 (bit-exact)
- *   - an independent numpy restatement of the DH chain (tests/np_restatement.py)
- *     and the sanity values of SURVEY.md B.4.
+ *   - Armadillo's sum/mean/dot order (two accumulators) and left-to-right small dense products;
+ *     real Armadillo may hand products to BLAS, whose order is unspecified: that residue is
+ *     unpinned and stated in DESIGN.md section 2.
  * Armadillo's RNG is replaced by a counter-based Philox4x32-10 stream that the
  * GPU replays ("RNG").
  *

@@ -1,6 +1,6 @@
 // The reference's driver test_full (src/testmodel.cpp:27-146) written against hpe_classes.hpp:
-// same constants, same call sequence (minus refine_init_pose), frames read from
-// Subject1-format files %06d_depth.bin.  Usage: test_full <dir/> <numframes> <num_p> <maxiter>
+// same constants, same call sequence (refine_init_pose, pso_evolve, cal_cost, x0 = bestp), frames read from
+// Subject1-format files %06d_depth.bin.  Usage: test_full <dir/> <numframes> <num_p> <maxiter> [x0 file] [norefine]
 // Prints "frameNNNNNN-cost: c" like the reference plus the pose, one line per frame.
 #include <cstdio>
 #include <cstdlib>
@@ -58,6 +58,7 @@ int main(int argc, char **argv)
             char name[64];
             std::snprintf(name, sizeof name, "%06d_depth.bin", frame);
             observation.next_frame(name);
+            if (argc <= 6) optimiser.refine_init_pose(x0, optfunc);      // src/testmodel.cpp:126
             hpe::vec bestp;
             optimiser.pso_evolve(optfunc, x0, num_p, bestp);
             double c = optfunc.cal_cost(bestp);

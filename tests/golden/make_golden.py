@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Regenerates tests/golden/golden_v1.npz from the CPU ORACLE (oracle/hpe_oracle.c).
 
-The reference itself ships no golden vectors and cannot be compiled here (Armadillo/OpenCV/GLUT are
-absent), so these are oracle outputs, not reference outputs: they pin the oracle against drift and
-give the GPU tests fixed expected values.  Run: python tests/golden/make_golden.py
+These are oracle outputs: they pin the oracle against drift and give the GPU tests fixed expected
+values.  The same inputs run through the REFERENCE'S OWN CODE (oracle/_ref) are in golden_ref_v1.npz
+(make_golden_ref.py); tests/test_ref_build.py checks that the two files agree field by field.
+Run: python tests/golden/make_golden.py
 """
 import os
 import sys

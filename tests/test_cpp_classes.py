@@ -44,7 +44,8 @@ def test_cpp_driver_tracks_like_the_oracle(tmp_path, hpe, orc, omodel, D):
     np.savetxt(str(tmp_path / "x0.txt"), x0[None], fmt="%.17g")
     exe = build_driver(tmp_path)
     num_p, maxiter = 32, 10
-    r = subprocess.run([exe, str(tmp_path) + "/", "3", str(num_p), str(maxiter), str(tmp_path / "x0.txt")],
+    # without refine_init_pose the loop follows the oracle's trajectory exactly
+    r = subprocess.run([exe, str(tmp_path) + "/", "3", str(num_p), str(maxiter), str(tmp_path / "x0.txt"), "norefine"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     lines = r.stdout.strip().splitlines()
@@ -57,6 +58,22 @@ def test_cpp_driver_tracks_like_the_oracle(tmp_path, hpe, orc, omodel, D):
         bo, co, _, _, _ = orc.pso_evolve(omodel, obs, prm, cur, num_p, 1000)
         assert abs(cost - co) <= 1e-8 * co and np.abs(pose_out - bo).max() < 1e-7
         cur = bo
+    # the driver as the reference wrote it (refine_init_pose before every pso_evolve, src/testmodel.cpp:126-130):
+    # joints within the north star's 1 mm of the oracle's loop
+    r2 = subprocess.run([exe, str(tmp_path) + "/", "3", str(num_p), str(maxiter), str(tmp_path / "x0.txt")],
+                        capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    lines2 = r2.stdout.strip().splitlines()
+    cur2 = x0
+    for k in range(3):
+        pose_out = np.array([float(v) for v in lines2[k].split()[3:]])
+        obs2 = orc.Observation(np.fromfile(str(tmp_path / f"{k:06d}_depth.bin"), dtype="<f4").reshape(240, 320))
+        ref_x, _ = orc.refine_init_pose(omodel, obs2, cur2)
+        bo2, _, _, _, _ = orc.pso_evolve(omodel, obs2, prm, ref_x, num_p, 1000)
+        _, Jg = orc.fk(omodel, pose_out)
+        _, Jo = orc.fk(omodel, bo2)
+        assert np.linalg.norm(Jg - Jo, axis=1).max() * 10.0 < 1.0, k
+        cur2 = bo2
     tail = lines[3].split()
     S, J = orc.fk(omodel, cur)
     assert abs(float(tail[1]) - obs.scale) <= 1e-12 * obs.scale
