@@ -403,8 +403,28 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
     HPE_CUDA(cudaEventRecord(ready, 0));          // prior default-stream work (frozen copy, observation kernels)
     HPE_CUDA(cudaStreamWaitEvent(pipe[0], ready, 0));
     HPE_CUDA(cudaStreamWaitEvent(pipe[1], ready, 0));
-    int64_t chunk = n > 24576 ? 16384 : n;
-    if ((n + chunk - 1) / chunk > MAX_CHUNKS) chunk = (n + MAX_CHUNKS - 1) / MAX_CHUNKS;
+    // upload schedule: chunks of 16,384 poses (3.4 MB copies run at the full PCIe rate; every extra copy costs
+    // ~20 us of fixed overhead on this platform, so the default path keeps them uniform).  The chase path ends
+    // with halving chunks so that little is left to score when the last one lands.  hpe_set_cost_pipeline can fix
+    // the chunk size.
+    ChaseChunks cks;
+    cks.count = 0;
+    if (n <= 24576 && g_hpe_cost_chunk == 0) {
+        cks.end[cks.count++] = n;
+    } else {
+        const bool halving = g_hpe_cost_chunk == 0 && g_hpe_cost_pipeline == 1;
+        int64_t big = g_hpe_cost_chunk > 0 ? g_hpe_cost_chunk : 16384;
+        if ((n + big - 1) / big > MAX_CHUNKS - 8) big = (n + MAX_CHUNKS - 9) / (MAX_CHUNKS - 8);
+        int64_t at = 0;
+        while (at < n && cks.count < MAX_CHUNKS - 1) {
+            int64_t left = n - at, take = big;
+            if (halving && left <= big) take = left > 4096 ? (left / 2 + 1023) / 1024 * 1024 : left;
+            if (take > left) take = left;
+            at += take;
+            cks.end[cks.count++] = at;
+        }
+        if (at < n) cks.end[cks.count - 1] = n;
+    }
     if (n >= 32768 && g_hpe_cost_pipeline == 1) {
         timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
         const double t_entry = ts0.tv_sec * 1e6 + ts0.tv_nsec * 1e-3;
@@ -415,22 +435,6 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
         if (!ones) {
             HPE_CUDA(cudaHostAlloc((void **)&ones, sizeof(unsigned) * MAX_CHUNKS, cudaHostAllocDefault));
             for (int i = 0; i < MAX_CHUNKS; ++i) ones[i] = 1u;
-        }
-        // upload schedule: full-rate chunks first, then halving ones so that little is left to score when the
-        // last chunk lands (a fixed chunk size when hpe_set_cost_pipeline gave one)
-        ChaseChunks cks;
-        cks.count = 0;
-        {
-            const int64_t big = g_hpe_cost_chunk > 0 ? g_hpe_cost_chunk : 16384;
-            int64_t at = 0;
-            while (at < n && cks.count < MAX_CHUNKS - 1) {
-                int64_t left = n - at, take = big;
-                if (g_hpe_cost_chunk == 0 && left <= big) take = left > 4096 ? (left / 2 + 1023) / 1024 * 1024 : left;
-                if (take > left) take = left;
-                at += take;
-                cks.end[cks.count++] = at;
-            }
-            if (at < n) cks.end[cks.count++] = n;
         }
         const int nck = cks.count;
         unsigned *d_flags = (unsigned *)(base + b_th + b_tm + b_fr + b_mo);
@@ -464,16 +468,14 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
         if (*timed_out_pin) return hpe_set_error(HPE_ERR_CUDA, "hpe_cost_batch: the pose upload did not arrive (kernel gave up waiting)");
         return HPE_OK;
     }
-    int k = 0;
-    for (int64_t c0 = 0; c0 < n; c0 += chunk, ++k) {
-        const int64_t cn = n - c0 < chunk ? n - c0 : chunk;
+    for (int k = 0; k < cks.count; ++k) {
+        const int64_t c0 = k ? cks.end[k - 1] : 0, cn = cks.end[k] - c0;
         HPE_CUDA(cudaMemcpyAsync(d_th + c0 * HPE_NDOF, theta + c0 * HPE_NDOF, sizeof(double) * cn * HPE_NDOF,
                                  cudaMemcpyHostToDevice, pipe[0]));
         HPE_CUDA(cudaEventRecord(up_done[k], pipe[0]));
     }
-    k = 0;
-    for (int64_t c0 = 0; c0 < n; c0 += chunk, ++k) {
-        const int64_t cn = n - c0 < chunk ? n - c0 : chunk;
+    for (int k = 0; k < cks.count; ++k) {
+        const int64_t c0 = k ? cks.end[k - 1] : 0, cn = cks.end[k] - c0;
         HPE_CUDA(cudaStreamWaitEvent(pipe[1], up_done[k], 0));
         HPE_CUDA(hpe_launch_cost(m->dm, o->v, slot, d_th + c0 * HPE_NDOF, cn, colli != nullptr, nullptr, d_tm + c0,
                                  frozen ? d_fr : nullptr, match_out ? d_mo + c0 * np : nullptr, pipe[1], n));
