@@ -426,8 +426,17 @@ def main():
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         extras["track_frames_per_sec"] = world * n_seq / dt
+        # accuracy the way the reference measures it (costfunc::gnd_truth_err, src/costfunc.cpp:476-507): summed
+        # distance of wrist + five finger tips to the ground truth, here the joints of the poses the frames were
+        # rendered from (mm, y and z negated like joint.txt); reported per joint
+        _, Jw = hand.build_hand_models(walk)
+        gt_rows = (Jw * 10.0 * np.array([1.0, -1.0, -1.0])).reshape(n_seq, 63)
+        err = cfs.gnd_truth_err_batch(poses, gt_rows) / 6.0
+        extras["track_joint_err_mm"] = {"median": float(np.median(err)), "p90": float(np.percentile(err, 90)),
+                                        "max": float(err.max())}
         extras["track"] = (f"{n_seq}-frame synthetic sequence per GPU, 64 particles x 30 generations per frame, temporal "
-                           f"init; median final cost {float(np.median(costs)):.3f}")
+                           f"init; median final cost {float(np.median(costs)):.3f}; track_joint_err_mm = gnd_truth_err / 6 "
+                           "against the rendered poses")
 
         # PSO::refine_init_pose for a batch of frames (one CTA per frame), and the complete
         # per-frame loop of test_full (refine_init_pose -> pso_evolve -> x0 = bestp) on the head of the sequence
@@ -449,6 +458,11 @@ def main():
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         extras["track_refined_frames_per_sec"] = world * n_ref / dt
+        poses_r, _, _ = pso.track_sequence_refined(cfs, xs0, 64, n_ref)
+        err_r = cfs.gnd_truth_err_batch(poses_r, gt_rows[:n_ref]) / 6.0
+        extras["track_refined_joint_err_mm"] = {"median": float(np.median(err_r)), "p90": float(np.percentile(err_r, 90)),
+                                                "max": float(err_r.max()), "same_frames_without_refine_median":
+                                                float(np.median(err[:n_ref]))}
         extras["track_refined"] = (f"first {n_ref} frames of the sequence, refine_init_pose before every pso_evolve "
                                    f"(src/testmodel.cpp:126-130); median final cost {float(np.median(costs_r)):.3f}")
         # configs[4]: offline batch, 262,144 independent frames x (64 x 30), frames sharded over the ranks and
