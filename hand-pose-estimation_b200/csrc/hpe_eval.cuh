@@ -50,6 +50,9 @@ static __device__ unsigned long long g_hpe_fallback_points;
 #ifndef HPE_PACKED_INDEX
 #define HPE_PACKED_INDEX 0   // 1: block index packed in the minimum's low mantissa bits (measured: no gain)
 #endif
+#ifndef HPE_FFMA2
+#define HPE_FFMA2 1          // 1: sweeps on packed fma.rn.f32x2 (two spheres per instruction, conflict-free operand fetch)
+#endif
 #ifndef HPE_MINBLOCKS
 #define HPE_MINBLOCKS 3                  // CTAs of 8 warps per SM the kernels are compiled for
 #endif
@@ -176,6 +179,32 @@ __device__ __forceinline__ float expanded(const float4 &p, const float4 &e)
     return fmaf(p.w, e.z, fmaf(p.z, e.y, fmaf(p.y, e.x, e.w)));
 }
 
+// packed pair of FP32 FMAs (same IEEE fma in each half): the three-register scalar FFMAs of the sweep average ~1.5
+// issue cycles because two of their operands often sit in the same register bank; the 64-bit operands of FFMA2
+// are fetched conflict-free (profiles/r1_issue_microbench.txt)
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long dup32(float v)
+{
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(v));
+    return d;
+}
+__device__ __forceinline__ void split32(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// s of the two spheres of a pair for one point: fma(z', ez, fma(y', ey, fma(x', ex, ew))) in each half
+__device__ __forceinline__ unsigned long long expanded2(unsigned long long px, unsigned long long py, unsigned long long pz,
+                                                         const ulonglong2 &xy, const ulonglong2 &zw)
+{
+    return ffma2(pz, zw.x, ffma2(py, xy.y, ffma2(px, xy.x, zw.y)));
+}
+
 // the reference's arithmetic on every pair, 4 points of the lane (cross-check: hpe_set_matcher(1))
 __device__ __forceinline__ void match_pass_direct(const FrameSmem &fs, const WarpScratch &ws, int k0, int lane,
                                                   int idx[HPE_PASS])
@@ -210,6 +239,56 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
                                            int idx[HPE_PASS])
 {
     const float INF = __int_as_float(0x7f800000);
+#if HPE_FFMA2
+    // ---- packed variant: spheres are staged in pairs (see depth_and_stage), point coordinates duplicated ----
+    unsigned long long px[HPE_PASS], py[HPE_PASS], pz[HPE_PASS];
+    float M1[HPE_PASS], M2[HPE_PASS];
+    int g1[HPE_PASS];
+#pragma unroll
+    for (int m = 0; m < HPE_PASS; ++m) {
+        const float4 q = fs.pre[k0 + 32 * m];
+        px[m] = dup32(q.y); py[m] = dup32(q.z); pz[m] = dup32(q.w);
+        M1[m] = INF; M2[m] = INF; g1[m] = 0;
+    }
+#pragma unroll 3
+    for (int g = 0; g < HPE_NBLK; ++g) {
+        const ulonglong2 *blk = reinterpret_cast<const ulonglong2 *>(ws.ex + g * HPE_EX_PITCH);
+        const ulonglong2 a0 = blk[0], a1 = blk[1], b0 = blk[2], b1 = blk[3];
+        unsigned long long sa[HPE_PASS], sb[HPE_PASS];
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) { sa[m] = ffma2(px[m], a0.x, a1.y); sb[m] = ffma2(px[m], b0.x, b1.y); }
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) { sa[m] = ffma2(py[m], a0.y, sa[m]); sb[m] = ffma2(py[m], b0.y, sb[m]); }
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) { sa[m] = ffma2(pz[m], a1.x, sa[m]); sb[m] = ffma2(pz[m], b1.x, sb[m]); }
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) {
+            float s0, s1, s2, s3;
+            split32(sa[m], s0, s1);
+            split32(sb[m], s2, s3);
+            float gm = fmin3(fminf(s0, s1), s2, s3);
+            M2[m] = fminf(M2[m], fmaxf(M1[m], gm));
+            bool better = gm < M1[m];
+            M1[m] = fminf(M1[m], gm);
+            g1[m] = better ? g : g1[m];
+        }
+    }
+    unsigned slow = 0u;
+#pragma unroll
+    for (int m = 0; m < HPE_PASS; ++m) {
+        const ulonglong2 *blk = reinterpret_cast<const ulonglong2 *>(ws.ex + g1[m] * HPE_EX_PITCH);
+        float s0, s1, s2, s3;
+        split32(expanded2(px[m], py[m], pz[m], blk[0], blk[1]), s0, s1);
+        split32(expanded2(px[m], py[m], pz[m], blk[2], blk[3]), s2, s3);
+        float lo01 = fminf(s0, s1), hi01 = fmaxf(s0, s1), lo23 = fminf(s2, s3), hi23 = fmaxf(s2, s3);
+        float r = fmin3(fmaxf(lo01, lo23), hi01, hi23);                   // runner-up inside the block
+        const float tau = fmaf(3.2e-6f, fabsf(M1[m]), fs.pre[k0 + 32 * m].x);   // 52 * 2^-24 = 3.0994e-6
+        bool cert = fminf(M2[m], r) - M1[m] > tau;                        // false on NaN
+        int i = s1 < s0 ? 1 : 0, j = s3 < s2 ? 3 : 2;
+        idx[m] = g1[m] * HPE_BLK + (lo23 < lo01 ? j : i);
+        slow |= (cert ? 0u : 1u) << m;
+    }
+#else
     float4 p[HPE_PASS];
     float M1[HPE_PASS], M2[HPE_PASS];
     int g1[HPE_PASS];
@@ -313,6 +392,7 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
         idx[m] = g1[m] * HPE_BLK + (lo23 < lo01 ? j : i);
         slow |= (cert ? 0u : 1u) << m;
     }
+#endif  // HPE_FFMA2
     // ---- fallback ----
     if (__any_sync(0xffffffffu, slow != 0u)) {
 #pragma unroll
@@ -431,8 +511,15 @@ __device__ __forceinline__ double depth_and_stage(const FrameSmem &fs, const War
             // c' = cf - q exactly (FP64), then one rounding each for -2c' and |c'|^2
             double cx = (double)c.x - (double)fs.qx, cy = (double)c.y - (double)fs.qy, cz = (double)c.z - (double)fs.qz;
             ws.cf[j] = c;
-            ws.ex[HPE_EX_AT(j)] = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz),
-                                   (float)(cx * cx + cy * cy + cz * cz));
+            const float4 e = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz),
+                                         (float)(cx * cx + cy * cy + cz * cz));
+#if HPE_FFMA2
+            // spheres 4g+2q and 4g+2q+1 share 64-bit words: block g = | x01 y01 | z01 w01 | x23 y23 | z23 w23 | pad |
+            float *fb = reinterpret_cast<float *>(ws.ex + (j / HPE_BLK) * HPE_EX_PITCH) + ((j % HPE_BLK) / 2) * 8 + (j & 1);
+            fb[0] = e.x; fb[2] = e.y; fb[4] = e.z; fb[6] = e.w;
+#else
+            ws.ex[HPE_EX_AT(j)] = e;
+#endif
         }
     }
     __syncwarp();
