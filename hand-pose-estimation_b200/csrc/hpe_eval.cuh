@@ -53,6 +53,21 @@ static __device__ unsigned long long g_hpe_fallback_points;
 #ifndef HPE_FFMA2
 #define HPE_FFMA2 1          // 1: sweeps on packed fma.rn.f32x2 (two spheres per instruction, conflict-free operand fetch)
 #endif
+#ifndef HPE_ALIGN8
+#define HPE_ALIGN8 0         // 1: alignment of the lane's 8 points after both matching passes (measured slower)
+#endif
+#ifndef HPE_ALIGN_BF
+#define HPE_ALIGN_BF 0       // 1: branch-free alignment chains inside a pass
+#endif
+#ifndef HPE_DEPTH_BATCH
+#define HPE_DEPTH_BATCH 1    // 1: all four depth-term gathers of a lane issued together (+2 %)
+#endif
+#ifndef HPE_SWEEP_UNROLL
+#define HPE_SWEEP_UNROLL 3   // sweep-A blocks per loop body
+#endif
+#define HPE_STR2(x) #x
+#define HPE_STR(x) HPE_STR2(x)
+#define HPE_UNROLL_SWEEP _Pragma(HPE_STR(unroll HPE_SWEEP_UNROLL))
 #ifndef HPE_MINBLOCKS
 #define HPE_MINBLOCKS 3                  // CTAs of 8 warps per SM the kernels are compiled for
 #endif
@@ -250,7 +265,7 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
         px[m] = dup32(q.y); py[m] = dup32(q.z); pz[m] = dup32(q.w);
         M1[m] = INF; M2[m] = INF; g1[m] = 0;
     }
-#pragma unroll 3
+    HPE_UNROLL_SWEEP
     for (int g = 0; g < HPE_NBLK; ++g) {
         const ulonglong2 *blk = reinterpret_cast<const ulonglong2 *>(ws.ex + g * HPE_EX_PITCH);
         const ulonglong2 a0 = blk[0], a1 = blk[1], b0 = blk[2], b1 = blk[3];
@@ -418,6 +433,46 @@ template <int MATCHER>
 __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScratch &ws, int g, int lane,
                                               const int32_t *frozen, int32_t *match_row)
 {
+#if HPE_ALIGN8
+    const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
+    const int n_pts = fs.n_pts;
+    constexpr int NPASS = HPE_PPL / HPE_PASS;
+    int idx[NPASS][HPE_PASS];
+#pragma unroll
+    for (int pass = 0; pass < NPASS; ++pass) {
+        const int k0 = lane + 32 * HPE_PASS * pass;
+        if (frozen) {
+#pragma unroll
+            for (int m = 0; m < HPE_PASS; ++m) idx[pass][m] = k0 + 32 * m < n_pts ? frozen[k0 + 32 * m] : 0;
+        } else if (MATCHER == 1) {
+            match_pass_direct(fs, ws, k0, lane, idx[pass]);
+        } else {
+            match_pass(fs, ws, k0, lane, idx[pass]);
+        }
+    }
+    // align_models for the lane's 8 points, FP64, the reference's operation order; the eight distance chains
+    // (each ends in a double-precision square root) are independent and branch-free, the sum keeps the order
+    // point 0..7 of the lane
+    double acc = 0.0;
+#pragma unroll
+    for (int pass = 0; pass < NPASS; ++pass) {
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) {
+            const int k = lane + 32 * (HPE_PASS * pass + m);
+            const bool valid = k < n_pts;
+            const int kk = valid ? k : 0;
+            const int j = idx[pass][m];
+            if (match_row && valid) match_row[k] = j;
+            // negated-frame centre = (cx, -cy, -cz)
+            double a = fs.cloud[kk] - sd[j * 3 + 0];
+            double b = fs.cloud[HPE_MAXPTS + kk] + sd[j * 3 + 1];
+            double e = fs.cloud[2 * HPE_MAXPTS + kk] + sd[j * 3 + 2];
+            double nor = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e)));
+            double df = fabs(nor - fs.rad[j]);
+            acc += valid ? __dmul_rn(df, df) : 0.0;
+        }
+    }
+#else
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
     const int n_pts = fs.n_pts;
     double acc = 0.0;
@@ -437,6 +492,19 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
 #pragma unroll
         for (int m = 0; m < HPE_PASS; ++m) {
             int k = k0 + 32 * m;
+#if HPE_ALIGN_BF
+            // branch-free: the padded slots (k >= n_pts) run the same chain on point 0 and contribute +0.0
+            const bool valid = k < n_pts;
+            const int kk = valid ? k : 0;
+            const int j = idx[m];
+            if (match_row && valid) match_row[k] = j;
+            double a = fs.cloud[kk] - sd[j * 3 + 0];
+            double b = fs.cloud[HPE_MAXPTS + kk] + sd[j * 3 + 1];
+            double e = fs.cloud[2 * HPE_MAXPTS + kk] + sd[j * 3 + 2];
+            double nor = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e)));
+            double df = fabs(nor - fs.rad[j]);
+            acc += valid ? __dmul_rn(df, df) : 0.0;
+#else
             if (k < n_pts) {
                 int j = idx[m];
                 if (match_row) match_row[k] = j;
@@ -448,8 +516,10 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
                 double df = fabs(nor - fs.rad[j]);
                 acc += __dmul_rn(df, df);
             }
+#endif
         }
     }
+#endif
     return __dmul_rn(warp_sum(acc), fs.lambda);
 }
 
@@ -498,6 +568,65 @@ __device__ __forceinline__ void group_fk(const DevModel &M, ThetaAt theta, int n
 // stage the pose's float32 centres (cf) and sweep-A operands (ex).  Result valid on all lanes.
 __device__ __forceinline__ double depth_and_stage(const FrameSmem &fs, const WarpScratch &ws, int g, int lane)
 {
+#if HPE_DEPTH_BATCH
+    const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
+    __syncwarp();      // previous pose's matcher is done with cf/ex
+    // depth_penalty (src/costfunc.cpp:251-300) for the lane's spheres j = lane and lane + 32.  Both spheres'
+    // projections are computed first and all four gathers (depth map and distance transform of both pixels) are
+    // issued together: the distance transform is read whether or not the pixel turns out to be background, so no
+    // load waits for another and the phase pays one L2/HBM latency instead of four.
+    double x[2], y[2], z[2];
+    int at[2];
+    bool act[2], inside[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+        act[h] = j < HPE_NSPH;
+        const int jj = act[h] ? j : 0;
+        x[h] = sd[jj * 3]; y[h] = sd[jj * 3 + 1]; z[h] = sd[jj * 3 + 2];
+        // K*c without FMA contraction: row0 = f*x + cx*z, row1 = f*y + cy*z, row2 = z; then floor(row / z)
+        const double rz = __drcp_rn(z[h]);
+        double dx = floor_div(__dadd_rn(__dmul_rn(fs.focal, x[h]), __dmul_rn(fs.cx, z[h])), z[h], rz);
+        double dy = floor_div(__dadd_rn(__dmul_rn(fs.focal, y[h]), __dmul_rn(fs.cy, z[h])), z[h], rz);
+        inside[h] = act[h] && dx >= 0.0 && dx < (double)HPE_W && dy >= 0.0 && dy < (double)HPE_H;
+        at[h] = inside[h] ? (int)dy * HPE_W + (int)dx : 0;
+    }
+    float mm[2], dtv[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        mm[h] = 0.f; dtv[h] = 0.f;
+        if (inside[h]) { mm[h] = __ldg(fs.depth_mm + at[h]); dtv[h] = __ldg(fs.dt_px + at[h]); }
+    }
+    double dv = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+        if (act[h]) {
+            const double r = fs.rad[j];
+            double v;
+            if (inside[h]) {
+                if (mm[h] != 0.0f) v = fmax(0.0, div10_exact(mm[h]) - z[h]);     // depthmp is the file value / 10
+                else v = __dadd_rn(__dmul_rn((double)dtv[h], fs.scale), r);
+            } else {
+                v = __dadd_rn(__dmul_rn(fs.dt_max, fs.scale), r);
+            }
+            dv += __dmul_rn(v, v);
+            float4 c = make_float4((float)x[h], (float)(-y[h]), (float)(-z[h]), 0.f);   // conv_to<fmat>, negated frame
+            // c' = cf - q exactly (FP64), then one rounding each for -2c' and |c'|^2
+            double cx = (double)c.x - (double)fs.qx, cy = (double)c.y - (double)fs.qy, cz = (double)c.z - (double)fs.qz;
+            ws.cf[j] = c;
+            const float4 e = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz),
+                                         (float)(cx * cx + cy * cy + cz * cz));
+#if HPE_FFMA2
+            // spheres 4g+2q and 4g+2q+1 share 64-bit words: block g = | x01 y01 | z01 w01 | x23 y23 | z23 w23 | pad |
+            float *fb = reinterpret_cast<float *>(ws.ex + (j / HPE_BLK) * HPE_EX_PITCH) + ((j % HPE_BLK) / 2) * 8 + (j & 1);
+            fb[0] = e.x; fb[2] = e.y; fb[4] = e.z; fb[6] = e.w;
+#else
+            ws.ex[HPE_EX_AT(j)] = e;
+#endif
+        }
+    }
+#else
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
     double dv = 0.0;
     __syncwarp();      // previous pose's matcher is done with cf/ex
@@ -522,6 +651,7 @@ __device__ __forceinline__ double depth_and_stage(const FrameSmem &fs, const War
 #endif
         }
     }
+#endif
     __syncwarp();
     return warp_sum(dv);
 }
