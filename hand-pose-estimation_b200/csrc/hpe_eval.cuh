@@ -282,12 +282,24 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
             split32(sa[m], s0, s1);
             split32(sb[m], s2, s3);
             float gm = fmin3(fminf(s0, s1), s2, s3);
+#if HPE_PACKED_INDEX
+            // the block index rides in the 4 low mantissa bits of the block minimum (a perturbation below 16 ulp,
+            // paid for in tau): no compare + select to remember the best block
+            gm = __uint_as_float((__float_as_uint(gm) & 0xfffffff0u) | (unsigned)g);
+            M2[m] = fminf(M2[m], fmaxf(M1[m], gm));
+            M1[m] = fminf(M1[m], gm);
+#else
             M2[m] = fminf(M2[m], fmaxf(M1[m], gm));
             bool better = gm < M1[m];
             M1[m] = fminf(M1[m], gm);
             g1[m] = better ? g : g1[m];
+#endif
         }
     }
+#if HPE_PACKED_INDEX
+#pragma unroll
+    for (int m = 0; m < HPE_PASS; ++m) g1[m] = (int)(__float_as_uint(M1[m]) & 15u);
+#endif
     unsigned slow = 0u;
 #pragma unroll
     for (int m = 0; m < HPE_PASS; ++m) {
@@ -297,8 +309,15 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
         split32(expanded2(px[m], py[m], pz[m], blk[2], blk[3]), s2, s3);
         float lo01 = fminf(s0, s1), hi01 = fmaxf(s0, s1), lo23 = fminf(s2, s3), hi23 = fmaxf(s2, s3);
         float r = fmin3(fmaxf(lo01, lo23), hi01, hi23);                   // runner-up inside the block
+#if HPE_PACKED_INDEX
+        // exact minimum of the best block; M2 carries an index in its low bits: |M2 - true| < 32u|M2|
+        const float m1 = fminf(lo01, lo23);
+        const float tau = fmaf(7.2e-6f, fabsf(m1), fs.pre[k0 + 32 * m].x);      // (52 + 2*32) * 2^-24 = 6.9e-6
+        bool cert = fminf(M2[m], r) - m1 > tau;                           // false on NaN
+#else
         const float tau = fmaf(3.2e-6f, fabsf(M1[m]), fs.pre[k0 + 32 * m].x);   // 52 * 2^-24 = 3.0994e-6
         bool cert = fminf(M2[m], r) - M1[m] > tau;                        // false on NaN
+#endif
         int i = s1 < s0 ? 1 : 0, j = s3 < s2 ? 3 : 2;
         idx[m] = g1[m] * HPE_BLK + (lo23 < lo01 ? j : i);
         slow |= (cert ? 0u : 1u) << m;

@@ -52,10 +52,13 @@ class Reference:
     """handmodel + observedmodel + costfunc + PSO of the reference, constructed with the values of
     src/testmodel.cpp:34-52 unless overridden."""
 
-    def __init__(self, threads=1):
+    def __init__(self, threads=1, geo_cm=None, spacing=None, cmc=None, rad_cm=None):
         L = lib()
-        self.h = C.c_void_p(L.ref_create(_p(f64(D.HGEO_CM)), _p(f64(D.SPACING)), _p(f64(D.CMC)),
-                                         _p(f64(D.TB_N)), _p(f64(D.FG_N)), _p(f64(D.RAD_CM))))
+        self.h = C.c_void_p(L.ref_create(_p(f64(D.HGEO_CM if geo_cm is None else geo_cm)),
+                                         _p(f64(D.SPACING if spacing is None else spacing)),
+                                         _p(f64(D.CMC if cmc is None else cmc)),
+                                         _p(f64(D.TB_N)), _p(f64(D.FG_N)),
+                                         _p(f64(D.RAD_CM if rad_cm is None else rad_cm))))
         self.n_pts = 0
         self._tmp = tempfile.TemporaryDirectory(prefix="hpe_ref_")
         self._frame_no = 0

@@ -81,6 +81,35 @@ def test_fk_bit_exact(orc, omodel, R, D):
         assert np.array_equal(So, Sr) and np.array_equal(Jo, Jr)
 
 
+def test_fk_and_costs_with_other_hand_geometries(orc, D):
+    """not only the geometry of misc/hgeo.dat / rad.dat: random segment lengths, palm spacings, CMC angles and
+    radii (the spacing goes through the reference's `float` member, src/fingermodel.h:43)"""
+    import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    rng = np.random.default_rng(15)
+    for trial in range(6):
+        geo = D.HGEO_CM * rng.uniform(0.7, 1.3, size=20)
+        spacing = D.SPACING + rng.normal(size=5) * 0.3
+        cmc = D.CMC + rng.normal(size=5) * 8.0
+        rad = D.RAD_CM * rng.uniform(0.8, 1.2, size=48)
+        om = orc.make_model(geo_cm=geo, spacing=spacing, cmc=cmc, rad_cm=rad)
+        Rg = ref.Reference(threads=1, geo_cm=geo, spacing=spacing, cmc=cmc, rad_cm=rad)
+        truth = np.clip(D.X0 + rng.normal(size=26) * D.STD * 0.5, D.LB, D.UB)
+        depth = orc.render_depth(om, truth)
+        oo = orc.Observation(depth)
+        Rg.load_depth(depth)
+        for k in range(40):
+            th = truth + rng.normal(size=26) * D.STD * (0.2 if k % 2 else 1.5)
+            So, Jo = orc.fk(om, th)
+            Sr, Jr = Rg.fk(th)
+            assert np.array_equal(So, Sr) and np.array_equal(Jo, Jr), (trial, k)
+            tot, terms, _ = orc.cal_cost2(om, oo, th)
+            t, _ = Rg.cost_terms(th)
+            assert np.array_equal(terms, t), (trial, k)
+        Rg.close()
+
+
 def test_observation_bit_exact(orc, omodel, R, D):
     """load_data + depth_to_ptncloud + dist_transform through next_frame, three frames in a row
     (the frame is swapped under the live costfunc like src/testmodel.cpp:124)"""
