@@ -48,7 +48,7 @@ static __device__ unsigned long long g_hpe_fallback_points;
 #define HPE_SWEEP_STAGED 1
 #endif
 #ifndef HPE_PACKED_INDEX
-#define HPE_PACKED_INDEX 0   // 1: block index packed in the minimum's low mantissa bits (measured: no gain)
+#define HPE_PACKED_INDEX 1   // 1: block index packed in the low mantissa bits of the block minimum (+1.4 % with the packed sweeps)
 #endif
 #ifndef HPE_FFMA2
 #define HPE_FFMA2 1          // 1: sweeps on packed fma.rn.f32x2 (two spheres per instruction, conflict-free operand fetch)
