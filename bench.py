@@ -502,6 +502,11 @@ def main():
 
     if rank == 0:
         flop = flops_per_eval(args.npts)
+        hbm_peak = 6543.4
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
         achieved = flop * N_POSES / (ms_step * 1e-3) * 1e-12
         traffic = None
         prof = os.path.join(ROOT, "profiles", "cost_kernel_dram_bytes.json")
@@ -522,7 +527,15 @@ def main():
                              "frac": achieved / peak_tf, "traffic": traffic,
                              "peak_source": "hpe_measure_fp32_peak: register-only FFMA kernel on this device "
                                             "(MEASURED_PEAKS.json has no FP32 non-tensor figure)",
-                             "flop_per_eval": flop, "kernel": "cost_kernel<false>", "kernel_ms": ms_step},
+                             "flop_per_eval": flop, "kernel": "cost_kernel<false>", "kernel_ms": ms_step,
+                             # the contract's bounds are "hbm" | "tensor"; this kernel is neither (a min over spheres
+                             # of FP32 distances: no contraction for the tensor cores, 232 B of HBM traffic per
+                             # 102 kflop evaluation), so the FP32 (non-tensor) pipe is the bound reported above and
+                             # the HBM view is given for completeness
+                             "hbm_view": {"bound": "hbm", "achieved": (N_POSES * (26 * 8 + 3 * 8)) / (ms_step * 1e-3) / 1e9,
+                                          "peak": hbm_peak, "unit": "GB/s",
+                                          "frac": (N_POSES * (26 * 8 + 3 * 8)) / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                                          "algorithmic_bytes_per_launch": N_POSES * (26 * 8 + 3 * 8)}},
                 "extras": extras}
         if world == 1:
             line["cpu_baseline"], _ = cpu_baseline(args.npts)
