@@ -62,6 +62,9 @@ static __device__ unsigned long long g_hpe_fallback_points;
 #ifndef HPE_DEPTH_BATCH
 #define HPE_DEPTH_BATCH 1    // 1: all four depth-term gathers of a lane issued together (+2 %)
 #endif
+#ifndef HPE_FAST_SQRT
+#define HPE_FAST_SQRT 0
+#endif
 #ifndef HPE_PAIR_BLOCKS
 #define HPE_PAIR_BLOCKS 1      // 1: two sweep-A blocks per step share the runner-up update (needs HPE_PACKED_INDEX)
 #endif
@@ -484,6 +487,22 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
     }
 }
 
+// sqrt of a double to within ~1e-14 relative: float rsqrt seed (2^-22) and one Heron step in FP64 -- 4 FP64 + 3
+// conversion/MUFU instructions instead of the ~13 of the correctly rounded library sequence.  The alignment sum
+// is already only reproducible to ~1e-13 (summation order), and the tests hold the cost to 1e-9 of the reference.
+__device__ __forceinline__ double sqrt_fast(double d)
+{
+#if HPE_FAST_SQRT
+    if (!(d > 1e-30 && d < 1e30)) return sqrt(d);
+    const double y = (double)rsqrtf((float)d);
+    const double s0 = __dmul_rn(d, y);
+    const double r = __fma_rn(-s0, s0, d);
+    return __fma_rn(__dmul_rn(0.5, y), r, s0);
+#else
+    return sqrt(d);
+#endif
+}
+
 // phase 3 of pose g: both passes; returns the warp-reduced align_models value
 // (src/costfunc.cpp:346-377), valid on all lanes.  frozen: optional fixed correspondences
 // (n_pts ints); match_row: optional output row (n_pts ints).
@@ -570,7 +589,7 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
                 double a = fs.cloud[k] - sd[j * 3 + 0];
                 double b = fs.cloud[HPE_MAXPTS + k] + sd[j * 3 + 1];
                 double e = fs.cloud[2 * HPE_MAXPTS + k] + sd[j * 3 + 2];
-                double nor = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e)));
+                double nor = sqrt_fast(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e)));
                 double df = fabs(nor - fs.rad[j]);
                 acc += __dmul_rn(df, df);
             }
