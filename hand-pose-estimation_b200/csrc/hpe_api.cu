@@ -403,8 +403,9 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
     HPE_CUDA(cudaEventRecord(ready, 0));          // prior default-stream work (frozen copy, observation kernels)
     HPE_CUDA(cudaStreamWaitEvent(pipe[0], ready, 0));
     HPE_CUDA(cudaStreamWaitEvent(pipe[1], ready, 0));
-    // upload schedule: chunks of 16,384 poses (3.4 MB copies run at the full PCIe rate; every extra copy costs
-    // ~20 us of fixed overhead on this platform, so the default path keeps them uniform).  The chase path ends
+    // upload schedule: chunks of ~16,384 poses (3.4 MB copies run at the full PCIe rate; every extra copy costs
+    // ~20 us of fixed overhead on this platform and other sizes were measured slower -- 4 x 18,432 + 10,240 poses:
+    // -8 % -- so the default path keeps them uniform).  The chase path ends
     // with halving chunks so that little is left to score when the last one lands.  hpe_set_cost_pipeline can fix
     // the chunk size.
     ChaseChunks cks;

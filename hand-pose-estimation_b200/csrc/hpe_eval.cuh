@@ -15,20 +15,27 @@
 // The nearest-centre search (compute_correspondences, src/costfunc.cpp:306-343) must return the
 // index cv::BFMatcher returns: first minimum over j of sqrtf(d_j), d_j = ((t0^2 + t1^2) + t2^2) in
 // float32, t = p - c_j.  Doing that directly costs 8 FP32-pipe + 5 ALU-pipe instructions per
-// (point, sphere) pair.  match_pass() gets the same index with ~5.5:
-//   sweep A  s_j = |c'_j|^2 - 2 p'.c'_j (3 FFMA, coordinates recentred on the cloud centroid q) for
-//            all 48 spheres, reduced to the minimum per block of 4 spheres, keeping the best
-//            block, its value M1 and the runner-up block value M2;
-//   sweep B  the 4 spheres of the best block once more (same FFMAs, bit-identical s): winner index
-//            and the runner-up r inside the block;
+// (point, sphere) pair.  match_pass() gets the same index with ~3:
+//   sweep A  s_j = |c'_j|^2 - 2 p'.c'_j (3 FMAs, coordinates recentred on the cloud centroid q) for
+//            all 48 spheres, issued as packed fma.rn.f32x2 on sphere PAIRS (the same IEEE fma in each
+//            half; 64-bit operands are fetched without the register-bank conflicts that make the scalar
+//            three-register FFMAs of this loop average 1.5 issue cycles), reduced to the minimum per block
+//            of 4 spheres, keeping the best block's value M1 and the runner-up block value M2.  The block
+//            index rides in the 4 low mantissa bits of the block minimum (no compare + select; a
+//            perturbation below 16 ulp) and two blocks per step share the runner-up update;
+//   sweep B  the 4 spheres of the best block once more (same FMAs, bit-identical s): winner index,
+//            the exact block minimum m1 and the runner-up r inside the block;
 //   certify  s_j + |p'|^2 equals the exact squared distance D_j up to E_j <= u(104|p'|^2 + 13|s_j|),
-//            u = 2^-24 (forward error of the 3 FFMAs plus the rounding of p', -2c', |c'|^2), and the
+//            u = 2^-24 (forward error of the 3 FMAs plus the rounding of p', -2c', |c'|^2), and the
 //            reference's d_j / sqrtf(d_j) order two spheres like D_j once D differs by more than 24u D
-//            (ties and sqrtf merges need smaller differences).  Hence if
-//            min(M2, r) - M1 > tau = u(260|p'|^2 + 52|M1|) EVERY other sphere is provably farther in
-//            the reference's own arithmetic and the winner is the reference's answer;
-//   fallback otherwise (2-5 points in 10,000) the point is redone with the exact restatement of the
+//            (ties and sqrtf merges need smaller differences); M2 carries an index in its low bits,
+//            |M2 - true| < 32u|M2|.  Hence if min(M2, r) - m1 > tau = u(260|p'|^2 + 116|m1|) EVERY
+//            other sphere is provably farther in the reference's own arithmetic and the winner is the
+//            reference's answer;
+//   fallback otherwise (5-6 points in 10,000) the point is redone with the exact restatement of the
 //            reference's arithmetic over all 48 spheres, the whole warp on one point.
+// Compile-time switches kept for cross-checks and measurements: HPE_FFMA2=0 (scalar FFMA sweeps),
+// HPE_PACKED_INDEX=0 (compare + select for the best block), HPE_PAIR_BLOCKS=0.
 #pragma once
 #include "hpe_device.cuh"
 
@@ -52,18 +59,6 @@ static __device__ unsigned long long g_hpe_fallback_points;
 #endif
 #ifndef HPE_FFMA2
 #define HPE_FFMA2 1          // 1: sweeps on packed fma.rn.f32x2 (two spheres per instruction, conflict-free operand fetch)
-#endif
-#ifndef HPE_ALIGN8
-#define HPE_ALIGN8 0         // 1: alignment of the lane's 8 points after both matching passes (measured slower)
-#endif
-#ifndef HPE_ALIGN_BF
-#define HPE_ALIGN_BF 0       // 1: branch-free alignment chains inside a pass
-#endif
-#ifndef HPE_DEPTH_BATCH
-#define HPE_DEPTH_BATCH 1    // 1: all four depth-term gathers of a lane issued together (+2 %)
-#endif
-#ifndef HPE_FAST_SQRT
-#define HPE_FAST_SQRT 0
 #endif
 #ifndef HPE_PAIR_BLOCKS
 #define HPE_PAIR_BLOCKS 1      // 1: two sweep-A blocks per step share the runner-up update (needs HPE_PACKED_INDEX)
@@ -487,22 +482,6 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
     }
 }
 
-// sqrt of a double to within ~1e-14 relative: float rsqrt seed (2^-22) and one Heron step in FP64 -- 4 FP64 + 3
-// conversion/MUFU instructions instead of the ~13 of the correctly rounded library sequence.  The alignment sum
-// is already only reproducible to ~1e-13 (summation order), and the tests hold the cost to 1e-9 of the reference.
-__device__ __forceinline__ double sqrt_fast(double d)
-{
-#if HPE_FAST_SQRT
-    if (!(d > 1e-30 && d < 1e30)) return sqrt(d);
-    const double y = (double)rsqrtf((float)d);
-    const double s0 = __dmul_rn(d, y);
-    const double r = __fma_rn(-s0, s0, d);
-    return __fma_rn(__dmul_rn(0.5, y), r, s0);
-#else
-    return sqrt(d);
-#endif
-}
-
 // phase 3 of pose g: both passes; returns the warp-reduced align_models value
 // (src/costfunc.cpp:346-377), valid on all lanes.  frozen: optional fixed correspondences
 // (n_pts ints); match_row: optional output row (n_pts ints).
@@ -510,46 +489,6 @@ template <int MATCHER>
 __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScratch &ws, int g, int lane,
                                               const int32_t *frozen, int32_t *match_row)
 {
-#if HPE_ALIGN8
-    const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
-    const int n_pts = fs.n_pts;
-    constexpr int NPASS = HPE_PPL / HPE_PASS;
-    int idx[NPASS][HPE_PASS];
-#pragma unroll
-    for (int pass = 0; pass < NPASS; ++pass) {
-        const int k0 = lane + 32 * HPE_PASS * pass;
-        if (frozen) {
-#pragma unroll
-            for (int m = 0; m < HPE_PASS; ++m) idx[pass][m] = k0 + 32 * m < n_pts ? frozen[k0 + 32 * m] : 0;
-        } else if (MATCHER == 1) {
-            match_pass_direct(fs, ws, k0, lane, idx[pass]);
-        } else {
-            match_pass(fs, ws, k0, lane, idx[pass]);
-        }
-    }
-    // align_models for the lane's 8 points, FP64, the reference's operation order; the eight distance chains
-    // (each ends in a double-precision square root) are independent and branch-free, the sum keeps the order
-    // point 0..7 of the lane
-    double acc = 0.0;
-#pragma unroll
-    for (int pass = 0; pass < NPASS; ++pass) {
-#pragma unroll
-        for (int m = 0; m < HPE_PASS; ++m) {
-            const int k = lane + 32 * (HPE_PASS * pass + m);
-            const bool valid = k < n_pts;
-            const int kk = valid ? k : 0;
-            const int j = idx[pass][m];
-            if (match_row && valid) match_row[k] = j;
-            // negated-frame centre = (cx, -cy, -cz)
-            double a = fs.cloud[kk] - sd[j * 3 + 0];
-            double b = fs.cloud[HPE_MAXPTS + kk] + sd[j * 3 + 1];
-            double e = fs.cloud[2 * HPE_MAXPTS + kk] + sd[j * 3 + 2];
-            double nor = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e)));
-            double df = fabs(nor - fs.rad[j]);
-            acc += valid ? __dmul_rn(df, df) : 0.0;
-        }
-    }
-#else
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
     const int n_pts = fs.n_pts;
     double acc = 0.0;
@@ -569,19 +508,6 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
 #pragma unroll
         for (int m = 0; m < HPE_PASS; ++m) {
             int k = k0 + 32 * m;
-#if HPE_ALIGN_BF
-            // branch-free: the padded slots (k >= n_pts) run the same chain on point 0 and contribute +0.0
-            const bool valid = k < n_pts;
-            const int kk = valid ? k : 0;
-            const int j = idx[m];
-            if (match_row && valid) match_row[k] = j;
-            double a = fs.cloud[kk] - sd[j * 3 + 0];
-            double b = fs.cloud[HPE_MAXPTS + kk] + sd[j * 3 + 1];
-            double e = fs.cloud[2 * HPE_MAXPTS + kk] + sd[j * 3 + 2];
-            double nor = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e)));
-            double df = fabs(nor - fs.rad[j]);
-            acc += valid ? __dmul_rn(df, df) : 0.0;
-#else
             if (k < n_pts) {
                 int j = idx[m];
                 if (match_row) match_row[k] = j;
@@ -589,14 +515,12 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
                 double a = fs.cloud[k] - sd[j * 3 + 0];
                 double b = fs.cloud[HPE_MAXPTS + k] + sd[j * 3 + 1];
                 double e = fs.cloud[2 * HPE_MAXPTS + k] + sd[j * 3 + 2];
-                double nor = sqrt_fast(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e)));
+                double nor = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e)));
                 double df = fabs(nor - fs.rad[j]);
                 acc += __dmul_rn(df, df);
             }
-#endif
         }
     }
-#endif
     return __dmul_rn(warp_sum(acc), fs.lambda);
 }
 
@@ -645,7 +569,6 @@ __device__ __forceinline__ void group_fk(const DevModel &M, ThetaAt theta, int n
 // stage the pose's float32 centres (cf) and sweep-A operands (ex).  Result valid on all lanes.
 __device__ __forceinline__ double depth_and_stage(const FrameSmem &fs, const WarpScratch &ws, int g, int lane)
 {
-#if HPE_DEPTH_BATCH
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
     __syncwarp();      // previous pose's matcher is done with cf/ex
     // depth_penalty (src/costfunc.cpp:251-300) for the lane's spheres j = lane and lane + 32.  Both spheres'
@@ -703,32 +626,6 @@ __device__ __forceinline__ double depth_and_stage(const FrameSmem &fs, const War
 #endif
         }
     }
-#else
-    const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
-    double dv = 0.0;
-    __syncwarp();      // previous pose's matcher is done with cf/ex
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        int j = lane + 32 * h;
-        if (j < HPE_NSPH) {
-            double x = sd[j * 3], y = sd[j * 3 + 1], z = sd[j * 3 + 2];
-            dv += depth_term(fs, x, y, z, fs.rad[j]);
-            float4 c = make_float4((float)x, (float)(-y), (float)(-z), 0.f);   // conv_to<fmat>, negated frame
-            // c' = cf - q exactly (FP64), then one rounding each for -2c' and |c'|^2
-            double cx = (double)c.x - (double)fs.qx, cy = (double)c.y - (double)fs.qy, cz = (double)c.z - (double)fs.qz;
-            ws.cf[j] = c;
-            const float4 e = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz),
-                                         (float)(cx * cx + cy * cy + cz * cz));
-#if HPE_FFMA2
-            // spheres 4g+2q and 4g+2q+1 share 64-bit words: block g = | x01 y01 | z01 w01 | x23 y23 | z23 w23 | pad |
-            float *fb = reinterpret_cast<float *>(ws.ex + (j / HPE_BLK) * HPE_EX_PITCH) + ((j % HPE_BLK) / 2) * 8 + (j & 1);
-            fb[0] = e.x; fb[2] = e.y; fb[4] = e.z; fb[6] = e.w;
-#else
-            ws.ex[HPE_EX_AT(j)] = e;
-#endif
-        }
-    }
-#endif
     __syncwarp();
     return warp_sum(dv);
 }

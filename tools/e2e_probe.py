@@ -19,7 +19,7 @@ def step(i):
     rc = lib.hpe_cost_batch(hand._h, obs._h, 0, C.c_void_p(th[i % sets].data_ptr()), C.c_int64(N),
                             C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()), None)
     assert rc == 0, lib.hpe_last_error_string()
-for mode, chunk in ((0, 0), (1, 0), (1, 4096), (1, 8192), (1, 16384), (1, 32768), (1, 65536)):
+for mode, chunk in ((0, 0), (0, 16384), (0, 0), (0, 16384), (1, 0), (1, 16384)):
     hpe_b200.set_cost_pipeline(mode, chunk)
     for i in range(5): step(i)
     torch.cuda.synchronize()
