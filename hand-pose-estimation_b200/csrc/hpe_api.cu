@@ -213,6 +213,22 @@ int hpe_fk_batch(const hpe_model *m, const double *theta, int64_t n, double *sph
     return HPE_OK;
 }
 
+// diagnostics: cycles of one evaluation by one warp on an idle SM: FK | depth term + staging | matching + alignment
+int hpe_debug_eval_latency(const hpe_model *m, const hpe_obs *o, int slot, const double theta[HPE_NDOF], long long cycles[3])
+{
+    if (!m || !theta || !cycles) return hpe_set_error(HPE_ERR_ARG, "hpe_debug_eval_latency: bad argument");
+    if (int rc = check_slot(o, slot, 1)) return rc;
+    if (int rc = check_filled(o, slot, 1)) return rc;
+    HPE_CUDA(g_ws.reserve(1024));
+    double *d_th = (double *)g_ws.p;
+    long long *d_cy = (long long *)((char *)g_ws.p + 512);
+    double *d_c = (double *)((char *)g_ws.p + 768);
+    HPE_CUDA(cudaMemcpy(d_th, theta, sizeof(double) * HPE_NDOF, cudaMemcpyHostToDevice));
+    HPE_CUDA(hpe_launch_eval_latency(m->dm, o->v, slot, d_th, 50, d_cy, d_c, 0));
+    HPE_CUDA(cudaMemcpy(cycles, d_cy, sizeof(long long) * 3, cudaMemcpyDeviceToHost));
+    return HPE_OK;
+}
+
 // costfunc::gnd_truth_err for n (pose, joint.txt row) pairs
 int hpe_gnd_truth_err(const hpe_model *m, const double *theta, const double *gt_mm, int64_t n, double *err)
 {

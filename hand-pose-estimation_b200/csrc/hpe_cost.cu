@@ -254,6 +254,7 @@ __device__ __forceinline__ unsigned long long run_cost_bits(double c)
     return c == c ? (unsigned long long)__double_as_longlong(c) : 0xfff8000000000000ull;
 }
 
+template <bool WARP1>     // WARP1: at most one particle per warp (small shards): whole-warp forward kinematics
 __global__ void __launch_bounds__(COST_WARPS * 32, HPE_MINBLOCKS)
 swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
 {
@@ -351,7 +352,7 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
                 }
                 __syncwarp();
             }
-            group_fk(sm.fs.M, [&](int gq) { return a.x + (p0 + gq) * D; }, cnt, ws, lane);
+            group_fk<false, WARP1>(sm.fs.M, [&](int gq) { return a.x + (p0 + gq) * D; }, cnt, ws, lane);
             for (int gq = 0; gq < cnt; ++gq) {
                 double depth = depth_and_stage(sm.fs, ws, gq, lane);
                 double align = match_align<0>(sm.fs, ws, gq, lane, nullptr, nullptr);
@@ -537,6 +538,34 @@ __global__ void gt_err_kernel(const double *__restrict__ joints, const double *_
     err[i] = __dadd_rn(__dadd_rn(__dadd_rn(d[0], d[2]), d[4]), __dadd_rn(__dadd_rn(d[1], d[3]), d[5]));
 }
 
+// ---------------------------------------------------------------------------------------
+// diagnostics: latency of ONE evaluation by ONE warp on an otherwise idle SM, per phase (clock64)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) eval_latency_kernel(DevModel m, ObsView o, int slot, const double *theta, int reps,
+                                                          long long *cycles, double *cost)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    stage_model(sm.fs, m);
+    stage_frame(sm.fs, frame_view(o, slot));
+    const WarpScratch ws = warp_scratch(sm.ws, 0, HPE_GROUP);
+    long long t_fk = 0, t_depth = 0, t_match = 0;
+    double acc = 0.0;
+    for (int r = 0; r < reps; ++r) {
+        long long t0 = clock64();
+        group_fk<false, true>(sm.fs.M, [&](int) { return theta; }, 1, ws, lane);
+        long long t1 = clock64();
+        double depth = depth_and_stage(sm.fs, ws, 0, lane);
+        long long t2 = clock64();
+        double align = match_align<0>(sm.fs, ws, 0, lane, nullptr, nullptr);
+        long long t3 = clock64();
+        acc += align + depth;
+        t_fk += t1 - t0; t_depth += t2 - t1; t_match += t3 - t2;
+    }
+    if (lane == 0) { cycles[0] = t_fk / reps; cycles[1] = t_depth / reps; cycles[2] = t_match / reps; *cost = acc / reps; }
+}
+
 }  // namespace
 
 HPE_DEFINE_FALLBACK_GETTER(hpe_fallbacks_cost)
@@ -574,6 +603,14 @@ cudaError_t hpe_launch_cost_chase(const DevModel &m, const ObsView &o, int slot,
     else
         cost_chase_kernel<false><<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, terms_dev, terms_stride,
                                                                                      frozen_dev, match_out_dev, arrived_dev, chunks, timeout_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t hpe_launch_eval_latency(const DevModel &m, const ObsView &o, int slot, const double *theta_dev, int reps,
+                                    long long *cycles_dev, double *cost_dev, cudaStream_t st)
+{
+    cudaFuncSetAttribute(eval_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
+    eval_latency_kernel<<<1, 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, reps, cycles_dev, cost_dev);
     return cudaGetLastError();
 }
 
@@ -646,8 +683,12 @@ cudaError_t hpe_launch_swarm_run(const DevModel &m, const ObsView &o, int slot, 
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(swarm_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, swarm_run_kernel, COST_WARPS * 32, sizeof(CostSmem));
+        cudaFuncSetAttribute(swarm_run_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
+        cudaFuncSetAttribute(swarm_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
+        int p0 = 0, p1 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p0, swarm_run_kernel<false>, COST_WARPS * 32, sizeof(CostSmem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p1, swarm_run_kernel<true>, COST_WARPS * 32, sizeof(CostSmem));
+        per_sm = p0 < p1 ? p0 : p1;
         if (per_sm > HPE_MINBLOCKS) per_sm = HPE_MINBLOCKS;
         if (per_sm < 1) per_sm = 1;
     }
@@ -656,11 +697,13 @@ cudaError_t hpe_launch_swarm_run(const DevModel &m, const ObsView &o, int slot, 
     int64_t want = (own + COST_WARPS - 1) / COST_WARPS;                 // one particle per warp is enough
     int blocks = (int)(want < (int64_t)per_sm * sms ? want : (int64_t)per_sm * sms);
     if (blocks < sms) blocks = sms;                                     // the scatter / reset phases want the whole chip
+    const bool warp1 = own <= (int64_t)blocks * COST_WARPS;             // no warp gets more than one particle
     DevModel mm = m;
     ObsView oo = o;
     SwarmRunArgs aa = a;
     void *args[] = {&mm, &oo, &slot, &aa};
-    return cudaLaunchCooperativeKernel((void *)swarm_run_kernel, dim3(blocks), dim3(COST_WARPS * 32), args, sizeof(CostSmem), st);
+    return cudaLaunchCooperativeKernel(warp1 ? (void *)swarm_run_kernel<true> : (void *)swarm_run_kernel<false>, dim3(blocks),
+                                       dim3(COST_WARPS * 32), args, sizeof(CostSmem), st);
 }
 
 cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_t n, double focal,

@@ -66,13 +66,22 @@ __device__ __forceinline__ void aff_planar(Aff &a, double c, double s, double L)
     a.tx += L * n00; a.ty += L * n10; a.tz += L * n20;
 }
 
-// Global pose T00 * Rz(t0+180) * Ry(t1) * Rx(t2)  (src/fingermodel.cpp:157-180, :289)
-__device__ __forceinline__ void aff_global(Aff &g, const double th[6])
+// sines and cosines a digit needs: sc[0..2] = global rotation about z (angle + 180 deg), y, x; sc[3..6] = its
+// four joint angles; [k][0] = sin, [k][1] = cos
+struct DigitTrig {
+    double s[7], c[7];
+};
+
+// the angle (degrees) whose sine / cosine is DigitTrig entry k of digit d
+__device__ __forceinline__ double trig_angle_deg(const double *th, int d, int k)
 {
-    double sz, cz, sy, cy, sx, cx;
-    sincos(hpe_deg2rad(th[0] + 180.0), &sz, &cz);
-    sincos(hpe_deg2rad(th[1]), &sy, &cy);
-    sincos(hpe_deg2rad(th[2]), &sx, &cx);
+    return k == 0 ? th[0] + 180.0 : k < 3 ? th[k] : th[6 + 4 * d + (k - 3)];
+}
+
+// Global pose T00 * Rz(t0+180) * Ry(t1) * Rx(t2)  (src/fingermodel.cpp:157-180, :289)
+__device__ __forceinline__ void aff_global(Aff &g, const double pos[3], const DigitTrig &t)
+{
+    const double sz = t.s[0], cz = t.c[0], sy = t.s[1], cy = t.c[1], sx = t.s[2], cx = t.c[2];
     // Rz*Ry = [[cz cy, -sz, cz sy],[sz cy, cz, sz sy],[-sy, 0, cy]]
     double a00 = cz * cy, a01 = -sz, a02 = cz * sy;
     double a10 = sz * cy, a11 = cz, a12 = sz * sy;
@@ -81,16 +90,16 @@ __device__ __forceinline__ void aff_global(Aff &g, const double th[6])
     g.r00 = a00; g.r01 = a01 * cx + a02 * sx; g.r02 = a02 * cx - a01 * sx;
     g.r10 = a10; g.r11 = a11 * cx + a12 * sx; g.r12 = a12 * cx - a11 * sx;
     g.r20 = a20; g.r21 = a22 * sx;            g.r22 = a22 * cx;
-    g.tx = th[3]; g.ty = th[4]; g.tz = th[5];
+    g.tx = pos[0]; g.ty = pos[1]; g.tz = pos[2];
 }
 
-// joints J[0..4] of digit d (0 = thumb) from the six global parameters g6 = theta[0:6] and the digit's four
-// joint angles ang = theta[6+4d : 10+4d]
-__device__ __forceinline__ void fk_digit_vals(const DevModel &M, int d, const double g6[6], const double ang[4],
+// joints J[0..4] of digit d (0 = thumb) from the global position pos = theta[3:6] and the sines / cosines of
+// the three global angles and the digit's four joint angles
+__device__ __forceinline__ void fk_digit_trig(const DevModel &M, int d, const double pos[3], const DigitTrig &t,
                                               double J[5][3])
 {
     Aff cur;
-    aff_global(cur, g6);
+    aff_global(cur, pos, t);
     // cur <- cur * base[d]   (general 3x4 product; base has r[2][*] = (0,0,1), t.z = 0)
     {
         const double *b = M.base[d];
@@ -111,9 +120,7 @@ __device__ __forceinline__ void fk_digit_vals(const DevModel &M, int d, const do
         J[0][2] = cur.r20 * bx + cur.r21 * by + cur.tz;
     }
     const double *L = M.geo + 4 * d;
-    double s1, c1, s2, c2;
-    sincos(hpe_deg2rad(ang[0]), &s1, &c1);
-    sincos(hpe_deg2rad(ang[1]), &s2, &c2);
+    const double s1 = t.s[3], c1 = t.c[3], s2 = t.s[4], c2 = t.c[4];
     double cp = d == 0 ? M.tc : 1.0, sp = d == 0 ? M.ts : 0.0;
     {   // S = twist(a0) * X(a1), X = [[c2,-s2 cp, s2 sp, L c2],[s2, c2 cp, -c2 sp, L s2],[0, sp, cp, 0]]
         double x00 = c2, x01 = -s2 * cp, x02 = s2 * sp, x03 = L[1] * c2;
@@ -139,9 +146,7 @@ __device__ __forceinline__ void fk_digit_vals(const DevModel &M, int d, const do
         cur = n;
     }
     J[2][0] = cur.tx; J[2][1] = cur.ty; J[2][2] = cur.tz;
-    double s3, c3, s4, c4;
-    sincos(hpe_deg2rad(ang[2]), &s3, &c3);
-    sincos(hpe_deg2rad(ang[3]), &s4, &c4);
+    const double s3 = t.s[5], c3 = t.c[5], s4 = t.s[6], c4 = t.c[6];
     aff_planar(cur, c3, s3, L[2]);
     J[3][0] = cur.tx; J[3][1] = cur.ty; J[3][2] = cur.tz;
     // last link: only the translation is needed
@@ -150,27 +155,58 @@ __device__ __forceinline__ void fk_digit_vals(const DevModel &M, int d, const do
     J[4][2] = cur.tz + L[3] * (cur.r20 * c4 + cur.r21 * s4);
 }
 
-// joints J[0..4] of digit d (0 = thumb) for pose th[26]
+// joints J[0..4] of digit d (0 = thumb) for pose th[26]: the lane computes its seven sincos itself
 __device__ __forceinline__ void fk_digit(const DevModel &M, int d, const double *th, double J[5][3])
 {
-    double g6[6], a4[4];
+    DigitTrig t;
+    double pos[3] = {th[3], th[4], th[5]};
 #pragma unroll
-    for (int i = 0; i < 6; ++i) g6[i] = th[i];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) a4[k] = th[6 + 4 * d + k];
-    fk_digit_vals(M, d, g6, a4, J);
+    for (int k = 0; k < 7; ++k) sincos(hpe_deg2rad(trig_angle_deg(th, d, k)), &t.s[k], &t.c[k]);
+    fk_digit_trig(M, d, pos, t, J);
 }
 
 // the same for a pose that may have been written while this kernel runs (chunks landing by DMA under a
 // persistent kernel): loads go to L2 (ld.global.cg), never through the non-coherent path
 __device__ __forceinline__ void fk_digit_cg(const DevModel &M, int d, const double *th, double J[5][3])
 {
-    double g6[6], a4[4];
+    double loc[10];                                  // theta[0:6] and the digit's four angles
 #pragma unroll
-    for (int i = 0; i < 6; ++i) g6[i] = __ldcg(th + i);
+    for (int i = 0; i < 6; ++i) loc[i] = __ldcg(th + i);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) a4[k] = __ldcg(th + 6 + 4 * d + k);
-    fk_digit_vals(M, d, g6, a4, J);
+    for (int k = 0; k < 4; ++k) loc[6 + k] = __ldcg(th + 6 + 4 * d + k);
+    DigitTrig t;
+    double pos[3] = {loc[3], loc[4], loc[5]};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const double deg = k == 0 ? loc[0] + 180.0 : k < 3 ? loc[k] : loc[6 + (k - 3)];
+        sincos(hpe_deg2rad(deg), &t.s[k], &t.c[k]);
+    }
+    fk_digit_trig(M, d, pos, t, J);
+}
+
+// One pose evaluated by a whole warp (the one-particle-per-warp latency paths): the 23 distinct sincos of the
+// pose are computed by 23 lanes at once -- lane l < 3: global angle l; lane 3 + 4d + k: joint k of digit d --
+// and handed to the five digit lanes by shuffles: one sincos latency instead of seven in a row.  Same values
+// (sincos of the same argument), same chain arithmetic, so the result is bit-identical to fk_digit.
+__device__ __forceinline__ void fk_digit_warp(const DevModel &M, const double *th, int lane, double J[5][3])
+{
+    double sn = 0.0, cs = 0.0;
+    if (lane < 23) {
+        const double deg = lane == 0 ? th[0] + 180.0 : lane < 3 ? th[lane] : th[6 + (lane - 3)];
+        sincos(hpe_deg2rad(deg), &sn, &cs);
+    }
+    const int d = lane < 5 ? lane : 0;
+    DigitTrig t;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int src = k < 3 ? k : 3 + 4 * d + (k - 3);
+        t.s[k] = __shfl_sync(0xffffffffu, sn, src);
+        t.c[k] = __shfl_sync(0xffffffffu, cs, src);
+    }
+    if (lane < 5) {
+        double pos[3] = {th[3], th[4], th[5]};
+        fk_digit_trig(M, d, pos, t, J);
+    }
 }
 
 // Sphere centres of a digit from its joints (src/fingermodel.cpp:208-267,

@@ -541,11 +541,33 @@ __device__ __forceinline__ double collision_lane(const double *rad_s, const doub
 
 // phase 1 for up to HPE_GROUP poses; theta(g) returns a pointer to pose g's 26 doubles.  CG: read the
 // pose through L2 (poses that land by DMA while the kernel runs)
-template <bool CG = false, class ThetaAt>
+// WARP1: take the whole-warp path when n == 1 (only the latency-bound callers ask for it: the extra code costs
+// the throughput kernels ~4 %)
+template <bool CG = false, bool WARP1 = false, class ThetaAt>
 __device__ __forceinline__ void group_fk(const DevModel &M, ThetaAt theta, int n, const WarpScratch &ws, int lane)
 {
     int g = lane / 5, d = lane - 5 * g;
     __syncwarp();
+    if (WARP1 && n == 1) {
+        // a single pose for the whole warp (warp-uniform branch): sincos spread over 23 lanes
+        double J[5][3], S[10][3];
+        fk_digit_warp(M, theta(0), lane, J);
+        if (lane < 5) {
+            int cnt = digit_spheres(lane, J, S);
+            int first = digit_first_sphere(lane);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                if (i < cnt) {
+                    double *sd = ws.sphd + (size_t)(first + i) * 3;
+                    sd[0] = S[i][0];
+                    sd[1] = S[i][1];
+                    sd[2] = S[i][2];
+                }
+            }
+        }
+        __syncwarp();
+        return;
+    }
     if (g < n) {
         double J[5][3], S[10][3];
         if (CG) fk_digit_cg(M, d, theta(g), J);

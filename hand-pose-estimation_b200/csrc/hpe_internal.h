@@ -136,6 +136,8 @@ cudaError_t hpe_launch_cost_chase(const DevModel &m, const ObsView &o, int slot,
                                   bool with_colli, double *terms_dev, int64_t terms_stride, const int32_t *frozen_dev,
                                   int32_t *match_out_dev, const unsigned *arrived_dev, const ChaseChunks &chunks, int *timeout_dev,
                                   cudaStream_t st);
+cudaError_t hpe_launch_eval_latency(const DevModel &m, const ObsView &o, int slot, const double *theta_dev, int reps,
+                                    long long *cycles_dev, double *cost_dev, cudaStream_t st);
 cudaError_t hpe_launch_gt_err(const double *joints_dev, const double *gt_dev, int64_t n, double *err_dev, cudaStream_t st);
 cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *scratch, cudaStream_t st);
 cudaError_t hpe_launch_dtmax(const ObsView &o, int slot, cudaStream_t st);

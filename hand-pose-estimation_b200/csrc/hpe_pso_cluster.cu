@@ -101,7 +101,7 @@ pso_cluster_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__
         for (int iter = 1;; ++iter) {
             // ---- evaluate: one particle per warp and round (src/PSO.cpp:748-752, 848-852) ----
             for (int i = cwarp; i < num_p; i += CL_SIZE * CL_WARPS) {
-                group_fk(sm.fs.M, [&](int) { return x + (size_t)i * D; }, 1, ws, lane);
+                group_fk<false, true>(sm.fs.M, [&](int) { return x + (size_t)i * D; }, 1, ws, lane);
                 double depth = depth_and_stage(sm.fs, ws, 0, lane);
                 double align = match_align<0>(sm.fs, ws, 0, lane, nullptr, nullptr);
                 if (lane == 0) fx[i] = align + depth;

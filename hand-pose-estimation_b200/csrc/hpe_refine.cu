@@ -39,7 +39,7 @@ struct __align__(16) RefineSmem {
 __device__ __forceinline__ double eval_cost2(RefineSmem &sm, const WarpScratch &ws, const double *theta, int lane,
                                              const int32_t *frozen, int32_t *match_out)
 {
-    group_fk(sm.fs.M, [&](int) { return theta; }, 1, ws, lane);
+    group_fk<false, true>(sm.fs.M, [&](int) { return theta; }, 1, ws, lane);
     double depth = depth_and_stage(sm.fs, ws, 0, lane);
     double align = match_align<0>(sm.fs, ws, 0, lane, frozen, match_out);
     double colli = warp_sum(collision_lane(sm.fs.rad, ws.sphd, lane));

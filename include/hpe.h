@@ -224,6 +224,10 @@ int hpe_set_pso_path(int mode);
  * the in-row recurrence as a prefix-minimum scan; 1 = closed-form row search; 2 = the two passes as a skewed
  * wavefront.  Bit-identical results; 1 and 2 exist to cross-check 0. */
 int hpe_set_chamfer(int mode);
+/* cycles of ONE evaluation by ONE warp on an otherwise idle SM, per phase: forward kinematics | depth term +
+ * staging | matching + alignment (the latency that bounds the one-particle-per-warp paths) */
+int hpe_debug_eval_latency(const hpe_model *m, const hpe_obs *o, int slot, const double theta[HPE_NDOF],
+                           long long cycles[3]);
 /* number of points the certified search handed to its exact fallback since the last reset */
 int hpe_debug_fallback_points(unsigned long long *count, int reset);
 
