@@ -114,8 +114,9 @@ int hpe_set_cost_pipeline(int mode, int chunk_poses)
 
 int hpe_set_pso_path(int mode)
 {
-    if (mode < 0 || mode > 2) return hpe_set_error(HPE_ERR_ARG, "pso path must be 0, 1 or 2");
-    g_hpe_pso_path = mode;
+    if (mode < 0 || mode > 3) return hpe_set_error(HPE_ERR_ARG, "pso path must be 0, 1, 2 or 3");
+    g_hpe_pso_path = mode == 3 ? 2 : mode;
+    g_hpe_cluster_dsm = mode == 3 ? 0 : 1;
     return HPE_OK;
 }
 

@@ -160,4 +160,5 @@ cudaError_t hpe_launch_swarm_run(const DevModel &m, const ObsView &o, int slot, 
 unsigned long long hpe_fallbacks_cost(int reset);
 unsigned long long hpe_fallbacks_pso(int reset);
 unsigned long long hpe_fallbacks_pso_cluster(int reset);
+extern int g_hpe_cluster_dsm; // 1 = the cluster kernel keeps the swarm state in distributed shared memory (num_p <= 128)
 extern int g_hpe_pso_path;   // hpe_set_pso_path(): 0 = automatic, 1 = one CTA per swarm, 2 = one cluster per swarm

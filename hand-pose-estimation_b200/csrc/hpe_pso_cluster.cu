@@ -216,22 +216,225 @@ pso_cluster_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// The same swarm-per-cluster scheme with the shared swarm state in DISTRIBUTED SHARED MEMORY (swarms of up to
+// CLD_MAXP particles): the warp that evaluates a particle pushes its (fx, position) row into every CTA of the
+// cluster (st.shared::cluster through map_shared_rank), so after ONE cluster barrier per generation each CTA
+// holds all rows and runs the whole bookkeeping -- pbest / pcost, first-minimum gbest, `count`, topology,
+// informants, the move of its own particles -- out of its own shared memory: no L2 round trips, no second
+// barrier.  Incoming rows are double buffered by generation parity (a CTA can be at most one barrier ahead of
+// a CTA that still reads the previous rows).  Same arithmetic and counters: bit-identical to pso_kernel.
+// ---------------------------------------------------------------------------------------
+constexpr int CLD_MAXP = 128;
+
+struct __align__(16) ClusterDsmHead {
+    FrameSmem fs;
+    double gbest[HPE_NDOF];
+    double x0[HPE_NDOF];
+    double gbest_cost;
+    int count;
+    int fmin_id;
+    int pad;
+    // followed by: warp scratch [CL_WARPS] x 1 slot; double rows[2][num_p][27] (fx, x) incoming; double pb[num_p][26];
+    //              double pcost[num_p]; int informant[num_p]; int R[num_p][3]
+};
+
+__host__ __device__ inline size_t cluster_dsm_smem_bytes(int num_p)
+{
+    return sizeof(ClusterDsmHead) + (size_t)CL_WARPS * HPE_WS_BYTES(1) +
+           (size_t)num_p * (2 * (HPE_NDOF + 1) * 8 + HPE_NDOF * 8 + 8 + 4 + CL_NK * 4) + 16;
+}
+
+__global__ void __launch_bounds__(CL_WARPS * 32, 2)
+pso_cluster_dsm_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, int first, int count_swarms,
+                       const uint64_t *__restrict__ seeds, double *__restrict__ state, double *__restrict__ bestp_out,
+                       double *__restrict__ best_cost_out, double *__restrict__ trace_out, int chain, double W1, double C1)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ClusterDsmHead &sm = *reinterpret_cast<ClusterDsmHead *>(smem_raw);
+    const int num_p = prm.num_p, D = HPE_NDOF, ROWD = HPE_NDOF + 1;
+    unsigned char *ws_base = smem_raw + sizeof(ClusterDsmHead);
+    double *rows = reinterpret_cast<double *>(ws_base + (size_t)CL_WARPS * HPE_WS_BYTES(1));     // [2][num_p][27]
+    double *pb = rows + 2 * (size_t)num_p * ROWD;                                                // [num_p][26]
+    double *pcost = pb + (size_t)num_p * D;                                                      // [num_p]
+    int *informant = reinterpret_cast<int *>(pcost + num_p);
+    int *R = informant + num_p;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    const int crank = (int)cluster.block_rank();
+    const int cluster_id = blockIdx.x / CL_SIZE, n_clusters = gridDim.x / CL_SIZE;
+    const int cwarp = crank * CL_WARPS + warp;                 // warp index inside the cluster, 0..63
+    // positions and velocities of this CTA's own particles stay in global scratch (only this CTA touches them)
+    double *x = state + (size_t)cluster_id * 2 * num_p * D;
+    double *v = x + (size_t)num_p * D;
+    const double C2 = C1;
+    const WarpScratch ws = warp_scratch(ws_base, warp, 1);
+    double *peer_rows[CL_SIZE];
+#pragma unroll
+    for (int r = 0; r < CL_SIZE; ++r) peer_rows[r] = cluster.map_shared_rank(rows, r);
+
+    stage_model(sm.fs, m);
+    __syncthreads();
+
+    for (int b = chain ? 0 : cluster_id; b < count_swarms; b += chain ? 1 : n_clusters) {
+        const int slot = first + b;
+        const uint64_t seed = seeds ? seeds[b] : 1000ull;
+        stage_frame(sm.fs, frame_view(o, slot));               // every CTA stages the frame; ends synchronised
+        if (tid < D) sm.x0[tid] = (chain && b > 0) ? sm.gbest[tid] : x0_in[(size_t)b * D + tid];
+        if (tid == 0) { sm.gbest_cost = 1e100; sm.count = 100; }
+        __syncthreads();
+        // generate_particles (src/PSO.cpp:56-74) for this CTA's own particles
+        const int rounds = (num_p + CL_SIZE * CL_WARPS - 1) / (CL_SIZE * CL_WARPS);
+        for (int it = tid; it < rounds * CL_WARPS * (D / 2); it += nthr) {
+            int li = it / (D / 2), dp = it - li * (D / 2);
+            int i = crank * CL_WARPS + (li % CL_WARPS) + (li / CL_WARPS) * CL_SIZE * CL_WARPS;
+            if (i >= num_p) continue;
+            double z[2];
+            normal2(seed, (uint32_t)dp, (uint32_t)i, 0u, z);
+            x[i * D + 2 * dp] = __dadd_rn(sm.x0[2 * dp], __dmul_rn(z[0], prm.std[2 * dp]));
+            x[i * D + 2 * dp + 1] = __dadd_rn(sm.x0[2 * dp + 1], __dmul_rn(z[1], prm.std[2 * dp + 1]));
+            v[i * D + 2 * dp] = 0.0;
+            v[i * D + 2 * dp + 1] = 0.0;
+        }
+        __syncthreads();
+
+        for (int iter = 1;; ++iter) {
+            double *in = rows + (size_t)(iter & 1) * num_p * ROWD;     // this generation's rows, local copy
+            // ---- evaluate: one particle per warp and round (src/PSO.cpp:748-752, 848-852); the row goes to every CTA ----
+            for (int i = cwarp; i < num_p; i += CL_SIZE * CL_WARPS) {
+                group_fk<false, true>(sm.fs.M, [&](int) { return x + (size_t)i * D; }, 1, ws, lane);
+                double depth = depth_and_stage(sm.fs, ws, 0, lane);
+                double align = match_align<0>(sm.fs, ws, 0, lane, nullptr, nullptr);
+                if (lane < ROWD) {
+                    const double val = lane == 0 ? align + depth : x[(size_t)i * D + lane - 1];
+                    const size_t at = ((size_t)(iter & 1) * num_p + i) * ROWD + lane;
+#pragma unroll
+                    for (int r = 0; r < CL_SIZE; ++r) peer_rows[r][at] = val;
+                }
+            }
+            cluster.sync();                                     // every row of this generation is in every CTA
+            // ---- pbest, pcost (:753, :855-860), every CTA for all particles, locally ----
+            for (int it = tid; it < num_p * D; it += nthr) {
+                int i = it / D;
+                bool take = iter == 1 || in[i * ROWD] < pcost[i];
+                if (take) pb[it] = in[i * ROWD + 1 + (it - i * D)];
+            }
+            __syncthreads();
+            for (int i = tid; i < num_p; i += nthr)
+                if (iter == 1 || in[i * ROWD] < pcost[i]) pcost[i] = in[i * ROWD];
+            __syncthreads();
+            // ---- gbest (:755-760, :864-876): first minimum of pcost ----
+            if (warp == 0) {
+                double c = __longlong_as_double(0x7ff0000000000000LL);
+                int ci = 0x7fffffff;
+                for (int i = lane; i < num_p; i += 32)
+                    if (pcost[i] < c) { c = pcost[i]; ci = i; }
+                warp_argmin_d(c, ci);
+                if (lane == 0) {
+                    if (ci == 0x7fffffff) ci = 0;
+                    sm.fmin_id = ci;
+                    if (pcost[ci] < sm.gbest_cost) {
+                        sm.gbest_cost = pcost[ci];
+                        sm.count = iter == 1 ? 100 : 0;
+                        sm.fmin_id = ci | 0x40000000;
+                    } else if (iter > 1) {
+                        sm.count += 1;
+                    }
+                }
+            }
+            __syncthreads();
+            // gbest_pos = particles.col(fmin_id): that particle has just improved, so x == pbest
+            if ((sm.fmin_id & 0x40000000) && tid < D) sm.gbest[tid] = pb[(sm.fmin_id & 0x3fffffff) * D + tid];
+            if (crank == 0 && tid == 0 && iter > 1 && trace_out)
+                trace_out[(size_t)b * (prm.maxiter - 1) + (iter - 2)] = sm.gbest_cost;
+            if (iter >= prm.maxiter) break;
+            const uint32_t gen = (uint32_t)iter;
+            __syncthreads();
+            // ---- topology (:790-803), every CTA draws the same R ----
+            if (sm.count > 0) {
+                for (int it = tid; it < num_p * CL_NK; it += nthr) {
+                    int s = it / CL_NK, k = it - s * CL_NK;
+                    double u[2];
+                    uniform2(seed, (uint32_t)(k >> 1), (uint32_t)s, gen, 3u, u);
+                    R[it] = (int)floor(__dadd_rn(__dmul_rn(u[k & 1], (double)(num_p - 1)), 0.5));
+                }
+            }
+            __syncthreads();
+            // ---- informants of this CTA's particles (:810-812) ----
+            for (int i = cwarp; i < num_p; i += CL_SIZE * CL_WARPS) {
+                const double INF = __longlong_as_double(0x7ff0000000000000LL);
+                double bc = INF;
+                int best = 0x7fffffff, first_linked = 0x7fffffff;
+                for (int s = lane; s < num_p; s += 32) {
+                    bool linked = (s == i) | (R[s * CL_NK] == i) | (R[s * CL_NK + 1] == i) | (R[s * CL_NK + 2] == i);
+                    if (linked) {
+                        double c = pcost[s];
+                        double key = c == c ? c : INF;
+                        first_linked = min(first_linked, s);
+                        if (key < bc || best == 0x7fffffff) { bc = key; best = s; }
+                    }
+                }
+                warp_argmin_d(bc, best);
+                for (int off = 16; off > 0; off >>= 1) first_linked = min(first_linked, __shfl_xor_sync(0xffffffffu, first_linked, off));
+                double cf = pcost[first_linked];
+                if (lane == 0) informant[i] = cf == cf ? best : first_linked;
+            }
+            __syncthreads();
+            // ---- velocity, position, check_constraints (:824-840, :358-377) for this CTA's particles ----
+            for (int it = tid; it < rounds * CL_WARPS * (D / 2); it += nthr) {
+                int li = it / (D / 2), dp = it - li * (D / 2);
+                int i = crank * CL_WARPS + (li % CL_WARPS) + (li / CL_WARPS) * CL_SIZE * CL_WARPS;
+                if (i >= num_p) continue;
+                int inf = informant[i];
+                double rp[2], rg[2];
+                uniform2(seed, (uint32_t)dp, (uint32_t)i, gen, 1u, rp);
+                uniform2(seed, (uint32_t)dp, (uint32_t)i, gen, 2u, rg);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    int d = 2 * dp + e, at = i * D + d;
+                    double xi = x[at];
+                    double nv = __dadd_rn(__dmul_rn(v[at], W1), __dmul_rn(__dmul_rn(rp[e], C1), __dadd_rn(pb[at], -xi)));
+                    if (inf != i)
+                        nv = __dadd_rn(nv, __dmul_rn(__dmul_rn(rg[e], C2), __dadd_rn(pb[inf * D + d], -xi)));
+                    double nx = __dadd_rn(xi, nv);
+                    if (nx < prm.lb[d] || nx > prm.ub[d]) { nx = prm.lb[d]; nv = 0.0; }   // :372
+                    x[at] = nx;
+                    v[at] = nv;
+                }
+            }
+            // a warp evaluates only particles its own CTA has just moved: a CTA barrier is enough
+            __syncthreads();
+        }
+        const bool frame_ok = o.meta[slot].ok != 0;
+        __syncthreads();
+        if (crank == 0) {
+            if (tid < D) bestp_out[(size_t)b * D + tid] = frame_ok ? sm.gbest[tid] : sm.x0[tid];
+            if (tid == 0) best_cost_out[b] = frame_ok ? sm.gbest_cost : __longlong_as_double(0x7ff8000000000000LL);
+        }
+        cluster.sync();      // nobody pushes rows of the next swarm while others still read this one's
+    }
+}
+
 }  // namespace
 
 HPE_DEFINE_FALLBACK_GETTER(hpe_fallbacks_pso_cluster)
+
+int g_hpe_cluster_dsm = 1;   // hpe_set_pso_path(3): keep the cluster kernel's swarm state in global memory (cross-check)
 
 cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev, int first,
                                    int count, const uint64_t *seeds_dev, double *bestp_dev, double *best_cost_dev,
                                    double *trace_dev, int chain, cudaStream_t st)
 {
     if (count <= 0) return cudaSuccess;
-    size_t smem = cluster_smem_bytes(p.num_p);
+    const bool dsm = p.num_p <= CLD_MAXP && g_hpe_cluster_dsm;       // swarm state in distributed shared memory
+    size_t smem = dsm ? cluster_dsm_smem_bytes(p.num_p) : cluster_smem_bytes(p.num_p);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pso_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t attr_set[2] = {0, 0};
+    if (smem > attr_set[dsm]) {
+        cudaError_t e = dsm ? cudaFuncSetAttribute(pso_cluster_dsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(pso_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = smem;
+        attr_set[dsm] = smem;
     }
     static int sms = 0;
     if (!sms) {
@@ -265,6 +468,9 @@ cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const Ps
     cfg.numAttrs = 1;
     const double W1 = 1. / (2 * log(2.0));       // src/PSO.cpp:772
     const double C1 = 0.5 + log(2.0);            // src/PSO.cpp:773-774
+    if (dsm)
+        return cudaLaunchKernelEx(&cfg, pso_cluster_dsm_kernel, m, o, p, x0_dev, first, count, seeds_dev, state, bestp_dev,
+                                  best_cost_dev, trace_dev, chain, W1, C1);
     return cudaLaunchKernelEx(&cfg, pso_cluster_kernel, m, o, p, x0_dev, first, count, seeds_dev, state, bestp_dev,
                               best_cost_dev, trace_dev, chain, W1, C1);
 }

@@ -218,7 +218,9 @@ int hpe_set_matcher(int mode);
 int hpe_set_cost_pipeline(int mode, int chunk_poses);
 /* kernel behind hpe_pso_evolve / hpe_track_sequence: 0 (default) = automatic (one 8-CTA cluster per swarm
  * for sequences and batches of <= 36 swarms, one CTA per swarm otherwise), 1 = always one CTA per swarm,
- * 2 = always one cluster per swarm.  Results are bit-identical. */
+ * 2 = always one cluster per swarm, 3 = one cluster per swarm with the swarm state in global memory instead of
+ * distributed shared memory (cross-check; the default for swarms of more than 128 particles).  Results are
+ * bit-identical. */
 int hpe_set_pso_path(int mode);
 /* distance transform used by hpe_obs_upload*: 0 (default) = OpenCV's two raster passes, a row at a time with
  * the in-row recurrence as a prefix-minimum scan; 1 = closed-form row search; 2 = the two passes as a skewed

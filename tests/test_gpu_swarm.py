@@ -93,8 +93,9 @@ def test_sharded_swarm_is_bit_identical(hpe, D, setup):
 
 
 def test_cluster_kernel_is_bit_identical_to_one_cta_kernel(hpe, orc, omodel, D):
-    """one swarm per 8-CTA cluster (latency path) == one swarm per CTA (throughput path), for batches,
-    odd particle counts and chained sequences"""
+    """one swarm per 8-CTA cluster (latency path; swarm state in distributed shared memory = path 2, in global
+    memory = path 3) == one swarm per CTA (throughput path = 1), for batches, odd particle counts, a swarm too
+    large for the shared-memory variant, and chained sequences"""
     rng = np.random.default_rng(52)
     n_fr = 5
     truths = [synth_pose(D, rng) for _ in range(n_fr)]
@@ -104,11 +105,11 @@ def test_cluster_kernel_is_bit_identical_to_one_cta_kernel(hpe, orc, omodel, D):
     obs.upload(frames)
     cf = hpe.costfunc(hand, obs)
     lib = hpe.lib()
-    for num_p, maxiter in ((64, 10), (37, 6), (130, 4)):
+    for num_p, maxiter in ((64, 10), (37, 6), (128, 5), (130, 4)):
         pso = hpe.PSO()
         pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, maxiter, 1e-8, 1e-8)
         res = {}
-        for path in (1, 2):
+        for path in (1, 2, 3):
             assert lib.hpe_set_pso_path(path) == 0
             try:
                 res[path] = (pso.pso_evolve_batch(cf, x0, num_p, seeds=[7, 8, 9, 10, 11]),
@@ -119,6 +120,9 @@ def test_cluster_kernel_is_bit_identical_to_one_cta_kernel(hpe, orc, omodel, D):
         (b2, c2, t2), (p2, k2) = res[2]
         assert np.array_equal(b1, b2) and np.array_equal(c1, c2) and np.array_equal(t1, t2)
         assert np.array_equal(p1, p2) and np.array_equal(k1, k2)
+        (b3, c3, t3), (p3, k3) = res[3]
+        assert np.array_equal(b1, b3) and np.array_equal(c1, c3) and np.array_equal(t1, t3)
+        assert np.array_equal(p1, p3) and np.array_equal(k1, k3)
 
 
 def test_one_launch_swarm_is_bit_identical_to_stepwise(hpe, D, setup):
