@@ -65,14 +65,12 @@ __device__ __forceinline__ void ls_shrink(double a, double b, double alpha, doub
 }
 
 __global__ void __launch_bounds__(RF_WARPS * 32, 2)
-refine_kernel(DevModel m, ObsView o, int first, int count, double *__restrict__ x_io, int *__restrict__ evals_out,
-              int chain_unused)
+refine_kernel(DevModel m, ObsView o, int first, int count, double *__restrict__ x_io, int *__restrict__ evals_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RefineSmem &sm = *reinterpret_cast<RefineSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, D = HPE_NDOF;
     const WarpScratch ws = warp_scratch(sm.ws, warp, 1);
-    (void)chain_unused;
     stage_model(sm.fs, m);
     __syncthreads();
 
@@ -83,7 +81,6 @@ refine_kernel(DevModel m, ObsView o, int first, int count, double *__restrict__ 
         if (tid == 0) sm.evals = 0;
         __syncthreads();
         if (o.meta[slot].ok == 0) continue;               // empty frame: pose unchanged (uniform branch)
-        const int n_pts = sm.fs.n_pts;
 
         for (int grp = 0; grp < 2; ++grp) {               // start_idx = {0, 3}, end_idx = {2, 5}
             const int d0 = 3 * grp;
@@ -190,7 +187,6 @@ refine_kernel(DevModel m, ObsView o, int first, int count, double *__restrict__ 
         }
         if (tid < D) x_io[(size_t)b * D + tid] = sm.x[tid];
         if (tid == 0 && evals_out) evals_out[b] = sm.evals;
-        (void)n_pts;
         __syncthreads();
     }
 }
@@ -211,6 +207,6 @@ cudaError_t hpe_launch_refine(const DevModel &m, const ObsView &o, int first, in
         cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefineSmem));
     }
     int grid = count < 2 * sms ? count : 2 * sms;
-    refine_kernel<<<grid, RF_WARPS * 32, sizeof(RefineSmem), st>>>(m, o, first, count, x_dev, evals_dev, 0);
+    refine_kernel<<<grid, RF_WARPS * 32, sizeof(RefineSmem), st>>>(m, o, first, count, x_dev, evals_dev);
     return cudaGetLastError();
 }
