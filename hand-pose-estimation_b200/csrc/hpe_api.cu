@@ -276,6 +276,7 @@ int hpe_obs_create(int capacity, int num_samples, double focal, hpe_obs **out)
     if (e == cudaSuccess) e = cudaMalloc(&v.cloud, sizeof(double) * 3 * num_samples * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&v.meta, sizeof(FrameMeta) * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&v.wf_halo, sizeof(unsigned) * 2 * HPE_W * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&v.mask, sizeof(unsigned) * (npix / 32) * capacity);
     if (e == cudaSuccess) e = cudaMemset(v.meta, 0, sizeof(FrameMeta) * capacity);
     if (e != cudaSuccess) {
         hpe_obs_destroy(o);
@@ -288,7 +289,7 @@ int hpe_obs_create(int capacity, int num_samples, double focal, hpe_obs **out)
 int hpe_obs_destroy(hpe_obs *o)
 {
     if (!o) return HPE_OK;
-    cudaFree(o->v.depth_mm); cudaFree(o->v.dt_px); cudaFree(o->v.cloud); cudaFree(o->v.meta); cudaFree(o->v.wf_halo);
+    cudaFree(o->v.depth_mm); cudaFree(o->v.dt_px); cudaFree(o->v.cloud); cudaFree(o->v.meta); cudaFree(o->v.wf_halo); cudaFree(o->v.mask);
     delete o;
     return HPE_OK;
 }

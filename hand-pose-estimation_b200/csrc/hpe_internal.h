@@ -21,6 +21,7 @@ struct ObsView {
     double    *cloud;     // [capacity][3][n_pts]
     FrameMeta *meta;      // [capacity]
     unsigned  *wf_halo;   // [capacity][2][320] scratch of the wavefront chamfer (band halo rows)
+    unsigned  *mask;      // [capacity][2400] hand-pixel bits, 32 consecutive pixels per word (cloud_kernel -> chamfer_scan_kernel)
     double focal, cx, cy;
     int n_pts;
     int capacity;

@@ -44,6 +44,12 @@ __global__ void __launch_bounds__(OBS_THREADS) cloud_kernel(ObsView o, int first
     __shared__ double two_over[256];
     if (threadIdx.x < 256) two_over[threadIdx.x] = threadIdx.x ? __ddiv_rn(2.0, (double)threadIdx.x) : 0.0;
     __syncthreads();
+    // the hand-pixel bit mask goes to global memory: the distance transform reads these 9.6 KB instead of the
+    // 307 KB frame
+    {
+        unsigned *gmask = o.mask + (size_t)slot * N_CHUNKS;
+        for (int c = threadIdx.x; c < N_CHUNKS; c += OBS_THREADS) gmask[c] = chunk_bits[c];
+    }
     // exclusive prefix sum over the chunk counts: thread t owns chunks 3t..3t+2 (800 threads), then a block scan
     {
         int a0 = 0, a1 = 0, a2 = 0;
@@ -371,7 +377,8 @@ __global__ void __launch_bounds__(WF_WARPS * 32) chamfer_wavefront_kernel(ObsVie
 // short in-lane scan plus a 5-step shuffle scan instead of 320 dependent steps.  The backward pass
 // is the mirror image (suffix minimum, rows bottom-up).  The previous two rows live in registers;
 // nothing is staged in shared memory, so 16+ frames are in flight per SM and the kernel streams
-// 4 x 307 KB per frame (depth in, forward result out and back in, float result out).
+// 3 x 307 KB per frame (forward result out and back in, float result out) plus the 9.6 KB hand-pixel mask
+// cloud_kernel leaves behind -- the frame itself is read once, by cloud_kernel.
 // Values that no feature pixel reaches stay at OpenCV's DIST_MAX-like sentinel (clamped to WF_MAX
 // per row); every such value is replaced by the backward pass when the frame has a hand pixel, so
 // the result is bit-identical to cv::distanceTransform (tests compare against cv2 and the oracle).
@@ -405,7 +412,6 @@ __global__ void __launch_bounds__(SC_WARPS * 32) chamfer_scan_kernel(ObsView o, 
     if (fr >= count) return;
     const int slot = first + fr;
     if (!o.meta[slot].ok) return;
-    const float *__restrict__ depth = o.depth_mm + (size_t)slot * NPIX;
     unsigned *tmp = reinterpret_cast<unsigned *>(o.dt_px + (size_t)slot * NPIX);
     float *out = o.dt_px + (size_t)slot * NPIX;
     const int c0 = lane * SC_CPL;
@@ -415,16 +421,16 @@ __global__ void __launch_bounds__(SC_WARPS * 32) chamfer_scan_kernel(ObsView o, 
     unsigned p1[SC_CPL], p2[SC_CPL];
 #pragma unroll
     for (int k = 0; k < SC_CPL; ++k) { p1[k] = WF_MAX; p2[k] = WF_MAX; }
-    float2 dn[SC_CPL / 2];
-#pragma unroll
-    for (int k = 0; k < SC_CPL / 2; ++k) dn[k] = __ldg(reinterpret_cast<const float2 *>(depth + c0) + k);
+    // hand bits of the lane's 10 pixels of a row: bits 10 lane .. 10 lane + 9 of the row's 320-bit mask (10 words
+    // written by cloud_kernel), i.e. a funnel shift over two neighbouring words
+    const unsigned *__restrict__ gmask = o.mask + (size_t)slot * (NPIX / 32);
+    const int mw = c0 >> 5, msh = c0 & 31;
+    unsigned wlo = __ldg(gmask + mw), whi = __ldg(gmask + min(mw + 1, 9));
     for (int i = 0; i < HPE_H; ++i) {
-        float2 dc[SC_CPL / 2];
-#pragma unroll
-        for (int k = 0; k < SC_CPL / 2; ++k) dc[k] = dn[k];
+        const unsigned hand = __funnelshift_r(wlo, whi, msh) & 0x3ffu;
         if (i + 1 < HPE_H) {
-#pragma unroll
-            for (int k = 0; k < SC_CPL / 2; ++k) dn[k] = __ldg(reinterpret_cast<const float2 *>(depth + (size_t)(i + 1) * HPE_W + c0) + k);
+            wlo = __ldg(gmask + (i + 1) * 10 + mw);
+            whi = __ldg(gmask + (i + 1) * 10 + min(mw + 1, 9));
         }
         // halo columns of the two previous rows from the neighbouring lanes (image border: sentinel)
         unsigned l1a = __shfl_up_sync(0xffffffffu, p1[SC_CPL - 2], 1), l1b = __shfl_up_sync(0xffffffffu, p1[SC_CPL - 1], 1);
@@ -435,10 +441,8 @@ __global__ void __launch_bounds__(SC_WARPS * 32) chamfer_scan_kernel(ObsView o, 
         unsigned u[SC_CPL];
         sc_gather(p1, p2, l1a, l1b, r1a, r1b, l2, r2, u);
 #pragma unroll
-        for (int k = 0; k < SC_CPL / 2; ++k) {
-            if (dc[k].x != 0.0f) u[2 * k] = 0u;
-            if (dc[k].y != 0.0f) u[2 * k + 1] = 0u;
-        }
+        for (int k = 0; k < SC_CPL; ++k)
+            if ((hand >> k) & 1u) u[k] = 0u;
         // in-lane scan with no carry, then the carry from the lanes to the left
 #pragma unroll
         for (int k = 1; k < SC_CPL; ++k) u[k] = min(u[k], u[k - 1] + WF_A);
