@@ -8,7 +8,10 @@
 
 namespace {
 
-constexpr int PSO_WARPS = 8;
+#ifndef HPE_PSO_WARPS
+#define HPE_PSO_WARPS 8
+#endif
+constexpr int PSO_WARPS = HPE_PSO_WARPS;
 constexpr int PSO_NK = 3;            // informants drawn per particle, src/PSO.cpp:769
 
 struct __align__(16) PsoSmemHead {
