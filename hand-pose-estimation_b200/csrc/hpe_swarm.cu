@@ -414,6 +414,8 @@ int hpe_swarm_best(hpe_swarm *s, double bestp[HPE_NDOF], double *best_cost, doub
     if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_best: NULL swarm");
     SwarmCtl c;
     HPE_CUDA(cudaMemcpy(&c, s->ctl, sizeof c, cudaMemcpyDeviceToHost));
+    if (c.count == -12345)     // set by the bounded waits of the peer exchange
+        return hpe_set_error(HPE_ERR_STATE, "sharded swarm: a peer did not deliver its rows in time (rank %d of %d)", s->rank, s->world);
     if (bestp) memcpy(bestp, c.gbest, sizeof c.gbest);
     if (best_cost) *best_cost = c.gbest_cost;
     if (trace && s->prm.maxiter > 1)
