@@ -173,6 +173,17 @@ def cpu_baseline(n_pts, seconds=12.0, reference_arm=False, steps=0, warmup=0):
         return {"value": steps * per_step / dt, "unit": UNIT, "cores": cores, "kind": kind,
                 "sample": f"{steps} steps x {per_step} of the workload's {N_POSES} poses, {what}, OpenMP, "
                           f"{cores} threads", "port_value": port_rate}, dt
+    track_fps = None
+    if have_ref:
+        # the other half of the metric, tracked frames/s: the reference's own PSO::pso_evolve (64 particles x 30
+        # generations, OpenMP over the particles as written, src/PSO.cpp:748,848) on the same frame
+        R.set_pso_params(maxiter=30)
+        x0 = truth + np.random.default_rng(7).normal(size=26) * D.STD * 0.3
+        R.pso_evolve(x0, 64)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            R.pso_evolve(x0, 64)
+        track_fps = 3 / (time.perf_counter() - t0)
     n = int(min(max(rate * seconds, 512), 256 * N_POSES))
     reps, rem = divmod(n, N_POSES)
     t0 = time.perf_counter()
@@ -183,7 +194,7 @@ def cpu_baseline(n_pts, seconds=12.0, reference_arm=False, steps=0, warmup=0):
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"{n} of the workload's poses (same frame), {what}, OpenMP, {dt:.1f} s",
-            "port_value": port_rate}, dt
+            "port_value": port_rate, "pso_evolve_64x30_frames_per_sec": track_fps}, dt
 
 
 def run_reference(args, rank):
