@@ -370,6 +370,19 @@ def main():
         extras["pso_evals_per_sec"] = world * n_fr * 64 * 30 / dt
         extras["pso_batch"] = f"{n_fr} frames x 64 particles x 30 generations per GPU, host x0 in, best pose out"
         extras["pso_median_final_cost"] = float(np.median(best))
+        # the same end to end from HOST frames (pinned): upload 307 KB per frame, observation, swarms, poses back
+        frames_host = frames_dev.cpu().pin_memory()
+        obsb.upload(frames_host.numpy())
+        barrier()
+        t0 = time.perf_counter()
+        obsb.upload(frames_host.numpy())
+        pso.pso_evolve_batch(cfb, x0, 64, want_trace=False)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        extras["pso_e2e_frames_per_sec"] = world * n_fr / dt
+        extras["pso_e2e"] = (f"{n_fr} host frames per GPU uploaded ({n_fr * 307200 / 1e6:.0f} MB), observed and fitted (64 x 30) "
+                             "in one timed region, no overlap between the stages")
+        del frames_host
         # configs[3]: one swarm of 16,384 particles x 30 generations, particles sharded over the ranks,
         # (pcost, pbest) rows all-gathered once per generation (NCCL over NVLink when N > 1)
         from hpe_b200 import sharding
