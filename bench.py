@@ -370,18 +370,21 @@ def main():
         extras["pso_evals_per_sec"] = world * n_fr * 64 * 30 / dt
         extras["pso_batch"] = f"{n_fr} frames x 64 particles x 30 generations per GPU, host x0 in, best pose out"
         extras["pso_median_final_cost"] = float(np.median(best))
-        # the same end to end from HOST frames (pinned): upload 307 KB per frame, observation, swarms, poses back
+        # the same end to end from HOST frames (pinned): hpe_fit_frames streams them through a buffer of 592 slots,
+        # the upload of a chunk (307 KB per frame) overlapped with the observation + swarms of the previous one
         frames_host = frames_dev.cpu().pin_memory()
-        obsb.upload(frames_host.numpy())
+        obse = hpe_b200.observedmodel(capacity=592, num_samples=250)
+        cfe = hpe_b200.costfunc(hand, obse)
+        pso.fit_frames(cfe, frames_host.numpy(), x0, 64)
         barrier()
         t0 = time.perf_counter()
-        obsb.upload(frames_host.numpy())
-        pso.pso_evolve_batch(cfb, x0, 64, want_trace=False)
+        bp_e, bc_e = pso.fit_frames(cfe, frames_host.numpy(), x0, 64)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        assert np.array_equal(bp_e, bestp) and np.array_equal(bc_e, best), "streamed fit differs from the resident one"
         extras["pso_e2e_frames_per_sec"] = world * n_fr / dt
-        extras["pso_e2e"] = (f"{n_fr} host frames per GPU uploaded ({n_fr * 307200 / 1e6:.0f} MB), observed and fitted (64 x 30) "
-                             "in one timed region, no overlap between the stages")
+        extras["pso_e2e"] = (f"{n_fr} host frames per GPU ({n_fr * 307200 / 1e6:.0f} MB) uploaded, observed and fitted (64 x 30) by "
+                             "hpe_fit_frames, uploads overlapped with the fits")
         del frames_host
         # configs[3]: one swarm of 16,384 particles x 30 generations, particles sharded over the ranks,
         # (pcost, pbest) rows all-gathered once per generation (NCCL over NVLink when N > 1)

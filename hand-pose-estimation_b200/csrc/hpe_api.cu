@@ -648,6 +648,65 @@ int hpe_track_sequence_refined(const hpe_model *m, const hpe_obs *o, const hpe_p
     return HPE_OK;
 }
 
+// Offline batch from HOST frames (BASELINE "offline batch"): count frames stream through the observation
+// buffer in chunks of capacity/2 -- the upload of chunk k+1 (307 KB per frame over PCIe) runs under the
+// observation + swarms of chunk k; initial poses go up and results come back once.
+int hpe_fit_frames(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles, const float *depth_mm,
+                   const double *x0, int64_t count, const uint64_t *seeds, double *bestp, double *best_cost)
+{
+    if (!m || !o || !p || !depth_mm || !x0 || !bestp || num_particles < 1 || p->maxiter < 1 || count < 0)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_fit_frames: bad argument");
+    if (count == 0) return HPE_OK;
+    if (int rc = check_device()) return rc;
+    const int half = o->v.capacity >= 2 ? o->v.capacity / 2 : 1;
+    const bool twobuf = o->v.capacity >= 2;
+    const size_t row = sizeof(double) * HPE_NDOF, npix = (size_t)HPE_W * HPE_H;
+    size_t b_x = align_up(row * count), b_bc = align_up(sizeof(double) * count), b_sd = align_up(sizeof(uint64_t) * count);
+    HPE_CUDA(g_ws.reserve(2 * b_x + b_bc + b_sd));
+    char *base = (char *)g_ws.p;
+    double *d_x0 = (double *)base, *d_bp = (double *)(base + b_x), *d_bc = (double *)(base + 2 * b_x);
+    uint64_t *d_sd = (uint64_t *)(base + 2 * b_x + b_bc);
+    static cudaStream_t up = nullptr, comp = nullptr;
+    static cudaEvent_t landed[2], fitted[2], ready;
+    if (!up) {
+        HPE_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+        HPE_CUDA(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            HPE_CUDA(cudaEventCreateWithFlags(&landed[i], cudaEventDisableTiming));
+            HPE_CUDA(cudaEventCreateWithFlags(&fitted[i], cudaEventDisableTiming));
+        }
+        HPE_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    }
+    HPE_CUDA(cudaEventRecord(ready, 0));
+    HPE_CUDA(cudaStreamWaitEvent(up, ready, 0));
+    HPE_CUDA(cudaStreamWaitEvent(comp, ready, 0));
+    HPE_CUDA(cudaMemcpyAsync(d_x0, x0, row * count, cudaMemcpyHostToDevice, comp));
+    if (seeds) HPE_CUDA(cudaMemcpyAsync(d_sd, seeds, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, comp));
+    const PsoDev prm = make_pso(p, num_particles);
+    int k = 0;
+    for (int64_t c0 = 0; c0 < count; c0 += half, ++k) {
+        const int n = (int)(count - c0 < half ? count - c0 : half);
+        const int h = twobuf ? (k & 1) : 0, first = h * half;
+        if (k >= (twobuf ? 2 : 1)) HPE_CUDA(cudaStreamWaitEvent(up, fitted[h], 0));      // the half is free again
+        HPE_CUDA(cudaMemcpyAsync(o->v.depth_mm + npix * first, depth_mm + npix * c0, sizeof(float) * npix * n,
+                                 cudaMemcpyHostToDevice, up));
+        HPE_CUDA(cudaEventRecord(landed[h], up));
+        HPE_CUDA(cudaStreamWaitEvent(comp, landed[h], 0));
+        HPE_CUDA(hpe_launch_observe(o->v, first, n, nullptr, comp));
+        cudaError_t e = hpe_launch_pso(m->dm, o->v, prm, d_x0 + c0 * HPE_NDOF, first, n, seeds ? d_sd + c0 : nullptr,
+                                       d_bp + c0 * HPE_NDOF, d_bc + c0, nullptr, 0, comp);
+        if (e != cudaSuccess)
+            return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
+                                 "pso launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));
+        HPE_CUDA(cudaEventRecord(fitted[h], comp));
+    }
+    HPE_CUDA(cudaMemcpyAsync(bestp, d_bp, row * count, cudaMemcpyDeviceToHost, comp));
+    if (best_cost) HPE_CUDA(cudaMemcpyAsync(best_cost, d_bc, sizeof(double) * count, cudaMemcpyDeviceToHost, comp));
+    HPE_CUDA(cudaStreamSynchronize(up));
+    HPE_CUDA(cudaStreamSynchronize(comp));
+    return HPE_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // synthetic frames
 // ------------------------------------------------------------------------------------------

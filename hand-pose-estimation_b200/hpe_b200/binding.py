@@ -323,6 +323,20 @@ class PSO:
                                         _p(poses), _p(costs)))
         return poses, costs
 
+    def fit_frames(self, optfunc, frames_mm, x0, num_particles, seeds=None):
+        """offline batch from host frames: upload, observation and one swarm per frame, the upload of the next
+        chunk overlapped with the fit of the current one (the observedmodel's capacity sets the chunk size)"""
+        fr = np.ascontiguousarray(frames_mm, dtype=np.float32).reshape(-1, D.H, D.W)
+        x0 = _f64(x0).reshape(-1, 26)
+        n = fr.shape[0]
+        if x0.shape[0] != n:
+            raise HpeError(1, "fit_frames: one initial pose per frame")
+        bestp, best = np.empty((n, 26)), np.empty(n)
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        _check(lib().hpe_fit_frames(optfunc.hand._h, optfunc.observation._h, C.byref(self.params), int(num_particles),
+                                    _p(fr, C.c_float), _p(x0), C.c_int64(n), _p(sd, C.c_uint64), _p(bestp), _p(best)))
+        return bestp, best
+
     def refine_init_pose(self, x0, optfunc, slot=0):
         """PSO::refine_init_pose(x0, optfunc) (src/PSO.cpp:216-266); returns the refined pose (the
         reference updates x0 in place)."""

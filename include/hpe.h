@@ -158,6 +158,15 @@ int hpe_track_sequence_refined(const hpe_model *m, const hpe_obs *o, const hpe_p
                                int num_particles, const double x0[HPE_NDOF], int first, int n_frames,
                                uint64_t seed, double *poses, double *costs, double *refined);
 
+/* Offline batch from HOST frames: count Subject1-format frames (float32 mm, count*240*320) are uploaded,
+ * observed (observedmodel::next_frame) and fitted with one pso_evolve swarm each (x0: count*26), streaming
+ * through the observation buffer `o` in chunks of capacity/2 so that the upload of the next chunk runs under
+ * the fit of the current one.  bestp: count*26, best_cost: count (NaN for a frame without hand pixels, whose
+ * bestp is its x0).  Afterwards `o` holds the last chunks.  HOST pointers (pinned memory makes the overlap real). */
+int hpe_fit_frames(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                   const float *depth_mm, const double *x0, int64_t count, const uint64_t *seeds,
+                   double *bestp, double *best_cost);
+
 /* ---- one large swarm, particles [lo,hi) of num_particles owned by this GPU ---- */
 /* State lives on the device; the caller (one process per GPU) exchanges the
  * pbest table between generations (all-gather of hpe_swarm_table rows). */

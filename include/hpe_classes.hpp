@@ -248,6 +248,15 @@ public:
         check(hpe_track_sequence(optfunc.hand->c_handle(), optfunc.observation->c_handle(), &p_, num_particles, x0.data(),
                                  first, n_frames, seed, poses, costs));
     }
+    // offline batch from host frames (count * 240 * 320 floats, mm): upload, observation, one swarm per frame,
+    // uploads overlapped with the fits; the observedmodel's capacity sets the chunk size
+    void fit_frames(costfunc &optfunc, const float *depth_mm, const double *x0, long count, int num_particles,
+                    double *bestp, double *best_cost, const uint64_t *seeds = nullptr)
+    {
+        check(hpe_fit_frames(optfunc.hand->c_handle(), const_cast<hpe_obs *>(optfunc.observation->c_handle()), &p_,
+                             num_particles, depth_mm, x0,
+                             count, seeds, bestp, best_cost));
+    }
     // void refine_init_pose(x0, optfunc), src/PSO.cpp:216-266: x0 is updated in place
     void refine_init_pose(vec &x0, costfunc &optfunc, int slot = 0)
     {

@@ -105,3 +105,32 @@ def test_config4_offline_batch_is_chunk_invariant(hpe, D):
         assert np.array_equal(bp2, bp[a:b]) and np.array_equal(bc2, bc[a:b]), a
     x0_cost = np.array([hpe.costfunc(hand, obs).cal_cost(x0[k], slot=k) for k in range(0, n, 256)])
     assert np.all(bc[::256] < x0_cost)
+
+
+def test_streaming_fit_from_host_frames(hpe, D):
+    """hpe_fit_frames: frames streamed from host memory through a small observation buffer (uploads overlapped
+    with the fits) == upload + pso_evolve_batch on a buffer that holds them all, bit for bit; an empty frame
+    comes back as NaN cost with its x0"""
+    rng = np.random.default_rng(8)
+    n = 1500
+    truths = np.clip(D.X0 + rng.normal(size=(n, 26)) * D.STD * 0.5, D.LB, D.UB)
+    x0 = truths + rng.normal(size=truths.shape) * D.STD * 0.3
+    hand = hpe.handmodel()
+    frames = hpe.render_frames(hand, truths)
+    pso = hpe.PSO()
+    pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, 12, 1e-8, 1e-8)
+    seeds = np.arange(n, dtype=np.uint64) + 5
+    big = hpe.observedmodel(capacity=n)
+    big.upload(frames)
+    bp, bc, _ = pso.pso_evolve_batch(hpe.costfunc(hand, big), x0, 32, seeds=seeds, want_trace=False)
+    for cap in (256, 2 * n, 77, 1):
+        m = n if cap > 1 else 5
+        small = hpe.observedmodel(capacity=cap)
+        bp2, bc2 = pso.fit_frames(hpe.costfunc(hand, small), frames[:m], x0[:m], 32, seeds=seeds[:m])
+        assert np.array_equal(bp2, bp[:m]) and np.array_equal(bc2, bc[:m]), cap
+    fr = frames[:10].copy()
+    fr[3] = 0.0
+    bp3, bc3 = pso.fit_frames(hpe.costfunc(hand, hpe.observedmodel(capacity=4)), fr, x0[:10], 32, seeds=seeds[:10])
+    assert np.isnan(bc3[3]) and np.array_equal(bp3[3], x0[3])
+    keep = np.arange(10) != 3
+    assert np.array_equal(bp3[keep], bp[:10][keep]) and np.array_equal(bc3[keep], bc[:10][keep])
