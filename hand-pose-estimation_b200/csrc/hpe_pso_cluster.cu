@@ -235,43 +235,48 @@ struct __align__(16) ClusterDsmHead {
     int count;
     int fmin_id;
     int pad;
-    // followed by: warp scratch [CL_WARPS] x 1 slot; double rows[2][num_p][27] (fx, x) incoming; double pb[num_p][26];
+    // followed by: warp scratch [CLW] x 1 slot; double rows[2][num_p][27] (fx, x) incoming; double pb[num_p][26];
     //              double pcost[num_p]; int informant[num_p]; int R[num_p][3]
 };
 
-__host__ __device__ inline size_t cluster_dsm_smem_bytes(int num_p)
+__host__ __device__ inline size_t cluster_dsm_smem_bytes(int num_p, int warps)
 {
-    return sizeof(ClusterDsmHead) + (size_t)CL_WARPS * HPE_WS_BYTES(1) +
+    return sizeof(ClusterDsmHead) + (size_t)warps * HPE_WS_BYTES(1) +
            (size_t)num_p * (2 * (HPE_NDOF + 1) * 8 + HPE_NDOF * 8 + 8 + 4 + CL_NK * 4) + 16;
 }
 
-__global__ void __launch_bounds__(CL_WARPS * 32, 2)
+// CLS CTAs per cluster, 64 / CLS warps per CTA: 8 x 8 (portable cluster size, two CTAs per SM) for small batches of
+// swarms, 16 x 4 (non-portable size, one CTA per SM so that a warp has its SM sub-partition to itself) for a single
+// sequence: +15 % frames/s
+template <int CLS>
+__global__ void __launch_bounds__(64 / CLS * 32, 2)
 pso_cluster_dsm_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, int first, int count_swarms,
                        const uint64_t *__restrict__ seeds, double *__restrict__ state, double *__restrict__ bestp_out,
                        double *__restrict__ best_cost_out, double *__restrict__ trace_out, int chain, double W1, double C1)
 {
+    constexpr int CLW = 64 / CLS;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ClusterDsmHead &sm = *reinterpret_cast<ClusterDsmHead *>(smem_raw);
     const int num_p = prm.num_p, D = HPE_NDOF, ROWD = HPE_NDOF + 1;
     unsigned char *ws_base = smem_raw + sizeof(ClusterDsmHead);
-    double *rows = reinterpret_cast<double *>(ws_base + (size_t)CL_WARPS * HPE_WS_BYTES(1));     // [2][num_p][27]
+    double *rows = reinterpret_cast<double *>(ws_base + (size_t)CLW * HPE_WS_BYTES(1));     // [2][num_p][27]
     double *pb = rows + 2 * (size_t)num_p * ROWD;                                                // [num_p][26]
     double *pcost = pb + (size_t)num_p * D;                                                      // [num_p]
     int *informant = reinterpret_cast<int *>(pcost + num_p);
     int *R = informant + num_p;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
     const int crank = (int)cluster.block_rank();
-    const int cluster_id = blockIdx.x / CL_SIZE, n_clusters = gridDim.x / CL_SIZE;
-    const int cwarp = crank * CL_WARPS + warp;                 // warp index inside the cluster, 0..63
+    const int cluster_id = blockIdx.x / CLS, n_clusters = gridDim.x / CLS;
+    const int cwarp = crank * CLW + warp;                 // warp index inside the cluster, 0..63
     // positions and velocities of this CTA's own particles stay in global scratch (only this CTA touches them)
     double *x = state + (size_t)cluster_id * 2 * num_p * D;
     double *v = x + (size_t)num_p * D;
     const double C2 = C1;
     const WarpScratch ws = warp_scratch(ws_base, warp, 1);
-    double *peer_rows[CL_SIZE];
+    double *peer_rows[CLS];
 #pragma unroll
-    for (int r = 0; r < CL_SIZE; ++r) peer_rows[r] = cluster.map_shared_rank(rows, r);
+    for (int r = 0; r < CLS; ++r) peer_rows[r] = cluster.map_shared_rank(rows, r);
 
     stage_model(sm.fs, m);
     __syncthreads();
@@ -284,10 +289,10 @@ pso_cluster_dsm_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restri
         if (tid == 0) { sm.gbest_cost = 1e100; sm.count = 100; }
         __syncthreads();
         // generate_particles (src/PSO.cpp:56-74) for this CTA's own particles
-        const int rounds = (num_p + CL_SIZE * CL_WARPS - 1) / (CL_SIZE * CL_WARPS);
-        for (int it = tid; it < rounds * CL_WARPS * (D / 2); it += nthr) {
+        const int rounds = (num_p + CLS * CLW - 1) / (CLS * CLW);
+        for (int it = tid; it < rounds * CLW * (D / 2); it += nthr) {
             int li = it / (D / 2), dp = it - li * (D / 2);
-            int i = crank * CL_WARPS + (li % CL_WARPS) + (li / CL_WARPS) * CL_SIZE * CL_WARPS;
+            int i = crank * CLW + (li % CLW) + (li / CLW) * CLS * CLW;
             if (i >= num_p) continue;
             double z[2];
             normal2(seed, (uint32_t)dp, (uint32_t)i, 0u, z);
@@ -301,7 +306,7 @@ pso_cluster_dsm_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restri
         for (int iter = 1;; ++iter) {
             double *in = rows + (size_t)(iter & 1) * num_p * ROWD;     // this generation's rows, local copy
             // ---- evaluate: one particle per warp and round (src/PSO.cpp:748-752, 848-852); the row goes to every CTA ----
-            for (int i = cwarp; i < num_p; i += CL_SIZE * CL_WARPS) {
+            for (int i = cwarp; i < num_p; i += CLS * CLW) {
                 group_fk<false, true>(sm.fs.M, [&](int) { return x + (size_t)i * D; }, 1, ws, lane);
                 double depth = depth_and_stage(sm.fs, ws, 0, lane);
                 double align = match_align<0>(sm.fs, ws, 0, lane, nullptr, nullptr);
@@ -309,7 +314,7 @@ pso_cluster_dsm_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restri
                     const double val = lane == 0 ? align + depth : x[(size_t)i * D + lane - 1];
                     const size_t at = ((size_t)(iter & 1) * num_p + i) * ROWD + lane;
 #pragma unroll
-                    for (int r = 0; r < CL_SIZE; ++r) peer_rows[r][at] = val;
+                    for (int r = 0; r < CLS; ++r) peer_rows[r][at] = val;
                 }
             }
             cluster.sync();                                     // every row of this generation is in every CTA
@@ -361,7 +366,7 @@ pso_cluster_dsm_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restri
             }
             __syncthreads();
             // ---- informants of this CTA's particles (:810-812) ----
-            for (int i = cwarp; i < num_p; i += CL_SIZE * CL_WARPS) {
+            for (int i = cwarp; i < num_p; i += CLS * CLW) {
                 const double INF = __longlong_as_double(0x7ff0000000000000LL);
                 double bc = INF;
                 int best = 0x7fffffff, first_linked = 0x7fffffff;
@@ -381,9 +386,9 @@ pso_cluster_dsm_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restri
             }
             __syncthreads();
             // ---- velocity, position, check_constraints (:824-840, :358-377) for this CTA's particles ----
-            for (int it = tid; it < rounds * CL_WARPS * (D / 2); it += nthr) {
+            for (int it = tid; it < rounds * CLW * (D / 2); it += nthr) {
                 int li = it / (D / 2), dp = it - li * (D / 2);
-                int i = crank * CL_WARPS + (li % CL_WARPS) + (li / CL_WARPS) * CL_SIZE * CL_WARPS;
+                int i = crank * CLW + (li % CLW) + (li / CLW) * CLS * CLW;
                 if (i >= num_p) continue;
                 int inf = informant[i];
                 double rp[2], rg[2];
@@ -427,22 +432,33 @@ cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const Ps
 {
     if (count <= 0) return cudaSuccess;
     const bool dsm = p.num_p <= CLD_MAXP && g_hpe_cluster_dsm;       // swarm state in distributed shared memory
-    size_t smem = dsm ? cluster_dsm_smem_bytes(p.num_p) : cluster_smem_bytes(p.num_p);
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t attr_set[2] = {0, 0};
-    if (smem > attr_set[dsm]) {
-        cudaError_t e = dsm ? cudaFuncSetAttribute(pso_cluster_dsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(pso_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set[dsm] = smem;
-    }
     static int sms = 0;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    int max_clusters = 2 * sms / CL_SIZE;
+    // a sequence (or a handful of swarms) gets 16-CTA clusters, one CTA per SM; more swarms get 8-CTA clusters
+    static bool wide_ok = true;                              // cleared if the device refuses 16-CTA clusters
+    const bool wide = wide_ok && dsm && (chain || count <= sms / 16);
+    const int cls = wide ? 16 : CL_SIZE;
+    size_t smem = dsm ? cluster_dsm_smem_bytes(p.num_p, 64 / cls) : cluster_smem_bytes(p.num_p);
+    if (wide && smem < 116 * 1024) smem = 116 * 1024;       // more than half of an SM's shared memory: one CTA per SM
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    static size_t attr_set[3] = {0, 0, 0};
+    const int which = dsm ? (wide ? 2 : 1) : 0;
+    if (smem > attr_set[which]) {
+        cudaError_t e;
+        if (which == 0) e = cudaFuncSetAttribute(pso_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else if (which == 1) e = cudaFuncSetAttribute(pso_cluster_dsm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else {
+            e = cudaFuncSetAttribute(pso_cluster_dsm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(pso_cluster_dsm_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        }
+        if (e != cudaSuccess) return e;
+        attr_set[which] = smem;
+    }
+    int max_clusters = (wide ? 1 : 2) * sms / cls;
     int n_clusters = chain ? 1 : (count < max_clusters ? count : max_clusters);
     static double *state = nullptr;
     static size_t state_bytes = 0;
@@ -455,21 +471,29 @@ cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const Ps
         state_bytes = need;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n_clusters * CL_SIZE);
-    cfg.blockDim = dim3(CL_WARPS * 32);
+    cfg.gridDim = dim3(n_clusters * cls);
+    cfg.blockDim = dim3(64 / cls * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL_SIZE;
+    attr[0].val.clusterDim.x = cls;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const double W1 = 1. / (2 * log(2.0));       // src/PSO.cpp:772
     const double C1 = 0.5 + log(2.0);            // src/PSO.cpp:773-774
+    if (dsm && wide) {
+        cudaError_t e = cudaLaunchKernelEx(&cfg, pso_cluster_dsm_kernel<16>, m, o, p, x0_dev, first, count, seeds_dev, state,
+                                           bestp_dev, best_cost_dev, trace_dev, chain, W1, C1);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();                                  // e.g. cudaErrorInvalidClusterSize: use 8-CTA clusters from now on
+        wide_ok = false;
+        return hpe_launch_pso_cluster(m, o, p, x0_dev, first, count, seeds_dev, bestp_dev, best_cost_dev, trace_dev, chain, st);
+    }
     if (dsm)
-        return cudaLaunchKernelEx(&cfg, pso_cluster_dsm_kernel, m, o, p, x0_dev, first, count, seeds_dev, state, bestp_dev,
+        return cudaLaunchKernelEx(&cfg, pso_cluster_dsm_kernel<8>, m, o, p, x0_dev, first, count, seeds_dev, state, bestp_dev,
                                   best_cost_dev, trace_dev, chain, W1, C1);
     return cudaLaunchKernelEx(&cfg, pso_cluster_kernel, m, o, p, x0_dev, first, count, seeds_dev, state, bestp_dev,
                               best_cost_dev, trace_dev, chain, W1, C1);
