@@ -126,6 +126,9 @@ def cpu_baseline(n_pts, seconds=12.0, reference_arm=False, steps=0, warmup=0):
     kind "port": the oracle restatement (plain C, OpenMP, cached maximum) when the .so is absent; its
     rate is always reported next to the reference's as "port_value"."""
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    # all the host threads this process may use -- torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # make the baseline single-threaded; the OpenMP runtime reads the variable when the oracle library is loaded
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
     import ref
