@@ -480,6 +480,20 @@ def main():
         extras["refine_evals_per_sec"] = world * float(ev.sum()) / dt
         extras["refine"] = (f"{n_fr} frames per GPU, gradient descent + Goldstein search on rotation then position, "
                             f"mean {float(ev.mean()):.0f} cal_cost2 evaluations per frame")
+        # PSO::pso_optimise (ten coordinate-descent steps per particle and iteration, then the
+        # canonical w/c1/c2 update), one CTA per swarm, a warp per particle in the descent phase
+        pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, 4, 1e-8, 1e-8)
+        pso.pso_optimise_batch(cfb, x0[:64], 16)
+        barrier()
+        t0 = time.perf_counter()
+        _, bc_o, ev_o = pso.pso_optimise_batch(cfb, x0, 16)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        extras["optimise_frames_per_sec"] = world * n_fr / dt
+        extras["optimise_evals_per_sec"] = world * float(ev_o.sum()) / dt
+        extras["optimise"] = (f"{n_fr} frames per GPU, pso_optimise 16 particles x 4 iterations, mean "
+                              f"{float(ev_o.mean()):.0f} evaluations per frame; median final cost {float(np.median(bc_o)):.3f}")
+        pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, GEN, 1e-8, 1e-8)
         n_ref = 200
         pso.track_sequence_refined(cfs, xs0, 64, 8)
         barrier()

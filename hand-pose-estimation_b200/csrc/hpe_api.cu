@@ -131,7 +131,7 @@ int hpe_debug_fallback_points(unsigned long long *count, int reset)
 {
     if (!count) return hpe_set_error(HPE_ERR_ARG, "hpe_debug_fallback_points: NULL output");
     *count = hpe_fallbacks_cost(reset) + hpe_fallbacks_pso(reset) + hpe_fallbacks_pso_cluster(reset) +
-             hpe_fallbacks_refine(reset);
+             hpe_fallbacks_refine(reset) + hpe_fallbacks_pso_opt(reset);
     return HPE_OK;
 }
 
@@ -603,6 +603,46 @@ int hpe_refine_init_pose(const hpe_model *m, const hpe_obs *o, double *x0, int f
     HPE_CUDA(hpe_launch_refine(m->dm, o->v, first, count, d_x, d_e, 0));
     HPE_CUDA(cudaMemcpyAsync(x0, d_x, sizeof(double) * count * HPE_NDOF, cudaMemcpyDeviceToHost, 0));
     if (evals) HPE_CUDA(cudaMemcpyAsync(evals, d_e, sizeof(int) * count, cudaMemcpyDeviceToHost, 0));
+    HPE_CUDA(cudaStreamSynchronize(0));
+    return HPE_OK;
+}
+
+// PSO::pso_optimise for `count` independent swarms (hpe_pso_opt.cu)
+int hpe_pso_optimise(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                     const double *x0, int first, int count, const uint64_t *seeds, double *bestp, double *best_cost,
+                     int64_t *evals, double *final_particles, double *final_pcost)
+{
+    if (!m || !p || !x0 || !bestp || num_particles < 1 || p->maxiter < 1)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_pso_optimise: bad argument");
+    if (int rc = check_slot(o, first, count)) return rc;
+    if (count == 0) return HPE_OK;
+    if (int rc = check_filled(o, first, count)) return rc;
+    const size_t np = (size_t)num_particles;
+    size_t b_x0 = align_up(sizeof(double) * count * HPE_NDOF), b_sd = align_up(sizeof(uint64_t) * count), b_bp = b_x0,
+           b_bc = align_up(sizeof(double) * count), b_ev = align_up(sizeof(long long) * count),
+           b_fx = final_particles ? align_up(sizeof(double) * count * np * HPE_NDOF) : 0,
+           b_fc = final_pcost ? align_up(sizeof(double) * count * np) : 0;
+    HPE_CUDA(g_ws.reserve(b_x0 + b_sd + b_bp + b_bc + b_ev + b_fx + b_fc));
+    char *base = (char *)g_ws.p;
+    double *d_x0 = (double *)base;
+    uint64_t *d_sd = (uint64_t *)(base + b_x0);
+    double *d_bp = (double *)(base + b_x0 + b_sd), *d_bc = (double *)(base + b_x0 + b_sd + b_bp);
+    long long *d_ev = (long long *)(base + b_x0 + b_sd + b_bp + b_bc);
+    double *d_fx = final_particles ? (double *)(base + b_x0 + b_sd + b_bp + b_bc + b_ev) : nullptr;
+    double *d_fc = final_pcost ? (double *)(base + b_x0 + b_sd + b_bp + b_bc + b_ev + b_fx) : nullptr;
+    HPE_CUDA(cudaMemcpyAsync(d_x0, x0, sizeof(double) * count * HPE_NDOF, cudaMemcpyHostToDevice, 0));
+    if (seeds) HPE_CUDA(cudaMemcpyAsync(d_sd, seeds, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, 0));
+    cudaError_t e = hpe_launch_pso_optimise(m->dm, o->v, make_pso(p, num_particles), p->w, p->c1, p->c2, d_x0, first, count,
+                                            seeds ? d_sd : nullptr, d_bp, d_bc, d_ev, d_fx, d_fc, 0);
+    if (e != cudaSuccess)
+        return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
+                             "pso_optimise launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));
+    HPE_CUDA(cudaMemcpyAsync(bestp, d_bp, sizeof(double) * count * HPE_NDOF, cudaMemcpyDeviceToHost, 0));
+    if (best_cost) HPE_CUDA(cudaMemcpyAsync(best_cost, d_bc, sizeof(double) * count, cudaMemcpyDeviceToHost, 0));
+    if (evals) HPE_CUDA(cudaMemcpyAsync(evals, d_ev, sizeof(long long) * count, cudaMemcpyDeviceToHost, 0));
+    if (final_particles)
+        HPE_CUDA(cudaMemcpyAsync(final_particles, d_fx, sizeof(double) * count * np * HPE_NDOF, cudaMemcpyDeviceToHost, 0));
+    if (final_pcost) HPE_CUDA(cudaMemcpyAsync(final_pcost, d_fc, sizeof(double) * count * np, cudaMemcpyDeviceToHost, 0));
     HPE_CUDA(cudaStreamSynchronize(0));
     return HPE_OK;
 }

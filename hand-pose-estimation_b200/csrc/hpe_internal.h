@@ -153,6 +153,12 @@ cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const Ps
 cudaError_t hpe_launch_refine(const DevModel &m, const ObsView &o, int first, int count, double *x_dev, int *evals_dev,
                               cudaStream_t st);
 unsigned long long hpe_fallbacks_refine(int reset);
+// PSO::pso_optimise for `count` independent swarms (hpe_pso_opt.cu); evals / final_* may be NULL
+cudaError_t hpe_launch_pso_optimise(const DevModel &m, const ObsView &o, const PsoDev &p, double w, double c1, double c2,
+                                    const double *x0_dev, int first, int count, const uint64_t *seeds_dev,
+                                    double *bestp_dev, double *best_cost_dev, long long *evals_dev, double *final_x_dev,
+                                    double *final_pcost_dev, cudaStream_t st);
+unsigned long long hpe_fallbacks_pso_opt(int reset);
 cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_t n, double focal,
                               float *depth_dev, cudaStream_t st);
 size_t hpe_observe_scratch_bytes(int count);

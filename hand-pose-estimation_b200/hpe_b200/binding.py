@@ -314,6 +314,27 @@ class PSO:
             trace = trace[:, :self.params.maxiter - 1]
         return bestp, best, trace
 
+    def pso_optimise(self, optfunc, x0, num_particles, seed=1000, slot=0):
+        """PSO::pso_optimise(optfunc, x0, num_particles, bestp) (src/PSO.cpp:539-712): the hybrid of coordinate
+        descent and canonical PSO with this object's w, c1, c2; returns bestp (26,)"""
+        return self.pso_optimise_batch(optfunc, np.asarray(x0, dtype=np.float64).reshape(1, 26), num_particles,
+                                       seeds=[seed], first=slot)[0][0]
+
+    def pso_optimise_batch(self, optfunc, x0, num_particles, seeds=None, first=0, want_state=False):
+        """one pso_optimise swarm per frame first+b; returns (bestp, gbest_cost, evaluations of the sequential
+        loop[, final particles, final pcost])"""
+        x0 = _f64(x0).reshape(-1, 26)
+        count = x0.shape[0]
+        bestp, best = np.empty((count, 26)), np.empty(count)
+        evals = np.zeros(count, dtype=np.int64)
+        fx = np.empty((count, int(num_particles), 26)) if want_state else None
+        fc = np.empty((count, int(num_particles))) if want_state else None
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        _check(lib().hpe_pso_optimise(optfunc.hand._h, optfunc.observation._h, C.byref(self.params), int(num_particles),
+                                      _p(x0), int(first), int(count), _p(sd, C.c_uint64), _p(bestp), _p(best),
+                                      _p(evals, C.c_int64), _p(fx), _p(fc)))
+        return (bestp, best, evals, fx, fc) if want_state else (bestp, best, evals)
+
     def track_sequence(self, optfunc, x0, num_particles, n_frames, seed=1000, first=0):
         x0 = _f64(x0).reshape(26)
         poses = np.empty((n_frames, 26))

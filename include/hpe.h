@@ -151,6 +151,17 @@ int hpe_track_sequence(const hpe_model *m, const hpe_obs *o, const hpe_pso_param
  * cal_cost2 (frozen correspondences for the probes and the line search).  evals (may be NULL)
  * receives the number of cal_cost2 evaluations the reference's sequential loop would have made. */
 int hpe_refine_init_pose(const hpe_model *m, const hpe_obs *o, double *x0, int first, int count, int *evals);
+/* PSO::pso_optimise (src/PSO.cpp:539-712; the reference's "gradient descent + pso" test method, call
+ * site src/visualiser.cpp:521) for `count` independent swarms, swarm b fitted to frame slot first+b
+ * from x0[b]: per iteration 10 coordinate-descent steps per particle (cal_gradient :380-405 +
+ * goldstein :438-480 on cal_cost2), then the canonical update with p->w, p->c1, p->c2 towards
+ * pbest and gbest, check_constraints and cal_cost.  Outputs (host): bestp count*26 (gbest_pos),
+ * best_cost count (gbest_cost; may be NULL), evals count (cal_cost + cal_cost2 calls of the
+ * sequential loop; may be NULL), final_particles count*num_particles*26 and final_pcost
+ * count*num_particles (may be NULL). */
+int hpe_pso_optimise(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                     const double *x0, int first, int count, const uint64_t *seeds, double *bestp,
+                     double *best_cost, int64_t *evals, double *final_particles, double *final_pcost);
 /* the tracking loop of test_full as written (src/testmodel.cpp:117-138): per frame
  * refine_init_pose(x0), pso_evolve(x0) -> bestp, x0 = bestp.  poses: n_frames*26 (bestp), costs:
  * n_frames (gbest_cost), refined (may be NULL): n_frames*26, the pose each swarm started from. */

@@ -241,6 +241,17 @@ public:
         check(hpe_pso_evolve(optfunc.hand->c_handle(), optfunc.observation->c_handle(), &p_, num_particles, x0, first,
                              count, seeds, bestp, best_cost, nullptr));
     }
+    // int pso_optimise(optfunc, x0, num_particles, bestp), src/PSO.cpp:539-712 (coordinate descent + canonical
+    // PSO with omega, phip, phig); returns 1 like the reference
+    int pso_optimise(costfunc &optfunc, const vec &x0, int num_particles, vec &bestp, unsigned long long seed = 1000,
+                     int slot = 0, double *best_cost = nullptr)
+    {
+        bestp.assign(HPE_NDOF, 0.0);
+        uint64_t s = seed;
+        check(hpe_pso_optimise(optfunc.hand->c_handle(), optfunc.observation->c_handle(), &p_, num_particles, x0.data(),
+                               slot, 1, &s, bestp.data(), best_cost, nullptr, nullptr, nullptr));
+        return 1;
+    }
     // the loop of test_full without refine_init_pose (src/testmodel.cpp:117-138)
     void track_sequence(costfunc &optfunc, const vec &x0, int num_particles, int first, int n_frames, double *poses,
                         double *costs, unsigned long long seed = 1000)

@@ -898,6 +898,140 @@ void orc_refine_init_pose(const orc_model *m, const orc_obs *o, double x0[ORC_ND
     free(match);
 }
 
+/* ------------------------------------------------------------------ */
+/* PSO::pso_optimise (gradient descent + canonical PSO) */
+/* ------------------------------------------------------------------ */
+
+/* PSO::pso_optimise, src/PSO.cpp:539-712.  Per iteration every particle first runs `graditer` = 10
+ * coordinate-descent steps (:592-626): parameter permu(m) = randi[0,25], f_k = cal_cost2 (fresh
+ * correspondences only for m == 0, :600-604), one-sided-parameter central difference cal_gradient
+ * (:380-405), Goldstein step (:438-480), f_k again -- for m == 0 this second call recomputes the
+ * correspondences at the moved pose (:616, cal_corr is still true), the later steps reuse them --
+ * and a pbest update against pcost (:619-625; the velocity fill is overwritten by :630).  Then the
+ * canonical update with w, c1, c2 towards pbest and gbest (:664-666), check_constraints, cal_cost
+ * and the second gbest test.  gbest_pos is the CURRENT position of the particle holding the
+ * smallest pcost (:637, :697), not its pbest, exactly as written.  The OpenMP races of :556-568
+ * (gbest) and :588 (randi from the shared generator) are resolved as the serial order; the random
+ * draws are counter-based: stream 0 initial normals, 1 rp, 2 rg (as pso_evolve), 4 permu
+ * (element m of particle i in generation gen = floor(26 u), u = uniform2(m>>1, i, gen, 4)[m&1]).
+ * evals (optional) counts cal_cost + cal_cost2 calls. */
+int orc_pso_optimise(const orc_model *m, const orc_obs *o, const orc_pso_params *p,
+                     double w, double c1, double c2, const double x0[ORC_NDOF], int num_p,
+                     uint64_t seed, double bestp[ORC_NDOF], double *best_cost, int64_t *evals,
+                     double *final_particles, double *final_pcost)
+{
+    const int D = ORC_NDOF, graditer = 10;
+    double *x = (double *)calloc((size_t)num_p * D, sizeof(double));
+    double *v = (double *)calloc((size_t)num_p * D, sizeof(double));
+    double *pb = (double *)calloc((size_t)num_p * D, sizeof(double));
+    double *pcost = (double *)calloc(num_p, sizeof(double));
+    double gbest[ORC_NDOF] = {0};
+    double gbest_cost = 1e100;
+    int64_t n_evals = 0;
+    const int npts = o->n_pts > 0 ? o->n_pts : 1;
+
+    orc_generate_particles(p, x0, num_p, seed, x);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < num_p; ++i) {
+        pcost[i] = orc_cal_cost(m, o, &x[i * D]);
+        memcpy(&pb[i * D], &x[i * D], D * sizeof(double));
+    }
+    n_evals += num_p;
+    for (int i = 0; i < num_p; ++i)
+        if (pcost[i] < gbest_cost) {
+            gbest_cost = pcost[i];
+            memcpy(gbest, &x[i * D], D * sizeof(double));
+        }
+
+    int iter = 1;
+    while (iter < p->maxiter) {
+        iter += 1;
+        const uint32_t gen = (uint32_t)(iter - 1);
+
+        /* :586-633 coordinate descent of every particle (particles are independent here) */
+#pragma omp parallel for schedule(dynamic) reduction(+ : n_evals)
+        for (int i = 0; i < num_p; ++i) {
+            int32_t *match = (int32_t *)malloc(sizeof(int32_t) * npts);
+            double ctheta[ORC_NDOF], cveloc[ORC_NDOF];
+            memcpy(ctheta, &x[i * D], sizeof ctheta);
+            memcpy(cveloc, &v[i * D], sizeof cveloc);
+            for (int mm = 0; mm < graditer; ++mm) {
+                double u[2];
+                orc_uniform2(seed, (uint32_t)(mm >> 1), (uint32_t)i, gen, 4u, u);
+                int param = (int)floor(u[mm & 1] * D);
+                if (param > D - 1) param = D - 1;
+                const int cal_corr = mm == 0;
+                double f_k = orc_cal_cost2(m, o, ctheta, match, cal_corr, 0);
+                int sel[ORC_NDOF] = {0};
+                double g_k[ORC_NDOF];
+                sel[param] = 1;
+                orc_cal_grad(m, o, ctheta, sel, match, g_k);      /* cal_gradient :380-405: same arithmetic */
+                double tk = 0;
+                int ls = orc_goldstein(m, o, ctheta, g_k, match, f_k, &tk, 30);
+                for (int d = 0; d < D; ++d) ctheta[d] = ctheta[d] - tk * g_k[d];
+                f_k = orc_cal_cost2(m, o, ctheta, match, cal_corr, 0);
+                n_evals += 4 + ls;
+                if (f_k < pcost[i]) {
+                    pcost[i] = f_k;
+                    memcpy(&pb[i * D], ctheta, sizeof ctheta);
+                }
+            }
+            orc_check_constraints(p, ctheta, cveloc);
+            memcpy(&x[i * D], ctheta, sizeof ctheta);
+            memcpy(&v[i * D], cveloc, sizeof cveloc);
+            free(match);
+        }
+        /* :635-642 */
+        int fmin_id = 0;
+        for (int i = 1; i < num_p; ++i) if (pcost[i] < pcost[fmin_id]) fmin_id = i;
+        if (pcost[fmin_id] < gbest_cost) {
+            memcpy(gbest, &x[fmin_id * D], D * sizeof(double));
+            gbest_cost = pcost[fmin_id];
+        }
+        /* :644-677 canonical velocity / position update */
+        for (int i = 0; i < num_p; ++i) {
+            for (int d = 0; d < D; d += 2) {
+                double rp[2], rg[2];
+                orc_uniform2(seed, (uint32_t)(d >> 1), (uint32_t)i, gen, 1u, rp);
+                orc_uniform2(seed, (uint32_t)(d >> 1), (uint32_t)i, gen, 2u, rg);
+                for (int e = 0; e < 2; ++e) {
+                    int dd = d + e;
+                    double xi = x[i * D + dd];
+                    double nv = (w * v[i * D + dd] + (c1 * rp[e]) * (pb[i * D + dd] - xi)) +
+                                (c2 * rg[e]) * (gbest[dd] - xi);
+                    v[i * D + dd] = nv;
+                    x[i * D + dd] = xi + nv;
+                }
+            }
+            orc_check_constraints(p, &x[i * D], &v[i * D]);
+        }
+        /* :679-690 */
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < num_p; ++i) {
+            double fx = orc_cal_cost(m, o, &x[i * D]);
+            if (fx < pcost[i]) {
+                pcost[i] = fx;
+                memcpy(&pb[i * D], &x[i * D], D * sizeof(double));
+            }
+        }
+        n_evals += num_p;
+        /* :693-704 */
+        fmin_id = 0;
+        for (int i = 1; i < num_p; ++i) if (pcost[i] < pcost[fmin_id]) fmin_id = i;
+        if (pcost[fmin_id] < gbest_cost) {
+            memcpy(gbest, &x[fmin_id * D], D * sizeof(double));
+            gbest_cost = pcost[fmin_id];
+        }
+    }
+    memcpy(bestp, gbest, D * sizeof(double));
+    if (best_cost) *best_cost = gbest_cost;
+    if (evals) *evals = n_evals;
+    if (final_particles) memcpy(final_particles, x, sizeof(double) * num_p * D);
+    if (final_pcost) memcpy(final_pcost, pcost, sizeof(double) * num_p);
+    free(x); free(v); free(pb); free(pcost);
+    return 1;
+}
+
 /* PSO::dim_restore, src/PSO.cpp:160-180: 22 -> 26 parameters with DIP = 2/3 PIP */
 void orc_dim_restore(const double in[22], double out[ORC_NDOF])
 {

@@ -126,6 +126,11 @@ void orc_cal_grad(const orc_model *m, const orc_obs *o, const double theta[ORC_N
 int  orc_goldstein(const orc_model *m, const orc_obs *o, const double theta[ORC_NDOF],
                    const double g_k[ORC_NDOF], int32_t *match, double f_k, double *tk, int maxiter);
 void orc_refine_init_pose(const orc_model *m, const orc_obs *o, double x0[ORC_NDOF], int *evals);
+/* PSO::pso_optimise (src/PSO.cpp:539-712): coordinate descent + canonical PSO; streams in hpe_oracle.c */
+int  orc_pso_optimise(const orc_model *m, const orc_obs *o, const orc_pso_params *p,
+                      double w, double c1, double c2, const double x0[ORC_NDOF], int num_p,
+                      uint64_t seed, double bestp[ORC_NDOF], double *best_cost, int64_t *evals,
+                      double *final_particles, double *final_pcost);
 void orc_dim_restore(const double in[22], double out[ORC_NDOF]);
 double orc_gnd_truth_err(const double joints[ORC_NJOINT * 3], const double gt_row[63]);
 

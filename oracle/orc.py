@@ -204,6 +204,21 @@ def pso_evolve(model, obs, params, x0, num_p, seed):
     return bestp, best.value, trace[:params.maxiter - 1], fin_x, fin_c
 
 
+def pso_optimise(model, obs, params, x0, num_p, seed, w=0.7298, c1=1.49618, c2=1.49618):
+    """PSO::pso_optimise (src/PSO.cpp:539-712); returns (bestp, gbest_cost, evaluations, final particles, final pcost)"""
+    x0 = f64(x0)
+    bestp = np.empty(26)
+    best = C.c_double()
+    n = C.c_int64()
+    fin_x = np.empty((num_p, 26))
+    fin_c = np.empty(num_p)
+    lib().orc_pso_optimise.restype = C.c_int
+    lib().orc_pso_optimise(C.byref(model), C.byref(obs.o), C.byref(params), C.c_double(w), C.c_double(c1),
+                           C.c_double(c2), _p(x0), int(num_p), C.c_uint64(seed), _p(bestp), C.byref(best),
+                           C.byref(n), _p(fin_x), _p(fin_c))
+    return bestp, best.value, n.value, fin_x, fin_c
+
+
 def philox(seed, c0, c1, c2, c3):
     out = (C.c_uint32 * 4)()
     lib().orc_philox(C.c_uint64(seed), c0, c1, c2, c3, out)

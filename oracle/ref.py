@@ -223,3 +223,33 @@ class PhiloxReplay:
         return rows == 3 * self.num_p
 
     num_p = 0
+
+
+class PhiloxReplayOptimise(PhiloxReplay):
+    """the same for PSO::pso_optimise (src/PSO.cpp:539-712), run with ONE OpenMP thread so that the
+    per-particle randi(10, [0,25]) draws of :588 arrive in particle order: the k-th such call after
+    the last rp/rg pair belongs to particle k of the coming generation and is fed stream 4 of
+    oracle/hpe_oracle.c:orc_pso_optimise; randn(26,N) / randu(26,N) as in the parent."""
+
+    def __init__(self, seed):
+        super().__init__(seed)
+        self.particle = 0
+        self.randi_calls = 0
+
+    def reseed(self, s):
+        super().reseed(s)
+        self.particle = 0
+
+    def fill(self, kind, rows, cols, a, b, out):
+        if kind == 2 and rows * cols == 10:
+            buf = np.ctypeslib.as_array(out, shape=(10,))
+            i, gen = self.particle, self.gen + 1
+            for m in range(10):
+                u = orc.uniform2(self.seed, m >> 1, i, gen, 4)[m & 1]
+                buf[m] = min(int(np.floor(u * (b - a + 1))) + a, b)
+            self.particle += 1
+            self.randi_calls += 1
+            return
+        if kind == 0 and rows == 26:
+            self.particle = 0
+        super().fill(kind, rows, cols, a, b, out)

@@ -188,3 +188,45 @@ def test_shim_primitives_against_numpy():
               "ref_cost_batch", "ref_set_pso_params", "ref_pso_evolve", "ref_pso_optimise",
               "ref_refine_init_pose", "ref_gnd_truth_err", "ref_dim_restore", "ref_set_rng"):
         assert hasattr(L, n)
+
+
+# ---------------------------------------------------------------- PSO::pso_optimise
+def test_oracle_reproduces_reference_pso_optimise_fixtures(orc, omodel):
+    """runs everywhere: orc_pso_optimise ends at exactly the pose the reference's PSO::pso_optimise returned
+    (tests/golden/golden_ref_opt_v1.npz, written from oracle/_ref by make_golden_ref_opt.py)"""
+    g = np.load(os.path.join(HERE, "golden", "golden_ref_opt_v1.npz"))
+    for k, (num_p, maxiter, seed, w, c1, c2) in enumerate(g["cases"]):
+        oo = orc.Observation(orc.render_depth(omodel, g["truth%d" % k]))
+        bo, co, n, _, fc = orc.pso_optimise(omodel, oo, orc.pso_params(maxiter=int(maxiter)), g["x0_%d" % k], int(num_p),
+                                            int(seed), w=w, c1=c1, c2=c2)
+        assert np.array_equal(bo, g["bestp%d" % k])
+        assert orc.cal_cost(omodel, oo, bo) == float(g["bestp_cost%d" % k])
+        assert co == fc.min() and n > int(num_p) * int(maxiter)
+
+
+@pytest.mark.parametrize("num_p,maxiter,seed,w", [(4, 3, 1000, 0.7298), (9, 4, 5, 0.5)])
+def test_pso_optimise_on_replayed_streams(orc, omodel, R, D, num_p, maxiter, seed, w):
+    """PSO::pso_optimise as written (src/PSO.cpp:539-712: ten coordinate-descent steps per particle with
+    cal_gradient + goldstein on cal_cost2, correspondences recomputed twice in step 0 and frozen afterwards,
+    gbest_pos = the CURRENT position of the best-pcost particle, canonical update with w, c1, c2) ends at
+    exactly the oracle's pose on the same counter-based streams.  One OpenMP thread: the reference draws
+    randi inside its parallel loop (:588) and races on gbest (:563-566)."""
+    import ref
+    rng = np.random.default_rng(40 + num_p)
+    truth = np.clip(D.X0 + rng.normal(size=26) * D.STD * 0.5, D.LB, D.UB)
+    depth = orc.render_depth(omodel, truth)
+    oo = orc.Observation(depth)
+    R.load_depth(depth)
+    x0 = truth + rng.normal(size=26) * D.STD * 0.3
+    R.set_pso_params(maxiter=maxiter, w=w, c1=1.3, c2=1.6)
+    hook = ref.PhiloxReplayOptimise(seed)
+    hook.num_p = num_p
+    hook.install()
+    try:
+        b = R.pso_optimise(x0, num_p)
+    finally:
+        ref.PhiloxReplay.uninstall()
+    assert hook.randi_calls == num_p * (maxiter - 1) and hook.gen == maxiter - 1
+    bo, co, n, fx, fc = orc.pso_optimise(omodel, oo, orc.pso_params(maxiter=maxiter), x0, num_p, seed, w=w, c1=1.3, c2=1.6)
+    assert np.array_equal(b, bo)
+    assert co == fc.min() and n > num_p * maxiter
