@@ -251,6 +251,29 @@ int hpe_gnd_truth_err(const hpe_model *m, const double *theta, const double *gt_
     return HPE_OK;
 }
 
+// costfunc::bincomp_penalty for n poses against one frame (hpe_bincomp.cu)
+int hpe_bincomp_batch(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n, double *penalty,
+                      uint32_t *silhouette)
+{
+    if (!m || n < 0 || ((!theta || !penalty) && n > 0)) return hpe_set_error(HPE_ERR_ARG, "hpe_bincomp_batch: bad argument");
+    if (int rc = check_slot(o, slot, 1)) return rc;
+    if (n == 0) return HPE_OK;
+    if (int rc = check_filled(o, slot, 1)) return rc;
+    const size_t words = (size_t)HPE_W * HPE_H / 32;
+    size_t b_th = align_up(sizeof(double) * n * HPE_NDOF), b_out = align_up(sizeof(double) * n),
+           b_sil = silhouette ? align_up(sizeof(uint32_t) * n * words) : 0;
+    HPE_CUDA(g_ws.reserve(b_th + b_out + b_sil));
+    char *base = (char *)g_ws.p;
+    double *d_th = (double *)base, *d_out = (double *)(base + b_th);
+    unsigned *d_sil = silhouette ? (unsigned *)(base + b_th + b_out) : nullptr;
+    HPE_CUDA(cudaMemcpyAsync(d_th, theta, sizeof(double) * n * HPE_NDOF, cudaMemcpyHostToDevice, 0));
+    HPE_CUDA(hpe_launch_bincomp(m->dm, o->v, slot, d_th, n, d_out, d_sil, 0));
+    HPE_CUDA(cudaMemcpyAsync(penalty, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, 0));
+    if (silhouette) HPE_CUDA(cudaMemcpyAsync(silhouette, d_sil, sizeof(uint32_t) * n * words, cudaMemcpyDeviceToHost, 0));
+    HPE_CUDA(cudaStreamSynchronize(0));
+    return HPE_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // observedmodel
 // ------------------------------------------------------------------------------------------

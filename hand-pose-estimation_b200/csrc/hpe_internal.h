@@ -159,6 +159,9 @@ cudaError_t hpe_launch_pso_optimise(const DevModel &m, const ObsView &o, const P
                                     double *bestp_dev, double *best_cost_dev, long long *evals_dev, double *final_x_dev,
                                     double *final_pcost_dev, cudaStream_t st);
 unsigned long long hpe_fallbacks_pso_opt(int reset);
+// costfunc::bincomp_penalty of n poses against frame `slot` (hpe_bincomp.cu); silhouette_dev: n*2400 words or NULL
+cudaError_t hpe_launch_bincomp(const DevModel &m, const ObsView &o, int slot, const double *theta_dev, int64_t n,
+                               double *out_dev, unsigned *silhouette_dev, cudaStream_t st);
 cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_t n, double focal,
                               float *depth_dev, cudaStream_t st);
 size_t hpe_observe_scratch_bytes(int count);

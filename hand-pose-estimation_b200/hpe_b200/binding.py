@@ -243,6 +243,24 @@ class costfunc:
                                            _p(m, C.c_int32), _p(a), _p(d), _p(c)))
         return a, d, c
 
+    def bincomp_penalty(self, theta, slot=0):
+        """costfunc::bincomp_penalty (src/costfunc.cpp:384-436) of the spheres of pose theta: pixels where the
+        silhouette of the projected spheres and the observed one differ"""
+        return self.bincomp_penalty_batch(np.asarray(theta, dtype=np.float64).reshape(1, 26), slot=slot)[0]
+
+    def bincomp_penalty_batch(self, thetas, slot=0, want_silhouette=False):
+        """returns penalties (n,) [and the drawn silhouettes as a bool array (n, 240, 320)]"""
+        th = _f64(thetas).reshape(-1, 26)
+        n = th.shape[0]
+        pen = np.empty(n)
+        sil = np.zeros((n, D.H * D.W // 32), dtype=np.uint32) if want_silhouette else None
+        _check(lib().hpe_bincomp_batch(self.hand._h, self.observation._h, int(slot), _p(th), C.c_int64(n), _p(pen),
+                                       _p(sil, C.c_uint32)))
+        if not want_silhouette:
+            return pen
+        bits = np.unpackbits(sil.view(np.uint8).reshape(n, -1), axis=1, bitorder="little")
+        return pen, bits.reshape(n, D.H, D.W).astype(bool)
+
     def gnd_truth_err(self, gnd_truth, frame, theta=None):
         """costfunc::gnd_truth_err(gnd_truth, frame) (src/costfunc.cpp:476-507): gnd_truth = joint.txt
         as an (n_frames, 63) array; uses the pose of the last build_hand_model call unless theta is given"""

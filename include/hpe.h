@@ -130,6 +130,14 @@ int hpe_correspondences(const hpe_model *m, const hpe_obs *o, int slot, const do
  * joints, mm); err[i] = summed distance over the wrist and the five finger tips (joints 0,4,8,12,16,20).
  * HOST pointers. */
 int hpe_gnd_truth_err(const hpe_model *m, const double *theta, const double *gt_mm, int64_t n, double *err);
+/* costfunc::bincomp_penalty (src/costfunc.cpp:384-436; "a new cost term used for testing") for n poses
+ * against frame `slot`: the 48 spheres of theta[i] drawn as filled discs (centre = trunc(K c / c_z),
+ * radius = trunc(r / img_scale), cv::circle with thickness -1) into an empty 240x320 image;
+ * penalty[i] = number of pixels where that silhouette and the observed one (depth != 0) differ.
+ * silhouette (may be NULL): n*2400 words, bit (x & 31) of word y*10 + x/32 = pixel (x, y) drawn --
+ * the projected-sphere image the reference's debug views show. */
+int hpe_bincomp_batch(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
+                      double *penalty, uint32_t *silhouette);
 
 /* ---- PSO (src/PSO.h:56-68) -------------------------------------------- */
 /* PSO::pso_evolve (src/PSO.cpp:717-886) for `count` independent swarms, swarm b fitted to

@@ -190,6 +190,14 @@ public:
         check(hpe_correspondences(hand->c_handle(), observation->c_handle(), slot, theta.data(), 1, matchId.data()));
     }
 
+    // double bincomp_penalty(spheres), src/costfunc.cpp:384-436: silhouette mismatch in pixels; takes the pose
+    // (the reference takes the spheres build_hand_model made of it)
+    double bincomp_penalty(const vec &theta, int slot = 0)
+    {
+        double c = 0;
+        check(hpe_bincomp_batch(hand->c_handle(), observation->c_handle(), slot, theta.data(), 1, &c, nullptr));
+        return c;
+    }
     // double gnd_truth_err(gnd_truth, frame), src/costfunc.cpp:476-507: gnd_truth = joint.txt, n_frames x 63
     // row-major (mm); theta = the pose whose joints are compared (the reference reads hand_joints left by the
     // last build_hand_model call)

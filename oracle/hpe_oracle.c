@@ -1032,6 +1032,72 @@ int orc_pso_optimise(const orc_model *m, const orc_obs *o, const orc_pso_params 
     return 1;
 }
 
+/* ------------------------------------------------------------------ */
+/* costfunc::bincomp_penalty (silhouette mismatch)   */
+/* ------------------------------------------------------------------ */
+
+/* cv::circle(img, centre, radius, colour, thickness = -1) with line_type 8 and shift 0, OpenCV
+ * imgproc drawing.cpp `Circle(..., fill = 1)` (third-party, not under /root/reference; call site
+ * src/costfunc.cpp:423): the midpoint circle walk -- dy grows from 0, dx shrinks from the radius
+ * while dx >= dy -- and for every step the four horizontal runs [cx-dx, cx+dx] on rows cy-+dy and
+ * [cx-dy, cx+dy] on rows cy-+dx, clipped to the image.  mask[y*w + x] = 1 for every covered pixel.
+ * Pinned bit for bit against cv2.circle (4.13) in tests/test_oracle_pins.py. */
+void orc_fill_circle(uint8_t *mask, int w, int h, int cx, int cy, int radius)
+{
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    while (dx >= dy) {
+        const int ys[4] = {cy - dy, cy + dy, cy - dx, cy + dx};
+        const int hw[4] = {dx, dx, dy, dy};
+        for (int k = 0; k < 4; ++k) {
+            if (ys[k] < 0 || ys[k] >= h) continue;
+            int xa = cx - hw[k], xb = cx + hw[k];
+            if (xa < 0) xa = 0;
+            if (xb > w - 1) xb = w - 1;
+            for (int x = xa; x <= xb; ++x) mask[(long)ys[k] * w + x] = 1;
+        }
+        dy++;
+        err += plus;
+        plus += 2;
+        if (err > 0) {            /* mask = (err <= 0) - 1 */
+            err -= minus;
+            dx -= 1;
+            minus -= 2;
+        }
+    }
+}
+
+/* double -> int as the reference's implicit conversions do it (truncation); values no image can
+ * hold are clamped so that the circle falls outside instead of invoking the undefined conversion */
+static int trunc_to_int(double v)
+{
+    if (!(v > -1048576.0)) return -1048576;      /* also NaN */
+    if (v > 1048576.0) return 1048576;
+    return (int)v;
+}
+
+/* costfunc::bincomp_penalty, src/costfunc.cpp:384-436: the 48 spheres are drawn as filled discs
+ * (centre = trunc(K c / c_z), radius = trunc(r / scale)) into an empty 240x320 image; the penalty
+ * is the number of pixels where that silhouette and the observed one (depth != 0) differ.
+ * spheres: 48x3 as build_hand_model returns them (negated y, z; un-negated at :401).
+ * silhouette (optional, H*W) receives the drawn mask. */
+double orc_bincomp_penalty(const orc_model *m, const orc_obs *o, const double *spheres, uint8_t *silhouette)
+{
+    uint8_t *mask = (uint8_t *)calloc((size_t)ORC_W * ORC_H, 1);
+    for (int i = 0; i < ORC_NSPH; ++i) {
+        double x = spheres[i * 3], y = -spheres[i * 3 + 1], z = -spheres[i * 3 + 2];
+        double pu = (o->focal * x + o->cx * z) / z;
+        double pv = (o->focal * y + o->cy * z) / z;
+        int rad = trunc_to_int(m->rad[i] / o->scale);
+        if (rad < 0) continue;                    /* cv::circle asserts radius >= 0 */
+        orc_fill_circle(mask, ORC_W, ORC_H, trunc_to_int(pu), trunc_to_int(pv), rad);
+    }
+    long c = 0;
+    for (long p = 0; p < (long)ORC_W * ORC_H; ++p) c += (mask[p] != 0) != (o->depth[p] != 0.0);
+    if (silhouette) memcpy(silhouette, mask, (size_t)ORC_W * ORC_H);
+    free(mask);
+    return (double)c;
+}
+
 /* PSO::dim_restore, src/PSO.cpp:160-180: 22 -> 26 parameters with DIP = 2/3 PIP */
 void orc_dim_restore(const double in[22], double out[ORC_NDOF])
 {

@@ -131,6 +131,10 @@ int  orc_pso_optimise(const orc_model *m, const orc_obs *o, const orc_pso_params
                       double w, double c1, double c2, const double x0[ORC_NDOF], int num_p,
                       uint64_t seed, double bestp[ORC_NDOF], double *best_cost, int64_t *evals,
                       double *final_particles, double *final_pcost);
+/* costfunc::bincomp_penalty (src/costfunc.cpp:384-436) and the filled cv::circle it draws with */
+void   orc_fill_circle(uint8_t *mask, int w, int h, int cx, int cy, int radius);
+double orc_bincomp_penalty(const orc_model *m, const orc_obs *o, const double *spheres /* 48x3, negated y,z */,
+                           uint8_t *silhouette /* H*W or NULL */);
 void orc_dim_restore(const double in[22], double out[ORC_NDOF]);
 double orc_gnd_truth_err(const double joints[ORC_NJOINT * 3], const double gt_row[63]);
 

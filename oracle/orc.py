@@ -219,6 +219,22 @@ def pso_optimise(model, obs, params, x0, num_p, seed, w=0.7298, c1=1.49618, c2=1
     return bestp, best.value, n.value, fin_x, fin_c
 
 
+def fill_circle(w, h, cx, cy, radius):
+    """cv::circle(..., thickness=-1) restated (OpenCV drawing.cpp Circle); returns the uint8 mask (h, w)"""
+    mask = np.zeros((h, w), dtype=np.uint8)
+    lib().orc_fill_circle(_p(mask, C.c_uint8), int(w), int(h), int(cx), int(cy), int(radius))
+    return mask
+
+
+def bincomp_penalty(model, obs, theta, want_silhouette=False):
+    """costfunc::bincomp_penalty (src/costfunc.cpp:384-436) of the spheres of pose theta"""
+    S, _ = fk(model, theta)
+    sil = np.zeros((H, W), dtype=np.uint8) if want_silhouette else None
+    lib().orc_bincomp_penalty.restype = C.c_double
+    v = lib().orc_bincomp_penalty(C.byref(model), C.byref(obs.o), _p(f64(S)), _p(sil, C.c_uint8) if want_silhouette else None)
+    return (v, sil) if want_silhouette else v
+
+
 def philox(seed, c0, c1, c2, c3):
     out = (C.c_uint32 * 4)()
     lib().orc_philox(C.c_uint64(seed), c0, c1, c2, c3, out)

@@ -37,7 +37,7 @@ def lib():
             raise RuntimeError("oracle/_ref/libhpe_ref.so is not built (needs /root/reference)")
         _LIB = C.CDLL(SO)
         _LIB.ref_create.restype = C.c_void_p
-        for n in ("ref_cal_cost", "ref_cal_cost2", "ref_obs_scale", "ref_gnd_truth_err"):
+        for n in ("ref_cal_cost", "ref_cal_cost2", "ref_obs_scale", "ref_gnd_truth_err", "ref_bincomp_penalty"):
             getattr(_LIB, n).restype = C.c_double
     return _LIB
 
@@ -124,6 +124,10 @@ class Reference:
         m = np.zeros(self.n_pts, dtype=np.int32)
         lib().ref_cost_terms(self.h, _p(f64(theta)), _p(t), _p(m, C.c_int))
         return t, m
+
+    def bincomp_penalty(self, theta):
+        """costfunc::bincomp_penalty (src/costfunc.cpp:384-436) of the spheres build_hand_model gives for theta"""
+        return lib().ref_bincomp_penalty(self.h, _p(f64(theta)))
 
     def cost_batch(self, theta):
         theta = f64(theta).reshape(-1, 26)

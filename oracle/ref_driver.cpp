@@ -158,6 +158,17 @@ void ref_cost_terms(void *h, const double theta[26], double terms[3], int *match
         for (uword i = 0; i < m.n_rows; ++i) match[i] = (int)m(i);
 }
 
+// costfunc::bincomp_penalty (src/costfunc.cpp:384-436) of the spheres of pose theta
+double ref_bincomp_penalty(void *h, const double theta[26])
+{
+    ref_ctx *c = (ref_ctx *)h;
+    vec th = to_vec(theta, 26);
+    mat::fixed<48, 3> S;
+    c->hand->build_hand_model(th, S);
+    mat Sm = S;
+    return c->cost->bincomp_penalty(Sm);
+}
+
 // n poses through costfunc::cal_cost, parallelised over poses the way PSO::pso_evolve does
 // (#pragma omp parallel for around cal_cost, src/PSO.cpp:848-852); used as the CPU baseline
 void ref_cost_batch(void *h, const double *theta, long n, double *total)

@@ -230,7 +230,27 @@ inline void distanceTransform(const Mat &src, Mat &dst, int distanceType, int ma
 inline void namedWindow(const std::string &, int = 1) { shim_unreachable("namedWindow"); }
 inline void imshow(const std::string &, const Mat &) { shim_unreachable("imshow"); }
 inline int waitKey(int = 0) { shim_unreachable("waitKey"); }
-inline void circle(Mat &, Point, int, const Scalar &, int = 1, int = 8, int = 0) { shim_unreachable("circle"); }
+// cv::circle: only the filled disc (thickness < 0, line_type 8, shift 0) that costfunc::bincomp_penalty draws
+// (src/costfunc.cpp:423) on a CV_64F image -- OpenCV's midpoint walk `Circle(..., fill)` of imgproc/drawing.cpp,
+// the same restatement as oracle/hpe_oracle.c:orc_fill_circle (pinned against cv2.circle in
+// tests/test_oracle_pins.py).  Outlines (thickness >= 0: depthMatch_penalty, the viewer) stay unreachable.
+inline void circle(Mat &img, Point c, int radius, const Scalar &colour, int thickness = 1, int line_type = 8, int shift = 0)
+{
+    if (thickness >= 0 || line_type != 8 || shift != 0 || img.type() != CV_64F || radius < 0) shim_unreachable("circle (outline)");
+    int e = 0, dx = radius, dy = 0, up = 1, down = 2 * radius - 1;
+    for (; dx >= dy; ++dy) {
+        for (int pass = 0; pass < 4; ++pass) {
+            const int row = pass == 0 ? c.y - dy : pass == 1 ? c.y + dy : pass == 2 ? c.y - dx : c.y + dx;
+            const int half = pass < 2 ? dx : dy;
+            if (row < 0 || row >= img.rows) continue;
+            double *line = img.ptr<double>(row);
+            for (int x = std::max(c.x - half, 0); x <= std::min(c.x + half, img.cols - 1); ++x) line[x] = colour.val[0];
+        }
+        e += up;
+        up += 2;
+        if (e > 0) { e -= down; --dx; down -= 2; }
+    }
+}
 inline void findContours(Mat &, std::vector<std::vector<Point> > &, std::vector<Vec4i> &, int, int, Point = Point())
 {
     shim_unreachable("findContours");

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Writes tests/golden/golden_ref_opt_v1.npz from the REFERENCE ITSELF (oracle/_ref/libhpe_ref.so, the
+"""Writes tests/golden/golden_ref_opt_v1.npz (the SURVEY 8(f) rank 3 and 4 rows) from the REFERENCE ITSELF (oracle/_ref/libhpe_ref.so, the
 reference's own sources compiled unmodified, see make_golden_ref.py): PSO::pso_optimise
 (src/PSO.cpp:539-712) on the replayed counter-based streams (ref.PhiloxReplayOptimise, one OpenMP
 thread so that the per-particle randi draws arrive in particle order).  Needs /root/reference: run in
-the development container; the committed .npz is what the GPU box checks the oracle and the CUDA path
+the development container; also costfunc::bincomp_penalty (src/costfunc.cpp:384-436) of 64 poses through the
+reference's code with the filled cv::circle of oracle/shim (pinned against cv2.circle).  The committed .npz is what the GPU box checks the oracle and the CUDA path
 against.  Run: python tests/golden/make_golden_ref_opt.py
 """
 import os
@@ -45,6 +46,12 @@ def main():
         out["x0_%d" % k] = x0
         out["bestp%d" % k] = bestp
         out["bestp_cost%d" % k] = np.array(R.cal_cost(bestp))     # cal_cost of the returned pose (not gbest_cost)
+    # costfunc::bincomp_penalty on the last frame: near, far and partly-outside poses
+    poses = truth + rng.normal(size=(64, 26)) * D.STD * np.array([0.0, 0.1, 1.0, 3.0])[np.arange(64) % 4][:, None]
+    poses[7::8, 3:6] += rng.normal(size=(8, 3)) * 15.0
+    out["bincomp_truth"] = truth
+    out["bincomp_poses"] = poses
+    out["bincomp"] = np.array([R.bincomp_penalty(p) for p in poses])
     np.savez_compressed(os.path.join(HERE, "golden_ref_opt_v1.npz"), **out)
     print("wrote golden_ref_opt_v1.npz:", {k: out["bestp_cost%d" % k].item() for k in range(len(CASES))})
 

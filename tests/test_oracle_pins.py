@@ -189,3 +189,18 @@ def test_oracle_reproduces_golden(orc, omodel, golden, D):
     bp, best, tr, _, _ = orc.pso_evolve(omodel, obs, prm, g["pso_x0"], int(g["pso_num_p"]), int(g["pso_seed"]))
     assert np.allclose(tr, g["pso_trace"], rtol=1e-10) and np.allclose(bp, g["pso_bestp"], atol=1e-8)
     assert list(g["philox_kat"]) == orc.philox(0x0123456789abcdef, 1, 2, 3, 4)
+
+
+def test_fill_circle_equals_cv2_circle(orc):
+    """cv::circle(..., thickness=-1), the third-party call of costfunc::bincomp_penalty (src/costfunc.cpp:423):
+    the oracle's restatement of OpenCV's midpoint walk covers exactly cv2.circle's pixels, also when the disc
+    is clipped by the border or lies outside, down to radius 0"""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(8)
+    for t in range(1500):
+        w, h = (320, 240) if t % 3 else (int(rng.integers(1, 90)), int(rng.integers(1, 90)))
+        r = int(rng.integers(0, 70 if t % 5 else 4))
+        cx, cy = int(rng.integers(-90, w + 90)), int(rng.integers(-90, h + 90))
+        img = np.zeros((h, w), dtype=np.float64)
+        cv2.circle(img, (cx, cy), r, 7.5, -1)
+        assert np.array_equal(img != 0, orc.fill_circle(w, h, cx, cy, r) != 0), (w, h, cx, cy, r)

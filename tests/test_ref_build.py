@@ -230,3 +230,29 @@ def test_pso_optimise_on_replayed_streams(orc, omodel, R, D, num_p, maxiter, see
     bo, co, n, fx, fc = orc.pso_optimise(omodel, oo, orc.pso_params(maxiter=maxiter), x0, num_p, seed, w=w, c1=1.3, c2=1.6)
     assert np.array_equal(b, bo)
     assert co == fc.min() and n > num_p * maxiter
+
+
+# ---------------------------------------------------------------- costfunc::bincomp_penalty
+def test_oracle_reproduces_reference_bincomp_fixtures(orc, omodel):
+    """runs everywhere: the silhouette-mismatch counts the reference's costfunc::bincomp_penalty returned"""
+    g = np.load(os.path.join(HERE, "golden", "golden_ref_opt_v1.npz"))
+    oo = orc.Observation(orc.render_depth(omodel, g["bincomp_truth"]))
+    got = np.array([orc.bincomp_penalty(omodel, oo, p) for p in g["bincomp_poses"]])
+    assert np.array_equal(got, g["bincomp"]) and got.min() > 0 and len(np.unique(got)) > 30
+
+
+def test_bincomp_penalty_bit_exact(orc, omodel, R, D):
+    """costfunc::bincomp_penalty as written (src/costfunc.cpp:384-436: centre and radius truncated, discs drawn by
+    cv::circle, binarised, compared with depth != 0) against the oracle, incl. discs clipped by the image border"""
+    rng = np.random.default_rng(60)
+    truth = np.clip(D.X0 + rng.normal(size=26) * D.STD * 0.5, D.LB, D.UB)
+    depth = orc.render_depth(omodel, truth)
+    oo = orc.Observation(depth)
+    R.load_depth(depth)
+    for k in range(120):
+        th = truth + rng.normal(size=26) * D.STD * [0.0, 0.1, 1.0, 3.0][k % 4]
+        if k % 6 == 5:
+            th[3:6] += rng.normal(size=3) * 15.0
+        assert R.bincomp_penalty(th) == orc.bincomp_penalty(omodel, oo, th)
+    v, sil = orc.bincomp_penalty(omodel, oo, truth, want_silhouette=True)
+    assert v == np.count_nonzero((sil != 0) != (depth != 0))
