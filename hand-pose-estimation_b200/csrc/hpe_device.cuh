@@ -15,7 +15,9 @@
 #define HPE_NJOINT 21
 #define HPE_W 320
 #define HPE_H 240
-#define HPE_GROUP 5          // poses evaluated together by one warp (5 poses x 5 digits = 25 FK lanes);
+#ifndef HPE_GROUP
+#define HPE_GROUP 5
+#endif                       // poses evaluated together by one warp (5 poses x 5 digits = 25 FK lanes);
                              // 6 would fill 30 lanes but its scratch leaves room for 2 CTAs per SM, not 3
 #define HPE_MAXPTS 256       // 8 points per lane
 #define HPE_PPL 8

@@ -74,7 +74,9 @@ static __device__ unsigned long long g_hpe_fallback_points;
 #endif
 #define HPE_BLK 4                        // spheres per sweep-A block
 #define HPE_NBLK (HPE_NSPH / HPE_BLK)    // 12 blocks
-#define HPE_PASS 4                       // points per lane and pass (2 passes cover 8 x 32 = 256 points)
+#ifndef HPE_PASS
+#define HPE_PASS 4
+#endif                                   // points per lane and pass (2 passes cover 8 x 32 = 256 points)
 
 // per-warp shared-memory scratch
 struct WarpScratch {
