@@ -322,13 +322,42 @@ def main():
         step_e2e(i)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * N_POSES * args.steps / e2e_s
+    e2e_one_call = world * N_POSES * args.steps / e2e_s
+    # the same through the streaming form (hpe_cost_batch_submit / _wait): two batches in flight, so the upload
+    # of step i+1 runs under the kernels of step i; every step still uploads its own poses from pinned host
+    # memory and gets its results back in host memory inside the timed region
+    ring = [torch.empty(3, N_POSES, dtype=torch.float64).pin_memory() for _ in range(3)]
+
+    def run_streamed(steps):
+        pending = []
+        for i in range(steps):
+            buf, job = ring[i % 3], C.c_int(-1)
+            rc = lib.hpe_cost_batch_submit(hand._h, obs._h, 0, C.c_void_p(th_pin.data_ptr() + (i % ROTATE) * set_bytes),
+                                           C.c_int64(N_POSES), C.c_void_p(buf[0].data_ptr()), C.c_void_p(buf[1].data_ptr()),
+                                           None, C.byref(job))
+            if rc != 0:
+                raise RuntimeError(lib.hpe_last_error_string().decode())
+            pending.append(job.value)
+            if len(pending) == 2 and lib.hpe_cost_batch_wait(pending.pop(0)) != 0:
+                raise RuntimeError(lib.hpe_last_error_string().decode())
+        for j in pending:
+            if lib.hpe_cost_batch_wait(j) != 0:
+                raise RuntimeError(lib.hpe_last_error_string().decode())
+
+    run_streamed(args.warmup)
+    barrier()
+    t0 = time.perf_counter()
+    run_streamed(args.steps)
+    barrier()
+    e2e_value = world * N_POSES * args.steps / max_over_ranks(time.perf_counter() - t0)
+    last = ring[(args.steps - 1) % 3]
     # the e2e result must equal the device-resident one for the same pose set
     step_dev(args.steps - 1)
     torch.cuda.synchronize()
     dev_cost = cost_dev.cpu().numpy()
     host_cost = (out_pin[0] + out_pin[1]).numpy()
     assert np.array_equal(dev_cost, host_cost), "e2e and device-resident results differ"
+    assert np.array_equal(dev_cost, (last[0] + last[1]).numpy()), "streamed e2e and device-resident results differ"
 
     extras = {}
     if not args.no_extras:
@@ -574,7 +603,11 @@ def main():
                 "vs_baseline": None, "dtype": "f32 matcher + f64 FK/depth/align (the reference's own split)",
                 "data": "synthetic", "config": workload_config(args),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POSES * 26 * 8,
-                        "d2h_bytes_per_step": N_POSES * 2 * 8},
+                        "d2h_bytes_per_step": N_POSES * 2 * 8,
+                        "api": "hpe_cost_batch_submit / hpe_cost_batch_wait, two batches in flight (pinned host poses in, "
+                               "host results out, every step)",
+                        "one_call_value": e2e_one_call,
+                        "one_call_api": "hpe_cost_batch, one blocking call per step"},
                 "gpu_launches": args.steps,
                 "clocks": clocks,
                 "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",

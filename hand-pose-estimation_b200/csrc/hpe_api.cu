@@ -541,6 +541,86 @@ int hpe_cost_batch(const hpe_model *m, const hpe_obs *o, int slot, const double 
     return cost_host(m, o, slot, theta, n, nullptr, nullptr, align, depth, colli);
 }
 
+// ------------------------------------------------------------------------------------------
+// Streaming form of hpe_cost_batch: submit queues the upload / kernels / download of one batch and returns,
+// wait blocks until its results are in the caller's buffers.  With two or three batches in flight the upload of
+// batch k+1 runs under the kernels of batch k (the copy engine never idles between calls), which the one-call
+// form cannot do: it has to drain the last chunk's kernel and the download before it returns.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct CostJob {
+    Workspace ws;
+    cudaEvent_t up_done[HPE_MAX_CHUNKS], k_done[HPE_MAX_CHUNKS], done;
+    bool events = false, busy = false;
+};
+CostJob g_jobs[HPE_COST_JOBS];
+cudaStream_t g_job_pipe[3] = {nullptr, nullptr, nullptr};      // upload, compute, download (FIFO across jobs)
+cudaEvent_t g_job_ready = nullptr;
+}  // namespace
+
+int hpe_cost_batch_submit(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n, double *align,
+                          double *depth, double *colli, int *job)
+{
+    if (!m || !job || n < 0 || (!theta && n > 0)) return hpe_set_error(HPE_ERR_ARG, "hpe_cost_batch_submit: bad argument");
+    if (int rc = check_slot(o, slot, 1)) return rc;
+    if (int rc = check_filled(o, slot, 1)) return rc;
+    int id = -1;
+    for (int i = 0; i < HPE_COST_JOBS && id < 0; ++i)
+        if (!g_jobs[i].busy) id = i;
+    if (id < 0) return hpe_set_error(HPE_ERR_STATE, "hpe_cost_batch_submit: %d batches already in flight, wait for one", HPE_COST_JOBS);
+    CostJob &J = g_jobs[id];
+    if (!g_job_pipe[0]) {
+        for (int i = 0; i < 3; ++i) HPE_CUDA(cudaStreamCreateWithFlags(&g_job_pipe[i], cudaStreamNonBlocking));
+        HPE_CUDA(cudaEventCreateWithFlags(&g_job_ready, cudaEventDisableTiming));
+    }
+    if (!J.events) {
+        for (int i = 0; i < HPE_MAX_CHUNKS; ++i) {
+            HPE_CUDA(cudaEventCreateWithFlags(&J.up_done[i], cudaEventDisableTiming));
+            HPE_CUDA(cudaEventCreateWithFlags(&J.k_done[i], cudaEventDisableTiming));
+        }
+        HPE_CUDA(cudaEventCreateWithFlags(&J.done, cudaEventDisableTiming));
+        J.events = true;
+    }
+    cudaStream_t up = g_job_pipe[0], run = g_job_pipe[1], down = g_job_pipe[2];
+    size_t b_th = align_up(sizeof(double) * (n > 0 ? n : 1) * HPE_NDOF), b_tm = align_up(sizeof(double) * (n > 0 ? n : 1) * 3);
+    HPE_CUDA(J.ws.reserve(b_th + b_tm));
+    double *d_th = (double *)J.ws.p, *d_tm = (double *)((char *)J.ws.p + b_th);
+    HPE_CUDA(cudaEventRecord(g_job_ready, 0));       // prior default-stream work (observation kernels)
+    HPE_CUDA(cudaStreamWaitEvent(up, g_job_ready, 0));
+    HPE_CUDA(cudaStreamWaitEvent(run, g_job_ready, 0));
+    // the chunk schedule of hpe_cost_batch: uniform chunks of 16,384 poses (3.4 MB copies reach the full PCIe rate)
+    int64_t big = g_hpe_cost_chunk > 0 ? g_hpe_cost_chunk : 16384;
+    if ((n + big - 1) / big > HPE_MAX_CHUNKS) big = (n + HPE_MAX_CHUNKS - 1) / HPE_MAX_CHUNKS;
+    int k = 0;
+    for (int64_t c0 = 0; c0 < n; c0 += big, ++k) {
+        const int64_t cn = n - c0 < big ? n - c0 : big;
+        HPE_CUDA(cudaMemcpyAsync(d_th + c0 * HPE_NDOF, theta + c0 * HPE_NDOF, sizeof(double) * cn * HPE_NDOF,
+                                 cudaMemcpyHostToDevice, up));
+        HPE_CUDA(cudaEventRecord(J.up_done[k], up));
+        HPE_CUDA(cudaStreamWaitEvent(run, J.up_done[k], 0));
+        HPE_CUDA(hpe_launch_cost(m->dm, o->v, slot, d_th + c0 * HPE_NDOF, cn, colli != nullptr, nullptr, d_tm + c0, nullptr,
+                                 nullptr, run, n));
+        HPE_CUDA(cudaEventRecord(J.k_done[k], run));
+        HPE_CUDA(cudaStreamWaitEvent(down, J.k_done[k], 0));
+        if (align) HPE_CUDA(cudaMemcpyAsync(align + c0, d_tm + c0, sizeof(double) * cn, cudaMemcpyDeviceToHost, down));
+        if (depth) HPE_CUDA(cudaMemcpyAsync(depth + c0, d_tm + n + c0, sizeof(double) * cn, cudaMemcpyDeviceToHost, down));
+        if (colli) HPE_CUDA(cudaMemcpyAsync(colli + c0, d_tm + 2 * n + c0, sizeof(double) * cn, cudaMemcpyDeviceToHost, down));
+    }
+    HPE_CUDA(cudaEventRecord(J.done, down));
+    J.busy = true;
+    *job = id;
+    return HPE_OK;
+}
+
+int hpe_cost_batch_wait(int job)
+{
+    if (job < 0 || job >= HPE_COST_JOBS || !g_jobs[job].busy)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_cost_batch_wait: job %d is not in flight", job);
+    g_jobs[job].busy = false;
+    HPE_CUDA(cudaEventSynchronize(g_jobs[job].done));
+    return HPE_OK;
+}
+
 int hpe_cost_batch_frozen(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
                           const int32_t *match, double *align, double *depth, double *colli)
 {

@@ -243,6 +243,12 @@ class costfunc:
                                            _p(m, C.c_int32), _p(a), _p(d), _p(c)))
         return a, d, c
 
+    def cal_cost_submit(self, thetas, slot=0, with_collision=False):
+        """streaming form of cal_cost_batch (hpe_cost_batch_submit): queues the batch and returns a job whose
+        wait() gives (align, depth, colli); up to 3 jobs in flight, the upload of one under the kernels of the
+        previous.  Pass page-locked arrays for real overlap."""
+        return CostJob(self, thetas, slot, with_collision)
+
     def bincomp_penalty(self, theta, slot=0):
         """costfunc::bincomp_penalty (src/costfunc.cpp:384-436) of the spheres of pose theta: pixels where the
         silhouette of the projected spheres and the observed one differ"""
@@ -293,6 +299,24 @@ class costfunc:
         _check(lib().hpe_cost_batch_dev(self.hand._h, self.observation._h, int(slot), C.c_void_p(theta_dev_ptr),
                                         C.c_int64(n), int(with_collision), C.c_void_p(cost_dev_ptr),
                                         C.c_void_p(terms_dev_ptr or 0), C.c_void_p(stream or 0)))
+
+
+class CostJob:
+    """one batch in flight (hpe_cost_batch_submit / hpe_cost_batch_wait); keeps its buffers alive until wait()"""
+
+    def __init__(self, cf, thetas, slot, with_collision):
+        self.th = _f64(thetas).reshape(-1, 26)
+        n = self.th.shape[0]
+        self.a, self.d = np.empty(n), np.empty(n)
+        self.c = np.zeros(n) if with_collision else None
+        job = C.c_int(-1)
+        _check(lib().hpe_cost_batch_submit(cf.hand._h, cf.observation._h, int(slot), _p(self.th), C.c_int64(n),
+                                           _p(self.a), _p(self.d), _p(self.c), C.byref(job)))
+        self.id = job.value
+
+    def wait(self):
+        _check(lib().hpe_cost_batch_wait(int(self.id)))
+        return self.a, self.d, (np.zeros_like(self.a) if self.c is None else self.c)
 
 
 class PSO:

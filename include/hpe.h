@@ -111,6 +111,17 @@ float *hpe_obs_depth_dev(hpe_obs *o);
  * output may be NULL. */
 int hpe_cost_batch(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
                    double *align, double *depth, double *colli);
+/* Streaming form for callers that score many independent batches (the CostFunc batch check, offline
+ * scoring): submit queues the upload, the kernels and the download of one batch and returns a job id,
+ * wait blocks until that batch's results are in its align/depth/colli buffers.  Up to HPE_COST_JOBS
+ * batches may be in flight (a further submit returns HPE_ERR_STATE); they run in submission order, the
+ * upload of the next under the kernels of the current.  theta and the output arrays must stay valid
+ * until the wait returns and should be page-locked (pageable memory makes the copies synchronous).
+ * Results are those of hpe_cost_batch, bit for bit.  One submitting host thread. */
+#define HPE_COST_JOBS 3
+int hpe_cost_batch_submit(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
+                          double *align, double *depth, double *colli, int *job);
+int hpe_cost_batch_wait(int job);
 /* same on DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be NULL).
  * cost receives align+depth(+colli when with_collision); terms (may be NULL) receives three
  * arrays of n: align | depth | colli. */
