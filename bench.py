@@ -6,8 +6,10 @@ poses scored by costfunc::cal_cost (FK + 48-sphere matching + alignment + depth 
 one synthetic 320x240 Subject1-format frame; a "step" is one pass over the 65,536 poses.
 
   value   evaluations/s, poses resident in HBM, CUDA events around K kernel launches
-  e2e     evaluations/s through the host-pointer C ABI (hpe_cost_batch): pinned host poses
-          copied in and the three cost terms copied out inside every step
+  e2e     evaluations/s through the host-pointer C ABI: pinned host poses copied in and the cost
+          terms copied out inside every step -- the streaming form (hpe_cost_batch_submit / _wait,
+          three steps in flight) is the headline, the one-call form (hpe_cost_batch) is reported
+          next to it as e2e.one_call_value
   roofline  FP32 (non-tensor) pipe: algorithmic flop of SURVEY 8(d) / kernel time against the
           FFMA peak measured on this device by hpe_measure_fp32_peak
   cpu_baseline  the reference build (oracle/_ref) or the oracle port on a bounded sample, rank 0, N=1
@@ -323,8 +325,8 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_one_call = world * N_POSES * args.steps / e2e_s
-    # the same through the streaming form (hpe_cost_batch_submit / _wait): two batches in flight, so the upload
-    # of step i+1 runs under the kernels of step i; every step still uploads its own poses from pinned host
+    # the same through the streaming form (hpe_cost_batch_submit / _wait): three batches in flight, so the uploads
+    # of steps i+1, i+2 run under the kernels of step i; every step still uploads its own poses from pinned host
     # memory and gets its results back in host memory inside the timed region
     ring = [torch.empty(3, N_POSES, dtype=torch.float64).pin_memory() for _ in range(3)]
 
@@ -338,7 +340,7 @@ def main():
             if rc != 0:
                 raise RuntimeError(lib.hpe_last_error_string().decode())
             pending.append(job.value)
-            if len(pending) == 2 and lib.hpe_cost_batch_wait(pending.pop(0)) != 0:
+            if len(pending) == 3 and lib.hpe_cost_batch_wait(pending.pop(0)) != 0:
                 raise RuntimeError(lib.hpe_last_error_string().decode())
         for j in pending:
             if lib.hpe_cost_batch_wait(j) != 0:
@@ -604,7 +606,7 @@ def main():
                 "data": "synthetic", "config": workload_config(args),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POSES * 26 * 8,
                         "d2h_bytes_per_step": N_POSES * 2 * 8,
-                        "api": "hpe_cost_batch_submit / hpe_cost_batch_wait, two batches in flight (pinned host poses in, "
+                        "api": "hpe_cost_batch_submit / hpe_cost_batch_wait, three batches in flight (pinned host poses in, "
                                "host results out, every step)",
                         "one_call_value": e2e_one_call,
                         "one_call_api": "hpe_cost_batch, one blocking call per step"},

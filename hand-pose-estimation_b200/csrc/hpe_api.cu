@@ -588,8 +588,10 @@ int hpe_cost_batch_submit(const hpe_model *m, const hpe_obs *o, int slot, const 
     HPE_CUDA(cudaEventRecord(g_job_ready, 0));       // prior default-stream work (observation kernels)
     HPE_CUDA(cudaStreamWaitEvent(up, g_job_ready, 0));
     HPE_CUDA(cudaStreamWaitEvent(run, g_job_ready, 0));
-    // the chunk schedule of hpe_cost_batch: uniform chunks of 16,384 poses (3.4 MB copies reach the full PCIe rate)
-    int64_t big = g_hpe_cost_chunk > 0 ? g_hpe_cost_chunk : 16384;
+    // chunks of 65,536 poses (13.6 MB): with other batches in flight nothing is gained by splitting a batch further --
+    // measured end to end on 65,536-pose batches, 3 in flight: one chunk 2.53e8 evaluations/s (52.6 GB/s of uploads, the
+    // resident kernel rate), 32,768: 2.37e8, 16,384: 2.14e8, 8,192: 1.49e8 (tools/stream_probe.py)
+    int64_t big = g_hpe_cost_chunk > 0 ? g_hpe_cost_chunk : 65536;
     if ((n + big - 1) / big > HPE_MAX_CHUNKS) big = (n + HPE_MAX_CHUNKS - 1) / HPE_MAX_CHUNKS;
     int k = 0;
     for (int64_t c0 = 0; c0 < n; c0 += big, ++k) {
