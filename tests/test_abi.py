@@ -29,7 +29,8 @@ def test_header_declares_the_expected_surface():
     for must in ("hpe_model_create", "hpe_fk_batch", "hpe_obs_upload", "hpe_obs_get", "hpe_cost_batch",
                  "hpe_cost_batch_dev", "hpe_cost_batch_frozen", "hpe_correspondences", "hpe_pso_evolve",
                  "hpe_track_sequence", "hpe_swarm_create", "hpe_swarm_step", "hpe_swarm_reduce",
-                 "hpe_render_dev", "hpe_last_error_string"):
+                 "hpe_render_dev", "hpe_last_error_string", "hpe_refine_init_pose", "hpe_pso_optimise",
+                 "hpe_bincomp_batch", "hpe_gnd_truth_err", "hpe_cost_batch_submit", "hpe_cost_batch_wait", "hpe_fit_frames"):
         assert must in names
 
 
@@ -69,6 +70,15 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.hpe_fk_batch(h, None, C.c_int64(0), None, None) == 0          # empty batch is fine
     assert lib.hpe_fk_batch(h, None, C.c_int64(-1), None, None) == 1
     assert lib.hpe_set_matcher(7) == 1 and lib.hpe_set_matcher(0) == 0
+    # the later entry points validate before they touch the device: NULL handles, a job that is not in flight
+    job = C.c_int(-1)
+    assert lib.hpe_cost_batch_submit(None, None, 0, None, C.c_int64(4), None, None, None, C.byref(job)) == 1
+    assert lib.hpe_cost_batch_submit(h, None, 0, None, C.c_int64(0), None, None, None, None) == 1      # no job output
+    assert lib.hpe_cost_batch_wait(0) == 1 and lib.hpe_cost_batch_wait(99) == 1 and lib.hpe_cost_batch_wait(-1) == 1
+    assert b"not in flight" in lib.hpe_last_error_string()
+    assert lib.hpe_pso_optimise(h, None, None, 8, None, 0, 1, None, None, None, None, None, None) == 1
+    assert lib.hpe_bincomp_batch(h, None, 0, None, C.c_int64(3), None, None) == 1
+    assert lib.hpe_bincomp_batch(h, None, 0, None, C.c_int64(0), None, None) == 1                        # NULL observation
     lib.hpe_model_destroy(h)
     o = C.c_void_p()
     assert lib.hpe_obs_create(0, 250, C.c_double(241.42), C.byref(o)) == 1
