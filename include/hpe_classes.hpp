@@ -184,6 +184,15 @@ public:
     {
         check(hpe_cost_batch(hand->c_handle(), observation->c_handle(), slot, thetas, n, align, depth, colli));
     }
+    // streaming form of cal_cost_batch (hpe_cost_batch_submit / hpe_cost_batch_wait): returns a job id; up to
+    // HPE_COST_JOBS batches in flight, buffers (page-locked for real overlap) must outlive cal_cost_wait(job)
+    int cal_cost_submit(const double *thetas, long n, double *align, double *depth, double *colli, int slot = 0)
+    {
+        int job = -1;
+        check(hpe_cost_batch_submit(hand->c_handle(), observation->c_handle(), slot, thetas, n, align, depth, colli, &job));
+        return job;
+    }
+    static void cal_cost_wait(int job) { check(hpe_cost_batch_wait(job)); }
     void compute_correspondences(const vec &theta, uvec &matchId, int slot = 0)
     {
         matchId.assign(hpe_obs_num_samples(observation->c_handle()), 0);
