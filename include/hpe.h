@@ -117,7 +117,8 @@ int hpe_cost_batch(const hpe_model *m, const hpe_obs *o, int slot, const double 
  * batches may be in flight (a further submit returns HPE_ERR_STATE); they run in submission order, the
  * upload of the next under the kernels of the current.  theta and the output arrays must stay valid
  * until the wait returns and should be page-locked (pageable memory makes the copies synchronous).
- * Results are those of hpe_cost_batch, bit for bit.  One submitting host thread. */
+ * Results are those of hpe_cost_batch, bit for bit.  One submitting host thread; the frame in `slot`
+ * must not be replaced (hpe_obs_upload / hpe_obs_set) while a job that reads it is in flight. */
 #define HPE_COST_JOBS 3
 int hpe_cost_batch_submit(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
                           double *align, double *depth, double *colli, int *job);
