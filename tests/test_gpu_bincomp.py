@@ -58,3 +58,20 @@ def test_bincomp_edge_cases(hpe, orc, omodel, frame0, D):
     assert e.value.code == 4
     with pytest.raises(hpe.HpeError):
         cf.bincomp_penalty(truth, slot=3)
+
+
+def test_bincomp_full_size_properties(hpe, frame0, D):
+    """65,536 poses (BASELINE configs[1]'s batch): the result of a pose does not depend on its place in the batch
+    or on how the batch is split"""
+    truth, depth, _ = frame0
+    hand, obs = hpe.handmodel(), hpe.observedmodel(capacity=1)
+    obs.upload(depth[None])
+    cf = hpe.costfunc(hand, obs)
+    rng = np.random.default_rng(71)
+    n = 65536
+    th = truth + rng.normal(size=(n, 26)) * D.STD
+    pen = cf.bincomp_penalty_batch(th)
+    perm = rng.permutation(n)
+    assert np.array_equal(cf.bincomp_penalty_batch(th[perm]), pen[perm])
+    assert np.array_equal(np.concatenate([cf.bincomp_penalty_batch(th[:30001]), cf.bincomp_penalty_batch(th[30001:])]), pen)
+    assert pen.min() >= 0 and pen.max() <= 240 * 320 and cf.bincomp_penalty(truth) < np.median(pen)

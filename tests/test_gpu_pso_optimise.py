@@ -114,3 +114,26 @@ def test_pso_optimise_edge_cases(hpe, orc, omodel, D):
     with pytest.raises(hpe.HpeError) as e:
         pso.pso_optimise_batch(hpe.costfunc(hand, obs), x0, 4)
     assert e.value.code == 4
+
+
+def test_pso_optimise_full_size_properties(hpe, orc, omodel, D):
+    """64 particles x 30 iterations (the swarm size of BASELINE's configs), too long for the scalar oracle in a test:
+    size-independent properties instead -- counter-based draws make a shorter run a prefix of a longer one, so the
+    best cost can only fall with maxiter; a swarm's result does not depend on the batch it runs in; the returned
+    cost is the smallest personal best."""
+    rng = np.random.default_rng(55)
+    truths, frames, cf, pso = _setup(hpe, orc, omodel, D, rng, 3)
+    x0 = truths + rng.normal(size=(3, 26)) * D.STD * 0.3
+    best = {}
+    for maxiter in (5, 30):
+        pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, maxiter, 1e-8, 1e-8)
+        bg, cg, eg, fx, fc = pso.pso_optimise_batch(cf, x0, 64, seeds=[9, 9, 9], want_state=True)
+        assert np.array_equal(cg, fc.min(axis=1)) and np.all(eg > 64 * maxiter)
+        best[maxiter] = cg
+        if maxiter == 30:
+            alone = pso.pso_optimise_batch(cf, x0[1:2], 64, seeds=[9], first=1)
+            assert np.array_equal(alone[0][0], bg[1]) and alone[1][0] == cg[1] and alone[2][0] == eg[1]
+    assert np.all(best[30] <= best[5])
+    # the fit is a real one: far below the cost of the start pose
+    for k in range(3):
+        assert best[30][k] < 0.2 * orc.cal_cost(omodel, orc.Observation(frames[k]), x0[k])
