@@ -300,6 +300,7 @@ int hpe_obs_create(int capacity, int num_samples, double focal, hpe_obs **out)
     if (e == cudaSuccess) e = cudaMalloc(&v.meta, sizeof(FrameMeta) * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&v.wf_halo, sizeof(unsigned) * 2 * HPE_W * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&v.mask, sizeof(unsigned) * (npix / 32) * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&v.perm, (size_t)HPE_MAXPTS * capacity);
     if (e == cudaSuccess) e = cudaMemset(v.meta, 0, sizeof(FrameMeta) * capacity);
     if (e != cudaSuccess) {
         hpe_obs_destroy(o);
@@ -312,7 +313,7 @@ int hpe_obs_create(int capacity, int num_samples, double focal, hpe_obs **out)
 int hpe_obs_destroy(hpe_obs *o)
 {
     if (!o) return HPE_OK;
-    cudaFree(o->v.depth_mm); cudaFree(o->v.dt_px); cudaFree(o->v.cloud); cudaFree(o->v.meta); cudaFree(o->v.wf_halo); cudaFree(o->v.mask);
+    cudaFree(o->v.depth_mm); cudaFree(o->v.dt_px); cudaFree(o->v.cloud); cudaFree(o->v.meta); cudaFree(o->v.wf_halo); cudaFree(o->v.mask); cudaFree(o->v.perm);
     delete o;
     return HPE_OK;
 }
@@ -371,6 +372,7 @@ int hpe_obs_set(hpe_obs *o, int slot, const float *depth_mm, const float *dt_px,
     HPE_CUDA(cudaMemcpy(o->v.cloud + (size_t)3 * np * slot, soa.data(), sizeof(double) * 3 * np, cudaMemcpyHostToDevice));
     HPE_CUDA(cudaMemcpy(o->v.meta + slot, &meta, sizeof meta, cudaMemcpyHostToDevice));
     HPE_CUDA(hpe_launch_dtmax(o->v, slot, 0));
+    HPE_CUDA(hpe_launch_cluster(o->v, slot, 1, 0));
     HPE_CUDA(cudaStreamSynchronize(0));
     return HPE_OK;
 }

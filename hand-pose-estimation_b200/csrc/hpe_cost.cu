@@ -63,7 +63,9 @@ struct __align__(16) CostSmem {
     __align__(16) unsigned char ws[COST_WARPS * HPE_WS_BYTES(HPE_GROUP)];
 };
 
-template <bool WITH_COLLI, int MATCHER>
+// AUX: frozen correspondences in and / or correspondences out (cal_cost2's matchId); the plain scoring kernel is
+// compiled without them (fewer live registers and no per-point predicates in the alignment loop)
+template <bool WITH_COLLI, int MATCHER, bool AUX>
 __global__ void __launch_bounds__(COST_WARPS * 32, HPE_MINBLOCKS)
 cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, int64_t n,
             double *__restrict__ cost, double *__restrict__ terms, int64_t tstride,
@@ -80,6 +82,12 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
     const int64_t total_warps = (int64_t)gridDim.x * COST_WARPS;
     const int64_t gw = (int64_t)blockIdx.x * COST_WARPS + warp;
     const int64_t lo = n * gw / total_warps, hi = n * (gw + 1) / total_warps;
+    // this warp's poses [lo, hi): everything below is relative to lo (32-bit loop control)
+    const int mine = (int)(hi - lo);
+    theta += lo * HPE_NDOF;
+    if (cost) cost += lo;
+    if (terms) terms += lo;
+    if (AUX && match_out) match_out += lo * n_pts;
 
 #if HPE_STAGGER
     // warps of an SM start with first groups of different sizes so that their FP64 / gather phases
@@ -88,13 +96,13 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
 #else
     int first_cnt = HPE_GROUP;
 #endif
-    for (int64_t p0 = lo; p0 < hi;) {
-        int cnt = (int)min((int64_t)(p0 == lo ? first_cnt : HPE_GROUP), hi - p0);
+    for (int p0 = 0; p0 < mine;) {
+        const int cnt = min(p0 == 0 ? first_cnt : HPE_GROUP, mine - p0);
         group_fk(sm.fs.M, [&](int g) { return theta + (p0 + g) * HPE_NDOF; }, cnt, ws, lane);
         for (int g = 0; g < cnt; ++g) {
             double depth = depth_and_stage(sm.fs, ws, g, lane);
-            double align = match_align<MATCHER>(sm.fs, ws, g, lane, frozen,
-                                                match_out ? match_out + (p0 + g) * n_pts : nullptr);
+            double align = match_align<MATCHER>(sm.fs, ws, g, lane, AUX ? frozen : nullptr,
+                                                AUX && match_out ? match_out + (size_t)(p0 + g) * n_pts : nullptr);
             double colli = 0.0;
             if (WITH_COLLI) colli = warp_sum(collision_lane(sm.fs.rad, ws.sphd + (size_t)g * HPE_NSPH * 3, lane));
             if (lane == 0) {
@@ -640,18 +648,22 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
     static bool attr = false;
     if (!attr) {
         const int smem = (int)sizeof(CostSmem);
-        cudaFuncSetAttribute(cost_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(cost_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(cost_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(cost_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(cost_kernel<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(cost_kernel<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(cost_kernel<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(cost_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(cost_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(cost_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr = true;
     }
     auto launch = [&](auto kern) {
         kern<<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev, terms_dev,
                                                                  terms_stride, frozen_match_dev, match_out_dev);
     };
-    if (g_hpe_matcher == 1) launch(with_colli ? cost_kernel<true, 1> : cost_kernel<false, 1>);
-    else launch(with_colli ? cost_kernel<true, 0> : cost_kernel<false, 0>);
+    const bool aux = frozen_match_dev || match_out_dev;
+    if (g_hpe_matcher == 1) launch(with_colli ? cost_kernel<true, 1, true> : cost_kernel<false, 1, true>);
+    else if (aux) launch(with_colli ? cost_kernel<true, 0, true> : cost_kernel<false, 0, true>);
+    else launch(with_colli ? cost_kernel<true, 0, false> : cost_kernel<false, 0, false>);
     return cudaGetLastError();
 }
 

@@ -36,6 +36,7 @@ struct FrameView {
     const float  *depth_mm;  // [240][320]
     const float  *dt_px;     // [240][320]
     const double *cloud;     // [3][n_pts] SoA: X, -Y, -Z
+    const unsigned char *perm;  // [HPE_MAXPTS] cluster order of the cloud (cluster_kernel): sorted position -> point index
     double scale;            // cm per pixel
     double dt_max;           // disttrans.max()
     double focal, cx, cy;

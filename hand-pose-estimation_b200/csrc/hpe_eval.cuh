@@ -87,7 +87,8 @@ struct WarpScratch {
 };
 #define HPE_EX_PITCH (HPE_BLK + 1)
 #define HPE_EX_AT(j) (((j) / HPE_BLK) * HPE_EX_PITCH + ((j) % HPE_BLK))
-#define HPE_WS_BYTES(slots) ((slots) * HPE_NSPH * 24 + HPE_NSPH * 16 + HPE_NBLK * HPE_EX_PITCH * 16)
+#define HPE_EX_BLOCKS (HPE_NBLK + 1)      // + the "no block" entry a lane sweeps once its cluster's list is exhausted
+#define HPE_WS_BYTES(slots) ((slots) * HPE_NSPH * 24 + HPE_NSPH * 16 + HPE_EX_BLOCKS * HPE_EX_PITCH * 16)
 
 __device__ __forceinline__ WarpScratch warp_scratch(unsigned char *base, int warp, int slots)
 {
@@ -95,20 +96,47 @@ __device__ __forceinline__ WarpScratch warp_scratch(unsigned char *base, int war
     unsigned char *p = base + (size_t)warp * HPE_WS_BYTES(slots);
     w.cf = reinterpret_cast<float4 *>(p);
     w.ex = w.cf + HPE_NSPH;
-    w.sphd = reinterpret_cast<double *>(p + HPE_NSPH * 16 + HPE_NBLK * HPE_EX_PITCH * 16);
+    w.sphd = reinterpret_cast<double *>(p + HPE_NSPH * 16 + HPE_EX_BLOCKS * HPE_EX_PITCH * 16);
     return w;
+}
+
+// Sphere slots of the matcher: the 48 centres are regrouped into 12 spatially compact blocks of 4 (the sweep's unit of
+// work and of pruning) -- thumb 0-3 | 4-7, the 2 x 2 palm patches of (index, middle) and (ring, little), each finger's
+// proximal + middle pair, the fingertips of (index, middle) and (ring, little).  Any grouping returns the reference's
+// index: exact ties never pass the certificate and are decided by the exact fallback in index order.
+#define HPE_NCL (HPE_MAXPTS / 32)        // point clusters of 32
+// Storage position of member i of cluster c.  A warp matches 128 positions per pass, position k0 + 32 m with
+// k0 = lane + 128 pass for m = 0..3; cluster c = 4 pass + q is given to the eight lanes 8q..8q+7 of that pass (four
+// members each), so that every quarter of the warp sweeps the block list of ONE cluster.
+__device__ __forceinline__ int cluster_storage(int c, int i)
+{
+    return 128 * (c >> 2) + 32 * (i >> 3) + 8 * (c & 3) + (i & 7);
+}
+__device__ __forceinline__ int sphere_slot(int j)
+{
+    if (j < 8) return j;
+    const int f = (j - 8) / 10, i = (j - 8) - 10 * f;
+    if (i < 4) return 4 * (2 + (f >> 1) * 2 + (i >> 1)) + (f & 1) * 2 + (i & 1);
+    if (i < 8) return 4 * (6 + f) + (i - 4);
+    return 4 * (10 + (f >> 1)) + (f & 1) * 2 + (i - 8);
 }
 
 // model + frame data every CTA stages once
 struct __align__(16) FrameSmem {
-    float4 pre[HPE_MAXPTS];          // (260u|p'|^2, x', y', z'): float32 points recentred on q
+    float4 pre[HPE_MAXPTS];          // (260u|p'|^2, x', y', z'): float32 points recentred on q, CLUSTER ORDER
+    float4 cbox[HPE_NCL];            // per cluster of 32 points: centre of the bounding box of p', w = 2 max|p'|^2
+    float4 chalf[HPE_NCL];           // ... its half extents (rounded outwards)
     DevModel M;
     double rad[HPE_NSPH];
-    double cloud[3 * HPE_MAXPTS];    // FP64 cloud, SoA with stride HPE_MAXPTS (X | -Y | -Z)
+    double cloud[3 * HPE_MAXPTS];    // FP64 cloud, SoA with stride HPE_MAXPTS (X | -Y | -Z), CLUSTER ORDER
     double scale, dt_max, focal, cx, cy, lambda;
     const float *depth_mm, *dt_px;
     float qx, qy, qz;
     int n_pts;
+    unsigned valid[HPE_MAXPTS / 32]; // bit k & 31 of word k / 32: storage position k holds a point (not a repeat)
+    unsigned char perm[HPE_MAXPTS];  // storage position -> point index of the observation
+    unsigned char slot_of[HPE_NSPH]; // sphere -> matcher slot
+    unsigned char sph_of[HPE_NSPH];  // matcher slot -> sphere
 };
 
 // all threads of the CTA; caller syncs afterwards
@@ -116,26 +144,43 @@ __device__ __forceinline__ void stage_model(FrameSmem &fs, const DevModel &m)
 {
     for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 8); i += blockDim.x)
         reinterpret_cast<double *>(&fs.M)[i] = reinterpret_cast<const double *>(&m)[i];
-    if (threadIdx.x < HPE_NSPH) fs.rad[threadIdx.x] = m.rad[threadIdx.x];
+    if (threadIdx.x < HPE_NSPH) {
+        fs.rad[threadIdx.x] = m.rad[threadIdx.x];
+        const int sl = sphere_slot(threadIdx.x);
+        fs.slot_of[threadIdx.x] = (unsigned char)sl;
+        fs.sph_of[sl] = (unsigned char)threadIdx.x;
+    }
 }
 
-// all threads of the CTA (blockDim >= 32); contains __syncthreads, ends synchronised
+// all threads of the CTA (blockDim >= 64, a multiple of 32); contains __syncthreads, ends synchronised.
+// The cloud is staged in the CLUSTER ORDER of the observation (F.perm, cluster_kernel): member i of cluster c is point
+// perm[32 c + i] and lives at storage position cluster_storage(c, i); members beyond n_pts repeat the last point, so all
+// HPE_NCL clusters are well defined (fs.valid tells the alignment which positions count).
 __device__ __forceinline__ void stage_frame(FrameSmem &fs, const FrameView &F)
 {
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * HPE_MAXPTS; i += blockDim.x) {
-        int c = i / HPE_MAXPTS, k = i - c * HPE_MAXPTS;
-        fs.cloud[i] = k < F.n_pts ? F.cloud[c * F.n_pts + k] : 0.0;
+    for (int t = threadIdx.x; t < HPE_MAXPTS; t += blockDim.x) {
+        const int k = cluster_storage(t >> 5, t & 31), src = F.perm[t];
+        fs.perm[k] = (unsigned char)src;
+        fs.cloud[k] = F.cloud[src];
+        fs.cloud[HPE_MAXPTS + k] = F.cloud[F.n_pts + src];
+        fs.cloud[2 * HPE_MAXPTS + k] = F.cloud[2 * F.n_pts + src];
     }
+    if (threadIdx.x < HPE_MAXPTS / 32) fs.valid[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
         fs.scale = F.scale; fs.dt_max = F.dt_max; fs.focal = F.focal; fs.cx = F.cx; fs.cy = F.cy;
         fs.lambda = (double)HPE_NSPH / (double)F.n_pts;       // |M|/|P|, src/costfunc.cpp:372
         fs.depth_mm = F.depth_mm; fs.dt_px = F.dt_px; fs.n_pts = F.n_pts;
     }
     __syncthreads();
+    for (int t = threadIdx.x; t < F.n_pts; t += blockDim.x) {
+        const int k = cluster_storage(t >> 5, t & 31);
+        atomicOr(&fs.valid[k >> 5], 1u << (k & 31));
+    }
     if (threadIdx.x < 32) {     // centroid of the float32 cloud (any float origin is valid)
         float sx = 0.f, sy = 0.f, sz = 0.f;
-        for (int k = threadIdx.x; k < F.n_pts; k += 32) {
+        for (int t = threadIdx.x; t < F.n_pts; t += 32) {
+            const int k = cluster_storage(t >> 5, t & 31);
             sx += (float)fs.cloud[k]; sy += (float)fs.cloud[HPE_MAXPTS + k]; sz += (float)fs.cloud[2 * HPE_MAXPTS + k];
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -153,6 +198,26 @@ __device__ __forceinline__ void stage_frame(FrameSmem &fs, const FrameView &F)
         float pp = x * x + y * y + z * z;
         fs.pre[k] = make_float4(1.56e-5f * pp, x, y, z);      // (260 * 2^-24 |p'|^2 rounded up, x', y', z'): the coordinates sit in
                                                               // register banks 1,2,3, the sphere operands they meet in 0,1,2
+    }
+    __syncthreads();
+    // bounding boxes of the clusters in p' space (prune_blocks): a warp per cluster
+    for (int c = threadIdx.x >> 5; c < HPE_NCL; c += blockDim.x >> 5) {
+        const float4 q = fs.pre[cluster_storage(c, threadIdx.x & 31)];
+        float lx = q.y, hx = q.y, ly = q.z, hy = q.z, lz = q.w, hz = q.w, pp = q.y * q.y + q.z * q.z + q.w * q.w;
+        for (int o = 16; o > 0; o >>= 1) {
+            lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+            ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
+            lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+            pp = fmaxf(pp, __shfl_xor_sync(0xffffffffu, pp, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            const float bx = 0.5f * (lx + hx), by = 0.5f * (ly + hy), bz = 0.5f * (lz + hz);
+            fs.cbox[c] = make_float4(bx, by, bz, 2.0f * pp);
+            // half extents rounded outwards: [b - h, b + h] contains [lo, hi] whatever the rounding of b
+            fs.chalf[c] = make_float4(fmaf(0.5f * (hx - lx), 1.00001f, 1e-6f * fabsf(bx) + 1e-30f),
+                                      fmaf(0.5f * (hy - ly), 1.00001f, 1e-6f * fabsf(by) + 1e-30f),
+                                      fmaf(0.5f * (hz - lz), 1.00001f, 1e-6f * fabsf(bz) + 1e-30f), 0.f);
+        }
     }
     __syncthreads();
 }
@@ -251,10 +316,94 @@ __device__ __forceinline__ void match_pass_direct(const FrameSmem &fs, const War
     }
 }
 
+// packed FP32 add (same IEEE add in each half)
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+#ifndef HPE_PRUNE
+#define HPE_PRUNE 1          // 1: sweep A visits only the sphere blocks prune_blocks() could not exclude for the cluster
+#endif
+
+// Which sphere blocks can hold the nearest centre of SOME point of a cluster?  Lane = (cluster c = lane / 4,
+// quarter = lane % 4); returns the 12-bit block mask of cluster c on the four lanes of its quad.
+//   s_j(p') = w_j + e_j . p' is linear in p', so against a reference sphere k (the one nearest to the centre b of the
+//   cluster's bounding box) s_j - s_k >= [s_j(b) - s_k(b)] - sum_i |e_j,i - e_k,i| h_i everywhere in the box (h = its
+//   half extents).  If that bound exceeds the margin below, sphere j is farther than sphere k from EVERY point of the
+//   cluster, in the reference's own float32 arithmetic, by more than the certificate of match_pass asks for: with
+//   u = 2^-24, |s_j + |p'|^2 - D_j| <= u(104|p'|^2 + 13|s_j|) (header comment), |s_j| <= 2 w_j + |p'|^2 (because
+//   |e_j . p'| = 2|c'_j . p'| <= w_j + |p'|^2), the reference orders D_j, D_k correctly beyond 24u D, the rounding of the
+//   bound itself is below 16u(w_j + w_k + |p'|^2): in total < 100u(w_j + w_k) + 400u max|p'|^2, and the margin is
+//   4e-5 (w_j + w_k + 2 max|p'|^2) = 671u(...).  A block is skipped when all four of its spheres are excluded; the block
+//   of k itself never is, and the true nearest sphere of a point cannot be excluded (it is not farther than k).
+//   NaN / inf operands fail the comparison and keep the block.
+__device__ __forceinline__ unsigned prune_blocks(const FrameSmem &fs, const WarpScratch &ws, int lane)
+{
+    const int c = lane >> 2, sub = lane & 3;
+    const float4 bc = fs.cbox[c], hc = fs.chalf[c];
+    const unsigned long long bx = dup32(bc.x), by = dup32(bc.y), bz = dup32(bc.z);
+    // s_j(b) for the 12 slots of blocks 3 sub .. 3 sub + 2, slot index in the 6 low mantissa bits (any sphere is a valid
+    // reference, so the perturbation only affects which near-minimal one is taken)
+    unsigned long long sv[6];
+    float best = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const ulonglong2 *blk = reinterpret_cast<const ulonglong2 *>(ws.ex + (3 * sub + t) * HPE_EX_PITCH);
+        sv[2 * t] = expanded2(bx, by, bz, blk[0], blk[1]);
+        sv[2 * t + 1] = expanded2(bx, by, bz, blk[2], blk[3]);
+        float s0, s1, s2, s3;
+        split32(sv[2 * t], s0, s1);
+        split32(sv[2 * t + 1], s2, s3);
+        const unsigned base = (unsigned)(4 * (3 * sub + t));
+        s0 = __uint_as_float((__float_as_uint(s0) & 0xffffffc0u) | base);
+        s1 = __uint_as_float((__float_as_uint(s1) & 0xffffffc0u) | (base + 1));
+        s2 = __uint_as_float((__float_as_uint(s2) & 0xffffffc0u) | (base + 2));
+        s3 = __uint_as_float((__float_as_uint(s3) & 0xffffffc0u) | (base + 3));
+        best = fmin3(best, fminf(s0, s1), fminf(s2, s3));
+    }
+    best = fminf(best, __shfl_xor_sync(0xffffffffu, best, 1));
+    best = fminf(best, __shfl_xor_sync(0xffffffffu, best, 2));
+    const int ks = min((int)(__float_as_uint(best) & 63u), HPE_NSPH - 1);
+    const float *rf = reinterpret_cast<const float *>(ws.ex + (ks >> 2) * HPE_EX_PITCH) + ((ks >> 1) & 1) * 8 + (ks & 1);
+    const float rx = rf[0], ry = rf[2], rz = rf[4], rw = rf[6];
+    const float sref = fmaf(bc.z, rz, fmaf(bc.y, ry, fmaf(bc.x, rx, rw)));
+    const unsigned long long nrx = dup32(-rx), nry = dup32(-ry), nrz = dup32(-rz), nsref = dup32(-sref),
+                             wk = dup32(rw + bc.w), nmrg = dup32(-4e-5f);
+    unsigned mask = 0u;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const ulonglong2 *blk = reinterpret_cast<const ulonglong2 *>(ws.ex + (3 * sub + t) * HPE_EX_PITCH);
+        float tmin = __int_as_float(0x7f800000);
+        bool bad = false;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const ulonglong2 xy = blk[2 * q], zw = blk[2 * q + 1];
+            // [s_j(b) - s_k(b)] - 4e-5 (w_j + w_k + 2 max|p'|^2), both spheres of the pair
+            unsigned long long acc = ffma2(nmrg, fadd2(zw.y, wk), fadd2(sv[2 * t + q], nsref));
+            float a0, a1, dx0, dx1, dy0, dy1, dz0, dz1;
+            split32(acc, a0, a1);
+            split32(fadd2(xy.x, nrx), dx0, dx1);
+            split32(fadd2(xy.y, nry), dy0, dy1);
+            split32(fadd2(zw.x, nrz), dz0, dz1);
+            a0 = fmaf(-fabsf(dz0), hc.z, fmaf(-fabsf(dy0), hc.y, fmaf(-fabsf(dx0), hc.x, a0)));
+            a1 = fmaf(-fabsf(dz1), hc.z, fmaf(-fabsf(dy1), hc.y, fmaf(-fabsf(dx1), hc.x, a1)));
+            bad = bad || !(a0 == a0) || !(a1 == a1);
+            tmin = fmin3(tmin, a0, a1);
+        }
+        if (bad || !(tmin > 0.0f)) mask |= 1u << (3 * sub + t);
+    }
+    mask |= __shfl_xor_sync(0xffffffffu, mask, 1);
+    mask |= __shfl_xor_sync(0xffffffffu, mask, 2);
+    return mask;
+}
+
 // phase 3a for 4 points of the lane, k = k0 + 32 m (see the header comment).  ws.cf / ws.ex must
 // hold the pose being matched.
 __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratch &ws, int k0, int lane,
-                                           int idx[HPE_PASS])
+                                           unsigned qmask, int idx[HPE_PASS])
 {
     const float INF = __int_as_float(0x7f800000);
 #if HPE_FFMA2
@@ -268,7 +417,41 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
         px[m] = dup32(q.y); py[m] = dup32(q.z); pz[m] = dup32(q.w);
         M1[m] = INF; M2[m] = INF; g1[m] = 0;
     }
-#if HPE_PACKED_INDEX && HPE_PAIR_BLOCKS
+#if HPE_PRUNE && HPE_PACKED_INDEX
+    // pruned sweep A: the eight lanes of quarter q hold the 32 points of cluster 4 pass + q (cluster_storage), whose
+    // block mask sits on the quad of lanes 4 * cluster (prune_blocks).  Every quarter walks its own list -- the block
+    // address differs per quarter, the control flow does not: all lanes run max(list length) steps, a lane whose list
+    // is exhausted sweeps the "no block" entry (s = 3e38, changes neither M1 nor a certified M2).
+    unsigned mk = __shfl_sync(0xffffffffu, qmask, 4 * (((k0 - lane) >> 5) + (lane >> 3)));
+    const int nit = __reduce_max_sync(0xffffffffu, __popc(mk));
+#ifdef HPE_COUNT_ITERS      // measurement build: the fallback counter counts sweep steps instead (tools/fallback_rate.py)
+    if (lane == 0) atomicAdd(&g_hpe_fallback_points, (unsigned long long)nit);
+#endif
+    HPE_UNROLL_SWEEP
+    for (int it = 0; it < nit; ++it) {
+        const int g = mk ? __ffs(mk) - 1 : HPE_NBLK;
+        mk &= mk - 1u;
+        const ulonglong2 *blk = reinterpret_cast<const ulonglong2 *>(ws.ex + g * HPE_EX_PITCH);
+        const ulonglong2 a0 = blk[0], a1 = blk[1], b0 = blk[2], b1 = blk[3];
+        unsigned long long sa[HPE_PASS], sb[HPE_PASS];
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) { sa[m] = ffma2(px[m], a0.x, a1.y); sb[m] = ffma2(px[m], b0.x, b1.y); }
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) { sa[m] = ffma2(py[m], a0.y, sa[m]); sb[m] = ffma2(py[m], b0.y, sb[m]); }
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) { sa[m] = ffma2(pz[m], a1.x, sa[m]); sb[m] = ffma2(pz[m], b1.x, sb[m]); }
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) {
+            float s0, s1, s2, s3;
+            split32(sa[m], s0, s1);
+            split32(sb[m], s2, s3);
+            float gm = fmin3(fminf(s0, s1), s2, s3);
+            gm = __uint_as_float((__float_as_uint(gm) & 0xfffffff0u) | (unsigned)g);
+            M2[m] = fminf(M2[m], fmaxf(M1[m], gm));
+            M1[m] = fminf(M1[m], gm);
+        }
+    }
+#elif HPE_PACKED_INDEX && HPE_PAIR_BLOCKS
     // two blocks per step: their (index-carrying) minima are ordered once, so the runner-up update costs one
     // fmax + one three-input min for both (5.5 instead of 6 ALU instructions per point and block)
     HPE_UNROLL_SWEEP
@@ -358,7 +541,7 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
         bool cert = fminf(M2[m], r) - M1[m] > tau;                        // false on NaN
 #endif
         int i = s1 < s0 ? 1 : 0, j = s3 < s2 ? 3 : 2;
-        idx[m] = g1[m] * HPE_BLK + (lo23 < lo01 ? j : i);
+        idx[m] = fs.sph_of[g1[m] * HPE_BLK + (lo23 < lo01 ? j : i)];     // matcher slot -> sphere
         slow |= (cert ? 0u : 1u) << m;
     }
 #else
@@ -462,7 +645,7 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
         bool cert = fminf(M2[m], r) - M1[m] > tau;                        // false on NaN
 #endif
         int i = s1 < s0 ? 1 : 0, j = s3 < s2 ? 3 : 2;
-        idx[m] = g1[m] * HPE_BLK + (lo23 < lo01 ? j : i);
+        idx[m] = fs.sph_of[g1[m] * HPE_BLK + (lo23 < lo01 ? j : i)];     // matcher slot -> sphere
         slow |= (cert ? 0u : 1u) << m;
     }
 #endif  // HPE_FFMA2
@@ -470,8 +653,10 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
     if (__any_sync(0xffffffffu, slow != 0u)) {
 #pragma unroll
         for (int m = 0; m < HPE_PASS; ++m) {
-            unsigned todo = __ballot_sync(0xffffffffu, ((slow >> m) & 1u) && k0 + 32 * m < fs.n_pts);
+            unsigned todo = __ballot_sync(0xffffffffu, (slow >> m) & 1u) & fs.valid[(k0 + 32 * m) >> 5];
+#ifndef HPE_COUNT_ITERS
             if (todo && lane == 0) atomicAdd(&g_hpe_fallback_points, (unsigned long long)__popc(todo));
+#endif
             while (todo) {
                 int src = __ffs(todo) - 1;
                 todo &= todo - 1;
@@ -492,27 +677,30 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
                                               const int32_t *frozen, int32_t *match_row)
 {
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
-    const int n_pts = fs.n_pts;
     double acc = 0.0;
+    unsigned qmask = 0xfffu;
+#if HPE_PRUNE && HPE_FFMA2 && HPE_PACKED_INDEX
+    if (!frozen && MATCHER == 0) qmask = prune_blocks(fs, ws, lane);
+#endif
 #pragma unroll 1
     for (int pass = 0; pass < HPE_PPL / HPE_PASS; ++pass) {
-        const int k0 = lane + 32 * HPE_PASS * pass;
+        const int k0 = lane + 32 * HPE_PASS * pass;      // storage positions (stage_frame)
         int idx[HPE_PASS];
         if (frozen) {
 #pragma unroll
-            for (int m = 0; m < HPE_PASS; ++m) idx[m] = k0 + 32 * m < n_pts ? frozen[k0 + 32 * m] : 0;
+            for (int m = 0; m < HPE_PASS; ++m) idx[m] = frozen[fs.perm[k0 + 32 * m]];
         } else if (MATCHER == 1) {
             match_pass_direct(fs, ws, k0, lane, idx);
         } else {
-            match_pass(fs, ws, k0, lane, idx);
+            match_pass(fs, ws, k0, lane, qmask, idx);
         }
         // align_models for these 4 points, FP64, the reference's operation order
 #pragma unroll
         for (int m = 0; m < HPE_PASS; ++m) {
             int k = k0 + 32 * m;
-            if (k < n_pts) {
+            if ((fs.valid[k >> 5] >> lane) & 1u) {
                 int j = idx[m];
-                if (match_row) match_row[k] = j;
+                if (match_row) match_row[fs.perm[k]] = j;
                 // negated-frame centre = (cx, -cy, -cz)
                 double a = fs.cloud[k] - sd[j * 3 + 0];
                 double b = fs.cloud[HPE_MAXPTS + k] + sd[j * 3 + 1];
@@ -641,15 +829,20 @@ __device__ __forceinline__ double depth_and_stage(const FrameSmem &fs, const War
             ws.cf[j] = c;
             const float4 e = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz),
                                          (float)(cx * cx + cy * cy + cz * cz));
+            const int sl = fs.slot_of[j];                  // matcher slot of sphere j (sphere_slot)
 #if HPE_FFMA2
-            // spheres 4g+2q and 4g+2q+1 share 64-bit words: block g = | x01 y01 | z01 w01 | x23 y23 | z23 w23 | pad |
-            float *fb = reinterpret_cast<float *>(ws.ex + (j / HPE_BLK) * HPE_EX_PITCH) + ((j % HPE_BLK) / 2) * 8 + (j & 1);
+            // slots 4g+2q and 4g+2q+1 share 64-bit words: block g = | x01 y01 | z01 w01 | x23 y23 | z23 w23 | pad |
+            float *fb = reinterpret_cast<float *>(ws.ex + (sl / HPE_BLK) * HPE_EX_PITCH) + ((sl % HPE_BLK) / 2) * 8 + (sl & 1);
             fb[0] = e.x; fb[2] = e.y; fb[4] = e.z; fb[6] = e.w;
 #else
-            ws.ex[HPE_EX_AT(j)] = e;
+            ws.ex[HPE_EX_AT(sl)] = e;
 #endif
         }
     }
+#if HPE_FFMA2
+    // the "no block" entry of the pruned sweep: e = 0, w = 3e38 for its four slots
+    if (lane < 4) ws.ex[HPE_NBLK * HPE_EX_PITCH + lane] = (lane & 1) ? make_float4(0.f, 0.f, 3e38f, 3e38f) : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
     __syncwarp();
     return warp_sum(dv);
 }

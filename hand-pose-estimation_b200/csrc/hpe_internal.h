@@ -22,6 +22,7 @@ struct ObsView {
     FrameMeta *meta;      // [capacity]
     unsigned  *wf_halo;   // [capacity][2][320] scratch of the wavefront chamfer (band halo rows)
     unsigned  *mask;      // [capacity][2400] hand-pixel bits, 32 consecutive pixels per word (cloud_kernel -> chamfer_scan_kernel)
+    unsigned char *perm;  // [capacity][HPE_MAXPTS] cluster order of the cloud: sorted position -> point index (cluster_kernel)
     double focal, cx, cy;
     int n_pts;
     int capacity;
@@ -33,6 +34,7 @@ __device__ __forceinline__ FrameView frame_view(const ObsView &o, int slot)
     f.depth_mm = o.depth_mm + (size_t)slot * HPE_W * HPE_H;
     f.dt_px = o.dt_px + (size_t)slot * HPE_W * HPE_H;
     f.cloud = o.cloud + (size_t)slot * 3 * o.n_pts;
+    f.perm = o.perm + (size_t)slot * HPE_MAXPTS;
     f.scale = o.meta[slot].scale;
     f.dt_max = o.meta[slot].dt_max;
     f.focal = o.focal; f.cx = o.cx; f.cy = o.cy;
@@ -142,6 +144,8 @@ cudaError_t hpe_launch_eval_latency(const DevModel &m, const ObsView &o, int slo
 cudaError_t hpe_launch_gt_err(const double *joints_dev, const double *gt_dev, int64_t n, double *err_dev, cudaStream_t st);
 cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *scratch, cudaStream_t st);
 cudaError_t hpe_launch_dtmax(const ObsView &o, int slot, cudaStream_t st);
+// cluster order of the clouds of slots [first, first+count) (run by hpe_launch_observe; separately for injected clouds)
+cudaError_t hpe_launch_cluster(const ObsView &o, int first, int count, cudaStream_t st);
 cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
                            int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
                            double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st);

@@ -144,6 +144,69 @@ __global__ void __launch_bounds__(OBS_THREADS) cloud_kernel(ObsView o, int first
     }
 }
 
+// Cluster order of a frame's cloud (consumed by stage_frame / match_pass, hpe_eval.cuh): the points are arranged so
+// that every run of 32 consecutive positions is spatially compact -- a k-d split three levels deep: widest axis of the
+// segment's bounding box, full sort along it (rank by counting, ties by point index), cut at a multiple of 32 points.
+// perm[position] = point index; positions >= n_pts repeat the last point.  One CTA of 256 threads per frame.
+__device__ __forceinline__ unsigned sortable_bits(float v)
+{
+    unsigned b = __float_as_uint(v);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);       // total order, also over -0 / NaN payloads
+}
+
+__global__ void __launch_bounds__(HPE_MAXPTS) cluster_kernel(ObsView o, int first)
+{
+    const int slot = first + blockIdx.x;
+    unsigned char *perm = o.perm + (size_t)slot * HPE_MAXPTS;
+    const int n = o.n_pts, t = threadIdx.x;
+    __shared__ float P[3][HPE_MAXPTS];
+    __shared__ unsigned char ord[2][HPE_MAXPTS];
+    if (!o.meta[slot].ok) {                                     // empty frame (uniform): identity, never consumed
+        perm[t] = (unsigned char)min(t, n - 1);
+        return;
+    }
+    const double *cloud = o.cloud + (size_t)slot * 3 * n;
+    if (t < n) {
+        P[0][t] = (float)cloud[t]; P[1][t] = (float)cloud[n + t]; P[2][t] = (float)cloud[2 * n + t];
+    }
+    ord[0][t] = (unsigned char)t;
+    __syncthreads();
+    int lo = 0, hi = n, cur = 0;
+    for (int level = 0; level < 3; ++level) {
+        const int id = ord[cur][t < n ? t : 0];
+        int dst = t;
+        const bool split = t < n && hi - lo > 32;
+        if (split) {
+            float mn0 = P[0][id], mx0 = mn0, mn1 = P[1][id], mx1 = mn1, mn2 = P[2][id], mx2 = mn2;
+            for (int u = lo; u < hi; ++u) {
+                const int i = ord[cur][u];
+                mn0 = fminf(mn0, P[0][i]); mx0 = fmaxf(mx0, P[0][i]);
+                mn1 = fminf(mn1, P[1][i]); mx1 = fmaxf(mx1, P[1][i]);
+                mn2 = fminf(mn2, P[2][i]); mx2 = fmaxf(mx2, P[2][i]);
+            }
+            const float e0 = mx0 - mn0, e1 = mx1 - mn1, e2 = mx2 - mn2;
+            const int axis = (e0 >= e1 && e0 >= e2) ? 0 : (e1 >= e2 ? 1 : 2);
+            const unsigned key = sortable_bits(P[axis][id]);
+            int rank = 0;
+            for (int u = lo; u < hi; ++u) {
+                const int i = ord[cur][u];
+                const unsigned ku = sortable_bits(P[axis][i]);
+                rank += (ku < key || (ku == key && i < id)) ? 1 : 0;
+            }
+            dst = lo + rank;
+        }
+        if (t < n) ord[cur ^ 1][dst] = (unsigned char)id;
+        __syncthreads();
+        cur ^= 1;
+        if (split) {
+            const int ncl = (hi - lo + 31) >> 5;
+            const int mid = lo + ((ncl + 1) >> 1) * 32;
+            if (t < mid) hi = mid; else lo = mid;
+        }
+    }
+    perm[t] = ord[cur][t < n ? t : n - 1];
+}
+
 // 5x5 chamfer metric in OpenCV's Q16 fixed point: a = 65536 (axis), b = 91750 (diagonal),
 // c = 143976 (knight).  Distance between two pixels with |dx|,|dy| = closed form below; the
 // two-pass raster algorithm of cv::distanceTransform computes exactly min over feature
@@ -561,6 +624,7 @@ cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *, c
         attr = true;
     }
     cloud_kernel<<<count, OBS_THREADS, 0, st>>>(o, first);
+    cluster_kernel<<<count, HPE_MAXPTS, 0, st>>>(o, first);
     if (g_hpe_chamfer == 1) {
         chamfer_kernel<<<count, OBS_THREADS, smem, st>>>(o, first);
     } else if (g_hpe_chamfer == 0) {
@@ -575,6 +639,13 @@ cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *, c
         chamfer_wavefront_kernel<<<(count + WF_WARPS - 1) / WF_WARPS, WF_WARPS * 32, WF_WARPS * WF_SMEM_PER_WARP, st>>>(
             o, first, count);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t hpe_launch_cluster(const ObsView &o, int first, int count, cudaStream_t st)
+{
+    if (count <= 0) return cudaSuccess;
+    cluster_kernel<<<count, HPE_MAXPTS, 0, st>>>(o, first);
     return cudaGetLastError();
 }
 
