@@ -11,6 +11,10 @@ namespace {
 #define HPE_STAGGER 0      // staggered first groups: measured -1 % with the packed sweeps
 #endif
 constexpr int COST_WARPS = 8;
+#ifndef HPE_GROUP_DEPTH
+#define HPE_GROUP_DEPTH 0  // 1: depth term of a whole group of poses at once (group_depth: fewer instructions, but its unrolled
+                           // rounds cost more in instruction-cache misses than they save -- measured -12 %), 0: pose by pose
+#endif
 }  // namespace
 
 int g_hpe_matcher = 0;   // 0 = certified two-sweep matcher, 1 = direct form on all 48 spheres (cross-check)
@@ -99,9 +103,18 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
     for (int p0 = 0; p0 < mine;) {
         const int cnt = min(p0 == 0 ? first_cnt : HPE_GROUP, mine - p0);
         group_fk(sm.fs.M, [&](int g) { return theta + (p0 + g) * HPE_NDOF; }, cnt, ws, lane);
+#if HPE_GROUP_DEPTH
+        group_depth<HPE_GROUP>(sm.fs, ws, cnt, lane);
+#endif
+#pragma unroll 1
         for (int g = 0; g < cnt; ++g) {
-            double depth = depth_and_stage(sm.fs, ws, g, lane);
-            double align = match_align<MATCHER>(sm.fs, ws, g, lane, AUX ? frozen : nullptr,
+#if HPE_GROUP_DEPTH
+            const double depth = ws.dep[g];
+            stage_pose(sm.fs, ws, g, lane);
+#else
+            const double depth = depth_and_stage(sm.fs, ws, g, lane);
+#endif
+            double align = match_align<MATCHER, AUX>(sm.fs, ws, g, lane, AUX ? frozen : nullptr,
                                                 AUX && match_out ? match_out + (size_t)(p0 + g) * n_pts : nullptr);
             double colli = 0.0;
             if (WITH_COLLI) colli = warp_sum(collision_lane(sm.fs.rad, ws.sphd + (size_t)g * HPE_NSPH * 3, lane));

@@ -158,13 +158,26 @@ __device__ __forceinline__ void fk_digit_trig(const DevModel &M, int d, const do
     J[4][2] = cur.tz + L[3] * (cur.r20 * c4 + cur.r21 * s4);
 }
 
+// sine and cosine of an angle in degrees.  One out-of-line copy for the seven (or 23) call sites of a kernel: the
+// evaluation kernels are instruction-cache bound in their straight-line FP64 phases (ncu: no_instruction stalls), and
+// seven inlined expansions of sincos are ~450 SASS instructions.  Measured: the out-of-line copy (HPE_SINCOS_INLINE=0)
+// shrinks cost_kernel from 5,030 to 4,440 instructions but its calls cost more than the misses they save (-2 %).
+#ifndef HPE_SINCOS_INLINE
+#define HPE_SINCOS_INLINE 1
+#endif
+#if HPE_SINCOS_INLINE
+__device__ __forceinline__ void sincos_deg(double deg, double *sn, double *cs) { sincos(hpe_deg2rad(deg), sn, cs); }
+#else
+static __device__ __noinline__ void sincos_deg(double deg, double *sn, double *cs) { sincos(hpe_deg2rad(deg), sn, cs); }
+#endif
+
 // joints J[0..4] of digit d (0 = thumb) for pose th[26]: the lane computes its seven sincos itself
 __device__ __forceinline__ void fk_digit(const DevModel &M, int d, const double *th, double J[5][3])
 {
     DigitTrig t;
     double pos[3] = {th[3], th[4], th[5]};
 #pragma unroll
-    for (int k = 0; k < 7; ++k) sincos(hpe_deg2rad(trig_angle_deg(th, d, k)), &t.s[k], &t.c[k]);
+    for (int k = 0; k < 7; ++k) sincos_deg(trig_angle_deg(th, d, k), &t.s[k], &t.c[k]);
     fk_digit_trig(M, d, pos, t, J);
 }
 
@@ -182,7 +195,7 @@ __device__ __forceinline__ void fk_digit_cg(const DevModel &M, int d, const doub
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         const double deg = k == 0 ? loc[0] + 180.0 : k < 3 ? loc[k] : loc[6 + (k - 3)];
-        sincos(hpe_deg2rad(deg), &t.s[k], &t.c[k]);
+        sincos_deg(deg, &t.s[k], &t.c[k]);
     }
     fk_digit_trig(M, d, pos, t, J);
 }
@@ -196,7 +209,7 @@ __device__ __forceinline__ void fk_digit_warp(const DevModel &M, const double *t
     double sn = 0.0, cs = 0.0;
     if (lane < 23) {
         const double deg = lane == 0 ? th[0] + 180.0 : lane < 3 ? th[lane] : th[6 + (lane - 3)];
-        sincos(hpe_deg2rad(deg), &sn, &cs);
+        sincos_deg(deg, &sn, &cs);
     }
     const int d = lane < 5 ? lane : 0;
     DigitTrig t;

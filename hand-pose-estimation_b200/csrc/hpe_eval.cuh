@@ -80,6 +80,7 @@ static __device__ unsigned long long g_hpe_fallback_points;
 
 // per-warp shared-memory scratch
 struct WarpScratch {
+    double *dep;    // [8] depth terms of the group's poses (group_depth -> the per-pose loop)
     double *sphd;   // [slot][48][3] un-negated FP64 centres of the group's poses
     float4 *cf;     // [48] (x,-y,-z,0): the float32 centres cv::BFMatcher sees, pose being matched
     float4 *ex;     // [12][5] (-2c'x, -2c'y, -2c'z, |c'|^2), c' = cf - q, pose being matched; blocks of 4 spheres
@@ -88,7 +89,7 @@ struct WarpScratch {
 #define HPE_EX_PITCH (HPE_BLK + 1)
 #define HPE_EX_AT(j) (((j) / HPE_BLK) * HPE_EX_PITCH + ((j) % HPE_BLK))
 #define HPE_EX_BLOCKS (HPE_NBLK + 1)      // + the "no block" entry a lane sweeps once its cluster's list is exhausted
-#define HPE_WS_BYTES(slots) ((slots) * HPE_NSPH * 24 + HPE_NSPH * 16 + HPE_EX_BLOCKS * HPE_EX_PITCH * 16)
+#define HPE_WS_BYTES(slots) ((slots) * HPE_NSPH * 24 + HPE_NSPH * 16 + HPE_EX_BLOCKS * HPE_EX_PITCH * 16 + 64)
 
 __device__ __forceinline__ WarpScratch warp_scratch(unsigned char *base, int warp, int slots)
 {
@@ -96,7 +97,8 @@ __device__ __forceinline__ WarpScratch warp_scratch(unsigned char *base, int war
     unsigned char *p = base + (size_t)warp * HPE_WS_BYTES(slots);
     w.cf = reinterpret_cast<float4 *>(p);
     w.ex = w.cf + HPE_NSPH;
-    w.sphd = reinterpret_cast<double *>(p + HPE_NSPH * 16 + HPE_EX_BLOCKS * HPE_EX_PITCH * 16);
+    w.dep = reinterpret_cast<double *>(p + HPE_NSPH * 16 + HPE_EX_BLOCKS * HPE_EX_PITCH * 16);
+    w.sphd = w.dep + 8;
     return w;
 }
 
@@ -672,7 +674,26 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
 // phase 3 of pose g: both passes; returns the warp-reduced align_models value
 // (src/costfunc.cpp:346-377), valid on all lanes.  frozen: optional fixed correspondences
 // (n_pts ints); match_row: optional output row (n_pts ints).
-template <int MATCHER>
+// sqrt of a non-negative finite double without the library's special-case branch: rsqrt seed (2^-22), two coupled
+// Newton steps and the FMA-residual correction -- within one ulp of the rounded root (almost always equal to it);
+// 0 and inputs below 1e-280 map to 0.  The alignment sums agree with the oracle to ~1e-15 relative either way (summation order).
+__device__ __forceinline__ double sqrt_pos(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = __dmul_rn(x, y), h = __dmul_rn(0.5, y);
+    double r = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, r, g);
+    h = __fma_rn(h, r, h);
+    r = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, r, g);
+    h = __fma_rn(h, r, h);
+    const double d = __fma_rn(-g, g, x);
+    g = __fma_rn(d, h, g);
+    return x > 1e-280 ? g : 0.0;      // 0 (seed = inf) and denormal-range inputs: the root is below 1e-140
+}
+
+template <int MATCHER, bool AUX = true>
 __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScratch &ws, int g, int lane,
                                               const int32_t *frozen, int32_t *match_row)
 {
@@ -680,13 +701,13 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
     double acc = 0.0;
     unsigned qmask = 0xfffu;
 #if HPE_PRUNE && HPE_FFMA2 && HPE_PACKED_INDEX
-    if (!frozen && MATCHER == 0) qmask = prune_blocks(fs, ws, lane);
+    if (!(AUX && frozen) && MATCHER == 0) qmask = prune_blocks(fs, ws, lane);
 #endif
 #pragma unroll 1
     for (int pass = 0; pass < HPE_PPL / HPE_PASS; ++pass) {
         const int k0 = lane + 32 * HPE_PASS * pass;      // storage positions (stage_frame)
         int idx[HPE_PASS];
-        if (frozen) {
+        if (AUX && frozen) {
 #pragma unroll
             for (int m = 0; m < HPE_PASS; ++m) idx[m] = frozen[fs.perm[k0 + 32 * m]];
         } else if (MATCHER == 1) {
@@ -694,21 +715,28 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
         } else {
             match_pass(fs, ws, k0, lane, qmask, idx);
         }
-        // align_models for these 4 points, FP64, the reference's operation order
+        // align_models for these 4 points, FP64, the reference's operation order.  Branch-free: positions that only
+        // repeat a point (fs.valid clear) are computed like the others and dropped by a select, the square root is the
+        // straight-line Newton sequence below, so the four chains interleave.
+        const unsigned vbits = (fs.valid[HPE_PASS * pass] >> lane & 1u) | (fs.valid[HPE_PASS * pass + 1] >> lane & 1u) << 1 |
+                               (fs.valid[HPE_PASS * pass + 2] >> lane & 1u) << 2 | (fs.valid[HPE_PASS * pass + 3] >> lane & 1u) << 3;
+        double n2[HPE_PASS], rj[HPE_PASS];
 #pragma unroll
         for (int m = 0; m < HPE_PASS; ++m) {
-            int k = k0 + 32 * m;
-            if ((fs.valid[k >> 5] >> lane) & 1u) {
-                int j = idx[m];
-                if (match_row) match_row[fs.perm[k]] = j;
-                // negated-frame centre = (cx, -cy, -cz)
-                double a = fs.cloud[k] - sd[j * 3 + 0];
-                double b = fs.cloud[HPE_MAXPTS + k] + sd[j * 3 + 1];
-                double e = fs.cloud[2 * HPE_MAXPTS + k] + sd[j * 3 + 2];
-                double nor = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e)));
-                double df = fabs(nor - fs.rad[j]);
-                acc += __dmul_rn(df, df);
-            }
+            const int k = k0 + 32 * m, j = idx[m];
+            if (AUX && match_row && (vbits >> m & 1u)) match_row[fs.perm[k]] = j;
+            // negated-frame centre = (cx, -cy, -cz)
+            const double a = fs.cloud[k] - sd[j * 3 + 0];
+            const double b = fs.cloud[HPE_MAXPTS + k] + sd[j * 3 + 1];
+            const double e = fs.cloud[2 * HPE_MAXPTS + k] + sd[j * 3 + 2];
+            n2[m] = __dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e));
+            rj[m] = fs.rad[j];
+        }
+#pragma unroll
+        for (int m = 0; m < HPE_PASS; ++m) {
+            const double df = sqrt_pos(n2[m]) - rj[m];
+            const double d2 = __dmul_rn(df, df);
+            acc += (vbits >> m & 1u) ? d2 : 0.0;
         }
     }
     return __dmul_rn(warp_sum(acc), fs.lambda);
@@ -777,53 +805,60 @@ __device__ __forceinline__ void group_fk(const DevModel &M, ThetaAt theta, int n
     __syncwarp();
 }
 
-// phase 2: depth_penalty (src/costfunc.cpp:227-304) of pose g, lanes = spheres; the same lanes
-// stage the pose's float32 centres (cf) and sweep-A operands (ex).  Result valid on all lanes.
-__device__ __forceinline__ double depth_and_stage(const FrameSmem &fs, const WarpScratch &ws, int g, int lane)
+// 1/z without the library's special-case branch: seed + two Newton steps (full precision for normal z; z = 0, denormals
+// and non-finite z give inf / NaN, which floor_div sends to the exact division).  floor_div's result does not depend on
+// the last bits of the reciprocal.
+__device__ __forceinline__ double rcp_pos(double z)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z));
+    double e = __fma_rn(-z, y, 1.0);
+    y = __fma_rn(y, e, y);
+    e = __fma_rn(-z, y, 1.0);
+    return __fma_rn(y, e, y);
+}
+
+// pixel (dy * 320 + dx) the un-negated centre (x, y, z) projects to (src/costfunc.cpp:251-255), -1 outside the image.
+// K*c without FMA contraction: row0 = f*x + cx*z, row1 = f*y + cy*z, row2 = z; then floor(row / z).  One rare branch
+// for both coordinates (a quotient within 1e-6 of an integer takes the IEEE division).
+__device__ __forceinline__ int project_pixel(const FrameSmem &fs, double x, double y, double z)
+{
+    const double rz = rcp_pos(z);
+    const double ax = __dadd_rn(__dmul_rn(fs.focal, x), __dmul_rn(fs.cx, z));
+    const double ay = __dadd_rn(__dmul_rn(fs.focal, y), __dmul_rn(fs.cy, z));
+    const double qx = __dmul_rn(ax, rz), qy = __dmul_rn(ay, rz);
+    double dx = floor(qx), dy = floor(qy);
+    const double fx = qx - dx, fy = qy - dy;
+    const bool safe = fx > 1e-6 && fx < 1.0 - 1e-6 && fy > 1e-6 && fy < 1.0 - 1e-6 && fabs(qx) < 1e9 && fabs(qy) < 1e9;
+    if (!safe) { dx = floor(__ddiv_rn(ax, z)); dy = floor(__ddiv_rn(ay, z)); }
+    const bool inside = dx >= 0.0 && dx < (double)HPE_W && dy >= 0.0 && dy < (double)HPE_H;
+    return inside ? (int)dy * HPE_W + (int)dx : -1;
+}
+
+// depth_penalty of one sphere from its pixel and the two gathered values (src/costfunc.cpp:274-300), squared
+__device__ __forceinline__ double depth_value(const FrameSmem &fs, int at, float mm, float dtv, double z, double r)
+{
+    double v;
+    if (at >= 0) {
+        if (mm != 0.0f) v = fmax(0.0, div10_exact(mm) - z);             // depthmp is the file value / 10
+        else v = __dadd_rn(__dmul_rn((double)dtv, fs.scale), r);
+    } else {
+        v = __dadd_rn(__dmul_rn(fs.dt_max, fs.scale), r);
+    }
+    return __dmul_rn(v, v);
+}
+
+// phase 2b: the float32 centres (cf) and sweep operands (ex) of pose g, lanes = spheres (j = lane, lane + 32)
+__device__ __forceinline__ void stage_pose(const FrameSmem &fs, const WarpScratch &ws, int g, int lane)
 {
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
     __syncwarp();      // previous pose's matcher is done with cf/ex
-    // depth_penalty (src/costfunc.cpp:251-300) for the lane's spheres j = lane and lane + 32.  Both spheres'
-    // projections are computed first and all four gathers (depth map and distance transform of both pixels) are
-    // issued together: the distance transform is read whether or not the pixel turns out to be background, so no
-    // load waits for another and the phase pays one L2/HBM latency instead of four.
-    double x[2], y[2], z[2];
-    int at[2];
-    bool act[2], inside[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int j = lane + 32 * h;
-        act[h] = j < HPE_NSPH;
-        const int jj = act[h] ? j : 0;
-        x[h] = sd[jj * 3]; y[h] = sd[jj * 3 + 1]; z[h] = sd[jj * 3 + 2];
-        // K*c without FMA contraction: row0 = f*x + cx*z, row1 = f*y + cy*z, row2 = z; then floor(row / z)
-        const double rz = __drcp_rn(z[h]);
-        double dx = floor_div(__dadd_rn(__dmul_rn(fs.focal, x[h]), __dmul_rn(fs.cx, z[h])), z[h], rz);
-        double dy = floor_div(__dadd_rn(__dmul_rn(fs.focal, y[h]), __dmul_rn(fs.cy, z[h])), z[h], rz);
-        inside[h] = act[h] && dx >= 0.0 && dx < (double)HPE_W && dy >= 0.0 && dy < (double)HPE_H;
-        at[h] = inside[h] ? (int)dy * HPE_W + (int)dx : 0;
-    }
-    float mm[2], dtv[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        mm[h] = 0.f; dtv[h] = 0.f;
-        if (inside[h]) { mm[h] = __ldg(fs.depth_mm + at[h]); dtv[h] = __ldg(fs.dt_px + at[h]); }
-    }
-    double dv = 0.0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int j = lane + 32 * h;
-        if (act[h]) {
-            const double r = fs.rad[j];
-            double v;
-            if (inside[h]) {
-                if (mm[h] != 0.0f) v = fmax(0.0, div10_exact(mm[h]) - z[h]);     // depthmp is the file value / 10
-                else v = __dadd_rn(__dmul_rn((double)dtv[h], fs.scale), r);
-            } else {
-                v = __dadd_rn(__dmul_rn(fs.dt_max, fs.scale), r);
-            }
-            dv += __dmul_rn(v, v);
-            float4 c = make_float4((float)x[h], (float)(-y[h]), (float)(-z[h]), 0.f);   // conv_to<fmat>, negated frame
+        if (j < HPE_NSPH) {
+            const double x = sd[j * 3], y = sd[j * 3 + 1], z = sd[j * 3 + 2];
+            float4 c = make_float4((float)x, (float)(-y), (float)(-z), 0.f);   // conv_to<fmat>, negated frame
             // c' = cf - q exactly (FP64), then one rounding each for -2c' and |c'|^2
             double cx = (double)c.x - (double)fs.qx, cy = (double)c.y - (double)fs.qy, cz = (double)c.z - (double)fs.qz;
             ws.cf[j] = c;
@@ -844,5 +879,87 @@ __device__ __forceinline__ double depth_and_stage(const FrameSmem &fs, const War
     if (lane < 4) ws.ex[HPE_NBLK * HPE_EX_PITCH + lane] = (lane & 1) ? make_float4(0.f, 0.f, 3e38f, 3e38f) : make_float4(0.f, 0.f, 0.f, 0.f);
 #endif
     __syncwarp();
+}
+
+// phase 2a for one pose: depth_penalty (src/costfunc.cpp:227-304), lanes = spheres j = lane and lane + 32; all four
+// gathers of a lane are issued together.  The value is DEFINED as the butterfly sum over lanes of
+// (v_lane^2 + v_{lane+32}^2); group_depth reproduces exactly that order.  Result valid on all lanes.
+__device__ __forceinline__ double depth_pose(const FrameSmem &fs, const WarpScratch &ws, int g, int lane)
+{
+    const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
+    int at[2];
+    double z[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h, jj = j < HPE_NSPH ? j : 0;
+        z[h] = sd[jj * 3 + 2];
+        at[h] = project_pixel(fs, sd[jj * 3], sd[jj * 3 + 1], z[h]);
+    }
+    float mm[2], dtv[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        mm[h] = 0.f; dtv[h] = 0.f;
+        if (at[h] >= 0) { mm[h] = __ldg(fs.depth_mm + at[h]); dtv[h] = __ldg(fs.dt_px + at[h]); }
+    }
+    double dv = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+        if (j < HPE_NSPH) dv += depth_value(fs, at[h], mm[h], dtv[h], z[h], fs.rad[j]);
+    }
     return warp_sum(dv);
+}
+
+// phases 2a + 2b of pose g (the one-pose-at-a-time callers)
+__device__ __forceinline__ double depth_and_stage(const FrameSmem &fs, const WarpScratch &ws, int g, int lane)
+{
+    const double d = depth_pose(fs, ws, g, lane);
+    stage_pose(fs, ws, g, lane);
+    return d;
+}
+
+// phase 2a for the cnt <= GROUP poses of a group at once: items (pose, sphere) = lane + 32 r fill every lane (7.5 rounds
+// for 5 poses instead of 10) and all gathers of the group are in flight together.  Sphere j of pose g sits on lane
+// (16 g + j) mod 32 -- the lane depth_pose uses, rotated by 16 for odd g, which the xor butterfly does not see -- and
+// lane-local partial sums add sphere j before sphere j + 32, so ws.dep[g] has the bits depth_pose returns.
+template <int GROUP>
+__device__ __forceinline__ void group_depth(const FrameSmem &fs, const WarpScratch &ws, int cnt, int lane)
+{
+    static_assert(GROUP <= 8, "ws.dep holds 8 values");
+    constexpr int ROUNDS = (GROUP * HPE_NSPH + 31) / 32;
+    const int n_items = cnt * HPE_NSPH;
+    int at[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int item = lane + 32 * r, it = item < n_items ? item : 0;
+        at[r] = project_pixel(fs, ws.sphd[it * 3], ws.sphd[it * 3 + 1], ws.sphd[it * 3 + 2]);
+    }
+    float mm[ROUNDS], dtv[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        mm[r] = 0.f; dtv[r] = 0.f;
+        if (at[r] >= 0 && lane + 32 * r < n_items) { mm[r] = __ldg(fs.depth_mm + at[r]); dtv[r] = __ldg(fs.dt_px + at[r]); }
+    }
+    double acc[GROUP];
+#pragma unroll
+    for (int g = 0; g < GROUP; ++g) acc[g] = 0.0;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int item = lane + 32 * r, it = item < n_items ? item : 0;
+        const int g_lo = (32 * r) / HPE_NSPH, g_hi = (32 * r + 31) / HPE_NSPH;      // compile-time after unrolling
+        const bool hi = item >= HPE_NSPH * (g_lo + 1);
+        const int j = it - HPE_NSPH * (hi ? g_hi : g_lo);
+        double v2 = depth_value(fs, at[r], mm[r], dtv[r], ws.sphd[it * 3 + 2], fs.rad[j]);
+        if (item >= n_items) v2 = 0.0;
+        if (g_lo < GROUP) acc[g_lo < GROUP ? g_lo : 0] += hi ? 0.0 : v2;
+        if (g_hi != g_lo && g_hi < GROUP) acc[g_hi < GROUP ? g_hi : 0] += hi ? v2 : 0.0;
+    }
+#pragma unroll
+    for (int g = 0; g < GROUP; ++g) {
+        if (g < cnt) {                      // warp-uniform
+            const double d = warp_sum(acc[g]);
+            if (lane == 0) ws.dep[g] = d;
+        }
+    }
+    __syncwarp();
 }
