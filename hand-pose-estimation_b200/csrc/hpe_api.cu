@@ -47,6 +47,23 @@ thread_local Workspace g_ws;
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
+}  // namespace
+
+// a handle is only valid on the device it was created on (hpe.h): refuse instead of launching with foreign pointers
+int hpe_check_device_of(int handle_device, const char *what)
+{
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) {      // no device at all: the compute call that follows reports it
+        cudaGetLastError();
+        return HPE_OK;
+    }
+    if (cur != handle_device)
+        return hpe_set_error(HPE_ERR_STATE, "%s handle belongs to device %d but the current device is %d", what, handle_device, cur);
+    return HPE_OK;
+}
+
+namespace {
+
 int check_device()
 {
     int n = 0;
@@ -60,6 +77,7 @@ int check_device()
 int check_slot(const hpe_obs *o, int first, int count)
 {
     if (!o) return hpe_set_error(HPE_ERR_ARG, "observation handle is NULL");
+    if (int rc = hpe_check_device_of(o->device, "observation")) return rc;
     if (first < 0 || count < 0 || first + count > o->v.capacity)
         return hpe_set_error(HPE_ERR_ARG, "slots [%d,%d) outside capacity %d", first, first + count, o->v.capacity);
     return HPE_OK;
@@ -199,6 +217,7 @@ int hpe_model_destroy(hpe_model *m)
 int hpe_fk_batch(const hpe_model *m, const double *theta, int64_t n, double *spheres, double *joints)
 {
     if (!m || (!theta && n > 0) || n < 0) return hpe_set_error(HPE_ERR_ARG, "hpe_fk_batch: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (n == 0) return HPE_OK;
     if (int rc = check_device()) return rc;
     size_t b_th = align_up(sizeof(double) * n * HPE_NDOF), b_sp = align_up(sizeof(double) * n * HPE_NSPH * 3),
@@ -218,6 +237,7 @@ int hpe_fk_batch(const hpe_model *m, const double *theta, int64_t n, double *sph
 int hpe_debug_eval_latency(const hpe_model *m, const hpe_obs *o, int slot, const double theta[HPE_NDOF], long long cycles[3])
 {
     if (!m || !theta || !cycles) return hpe_set_error(HPE_ERR_ARG, "hpe_debug_eval_latency: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (int rc = check_slot(o, slot, 1)) return rc;
     if (int rc = check_filled(o, slot, 1)) return rc;
     HPE_CUDA(g_ws.reserve(1024));
@@ -234,6 +254,7 @@ int hpe_debug_eval_latency(const hpe_model *m, const hpe_obs *o, int slot, const
 int hpe_gnd_truth_err(const hpe_model *m, const double *theta, const double *gt_mm, int64_t n, double *err)
 {
     if (!m || n < 0 || ((!theta || !gt_mm || !err) && n > 0)) return hpe_set_error(HPE_ERR_ARG, "hpe_gnd_truth_err: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (n == 0) return HPE_OK;
     if (int rc = check_device()) return rc;
     size_t b_th = align_up(sizeof(double) * n * HPE_NDOF), b_jt = align_up(sizeof(double) * n * HPE_NJOINT * 3),
@@ -256,6 +277,7 @@ int hpe_bincomp_batch(const hpe_model *m, const hpe_obs *o, int slot, const doub
                       uint32_t *silhouette)
 {
     if (!m || n < 0 || ((!theta || !penalty) && n > 0)) return hpe_set_error(HPE_ERR_ARG, "hpe_bincomp_batch: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (int rc = check_slot(o, slot, 1)) return rc;
     if (n == 0) return HPE_OK;
     if (int rc = check_filled(o, slot, 1)) return rc;
@@ -405,6 +427,7 @@ int hpe_cost_batch_dev(const hpe_model *m, const hpe_obs *o, int slot, const dou
                        int with_collision, double *cost_dev, double *terms_dev, void *stream)
 {
     if (!m || n < 0) return hpe_set_error(HPE_ERR_ARG, "hpe_cost_batch_dev: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (int rc = check_slot(o, slot, 1)) return rc;
     if (n == 0) return HPE_OK;
     if (!theta_dev) return hpe_set_error(HPE_ERR_ARG, "hpe_cost_batch_dev: NULL theta");
@@ -417,6 +440,7 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
                      const int32_t *frozen, int32_t *match_out, double *align, double *depth, double *colli)
 {
     if (!m || n < 0 || (!theta && n > 0)) return hpe_set_error(HPE_ERR_ARG, "cost: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (int rc = check_slot(o, slot, 1)) return rc;
     if (n == 0) return HPE_OK;
     if (int rc = check_filled(o, slot, 1)) return rc;
@@ -433,8 +457,11 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
     // compute stream scores chunk i as soon as it has landed, a download stream returns the three term arrays
     // -- the kernel writes them as separate arrays that go straight into the caller's buffers.
     enum { MAX_CHUNKS = HPE_MAX_CHUNKS };
-    static cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};        // upload, compute, download
-    static cudaEvent_t ready = nullptr, up_done[MAX_CHUNKS], k_done[MAX_CHUNKS];
+    struct Pipe { cudaStream_t pipe[3]; cudaEvent_t ready, up_done[MAX_CHUNKS], k_done[MAX_CHUNKS]; };
+    static PerDevice<Pipe> pipe_pd;                                    // per device (hpe_internal.h)
+    Pipe &P = pipe_pd.get();
+    cudaStream_t *pipe = P.pipe;                                       // upload, compute, download
+    cudaEvent_t &ready = P.ready, *up_done = P.up_done, *k_done = P.k_done;
     if (!pipe[0]) {
         for (int i = 0; i < 3; ++i) HPE_CUDA(cudaStreamCreateWithFlags(&pipe[i], cudaStreamNonBlocking));
         HPE_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
@@ -475,7 +502,8 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
         // Large batch: ONE kernel launched before the upload chases the chunks as they land (cost_chase_kernel):
         // no per-chunk launch, no lock-step of small launches; the flags are raised by 4-byte DMA copies queued
         // behind each chunk on the upload stream.
-        static unsigned *ones = nullptr;              // pinned source of the flag copies
+        static PerDevice<unsigned *> ones_pd;         // pinned source of the flag copies
+        unsigned *&ones = ones_pd.get();
         if (!ones) {
             HPE_CUDA(cudaHostAlloc((void **)&ones, sizeof(unsigned) * MAX_CHUNKS, cudaHostAllocDefault));
             for (int i = 0; i < MAX_CHUNKS; ++i) ones[i] = 1u;
@@ -495,7 +523,8 @@ static int cost_host(const hpe_model *m, const hpe_obs *o, int slot, const doubl
             HPE_CUDA(cudaMemcpyAsync(d_flags + c, ones + c, sizeof(unsigned), cudaMemcpyHostToDevice, pipe[0]));
         }
         cudaStream_t st = pipe[1];
-        static int *timed_out_pin = nullptr;
+        static PerDevice<int *> timed_out_pd;
+        int *&timed_out_pin = timed_out_pd.get();
         if (!timed_out_pin) HPE_CUDA(cudaHostAlloc((void **)&timed_out_pin, sizeof(int), cudaHostAllocDefault));
         if (align) HPE_CUDA(cudaMemcpyAsync(align, d_tm, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
         if (depth) HPE_CUDA(cudaMemcpyAsync(depth, d_tm + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
@@ -555,22 +584,40 @@ struct CostJob {
     cudaEvent_t up_done[HPE_MAX_CHUNKS], k_done[HPE_MAX_CHUNKS], done;
     bool events = false, busy = false;
 };
-CostJob g_jobs[HPE_COST_JOBS];
-cudaStream_t g_job_pipe[3] = {nullptr, nullptr, nullptr};      // upload, compute, download (FIFO across jobs)
-cudaEvent_t g_job_ready = nullptr;
+// per device: the job slots, the three pipeline streams (FIFO across the device's jobs) and the "prior work" event.
+// A job id encodes its device: id = device * HPE_COST_JOBS + slot.
+struct JobSet {
+    CostJob jobs[HPE_COST_JOBS];
+    cudaStream_t pipe[3];          // upload, compute, download
+    cudaEvent_t ready;
+};
+JobSet *g_jobsets[HPE_MAX_DEVICES];
+std::mutex g_jobs_mutex;
+JobSet *jobset(int dev)
+{
+    std::lock_guard<std::mutex> lk(g_jobs_mutex);
+    if (!g_jobsets[dev]) g_jobsets[dev] = new (std::nothrow) JobSet();
+    return g_jobsets[dev];
+}
 }  // namespace
 
-int hpe_cost_batch_submit(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n, double *align,
-                          double *depth, double *colli, int *job)
+static int cost_batch_submit_impl(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n, double *align,
+                                  double *depth, double *colli, int *job)
 {
     if (!m || !job || n < 0 || (!theta && n > 0)) return hpe_set_error(HPE_ERR_ARG, "hpe_cost_batch_submit: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (int rc = check_slot(o, slot, 1)) return rc;
     if (int rc = check_filled(o, slot, 1)) return rc;
+    const int dev = hpe_device_index();
+    JobSet *S = jobset(dev);
+    if (!S) return hpe_set_error(HPE_ERR_ARG, "out of host memory");
     int id = -1;
     for (int i = 0; i < HPE_COST_JOBS && id < 0; ++i)
-        if (!g_jobs[i].busy) id = i;
+        if (!S->jobs[i].busy) id = i;
     if (id < 0) return hpe_set_error(HPE_ERR_STATE, "hpe_cost_batch_submit: %d batches already in flight, wait for one", HPE_COST_JOBS);
-    CostJob &J = g_jobs[id];
+    CostJob &J = S->jobs[id];
+    cudaStream_t *g_job_pipe = S->pipe;
+    cudaEvent_t &g_job_ready = S->ready;
     if (!g_job_pipe[0]) {
         for (int i = 0; i < 3; ++i) HPE_CUDA(cudaStreamCreateWithFlags(&g_job_pipe[i], cudaStreamNonBlocking));
         HPE_CUDA(cudaEventCreateWithFlags(&g_job_ready, cudaEventDisableTiming));
@@ -612,16 +659,32 @@ int hpe_cost_batch_submit(const hpe_model *m, const hpe_obs *o, int slot, const 
     }
     HPE_CUDA(cudaEventRecord(J.done, down));
     J.busy = true;
-    *job = id;
+    *job = dev * HPE_COST_JOBS + id;
     return HPE_OK;
+}
+
+int hpe_cost_batch_submit(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n, double *align,
+                          double *depth, double *colli, int *job)
+{
+    const int rc = cost_batch_submit_impl(m, o, slot, theta, n, align, depth, colli, job);
+    if (rc != HPE_OK) {
+        // part of the batch may already be queued: let it drain so that nothing untracked keeps writing into the
+        // caller's buffers (the job slot was never marked busy)
+        if (JobSet *S = g_jobsets[hpe_device_index()])
+            for (int i = 0; i < 3; ++i)
+                if (S->pipe[i]) cudaStreamSynchronize(S->pipe[i]);
+    }
+    return rc;
 }
 
 int hpe_cost_batch_wait(int job)
 {
-    if (job < 0 || job >= HPE_COST_JOBS || !g_jobs[job].busy)
+    const int dev = job / HPE_COST_JOBS, id = job % HPE_COST_JOBS;
+    JobSet *S = (job >= 0 && dev < HPE_MAX_DEVICES) ? g_jobsets[dev] : nullptr;
+    if (!S || !S->jobs[id].busy)
         return hpe_set_error(HPE_ERR_ARG, "hpe_cost_batch_wait: job %d is not in flight", job);
-    g_jobs[job].busy = false;
-    HPE_CUDA(cudaEventSynchronize(g_jobs[job].done));
+    S->jobs[id].busy = false;
+    HPE_CUDA(cudaEventSynchronize(S->jobs[id].done));        // events may be waited on from any current device
     return HPE_OK;
 }
 
@@ -629,6 +692,11 @@ int hpe_cost_batch_frozen(const hpe_model *m, const hpe_obs *o, int slot, const 
                           const int32_t *match, double *align, double *depth, double *colli)
 {
     if (!match) return hpe_set_error(HPE_ERR_ARG, "hpe_cost_batch_frozen: NULL match");
+    // matchId indexes the 48 sphere centres (src/costfunc.cpp:346-377); Armadillo would raise on anything else
+    if (o)
+        for (int k = 0; k < o->v.n_pts; ++k)
+            if (match[k] < 0 || match[k] >= HPE_NSPH)
+                return hpe_set_error(HPE_ERR_ARG, "hpe_cost_batch_frozen: match[%d] = %d is not a sphere index", k, match[k]);
     return cost_host(m, o, slot, theta, n, match, nullptr, align, depth, colli);
 }
 
@@ -641,13 +709,15 @@ int hpe_correspondences(const hpe_model *m, const hpe_obs *o, int slot, const do
 // ------------------------------------------------------------------------------------------
 // PSO
 // ------------------------------------------------------------------------------------------
+// chain = 0: `count` independent swarms; chain = L > 0: count / L sequences of L frames each (see hpe_launch_pso)
 static int pso_host(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
                     const double *x0, int n_x0, int first, int count, const uint64_t *seeds, double *bestp,
-                    double *best_cost, double *trace, int chain)
+                    double *best_cost, double *trace, int chain, int seq_stride = 0, int frame_stride = 1)
 {
     if (!m || !p || !x0 || !bestp || num_particles < 1 || p->maxiter < 1)
         return hpe_set_error(HPE_ERR_ARG, "pso: bad argument");
-    if (int rc = check_slot(o, first, count)) return rc;
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
+    if (int rc = check_slot(o, first, count)) return rc;     // the sequences' slots tile [first, first + count)
     if (count == 0) return HPE_OK;
     if (int rc = check_filled(o, first, count)) return rc;
     const int tl = p->maxiter > 1 ? p->maxiter - 1 : 1;
@@ -663,12 +733,13 @@ static int pso_host(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *
     HPE_CUDA(cudaMemcpyAsync(d_x0, x0, sizeof(double) * n_x0 * HPE_NDOF, cudaMemcpyHostToDevice, 0));
     if (seeds) HPE_CUDA(cudaMemcpyAsync(d_sd, seeds, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, 0));
     // few swarms (or a sequence): one swarm per 8-CTA cluster; many swarms: one per CTA
-    const bool use_cluster = g_hpe_pso_path == 2 || (g_hpe_pso_path == 0 && (chain || count <= 36));
+    const int units = chain ? count / chain : count;
+    const bool use_cluster = g_hpe_pso_path == 2 || (g_hpe_pso_path == 0 && units <= 36);
     cudaError_t e = use_cluster
         ? hpe_launch_pso_cluster(m->dm, o->v, make_pso(p, num_particles), d_x0, first, count, seeds ? d_sd : nullptr,
-                                 d_bp, d_bc, trace ? d_tr : nullptr, chain, 0)
+                                 d_bp, d_bc, trace ? d_tr : nullptr, chain, 0, seq_stride, frame_stride)
         : hpe_launch_pso(m->dm, o->v, make_pso(p, num_particles), d_x0, first, count, seeds ? d_sd : nullptr,
-                         d_bp, d_bc, trace ? d_tr : nullptr, chain, 0);
+                         d_bp, d_bc, trace ? d_tr : nullptr, chain, 0, seq_stride, frame_stride);
     if (e != cudaSuccess)
         return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
                              "pso launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));
@@ -692,13 +763,35 @@ int hpe_track_sequence(const hpe_model *m, const hpe_obs *o, const hpe_pso_param
 {
     if (n_frames < 0) return hpe_set_error(HPE_ERR_ARG, "hpe_track_sequence: bad frame count");
     std::vector<uint64_t> seeds((size_t)(n_frames > 0 ? n_frames : 1), seed);
-    return pso_host(m, o, p, num_particles, x0, 1, first, n_frames, seeds.data(), poses, costs, nullptr, 1);
+    return pso_host(m, o, p, num_particles, x0, 1, first, n_frames, seeds.data(), poses, costs, nullptr, n_frames);
+}
+
+// n_seq independent sequences tracked at once, one thread-block cluster (or CTA) per sequence, all of them in one
+// launch; each sequence's result is bit-identical to hpe_track_sequence on it alone
+int hpe_track_sequences(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                        const double *x0, int first, int n_seq, int n_frames, int seq_stride, int frame_stride,
+                        const uint64_t *seeds, double *poses, double *costs)
+{
+    if (n_seq < 0 || n_frames < 0 || (int64_t)n_seq * n_frames > 0x7fffffff)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_track_sequences: bad sequence / frame count");
+    if (n_seq == 0 || n_frames == 0) return HPE_OK;
+    // the two layouts whose slots tile [first, first + n_seq * n_frames) without overlap
+    const bool seq_major = seq_stride == n_frames && frame_stride == 1, frame_major = seq_stride == 1 && frame_stride == n_seq;
+    if (!seq_major && !frame_major)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_track_sequences: slot(q, k) = first + q * seq_stride + k * frame_stride needs "
+                             "(seq_stride, frame_stride) = (n_frames, 1) or (1, n_seq)");
+    std::vector<uint64_t> sd((size_t)n_seq * n_frames);
+    for (int q = 0; q < n_seq; ++q)
+        for (int k = 0; k < n_frames; ++k) sd[(size_t)q * n_frames + k] = seeds ? seeds[q] : 1000ull;
+    return pso_host(m, o, p, num_particles, x0, n_seq, first, n_seq * n_frames, sd.data(), poses, costs, nullptr, n_frames,
+                    seq_stride, frame_stride);
 }
 
 // PSO::refine_init_pose for `count` frames (hpe_refine.cu)
 int hpe_refine_init_pose(const hpe_model *m, const hpe_obs *o, double *x0, int first, int count, int *evals)
 {
     if (!m || !x0) return hpe_set_error(HPE_ERR_ARG, "hpe_refine_init_pose: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (int rc = check_slot(o, first, count)) return rc;
     if (count == 0) return HPE_OK;
     if (int rc = check_filled(o, first, count)) return rc;
@@ -721,6 +814,7 @@ int hpe_pso_optimise(const hpe_model *m, const hpe_obs *o, const hpe_pso_params 
 {
     if (!m || !p || !x0 || !bestp || num_particles < 1 || p->maxiter < 1)
         return hpe_set_error(HPE_ERR_ARG, "hpe_pso_optimise: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (int rc = check_slot(o, first, count)) return rc;
     if (count == 0) return HPE_OK;
     if (int rc = check_filled(o, first, count)) return rc;
@@ -754,45 +848,74 @@ int hpe_pso_optimise(const hpe_model *m, const hpe_obs *o, const hpe_pso_params 
     return HPE_OK;
 }
 
-// the complete per-frame loop of test_full (src/testmodel.cpp:117-138): refine_init_pose, pso_evolve,
-// x0 = bestp.  Everything is queued on one stream (two launches and one 208-byte copy per frame), the
-// host synchronises once at the end.
-int hpe_track_sequence_refined(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
-                               const double x0[HPE_NDOF], int first, int n_frames, uint64_t seed, double *poses,
-                               double *costs, double *refined)
+// the complete per-frame loop of test_full (src/testmodel.cpp:117-138): refine_init_pose, pso_evolve, x0 = bestp, for
+// n_seq sequences in lock step.  Slots are frame-interleaved (frame k of sequence q in slot first + k * n_seq + q), so that
+// time step k is ONE refine launch and ONE swarm launch over n_seq contiguous slots; everything is queued on one stream
+// (two launches and one copy per time step), the host synchronises once at the end.
+static int track_refined(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles, const double *x0,
+                         int first, int n_seq, int n_frames, const uint64_t *seeds, double *poses, double *costs,
+                         double *refined)
 {
-    if (!m || !p || !x0 || !poses || num_particles < 1 || p->maxiter < 1 || n_frames < 0)
-        return hpe_set_error(HPE_ERR_ARG, "hpe_track_sequence_refined: bad argument");
-    if (int rc = check_slot(o, first, n_frames)) return rc;
+    if (!m || !p || !x0 || !poses || num_particles < 1 || p->maxiter < 1 || n_frames < 0 || n_seq < 1 ||
+        (int64_t)n_seq * n_frames > 0x7fffffff)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_track_sequence(s)_refined: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
+    const int total = n_seq * n_frames;
+    if (int rc = check_slot(o, first, total)) return rc;
     if (n_frames == 0) return HPE_OK;
-    if (int rc = check_filled(o, first, n_frames)) return rc;
-    const size_t row = sizeof(double) * HPE_NDOF;
-    size_t b_x = align_up(row * n_frames), b_bp = b_x, b_bc = align_up(sizeof(double) * n_frames),
-           b_sd = align_up(sizeof(uint64_t) * n_frames);
+    if (int rc = check_filled(o, first, total)) return rc;
+    const size_t row = sizeof(double) * HPE_NDOF, step = row * n_seq;
+    size_t b_x = align_up(row * total), b_bp = b_x, b_bc = align_up(sizeof(double) * total),
+           b_sd = align_up(sizeof(uint64_t) * n_seq);
     HPE_CUDA(g_ws.reserve(b_x + b_bp + b_bc + b_sd));
     char *base = (char *)g_ws.p;
-    double *d_x = (double *)base, *d_bp = (double *)(base + b_x), *d_bc = (double *)(base + b_x + b_bp);
+    double *d_x = (double *)base, *d_bp = (double *)(base + b_x), *d_bc = (double *)(base + b_x + b_bp);   // [k][q]
     uint64_t *d_sd = (uint64_t *)(base + b_x + b_bp + b_bc);
-    std::vector<uint64_t> seeds((size_t)n_frames, seed);
-    HPE_CUDA(cudaMemcpyAsync(d_sd, seeds.data(), sizeof(uint64_t) * n_frames, cudaMemcpyHostToDevice, 0));
-    HPE_CUDA(cudaMemcpyAsync(d_x, x0, row, cudaMemcpyHostToDevice, 0));
+    std::vector<uint64_t> sd((size_t)n_seq);
+    for (int q = 0; q < n_seq; ++q) sd[q] = seeds ? seeds[q] : 1000ull;
+    HPE_CUDA(cudaMemcpyAsync(d_sd, sd.data(), sizeof(uint64_t) * n_seq, cudaMemcpyHostToDevice, 0));
+    HPE_CUDA(cudaMemcpyAsync(d_x, x0, step, cudaMemcpyHostToDevice, 0));
     const PsoDev prm = make_pso(p, num_particles);
+    const bool one_cta = g_hpe_pso_path == 1 || (g_hpe_pso_path == 0 && n_seq > 36);
     for (int k = 0; k < n_frames; ++k) {
-        double *xk = d_x + (size_t)k * HPE_NDOF, *bk = d_bp + (size_t)k * HPE_NDOF;
-        if (k > 0) HPE_CUDA(cudaMemcpyAsync(xk, bk - HPE_NDOF, row, cudaMemcpyDeviceToDevice, 0));
-        HPE_CUDA(hpe_launch_refine(m->dm, o->v, first + k, 1, xk, nullptr, 0));
-        cudaError_t e = g_hpe_pso_path == 1
-            ? hpe_launch_pso(m->dm, o->v, prm, xk, first + k, 1, d_sd + k, bk, d_bc + k, nullptr, 0, 0)
-            : hpe_launch_pso_cluster(m->dm, o->v, prm, xk, first + k, 1, d_sd + k, bk, d_bc + k, nullptr, 0, 0);
+        double *xk = d_x + (size_t)k * n_seq * HPE_NDOF, *bk = d_bp + (size_t)k * n_seq * HPE_NDOF;
+        if (k > 0) HPE_CUDA(cudaMemcpyAsync(xk, bk - (size_t)n_seq * HPE_NDOF, step, cudaMemcpyDeviceToDevice, 0));
+        HPE_CUDA(hpe_launch_refine(m->dm, o->v, first + k * n_seq, n_seq, xk, nullptr, 0));
+        cudaError_t e = one_cta
+            ? hpe_launch_pso(m->dm, o->v, prm, xk, first + k * n_seq, n_seq, d_sd, bk, d_bc + (size_t)k * n_seq, nullptr, 0, 0)
+            : hpe_launch_pso_cluster(m->dm, o->v, prm, xk, first + k * n_seq, n_seq, d_sd, bk, d_bc + (size_t)k * n_seq, nullptr, 0, 0);
         if (e != cudaSuccess)
             return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
                                  "pso launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));
     }
-    HPE_CUDA(cudaMemcpyAsync(poses, d_bp, row * n_frames, cudaMemcpyDeviceToHost, 0));
-    if (costs) HPE_CUDA(cudaMemcpyAsync(costs, d_bc, sizeof(double) * n_frames, cudaMemcpyDeviceToHost, 0));
-    if (refined) HPE_CUDA(cudaMemcpyAsync(refined, d_x, row * n_frames, cudaMemcpyDeviceToHost, 0));
+    // results come back frame-major and are handed out sequence-major
+    std::vector<double> h_bp((size_t)total * HPE_NDOF), h_x(refined ? (size_t)total * HPE_NDOF : 0), h_bc(costs ? (size_t)total : 0);
+    HPE_CUDA(cudaMemcpyAsync(h_bp.data(), d_bp, row * total, cudaMemcpyDeviceToHost, 0));
+    if (costs) HPE_CUDA(cudaMemcpyAsync(h_bc.data(), d_bc, sizeof(double) * total, cudaMemcpyDeviceToHost, 0));
+    if (refined) HPE_CUDA(cudaMemcpyAsync(h_x.data(), d_x, row * total, cudaMemcpyDeviceToHost, 0));
     HPE_CUDA(cudaStreamSynchronize(0));
+    for (int q = 0; q < n_seq; ++q)
+        for (int k = 0; k < n_frames; ++k) {
+            const size_t src = (size_t)k * n_seq + q, dst = (size_t)q * n_frames + k;
+            memcpy(poses + dst * HPE_NDOF, h_bp.data() + src * HPE_NDOF, row);
+            if (costs) costs[dst] = h_bc[src];
+            if (refined) memcpy(refined + dst * HPE_NDOF, h_x.data() + src * HPE_NDOF, row);
+        }
     return HPE_OK;
+}
+
+int hpe_track_sequence_refined(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                               const double x0[HPE_NDOF], int first, int n_frames, uint64_t seed, double *poses,
+                               double *costs, double *refined)
+{
+    return track_refined(m, o, p, num_particles, x0, first, 1, n_frames, &seed, poses, costs, refined);
+}
+
+int hpe_track_sequences_refined(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                                const double *x0, int first, int n_seq, int n_frames, const uint64_t *seeds, double *poses,
+                                double *costs, double *refined)
+{
+    return track_refined(m, o, p, num_particles, x0, first, n_seq, n_frames, seeds, poses, costs, refined);
 }
 
 // Offline batch from HOST frames (BASELINE "offline batch"): count frames stream through the observation
@@ -803,6 +926,7 @@ int hpe_fit_frames(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int 
 {
     if (!m || !o || !p || !depth_mm || !x0 || !bestp || num_particles < 1 || p->maxiter < 1 || count < 0)
         return hpe_set_error(HPE_ERR_ARG, "hpe_fit_frames: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (count == 0) return HPE_OK;
     if (int rc = check_device()) return rc;
     const int half = o->v.capacity >= 2 ? o->v.capacity / 2 : 1;
@@ -813,8 +937,11 @@ int hpe_fit_frames(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int 
     char *base = (char *)g_ws.p;
     double *d_x0 = (double *)base, *d_bp = (double *)(base + b_x), *d_bc = (double *)(base + 2 * b_x);
     uint64_t *d_sd = (uint64_t *)(base + 2 * b_x + b_bc);
-    static cudaStream_t up = nullptr, comp = nullptr;
-    static cudaEvent_t landed[2], fitted[2], ready;
+    struct Fit { cudaStream_t up, comp; cudaEvent_t landed[2], fitted[2], ready; };
+    static PerDevice<Fit> fit_pd;                                      // per device (hpe_internal.h)
+    Fit &F = fit_pd.get();
+    cudaStream_t &up = F.up, &comp = F.comp;
+    cudaEvent_t *landed = F.landed, *fitted = F.fitted, &ready = F.ready;
     if (!up) {
         HPE_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
         HPE_CUDA(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
@@ -862,6 +989,7 @@ int hpe_render_dev(const hpe_model *m, const double *theta_dev, int64_t n, doubl
 {
     if (!m || n < 0 || ((!theta_dev || !depth_mm_dev) && n > 0))
         return hpe_set_error(HPE_ERR_ARG, "hpe_render_dev: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     HPE_CUDA(hpe_launch_render(m->dm, theta_dev, n, focal, depth_mm_dev, (cudaStream_t)stream));
     return HPE_OK;
 }
@@ -869,6 +997,7 @@ int hpe_render_dev(const hpe_model *m, const double *theta_dev, int64_t n, doubl
 int hpe_render(const hpe_model *m, const double *theta, int64_t n, double focal, float *depth_mm)
 {
     if (!m || n < 0 || ((!theta || !depth_mm) && n > 0)) return hpe_set_error(HPE_ERR_ARG, "hpe_render: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (n == 0) return HPE_OK;
     if (int rc = check_device()) return rc;
     size_t npix = (size_t)HPE_W * HPE_H;

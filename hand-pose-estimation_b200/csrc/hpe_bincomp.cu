@@ -118,12 +118,7 @@ cudaError_t hpe_launch_bincomp(const DevModel &m, const ObsView &o, int slot, co
                                double *out_dev, unsigned *silhouette_dev, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = hpe_sm_count();
     // every CTA rebuilds the frame's mask (307 KB from L2), so no more CTAs than keep the SMs busy
     int64_t grid = n < 4 * (int64_t)sms ? n : 4 * (int64_t)sms;
     bincomp_kernel<<<(int)grid, BC_THREADS, 0, st>>>(m, o, slot, theta_dev, n, out_dev, silhouette_dev);

@@ -309,7 +309,7 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
         a.v[li * D + 2 * dp + 1] = 0.0;
     }
     for (int64_t i = gtid; i < num_p; i += gthreads) { a.key[i] = ~0ull; a.inf[i] = 0x7fffffff; }
-    if (gtid == 0) { ctl->gbest_cost = 1e100; ctl->count = 100; ctl->iter = 0; }
+    if (gtid == 0) { ctl->gbest_cost = 1e100; ctl->count = 100; ctl->iter = 0; ctl->error = 0; }
     grid.sync();
 
     int cur = 0;
@@ -448,7 +448,7 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
                     __threadfence_system();
                     long long spins = 0;
                     while (a.my_flags[lane] < want) {
-                        if (++spins > (1ll << 28)) { ctl->count = -12345; break; }   // a lost peer must not hang the GPU
+                        if (++spins > (1ll << 28)) { ctl->error = 1; break; }   // a lost peer must not hang the GPU
                         __nanosleep(32);
                     }
                     __threadfence_system();
@@ -475,7 +475,7 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
                     if (improved) {
                         ctl->gbest_cost = fmin;
                         ctl->count = g == 0 ? 100 : 0;
-                    } else if (g > 0 && ctl->count != -12345) {
+                    } else if (g > 0) {
                         ctl->count += 1;
                     }
                     ctl->iter = g + 1;
@@ -607,13 +607,12 @@ cudaError_t hpe_launch_cost_chase(const DevModel &m, const ObsView &o, int slot,
                                   cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = hpe_sm_count();
+    static PerDevice<bool> attr_pd;
+    if (bool &attr = attr_pd.get(); !attr) {
         cudaFuncSetAttribute(cost_chase_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
         cudaFuncSetAttribute(cost_chase_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
+        attr = true;
     }
     int64_t groups = (n + HPE_GROUP - 1) / HPE_GROUP;
     int64_t want = (groups + COST_WARPS - 1) / COST_WARPS;
@@ -649,16 +648,12 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
 {
     if (n <= 0) return cudaSuccess;
     if (terms_stride <= 0) terms_stride = n;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = hpe_sm_count();
     int64_t groups = (n + HPE_GROUP - 1) / HPE_GROUP;
     int64_t want = (groups + COST_WARPS - 1) / COST_WARPS;
     int blocks = (int)(want < (long long)HPE_MINBLOCKS * sms ? want : (long long)HPE_MINBLOCKS * sms);
-    static bool attr = false;
+    static PerDevice<bool> attr_pd;
+    bool &attr = attr_pd.get();
     if (!attr) {
         const int smem = (int)sizeof(CostSmem);
         cudaFuncSetAttribute(cost_kernel<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -683,13 +678,9 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
 cudaError_t hpe_launch_swarm_step(const DevModel &m, const ObsView &o, int slot, const SwarmStepArgs &a, cudaStream_t st)
 {
     if (a.own <= 0) return cudaSuccess;
-    static int sms = 0;
-    static bool attr = false;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = hpe_sm_count();
+    static PerDevice<bool> attr_pd;
+    bool &attr = attr_pd.get();
     if (!attr) {
         cudaFuncSetAttribute(swarm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
         attr = true;
@@ -703,11 +694,10 @@ cudaError_t hpe_launch_swarm_step(const DevModel &m, const ObsView &o, int slot,
 
 cudaError_t hpe_launch_swarm_run(const DevModel &m, const ObsView &o, int slot, const SwarmRunArgs &a, cudaStream_t st)
 {
-    static int sms = 0, per_sm = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = hpe_sm_count();
+    static PerDevice<int> per_sm_pd;
+    int &per_sm = per_sm_pd.get();
+    if (!per_sm) {
         cudaFuncSetAttribute(swarm_run_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
         cudaFuncSetAttribute(swarm_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CostSmem));
         int p0 = 0, p1 = 0;

@@ -66,6 +66,8 @@ struct SwarmCtl {
     double gbest[HPE_NDOF];
     int count;
     int iter;                         // evaluations done so far (1 after init)
+    int error;                        // sticky: a bounded wait of the peer exchange gave up (nothing else writes it)
+    int pad;
 };
 
 // arguments of the fused update + evaluate + pbest kernel (swarm_step_kernel, hpe_cost.cu)
@@ -112,6 +114,30 @@ struct SwarmRunArgs {
 };
 
 int hpe_set_error(int code, const char *fmt, ...);
+int hpe_check_device_of(int handle_device, const char *what);
+
+// Host-side caches (SM count, kernel attributes, streams, events, scratch buffers) are kept PER DEVICE: a process may
+// drive several GPUs (cudaSetDevice between calls); a handle is only valid on the device it was created on, which the
+// entry points check (hpe_check_device_of).  Calls on ONE device are not thread-safe (the scratch buffers are shared
+// by the launches of that device), calls on different devices are independent.
+#define HPE_MAX_DEVICES 64
+inline int hpe_device_index()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 ? 0 : (dev >= HPE_MAX_DEVICES ? HPE_MAX_DEVICES - 1 : dev);
+}
+template <class T> struct PerDevice {
+    T v[HPE_MAX_DEVICES];                 // zero-initialised (static storage)
+    T &get() { return v[hpe_device_index()]; }
+};
+inline int hpe_sm_count()
+{
+    static PerDevice<int> sms;
+    int &n = sms.get();
+    if (!n) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, hpe_device_index());
+    return n;
+}
 extern int g_hpe_chamfer;   // hpe_set_chamfer(): 0 = wavefront two-pass, 1 = row-search closed form
 extern int g_hpe_matcher;   // hpe_set_matcher(): 0 = certified two-sweep search, 1 = direct form
 #define HPE_CUDA(call)                                                                           \
@@ -148,11 +174,16 @@ cudaError_t hpe_launch_dtmax(const ObsView &o, int slot, cudaStream_t st);
 cudaError_t hpe_launch_cluster(const ObsView &o, int first, int count, cudaStream_t st);
 cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
                            int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
-                           double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st);
+                           double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st, int seq_stride = 0,
+                           int frame_stride = 1);
+// chain: 0 = `count` independent swarms on slots first + b; L > 0 = count / L sequences of L frames (count a multiple of
+// L): frame k of sequence q is swarm q * L + k on slot first + q * seq_stride + k * frame_stride (seq_stride 0 = L), starts
+// from the best pose of frame k - 1, and x0_dev holds one pose per SEQUENCE
 // the same for one swarm per 8-CTA cluster (latency path: sequences, small batches)
 cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
                                    int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
-                                   double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st);
+                                   double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st, int seq_stride = 0,
+                                   int frame_stride = 1);
 // PSO::refine_init_pose for frames [first, first+count): x_dev count*26 in place, evals_dev count or NULL
 cudaError_t hpe_launch_refine(const DevModel &m, const ObsView &o, int first, int count, double *x_dev, int *evals_dev,
                               cudaStream_t st);

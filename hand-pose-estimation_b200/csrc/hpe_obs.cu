@@ -617,7 +617,8 @@ int g_hpe_chamfer = 0;   // 0 = row-parallel two-pass (prefix-min scans, default
 cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *, cudaStream_t st)
 {
     if (count <= 0) return cudaSuccess;
-    static bool attr = false;
+    static PerDevice<bool> attr_pd;
+    bool &attr = attr_pd.get();
     const int smem = HPE_W * HPE_H * (int)sizeof(unsigned short);
     if (!attr) {
         cudaFuncSetAttribute(chamfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -630,7 +631,8 @@ cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *, c
     } else if (g_hpe_chamfer == 0) {
         chamfer_scan_kernel<<<(count + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, st>>>(o, first, count);
     } else {
-        static bool attr2 = false;
+        static PerDevice<bool> attr2_pd;
+        bool &attr2 = attr2_pd.get();
         if (!attr2) {
             cudaFuncSetAttribute(chamfer_wavefront_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  WF_WARPS * WF_SMEM_PER_WARP);

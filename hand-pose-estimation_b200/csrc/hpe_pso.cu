@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(PSO_WARPS * 32, HPE_MINBLOCKS)
 pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, int first, int count_swarms,
            const uint64_t *__restrict__ seeds, double *__restrict__ state_scratch,
            double *__restrict__ bestp_out, double *__restrict__ best_cost_out, double *__restrict__ trace_out,
-           int chain, int gsz, double W1, double C1)
+           int chain, int seq_stride, int frame_stride, int gsz, double W1, double C1)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PsoSmemHead &sm = *reinterpret_cast<PsoSmemHead *>(smem_raw);
@@ -69,13 +69,18 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
     __syncthreads();
 
     // independent swarms: CTA-strided; chain mode: one CTA walks the sequence
-    for (int b = chain ? 0 : (int)blockIdx.x; b < count_swarms; b += chain ? 1 : (int)gridDim.x) {
-        const int slot = first + b;
+    // sequences (chain = frames per sequence, count_swarms = sequences x chain): this CTA walks sequences q = blockIdx.x,
+    // blockIdx.x + gridDim.x, ...; frame k of sequence q is swarm b = q * chain + k on slot
+    // first + q * seq_stride + k * frame_stride and starts from the best pose of frame k - 1
+    for (int q = chain ? (int)blockIdx.x : 0; q < (chain ? count_swarms / chain : 1); q += chain ? (int)gridDim.x : 1)
+    for (int b = chain ? q * chain : (int)blockIdx.x; b < (chain ? (q + 1) * chain : count_swarms); b += chain ? 1 : (int)gridDim.x) {
+        const bool head = !chain || b == q * chain;
+        const int slot = first + (chain ? q * seq_stride + (b - q * chain) * frame_stride : b);
         const uint64_t seed = seeds ? seeds[b] : 1000ull;
         stage_frame(sm.fs, frame_view(o, slot));     // ends synchronised
         if (tid < D) {
             // chain mode: x0 = bestp of the previous frame (src/testmodel.cpp:138)
-            sm.x0[tid] = (chain && b > 0) ? sm.gbest[tid] : x0_in[(size_t)b * D + tid];
+            sm.x0[tid] = head ? x0_in[(size_t)(chain ? q : b) * D + tid] : sm.gbest[tid];
         }
         __syncthreads();
         const bool frame_ok = o.meta[slot].ok != 0;
@@ -199,9 +204,12 @@ HPE_DEFINE_FALLBACK_GETTER(hpe_fallbacks_pso)
 
 cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
                            int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
-                           double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st)
+                           double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st, int seq_stride, int frame_stride)
 {
     if (count <= 0) return cudaSuccess;
+    if (chain < 0 || (chain > 0 && count % chain != 0)) return cudaErrorInvalidValue;
+    if (seq_stride == 0) seq_stride = chain;
+    const int units = chain ? count / chain : count;         // sequences or independent swarms
     // balance: rounds of PSO_WARPS groups, group size <= HPE_GROUP
     int rounds = (p.num_p + PSO_WARPS * HPE_GROUP - 1) / (PSO_WARPS * HPE_GROUP);
     int gsz = (p.num_p + PSO_WARPS * rounds - 1) / (PSO_WARPS * rounds);
@@ -209,25 +217,23 @@ cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p,
     if (gsz > HPE_GROUP) gsz = HPE_GROUP;
     size_t smem = pso_smem_bytes(p.num_p, gsz);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t attr_set = 0;
+    static PerDevice<size_t> attr_set_pd;
+    size_t &attr_set = attr_set_pd.get();
     if (smem > attr_set) {
         cudaError_t e = cudaFuncSetAttribute(pso_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = smem;
     }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = hpe_sm_count();
     int resident = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pso_kernel, PSO_WARPS * 32, smem);
     if (resident < 1) resident = 1;
-    int blocks = chain ? 1 : (count < resident * sms ? count : resident * sms);
+    int blocks = units < resident * sms ? units : resident * sms;
     // velocity + pbest of the resident swarms: grow-only scratch (L2-resident, 27 KB per swarm)
-    static double *scratch = nullptr;
-    static size_t scratch_bytes = 0;
+    static PerDevice<double *> scratch_pd;
+    static PerDevice<size_t> scratch_bytes_pd;
+    double *&scratch = scratch_pd.get();
+    size_t &scratch_bytes = scratch_bytes_pd.get();
     size_t per = (size_t)p.num_p * HPE_NDOF * sizeof(double);
     if (3 * per * blocks > scratch_bytes) {
         if (scratch) cudaFree(scratch);
@@ -240,7 +246,7 @@ cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p,
     const double W1 = 1. / (2 * log(2.0));       // src/PSO.cpp:772
     const double C1 = 0.5 + log(2.0);            // src/PSO.cpp:773-774
     pso_kernel<<<blocks, PSO_WARPS * 32, smem, st>>>(m, o, p, x0_dev, first, count, seeds_dev, scratch, bestp_dev,
-                                                     best_cost_dev, trace_dev, chain, gsz, W1, C1);
+                                                     best_cost_dev, trace_dev, chain, seq_stride, frame_stride, gsz, W1, C1);
     e = cudaGetLastError();
     return e;
 }

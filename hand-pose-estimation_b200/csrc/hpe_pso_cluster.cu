@@ -53,7 +53,8 @@ __host__ __device__ inline size_t cluster_state_doubles(int num_p) { return (siz
 __global__ void __launch_bounds__(CL_WARPS * 32, 2)
 pso_cluster_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, int first, int count_swarms,
                    const uint64_t *__restrict__ seeds, double *__restrict__ state, double *__restrict__ bestp_out,
-                   double *__restrict__ best_cost_out, double *__restrict__ trace_out, int chain, double W1, double C1)
+                   double *__restrict__ best_cost_out, double *__restrict__ trace_out, int chain, int seq_stride, int frame_stride,
+                   double W1, double C1)
 {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -78,11 +79,17 @@ pso_cluster_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__
     stage_model(sm.fs, m);
     __syncthreads();
 
-    for (int b = chain ? 0 : cluster_id; b < count_swarms; b += chain ? 1 : n_clusters) {
-        const int slot = first + b;
+    // independent swarms (chain == 0): swarm b on slot first + b, cluster-strided.  Sequences (chain = frames per sequence,
+    // count_swarms = sequences x chain): this cluster walks sequences q = cluster_id, cluster_id + n_clusters, ...; frame k
+    // of sequence q is swarm b = q * chain + k on slot first + q * seq_stride + k * frame_stride and starts from the best
+    // pose of frame k - 1 (src/testmodel.cpp:138)
+    for (int q = chain ? cluster_id : 0; q < (chain ? count_swarms / chain : 1); q += chain ? n_clusters : 1)
+    for (int b = chain ? q * chain : cluster_id; b < (chain ? (q + 1) * chain : count_swarms); b += chain ? 1 : n_clusters) {
+        const bool head = !chain || b == q * chain;             // first frame of its sequence: x0 comes from the caller
+        const int slot = first + (chain ? q * seq_stride + (b - q * chain) * frame_stride : b);
         const uint64_t seed = seeds ? seeds[b] : 1000ull;
         stage_frame(sm.fs, frame_view(o, slot));               // every CTA stages the frame; ends synchronised
-        if (tid < D) sm.x0[tid] = (chain && b > 0) ? sm.gbest[tid] : x0_in[(size_t)b * D + tid];
+        if (tid < D) sm.x0[tid] = head ? x0_in[(size_t)(chain ? q : b) * D + tid] : sm.gbest[tid];
         if (tid == 0) { sm.gbest_cost = 1e100; sm.count = 100; }
         __syncthreads();
         // generate_particles (src/PSO.cpp:56-74): the cluster's threads share the num_p x 13 pairs
@@ -252,7 +259,8 @@ template <int CLS>
 __global__ void __launch_bounds__(64 / CLS * 32, 2)
 pso_cluster_dsm_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, int first, int count_swarms,
                        const uint64_t *__restrict__ seeds, double *__restrict__ state, double *__restrict__ bestp_out,
-                       double *__restrict__ best_cost_out, double *__restrict__ trace_out, int chain, double W1, double C1)
+                       double *__restrict__ best_cost_out, double *__restrict__ trace_out, int chain, int seq_stride, int frame_stride,
+                   double W1, double C1)
 {
     constexpr int CLW = 64 / CLS;
     cg::cluster_group cluster = cg::this_cluster();
@@ -281,11 +289,17 @@ pso_cluster_dsm_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restri
     stage_model(sm.fs, m);
     __syncthreads();
 
-    for (int b = chain ? 0 : cluster_id; b < count_swarms; b += chain ? 1 : n_clusters) {
-        const int slot = first + b;
+    // independent swarms (chain == 0): swarm b on slot first + b, cluster-strided.  Sequences (chain = frames per sequence,
+    // count_swarms = sequences x chain): this cluster walks sequences q = cluster_id, cluster_id + n_clusters, ...; frame k
+    // of sequence q is swarm b = q * chain + k on slot first + q * seq_stride + k * frame_stride and starts from the best
+    // pose of frame k - 1 (src/testmodel.cpp:138)
+    for (int q = chain ? cluster_id : 0; q < (chain ? count_swarms / chain : 1); q += chain ? n_clusters : 1)
+    for (int b = chain ? q * chain : cluster_id; b < (chain ? (q + 1) * chain : count_swarms); b += chain ? 1 : n_clusters) {
+        const bool head = !chain || b == q * chain;             // first frame of its sequence: x0 comes from the caller
+        const int slot = first + (chain ? q * seq_stride + (b - q * chain) * frame_stride : b);
         const uint64_t seed = seeds ? seeds[b] : 1000ull;
         stage_frame(sm.fs, frame_view(o, slot));               // every CTA stages the frame; ends synchronised
-        if (tid < D) sm.x0[tid] = (chain && b > 0) ? sm.gbest[tid] : x0_in[(size_t)b * D + tid];
+        if (tid < D) sm.x0[tid] = head ? x0_in[(size_t)(chain ? q : b) * D + tid] : sm.gbest[tid];
         if (tid == 0) { sm.gbest_cost = 1e100; sm.count = 100; }
         __syncthreads();
         // generate_particles (src/PSO.cpp:56-74) for this CTA's own particles
@@ -428,24 +442,42 @@ int g_hpe_cluster_dsm = 1;   // hpe_set_pso_path(3): keep the cluster kernel's s
 
 cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev, int first,
                                    int count, const uint64_t *seeds_dev, double *bestp_dev, double *best_cost_dev,
-                                   double *trace_dev, int chain, cudaStream_t st)
+                                   double *trace_dev, int chain, cudaStream_t st, int seq_stride, int frame_stride)
 {
     if (count <= 0) return cudaSuccess;
+    if (chain < 0 || (chain > 0 && count % chain != 0)) return cudaErrorInvalidValue;
+    if (seq_stride == 0) seq_stride = chain;
+    const int units = chain ? count / chain : count;         // sequences or independent swarms
     const bool dsm = p.num_p <= CLD_MAXP && g_hpe_cluster_dsm;       // swarm state in distributed shared memory
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = hpe_sm_count();
     // a sequence (or a handful of swarms) gets 16-CTA clusters, one CTA per SM; more swarms get 8-CTA clusters
-    static bool wide_ok = true;                              // cleared if the device refuses 16-CTA clusters
-    const bool wide = wide_ok && dsm && (chain || count <= sms / 16);
+    static PerDevice<bool> wide_refused_pd;                  // set if the device refuses 16-CTA clusters
+    bool &wide_refused = wide_refused_pd.get();
+    // how many 16-CTA clusters the device can hold at once (a cluster lives inside one GPC): asked once per device
+    static PerDevice<int> wide_max_pd;
+    int &wide_max = wide_max_pd.get();
+    if (!wide_max && dsm && !wide_refused) {
+        cudaFuncSetAttribute(pso_cluster_dsm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024);
+        cudaFuncSetAttribute(pso_cluster_dsm_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(16 * (sms / 16)); q.blockDim = dim3(64 / 16 * 32); q.dynamicSmemBytes = 116 * 1024;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        q.attrs = qa; q.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, pso_cluster_dsm_kernel<16>, &q) != cudaSuccess || n < 1) { cudaGetLastError(); n = -1; }
+        wide_max = n;
+    }
+    // sequences / swarms that all fit at once get 16-CTA clusters (one CTA per SM); more get 8-CTA clusters
+    const bool wide = !wide_refused && dsm && wide_max > 0 && units <= wide_max;
     const int cls = wide ? 16 : CL_SIZE;
     size_t smem = dsm ? cluster_dsm_smem_bytes(p.num_p, 64 / cls) : cluster_smem_bytes(p.num_p);
     if (wide && smem < 116 * 1024) smem = 116 * 1024;       // more than half of an SM's shared memory: one CTA per SM
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t attr_set[3] = {0, 0, 0};
+    struct Attr3 { size_t v[3]; };
+    static PerDevice<Attr3> attr_pd;
+    size_t *attr_set = attr_pd.get().v;
     const int which = dsm ? (wide ? 2 : 1) : 0;
     if (smem > attr_set[which]) {
         cudaError_t e;
@@ -458,10 +490,12 @@ cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const Ps
         if (e != cudaSuccess) return e;
         attr_set[which] = smem;
     }
-    int max_clusters = (wide ? 1 : 2) * sms / cls;
-    int n_clusters = chain ? 1 : (count < max_clusters ? count : max_clusters);
-    static double *state = nullptr;
-    static size_t state_bytes = 0;
+    int max_clusters = wide ? wide_max : 2 * sms / cls;
+    int n_clusters = units < max_clusters ? units : max_clusters;
+    static PerDevice<double *> state_pd;
+    static PerDevice<size_t> state_bytes_pd;
+    double *&state = state_pd.get();
+    size_t &state_bytes = state_bytes_pd.get();
     size_t need = cluster_state_doubles(p.num_p) * sizeof(double) * n_clusters;
     if (need > state_bytes) {
         if (state) cudaFree(state);
@@ -486,15 +520,16 @@ cudaError_t hpe_launch_pso_cluster(const DevModel &m, const ObsView &o, const Ps
     const double C1 = 0.5 + log(2.0);            // src/PSO.cpp:773-774
     if (dsm && wide) {
         cudaError_t e = cudaLaunchKernelEx(&cfg, pso_cluster_dsm_kernel<16>, m, o, p, x0_dev, first, count, seeds_dev, state,
-                                           bestp_dev, best_cost_dev, trace_dev, chain, W1, C1);
+                                           bestp_dev, best_cost_dev, trace_dev, chain, seq_stride, frame_stride, W1, C1);
         if (e == cudaSuccess) return e;
         cudaGetLastError();                                  // e.g. cudaErrorInvalidClusterSize: use 8-CTA clusters from now on
-        wide_ok = false;
-        return hpe_launch_pso_cluster(m, o, p, x0_dev, first, count, seeds_dev, bestp_dev, best_cost_dev, trace_dev, chain, st);
+        wide_refused = true;
+        return hpe_launch_pso_cluster(m, o, p, x0_dev, first, count, seeds_dev, bestp_dev, best_cost_dev, trace_dev, chain, st,
+                                      seq_stride, frame_stride);
     }
     if (dsm)
         return cudaLaunchKernelEx(&cfg, pso_cluster_dsm_kernel<8>, m, o, p, x0_dev, first, count, seeds_dev, state, bestp_dev,
-                                  best_cost_dev, trace_dev, chain, W1, C1);
+                                  best_cost_dev, trace_dev, chain, seq_stride, frame_stride, W1, C1);
     return cudaLaunchKernelEx(&cfg, pso_cluster_kernel, m, o, p, x0_dev, first, count, seeds_dev, state, bestp_dev,
-                              best_cost_dev, trace_dev, chain, W1, C1);
+                              best_cost_dev, trace_dev, chain, seq_stride, frame_stride, W1, C1);
 }

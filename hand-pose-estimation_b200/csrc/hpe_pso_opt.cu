@@ -281,25 +281,23 @@ cudaError_t hpe_launch_pso_optimise(const DevModel &m, const ObsView &o, const P
     if (count <= 0) return cudaSuccess;
     size_t smem = opt_smem_bytes(p.num_p);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t attr_set = 0;
+    static PerDevice<size_t> attr_set_pd;
+    size_t &attr_set = attr_set_pd.get();
     if (smem > attr_set) {
         cudaError_t e = cudaFuncSetAttribute(pso_optimise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = smem;
     }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = hpe_sm_count();
     int resident = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pso_optimise_kernel, PO_WARPS * 32, smem);
     if (resident < 1) resident = 1;
     int blocks = count < resident * sms ? count : resident * sms;
     // positions, velocities, personal bests of the resident swarms: grow-only scratch (L2-resident)
-    static double *scratch = nullptr;
-    static size_t scratch_bytes = 0;
+    static PerDevice<double *> scratch_pd;
+    static PerDevice<size_t> scratch_bytes_pd;
+    double *&scratch = scratch_pd.get();
+    size_t &scratch_bytes = scratch_bytes_pd.get();
     size_t per = (size_t)p.num_p * HPE_NDOF * sizeof(double);
     if (3 * per * blocks > scratch_bytes) {
         if (scratch) cudaFree(scratch);

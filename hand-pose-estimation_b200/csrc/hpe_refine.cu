@@ -199,12 +199,11 @@ cudaError_t hpe_launch_refine(const DevModel &m, const ObsView &o, int first, in
                               cudaStream_t st)
 {
     if (count <= 0) return cudaSuccess;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = hpe_sm_count();
+    static PerDevice<bool> attr_pd;
+    if (bool &attr = attr_pd.get(); !attr) {
         cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefineSmem));
+        attr = true;
     }
     int grid = count < 2 * sms ? count : 2 * sms;
     refine_kernel<<<grid, RF_WARPS * 32, sizeof(RefineSmem), st>>>(m, o, first, count, x_dev, evals_dev);

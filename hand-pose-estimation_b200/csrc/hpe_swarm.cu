@@ -165,7 +165,7 @@ __global__ void swarm_wait(volatile unsigned *flags, int world, int rank, unsign
     if (threadIdx.x < world && threadIdx.x != rank) {
         long long spins = 0;
         while (flags[threadIdx.x] < gen) {
-            if (++spins > (1ll << 31)) { ctl->count = -12345; break; }   // bounded: a lost peer must not hang the GPU
+            if (++spins > (1ll << 31)) { ctl->error = 1; break; }   // bounded: a lost peer must not hang the GPU
             __nanosleep(100);
         }
     }
@@ -414,7 +414,7 @@ int hpe_swarm_best(hpe_swarm *s, double bestp[HPE_NDOF], double *best_cost, doub
     if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_best: NULL swarm");
     SwarmCtl c;
     HPE_CUDA(cudaMemcpy(&c, s->ctl, sizeof c, cudaMemcpyDeviceToHost));
-    if (c.count == -12345)     // set by the bounded waits of the peer exchange
+    if (c.error)               // set by the bounded waits of the peer exchange, cleared by hpe_swarm_init / _run
         return hpe_set_error(HPE_ERR_STATE, "sharded swarm: a peer did not deliver its rows in time (rank %d of %d)", s->rank, s->world);
     if (bestp) memcpy(bestp, c.gbest, sizeof c.gbest);
     if (best_cost) *best_cost = c.gbest_cost;

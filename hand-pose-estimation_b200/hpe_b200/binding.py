@@ -424,6 +424,31 @@ class PSO:
                                                 C.c_uint64(seed), _p(poses), _p(costs), _p(refined)))
         return poses, costs, refined
 
+    def track_sequences(self, optfunc, x0, num_particles, n_seq, n_frames, seeds=None, first=0, interleaved=False):
+        """n_seq independent sequences tracked in one launch (hpe_track_sequences).  Frame k of sequence q lives in slot
+        first + q*n_frames + k, or first + k*n_seq + q when interleaved.  Returns (poses [n_seq, n_frames, 26],
+        costs [n_seq, n_frames])"""
+        x0 = _f64(x0).reshape(n_seq, 26)
+        poses, costs = np.empty((n_seq, n_frames, 26)), np.empty((n_seq, n_frames))
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        ss, fs = (1, n_seq) if interleaved else (n_frames, 1)
+        _check(lib().hpe_track_sequences(optfunc.hand._h, optfunc.observation._h, C.byref(self.params), int(num_particles),
+                                         _p(x0), int(first), int(n_seq), int(n_frames), int(ss), int(fs),
+                                         _p(sd, C.c_uint64), _p(poses), _p(costs)))
+        return poses, costs
+
+    def track_sequences_refined(self, optfunc, x0, num_particles, n_seq, n_frames, seeds=None, first=0):
+        """test_full's loop (refine_init_pose, pso_evolve, x0 = bestp) for n_seq sequences in lock step; slots are
+        frame-interleaved (first + k*n_seq + q).  Returns (poses, costs, refined start poses), sequence-major"""
+        x0 = _f64(x0).reshape(n_seq, 26)
+        poses, refined = np.empty((n_seq, n_frames, 26)), np.empty((n_seq, n_frames, 26))
+        costs = np.empty((n_seq, n_frames))
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        _check(lib().hpe_track_sequences_refined(optfunc.hand._h, optfunc.observation._h, C.byref(self.params),
+                                                 int(num_particles), _p(x0), int(first), int(n_seq), int(n_frames),
+                                                 _p(sd, C.c_uint64), _p(poses), _p(costs), _p(refined)))
+        return poses, costs, refined
+
 
 class Swarm:
     """One large swarm (pso_evolve semantics) whose particles [lo,hi) live on this GPU.  Drive it as

@@ -11,9 +11,17 @@
  * Conventions: plain pointers and sizes, no C++/torch types; every function
  * returns an hpe_status (0 = ok); the caller owns every buffer; opaque handles
  * own device memory on the CUDA device that was current when they were
- * created; a handle is not thread-safe, distinct handles are independent.
- * There is no CPU fallback: without a CUDA device every compute call returns
- * HPE_ERR_CUDA.
+ * created.  There is no CPU fallback: without a CUDA device every compute call
+ * returns HPE_ERR_CUDA.
+ *
+ * Devices and threads: a process may drive several GPUs (cudaSetDevice between
+ * calls).  A handle is only valid while ITS device is current -- a call with a
+ * handle of another device returns HPE_ERR_STATE instead of launching with
+ * foreign pointers.  The library's own caches (SM count, kernel attributes,
+ * streams, events, scratch buffers, the streaming-job slots of
+ * hpe_cost_batch_submit) are kept per device, so calls on different devices
+ * are independent.  Calls on ONE device must come from one host thread at a
+ * time: the launches of a device share its scratch buffers and streams.
  *
  * Units follow the reference after its mm->cm conversion: lengths in cm,
  * angles in degrees, depth frames in mm (the on-disk format), distance
@@ -165,6 +173,16 @@ int hpe_track_sequence(const hpe_model *m, const hpe_obs *o, const hpe_pso_param
                        int num_particles, const double x0[HPE_NDOF], int first, int n_frames,
                        uint64_t seed, double *poses, double *costs);
 
+/* n_seq independent sequences tracked AT ONCE (one launch; one thread-block cluster -- or CTA -- per sequence, so the
+ * whole GPU works where hpe_track_sequence occupies 16 SMs).  The reference's loop (src/testmodel.cpp:117-138,
+ * src/visualiser.cpp:262-296) is one sequence; this is the same loop over n_seq of them.  Frame k of sequence q lives in
+ * slot first + q*seq_stride + k*frame_stride with (seq_stride, frame_stride) = (n_frames, 1) (sequence after sequence) or
+ * (1, n_seq) (frame-interleaved); x0: n_seq*26; seeds: n_seq values (every frame of sequence q uses seeds[q]) or NULL
+ * (1000); poses: n_seq*n_frames*26 and costs: n_seq*n_frames, sequence-major.  Each sequence's result is bit-identical
+ * to hpe_track_sequence on that sequence alone. */
+int hpe_track_sequences(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                        const double *x0, int first, int n_seq, int n_frames, int seq_stride, int frame_stride,
+                        const uint64_t *seeds, double *poses, double *costs);
 /* PSO::refine_init_pose (src/PSO.cpp:216-266) with cal_grad (:183-214) and goldstein (:438-480) for
  * `count` frames: x0 (host, count*26) is refined in place against frame slot first+b -- gradient
  * descent with a Goldstein line search on theta[0:3], then on theta[3:6], every evaluation a
@@ -188,6 +206,12 @@ int hpe_pso_optimise(const hpe_model *m, const hpe_obs *o, const hpe_pso_params 
 int hpe_track_sequence_refined(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p,
                                int num_particles, const double x0[HPE_NDOF], int first, int n_frames,
                                uint64_t seed, double *poses, double *costs, double *refined);
+/* the same loop for n_seq sequences in lock step; slots are frame-interleaved: frame k of sequence q in slot
+ * first + k*n_seq + q.  x0: n_seq*26, seeds: n_seq or NULL (1000); poses / refined: n_seq*n_frames*26 and costs:
+ * n_seq*n_frames, sequence-major.  Per sequence bit-identical to hpe_track_sequence_refined. */
+int hpe_track_sequences_refined(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p,
+                                int num_particles, const double *x0, int first, int n_seq, int n_frames,
+                                const uint64_t *seeds, double *poses, double *costs, double *refined);
 
 /* Offline batch from HOST frames: count Subject1-format frames (float32 mm, count*240*320) are uploaded,
  * observed (observedmodel::next_frame) and fitted with one pso_evolve swarm each (x0: count*26), streaming

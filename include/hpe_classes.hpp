@@ -276,6 +276,15 @@ public:
         check(hpe_track_sequence(optfunc.hand->c_handle(), optfunc.observation->c_handle(), &p_, num_particles, x0.data(),
                                  first, n_frames, seed, poses, costs));
     }
+    // the same loop over n_seq independent sequences at once (one launch, one thread-block cluster per sequence): frame k
+    // of sequence q in slot first + q * n_frames + k, or first + k * n_seq + q when interleaved; x0: n_seq * 26, seeds:
+    // n_seq values or nullptr; poses: n_seq * n_frames * 26, costs: n_seq * n_frames
+    void track_sequences(costfunc &optfunc, const double *x0, int num_particles, int first, int n_seq, int n_frames,
+                         double *poses, double *costs, const uint64_t *seeds = nullptr, bool interleaved = false)
+    {
+        check(hpe_track_sequences(optfunc.hand->c_handle(), optfunc.observation->c_handle(), &p_, num_particles, x0, first,
+                                  n_seq, n_frames, interleaved ? 1 : n_frames, interleaved ? n_seq : 1, seeds, poses, costs));
+    }
     // offline batch from host frames (count * 240 * 320 floats, mm): upload, observation, one swarm per frame,
     // uploads overlapped with the fits; the observedmodel's capacity sets the chunk size
     void fit_frames(costfunc &optfunc, const float *depth_mm, const double *x0, long count, int num_particles,
@@ -297,6 +306,13 @@ public:
     {
         check(hpe_track_sequence_refined(optfunc.hand->c_handle(), optfunc.observation->c_handle(), &p_, num_particles,
                                          x0.data(), first, n_frames, seed, poses, costs, refined));
+    }
+    // ... for n_seq sequences in lock step; slots frame-interleaved (first + k * n_seq + q)
+    void track_sequences_refined(costfunc &optfunc, const double *x0, int num_particles, int first, int n_seq, int n_frames,
+                                 double *poses, double *costs, double *refined = nullptr, const uint64_t *seeds = nullptr)
+    {
+        check(hpe_track_sequences_refined(optfunc.hand->c_handle(), optfunc.observation->c_handle(), &p_, num_particles, x0,
+                                          first, n_seq, n_frames, seeds, poses, costs, refined));
     }
     const hpe_pso_params &params() const { return p_; }
 
