@@ -734,7 +734,10 @@ static int pso_host(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *
     if (seeds) HPE_CUDA(cudaMemcpyAsync(d_sd, seeds, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, 0));
     // few swarms (or a sequence): one swarm per 8-CTA cluster; many swarms: one per CTA
     const int units = chain ? count / chain : count;
-    const bool use_cluster = g_hpe_pso_path == 2 || (g_hpe_pso_path == 0 && units <= 36);
+    // clusters walk their units in rounds of 37 (8-CTA clusters, two CTAs per SM): measured on B200 (tools/track_multi_probe.py,
+    // 64 x 30) a cluster finishes a frame in 0.73 ms, a CTA of the one-CTA kernel in 2-6 ms depending on how full the SMs
+    // are, so the cluster kernel wins up to ~250 units (37: 50.6k tracked frames/s, 148: 50.6k against 28k; 296: 45k against 49k; 444 CTAs: 117k)
+    const bool use_cluster = g_hpe_pso_path == 2 || (g_hpe_pso_path == 0 && units <= 222);
     cudaError_t e = use_cluster
         ? hpe_launch_pso_cluster(m->dm, o->v, make_pso(p, num_particles), d_x0, first, count, seeds ? d_sd : nullptr,
                                  d_bp, d_bc, trace ? d_tr : nullptr, chain, 0, seq_stride, frame_stride)
@@ -876,7 +879,7 @@ static int track_refined(const hpe_model *m, const hpe_obs *o, const hpe_pso_par
     HPE_CUDA(cudaMemcpyAsync(d_sd, sd.data(), sizeof(uint64_t) * n_seq, cudaMemcpyHostToDevice, 0));
     HPE_CUDA(cudaMemcpyAsync(d_x, x0, step, cudaMemcpyHostToDevice, 0));
     const PsoDev prm = make_pso(p, num_particles);
-    const bool one_cta = g_hpe_pso_path == 1 || (g_hpe_pso_path == 0 && n_seq > 36);
+    const bool one_cta = g_hpe_pso_path == 1 || (g_hpe_pso_path == 0 && n_seq > 222);
     for (int k = 0; k < n_frames; ++k) {
         double *xk = d_x + (size_t)k * n_seq * HPE_NDOF, *bk = d_bp + (size_t)k * n_seq * HPE_NDOF;
         if (k > 0) HPE_CUDA(cudaMemcpyAsync(xk, bk - (size_t)n_seq * HPE_NDOF, step, cudaMemcpyDeviceToDevice, 0));

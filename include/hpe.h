@@ -281,7 +281,7 @@ int hpe_set_matcher(int mode);
  * HPE_ERR_CUDA.  Results are identical. */
 int hpe_set_cost_pipeline(int mode, int chunk_poses);
 /* kernel behind hpe_pso_evolve / hpe_track_sequence: 0 (default) = automatic (one 8-CTA cluster per swarm
- * for sequences and batches of <= 36 swarms, one CTA per swarm otherwise), 1 = always one CTA per swarm,
+ * for sequences and batches of <= 222 swarms or sequences, one CTA per swarm otherwise), 1 = always one CTA per swarm,
  * 2 = always one cluster per swarm, 3 = one cluster per swarm with the swarm state in global memory instead of
  * distributed shared memory (cross-check; the default for swarms of more than 128 particles).  Results are
  * bit-identical. */
