@@ -260,19 +260,39 @@ swarm_step_kernel(DevModel m, ObsView o, int slot, SwarmStepArgs sw)
 // every generation's topology draw, informant search, move + evaluate + pbest, the exchange of the
 // owned (pcost, pbest) rows with the other GPUs and the global argmin run inside this kernel.
 //   * exchange: the warp that finishes a particle stores its 27-double row into the local table AND
-//     straight into every peer's table over NVLink (CUDA IPC mappings); after a grid barrier one
-//     thread per peer raises this rank's generation flag in the peer's memory and waits for theirs.
-//     No NCCL call, no host involvement; compute and transfer overlap particle by particle.
+//     straight into every peer's table over NVLink (CUDA IPC mappings).  After the step barrier CTA 0
+//     posts this rank's (minimum cost, index) on every peer's board (and its own) and raises the
+//     generation flag next to it; EVERY CTA then waits for the flags of all ranks, takes the first
+//     minimum over the boards and updates its own copy of (gbest_cost, count) -- all CTAs compute the
+//     same values, so no barrier is needed to publish them.  No NCCL call, no host involvement.
+//   * informants: ONE pass over the num_p * 4 links: a 128-bit compare-and-swap minimum on
+//     (cost bits, index) keeps the first minimum (src/PSO.cpp:810-812) in one go, and only links that
+//     end in a particle this rank owns are looked at.  The keys are double buffered by generation
+//     parity (a CTA may start the next generation's pass while another still resets the old keys).
 //   * rows are double buffered exactly like the stepwise path (hpe_swarm.cu), and a rank enters
 //     generation g+1 only after seeing every peer's flag of generation g, so stores into the buffer a
-//     peer still reads cannot happen.
-//   * 4 grid barriers per generation (informant cost pass | index pass | step | reduce).
+//     peer still reads cannot happen; boards are double buffered by generation parity.
+//   * 2 grid barriers per generation (informants | step).
 // Counters are keyed by the global particle index: the result is bit-identical to the stepwise
 // all-gather path, to any other sharding and to pso_kernel.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long run_cost_bits(double c)
 {
     return c == c ? (unsigned long long)__double_as_longlong(c) : 0xfff8000000000000ull;
+}
+
+// lexicographic minimum on (hi, lo) at a 16-byte aligned address: atom.cas.b128 loop
+__device__ __forceinline__ void atomic_min_u128(unsigned long long *addr, unsigned long long hi, unsigned long long lo)
+{
+    ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2 *>(addr));      // x = lo, y = hi
+    while (hi < cur.y || (hi == cur.y && lo < cur.x)) {
+        unsigned long long olo, ohi;
+        asm volatile("{\n\t.reg .b128 c, n, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 n, {%4, %5};\n\t"
+                     "atom.global.relaxed.gpu.cas.b128 o, [%6], c, n;\n\tmov.b128 {%0, %1}, o;\n\t}"
+                     : "=l"(olo), "=l"(ohi) : "l"(cur.x), "l"(cur.y), "l"(lo), "l"(hi), "l"(addr) : "memory");
+        if (olo == cur.x && ohi == cur.y) break;
+        cur.x = olo; cur.y = ohi;
+    }
 }
 
 template <bool WARP1>     // WARP1: at most one particle per warp (small shards): whole-warp forward kinematics
@@ -285,6 +305,8 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
     CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
     __shared__ unsigned long long skey[COST_WARPS];
     __shared__ int sidx[COST_WARPS];
+    __shared__ double s_gbest_cost;             // this CTA's copy of the swarm's control state (identical in every CTA)
+    __shared__ int s_count, s_err;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     stage_model(sm.fs, m);
     stage_frame(sm.fs, frame_view(o, slot));     // ends synchronised
@@ -295,6 +317,8 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
     const int64_t total_warps = (int64_t)gridDim.x * COST_WARPS, gw = (int64_t)blockIdx.x * COST_WARPS + warp;
     const int64_t plo = (int64_t)own * gw / total_warps, phi = (int64_t)own * (gw + 1) / total_warps;
     SwarmCtl *ctl = a.ctl;
+    ulonglong2 *key2 = reinterpret_cast<ulonglong2 *>(a.key2);          // [2][own]: (x = index, y = cost bits)
+    const ulonglong2 KEY_NONE = make_ulonglong2(0x7fffffffull, ~0ull);
     // optional phase timestamps (hpe_swarm_debug_times): 8 slots per generation, written by one thread
 #define RUN_STAMP(slot_) do { if (a.times && gtid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.times[g * 8 + (slot_)] = t_; } } while (0)
 
@@ -308,8 +332,9 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
         a.v[li * D + 2 * dp] = 0.0;
         a.v[li * D + 2 * dp + 1] = 0.0;
     }
-    for (int64_t i = gtid; i < num_p; i += gthreads) { a.key[i] = ~0ull; a.inf[i] = 0x7fffffff; }
+    for (int64_t i = gtid; i < 2 * (int64_t)own; i += gthreads) key2[i] = KEY_NONE;
     if (gtid == 0) { ctl->gbest_cost = 1e100; ctl->count = 100; ctl->iter = 0; ctl->error = 0; }
+    if (tid == 0) { s_gbest_cost = 1e100; s_count = 100; s_err = 0; }
     grid.sync();
 
     int cur = 0;
@@ -317,11 +342,13 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
         const double *table = a.table[cur];                 // rows of the previous generation, complete
         double *out = g == 0 ? a.table[0] : a.table[cur ^ 1];
         const int ob = g == 0 ? 0 : cur ^ 1;
-        const int iter = g;                                 // = ctl->iter: evaluations done so far
+        const int iter = g;                                 // evaluations done so far
+        ulonglong2 *keys = key2 + (size_t)(g & 1) * own;    // this generation's informant keys
         RUN_STAMP(0);
         if (g > 0) {
-            // ---- topology (redrawn when count > 0, src/PSO.cpp:790-803) + informant cost pass (:810-812) ----
-            const bool redraw = ((volatile SwarmCtl *)ctl)->count > 0;
+            // ---- topology (redrawn when count > 0, src/PSO.cpp:790-803) + informants (:810-812): link (s -> r) offers
+            //      (pcost[s], s) to r; only targets this rank owns are kept ----
+            const bool redraw = s_count > 0;
             for (int64_t it = gtid; it < (int64_t)num_p * (NK + 1); it += gthreads) {
                 int s = (int)(it / (NK + 1)), k = (int)(it - (int64_t)s * (NK + 1));
                 int r = s;                                  // L = eye + links
@@ -329,20 +356,17 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
                     if (redraw) {
                         double u[2];
                         uniform2(a.seed, (uint32_t)(k >> 1), (uint32_t)s, (uint32_t)iter, 3u, u);
-                        a.R[s * NK + k] = (int)floor(__dadd_rn(__dmul_rn(u[k & 1], (double)(num_p - 1)), 0.5));
+                        r = (int)floor(__dadd_rn(__dmul_rn(u[k & 1], (double)(num_p - 1)), 0.5));
+                        a.R[s * NK + k] = r;
+                    } else {
+                        r = a.R[s * NK + k];
                     }
-                    r = a.R[s * NK + k];
                 }
-                atomicMin(&a.key[r], run_cost_bits(__ldcg(table + (size_t)s * ROW)));
+                if (r >= a.lo && r < a.hi)
+                    atomic_min_u128(reinterpret_cast<unsigned long long *>(keys + (r - a.lo)),
+                                    run_cost_bits(__ldcg(table + (size_t)s * ROW)), (unsigned long long)s);
             }
-            grid.sync();
             RUN_STAMP(1);
-            // ---- informant index pass: lowest index attaining the minimum ----
-            for (int64_t it = gtid; it < (int64_t)num_p * (NK + 1); it += gthreads) {
-                int s = (int)(it / (NK + 1)), k = (int)(it - (int64_t)s * (NK + 1));
-                int r = k < NK ? a.R[s * NK + k] : s;
-                if (run_cost_bits(__ldcg(table + (size_t)s * ROW)) == __ldcg(a.key + r)) atomicMin(&a.inf[r], s);
-            }
             grid.sync();
             RUN_STAMP(2);
         }
@@ -354,7 +378,7 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
             if (g > 0) {
                 for (int it = lane; it < cnt * (D / 2); it += 32) {
                     int gq = it / (D / 2), dp = it - gq * (D / 2);
-                    int li = (int)(p0 + gq), i = a.lo + li, informant = __ldcg(a.inf + i);
+                    int li = (int)(p0 + gq), i = a.lo + li, informant = (int)__ldcg(&keys[li].x);
                     const double *pb = table + (size_t)i * ROW + 1, *pbi = table + (size_t)informant * ROW + 1;
                     double rp[2], rg[2];
                     uniform2(a.seed, (uint32_t)dp, (uint32_t)i, (uint32_t)iter, 1u, rp);
@@ -409,9 +433,15 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
         __threadfence_system();
         grid.sync();
         RUN_STAMP(4);
-        // informant search state for the next generation (nobody reads it any more in this one)
-        for (int64_t i = gtid; i < num_p; i += gthreads) { a.key[i] = ~0ull; a.inf[i] = 0x7fffffff; }
-        // ---- exchange point + global first minimum (src/PSO.cpp:755-760, 864-876): CTA 0 ----
+        // the keys of this generation have been consumed; its buffer is next used two generations from now
+        for (int64_t i = gtid; i < own; i += gthreads) keys[i] = KEY_NONE;
+        const int par = g & 1;
+        const unsigned want = a.gen_base + (unsigned)g + 1u;
+        // ---- CTA 0: this rank's first minimum -> every peer's board, then the flag; wait for the peers' flags; the
+        //      global first minimum (src/PSO.cpp:755-760, 864-876) is published to the other CTAs of this GPU ----
+        unsigned long long gkey = ~0ull;
+        int gidx = 0x7fffffff;
+        bool lost = false;
         if (blockIdx.x == 0) {
             unsigned long long key = ~0ull;
             int idx = 0x7fffffff;
@@ -428,8 +458,6 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
             __syncthreads();                                  // skey / sidx of the step phase have been consumed
             if (lane == 0) { skey[warp] = key; sidx[warp] = idx; }
             __syncthreads();
-            const int par = g & 1;
-            const unsigned want = a.gen_base + (unsigned)g + 1u;
             if (warp == 0) {
                 key = lane < COST_WARPS ? skey[lane] : ~0ull;
                 idx = lane < COST_WARPS ? sidx[lane] : 0x7fffffff;
@@ -438,17 +466,15 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
                     int oi = __shfl_xor_sync(0xffffffffu, idx, off);
                     if (ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; }
                 }
-                // this rank's minimum goes to every peer next to the rows, then the flag: "generation g delivered"
                 if (lane < a.world && lane != a.rank) {
                     SwarmMin *dst = a.peer_min[lane] + par * HPE_MAX_PEERS + a.rank;
                     dst->key = key;
                     dst->idx = idx;
                     __threadfence_system();
                     a.peer_flags[lane][a.rank] = want;
-                    __threadfence_system();
                     long long spins = 0;
                     while (a.my_flags[lane] < want) {
-                        if (++spins > (1ll << 28)) { ctl->error = 1; break; }   // a lost peer must not hang the GPU
+                        if (++spins > a.spin_limit) { lost = true; break; }   // a lost peer must not hang the GPU
                         __nanosleep(32);
                     }
                     __threadfence_system();
@@ -459,6 +485,7 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
                     key = ~0ull;
                     idx = 0x7fffffff;
                 }
+                lost = __any_sync(0xffffffffu, lost);
                 RUN_STAMP(5);
                 for (int off = 16; off > 0; off >>= 1) {
                     unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, off);
@@ -466,25 +493,53 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
                     if (ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; }
                 }
                 if (idx == 0x7fffffff) idx = 0;
-                const double *vt = out;                       // the winner's row (remote rows arrived by NVLink stores)
-                const double fmin = __ldcg(vt + (size_t)idx * ROW);
-                const bool improved = fmin < ctl->gbest_cost;
-                if (improved && lane < D) ctl->gbest[lane] = __ldcg(vt + (size_t)idx * ROW + 1 + lane);
-                __syncwarp();
-                if (lane == 0) {
-                    if (improved) {
-                        ctl->gbest_cost = fmin;
-                        ctl->count = g == 0 ? 100 : 0;
-                    } else if (g > 0) {
-                        ctl->count += 1;
-                    }
-                    ctl->iter = g + 1;
-                    if (a.trace && g >= 1) a.trace[g - 1] = ctl->gbest_cost;
+                gkey = key; gidx = idx;
+                if (lane == 0) {                              // release the other CTAs of this GPU
+                    volatile SwarmResult *res = a.result + par;
+                    res->idx = idx;
+                    res->lost = lost ? 1 : 0;
+                    __threadfence();
+                    res->gen = want;
                 }
             }
+        } else if (warp == 0) {
+            volatile SwarmResult *res = a.result + par;
+            if (lane == 0) {
+                long long spins = 0;
+                while (res->gen != want) {
+                    if (++spins > 4 * a.spin_limit) { lost = true; break; }
+                    __nanosleep(64);
+                }
+                __threadfence();
+                gidx = res->idx;
+                lost = lost || res->lost != 0;
+            }
+            gidx = __shfl_sync(0xffffffffu, gidx, 0);
+            lost = __any_sync(0xffffffffu, lost);
         }
+        (void)gkey;
+        if (warp == 0) {
+            const double fmin = __ldcg(out + (size_t)gidx * ROW);   // the winner's row (remote rows arrived by NVLink stores)
+            const bool improved = fmin < s_gbest_cost;
+            if (blockIdx.x == 0) {
+                if (improved && lane < D) ctl->gbest[lane] = __ldcg(out + (size_t)gidx * ROW + 1 + lane);
+                if (lane == 0) {
+                    if (improved) ctl->gbest_cost = fmin;
+                    ctl->count = improved ? (g == 0 ? 100 : 0) : (g > 0 ? s_count + 1 : s_count);
+                    ctl->iter = g + 1;
+                    if (lost) ctl->error = 1;
+                    if (a.trace && g >= 1) a.trace[g - 1] = improved ? fmin : s_gbest_cost;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (improved) { s_gbest_cost = fmin; s_count = g == 0 ? 100 : 0; }
+                else if (g > 0) s_count += 1;
+                if (lost) s_err = 1;
+            }
+        }
+        __syncthreads();
         RUN_STAMP(6);
-        grid.sync();
         RUN_STAMP(7);
         if (g > 0) cur ^= 1;
     }

@@ -89,6 +89,10 @@ struct SwarmMin {                              // a rank's first minimum of pcos
     unsigned long long key;                    // IEEE bits of the cost (costs are >= 0)
     int idx, pad;
 };
+struct SwarmResult {                           // global first minimum of a generation, published by CTA 0 to its GPU's CTAs
+    int idx, lost;
+    unsigned gen, pad;
+};
 struct SwarmRunArgs {
     PsoDev prm;
     uint64_t seed;
@@ -99,6 +103,9 @@ struct SwarmRunArgs {
     const double *x0;
     int *R, *inf;
     unsigned long long *key;
+    unsigned long long *key2;                  // [2][own][2] informant keys of hpe_swarm_run: (index, cost bits) per owned particle
+    long long spin_limit;                      // bound of the flag waits (a lost peer must not hang the GPU)
+    volatile SwarmResult *result;              // [2] by generation parity, local
     SwarmCtl *ctl;
     double *trace;
     double *peer_table[2][HPE_MAX_PEERS];      // the peers' row buffers (NULL for self / absent)

@@ -160,17 +160,19 @@ __global__ void swarm_signal(PeerPtrs peers, int world, int rank, unsigned gen)
 }
 
 // first kernel after the exchange point: wait until every peer has delivered generation `gen`
-__global__ void swarm_wait(volatile unsigned *flags, int world, int rank, unsigned gen, SwarmCtl *ctl)
+__global__ void swarm_wait(volatile unsigned *flags, int world, int rank, unsigned gen, SwarmCtl *ctl, long long spin_limit)
 {
     if (threadIdx.x < world && threadIdx.x != rank) {
         long long spins = 0;
         while (flags[threadIdx.x] < gen) {
-            if (++spins > (1ll << 31)) { ctl->error = 1; break; }   // bounded: a lost peer must not hang the GPU
+            if (++spins > spin_limit) { ctl->error = 1; break; }   // bounded: a lost peer must not hang the GPU
             __nanosleep(100);
         }
     }
     __threadfence_system();
 }
+
+long long g_swarm_spin_limit = 1ll << 28;      // hpe_swarm_set_wait_limit(): polls before a flag wait gives up
 
 inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
@@ -186,6 +188,8 @@ struct hpe_swarm {
     double *x0, *x, *v, *table[2], *trace;
     int *R, *inf;
     unsigned long long *key;
+    unsigned long long *key2;          // informant keys of hpe_swarm_run: [2][own] x 16 bytes
+    SwarmResult *result;               // [2] release slots of hpe_swarm_run
     SwarmCtl *ctl;
     // peer exchange
     void *shared_base;                 // one allocation: table[0] | table[1] | flags
@@ -236,7 +240,7 @@ int hpe_swarm_destroy(hpe_swarm *s)
     for (int p = 0; p < MAX_PEERS; ++p)
         if (s->peer_base[p]) cudaIpcCloseMemHandle(s->peer_base[p]);
     cudaFree(s->x0); cudaFree(s->x); cudaFree(s->v); cudaFree(s->shared_base); cudaFree(s->trace);
-    cudaFree(s->R); cudaFree(s->inf); cudaFree(s->key); cudaFree(s->ctl); cudaFree(s->times); cudaFree(s->cta_key); cudaFree(s->cta_idx);
+    cudaFree(s->R); cudaFree(s->inf); cudaFree(s->key); cudaFree(s->key2); cudaFree(s->result); cudaFree(s->ctl); cudaFree(s->times); cudaFree(s->cta_key); cudaFree(s->cta_idx);
     delete s;
     return HPE_OK;
 }
@@ -278,6 +282,9 @@ int hpe_swarm_create(const hpe_model *m, const hpe_obs *o, int slot, const hpe_p
     if (e == cudaSuccess) e = cudaMalloc(&s->R, sizeof(int) * np * NK);
     if (e == cudaSuccess) e = cudaMalloc(&s->inf, sizeof(int) * np);
     if (e == cudaSuccess) e = cudaMalloc(&s->key, sizeof(unsigned long long) * np);
+    if (e == cudaSuccess) e = cudaMalloc(&s->key2, 2 * own * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&s->result, 2 * sizeof(SwarmResult));
+    if (e == cudaSuccess) e = cudaMemset(s->result, 0, 2 * sizeof(SwarmResult));
     if (e == cudaSuccess) e = cudaMalloc(&s->ctl, sizeof(SwarmCtl));
     if (e == cudaSuccess) e = cudaMemcpy(s->x0, x0, sizeof(double) * HPE_NDOF, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the cleared flags must be in place before a peer can attach
@@ -314,7 +321,7 @@ int hpe_swarm_init(hpe_swarm *s, void *stream)
 int hpe_swarm_reduce(hpe_swarm *s, void *stream)
 {
     if (!s) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_reduce: NULL swarm");
-    if (s->world > 1) swarm_wait<<<1, 32, 0, (cudaStream_t)stream>>>(s->flags, s->world, s->rank, s->gen, s->ctl);
+    if (s->world > 1) swarm_wait<<<1, 32, 0, (cudaStream_t)stream>>>(s->flags, s->world, s->rank, s->gen, s->ctl, g_swarm_spin_limit * 8);
     swarm_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(s->num_p, s->table[s->cur], s->ctl, s->trace);
     HPE_CUDA(cudaGetLastError());
     return HPE_OK;
@@ -372,7 +379,9 @@ int hpe_swarm_run(hpe_swarm *s, void *stream)
     a.prm = s->prm; a.seed = s->seed; a.W1 = s->W1; a.C1 = s->C1;
     a.num_p = s->num_p; a.lo = s->lo; a.hi = s->hi; a.maxiter = s->prm.maxiter;
     a.table[0] = s->table[0]; a.table[1] = s->table[1];
-    a.x = s->x; a.v = s->v; a.x0 = s->x0; a.R = s->R; a.inf = s->inf; a.key = s->key; a.ctl = s->ctl; a.trace = s->trace;
+    a.x = s->x; a.v = s->v; a.x0 = s->x0; a.R = s->R; a.inf = s->inf; a.key = s->key; a.key2 = s->key2; a.ctl = s->ctl; a.trace = s->trace;
+    a.spin_limit = g_swarm_spin_limit;
+    a.result = s->result;
     a.world = s->world; a.rank = s->rank; a.gen_base = s->gen; a.my_flags = s->flags;
     const size_t tb = table_bytes(s->num_p);
     a.my_min = (volatile SwarmMin *)((char *)s->shared_base + 2 * tb + 256);
@@ -390,6 +399,15 @@ int hpe_swarm_run(hpe_swarm *s, void *stream)
     s->gen += (unsigned)s->prm.maxiter;
     // the last generation g = maxiter-1 wrote buffer (g == 0 ? 0 : 1 - (g-1)%2 ...): track it like the stepwise path
     s->cur = s->prm.maxiter > 1 ? (s->prm.maxiter - 1) & 1 : 0;
+    return HPE_OK;
+}
+
+// bound of the peer-flag waits, in polls (~50-100 ns each): default 2^28 (tens of seconds).  Tests lower it to see the
+// HPE_ERR_STATE of a peer that never delivers.
+int hpe_swarm_set_wait_limit(long long polls)
+{
+    if (polls < 1) return hpe_set_error(HPE_ERR_ARG, "hpe_swarm_set_wait_limit: polls must be positive");
+    g_swarm_spin_limit = polls;
     return HPE_OK;
 }
 

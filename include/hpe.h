@@ -250,10 +250,13 @@ int hpe_swarm_ipc_handle(hpe_swarm *s, unsigned char handle[64]);
 int hpe_swarm_attach_peers(hpe_swarm *s, const unsigned char *handles /* world*64 */, int world, int rank);
 /* The whole run -- hpe_swarm_init, then (hpe_swarm_step, exchange, hpe_swarm_reduce) x (maxiter-1) -- as ONE
  * cooperative kernel launch per GPU: rows go to the peers by NVLink stores from the warp that produced
- * them, ranks meet on device-side flags, 4 grid barriers per generation.  Peers must be attached when more
+ * them, ranks meet on device-side flags, 2 grid barriers per generation.  Peers must be attached when more
  * than one rank takes part (hpe_swarm_attach_peers); every rank calls it once.  Bit-identical to the
  * stepwise path.  Asynchronous on `stream`. */
 int hpe_swarm_run(hpe_swarm *s, void *stream);
+/* bound of the device-side waits on peer flags, in polls of ~50-100 ns (default 2^28): a peer that never delivers makes
+ * hpe_swarm_best return HPE_ERR_STATE instead of hanging the GPU; tests lower the bound */
+int hpe_swarm_set_wait_limit(long long polls);
 /* diagnostics: first call switches phase-timestamp recording on; later calls copy the stamps of the last
  * hpe_swarm_run to out (maxiter*8 values, ns) */
 int hpe_swarm_debug_times(hpe_swarm *s, unsigned long long *out);

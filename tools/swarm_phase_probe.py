@@ -31,11 +31,13 @@ for _ in range(3):
     torch.cuda.synchronize()
 t = sw.debug_times().astype(np.int64)
 if rank == 0:
-    names = ["inf cost pass", "inf index pass", "step (CTA 0 done)", "step barrier", "exchange wait", "reduce", "closing barrier"]
+    names = ["informant pass", "informant barrier", "step (CTA 0 done)", "step barrier", "post + flag wait", "reduce", "-"]
     d = np.diff(t, axis=1)[3:] / 1e3          # skip the first generations
     print(f"world={world} {NP} particles: mean us per phase over generations 3..{GEN - 1}")
     for n, v in zip(names, d.mean(axis=0)):
         print(f"  {n:20s} {v:8.2f}")
     print(f"  {'generation':20s} {(t[3:, 7] - t[3:, 0]).mean() / 1e3:8.2f}   whole run {(t[-1, 7] - t[0, 0]) / 1e6:.3f} ms")
+    bp, bc, tr = sw.best()
+    print(f"  best cost {bc!r}")
 if world > 1:
     dist.destroy_process_group()
