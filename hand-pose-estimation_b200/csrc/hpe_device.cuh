@@ -96,13 +96,23 @@ __device__ __forceinline__ void aff_global(Aff &g, const double pos[3], const Di
     g.tx = pos[0]; g.ty = pos[1]; g.tz = pos[2];
 }
 
-// joints J[0..4] of digit d (0 = thumb) from the global position pos = theta[3:6] and the sines / cosines of
-// the three global angles and the digit's four joint angles
-__device__ __forceinline__ void fk_digit_trig(const DevModel &M, int d, const double pos[3], const DigitTrig &t,
-                                              double J[5][3])
+// wa * a + wb * b with a fixed contraction (one multiply, one FMA), so that every code path that interpolates sphere
+// centres produces the same bits whatever the compiler would have fused
+__device__ __forceinline__ double mix2(double wa, double a, double wb, double b) { return __fma_rn(wa, a, __dmul_rn(wb, b)); }
+
+// The forward-kinematics chain of digit d (0 = thumb) from the global position pos = theta[3:6]: TRIG hands out the
+// sine / cosine of entry k of the digit's seven angles when the chain gets to it (aff_global takes 0..2 together, the
+// twist link 3 and 4, then 5, then 6), SINK receives the joints as they become final, in the order 1, 0, 2, 3, 4.
+// One body for every caller, so all paths produce the same bits.
+template <class TRIG, class SINK>
+__device__ __forceinline__ void fk_chain(const DevModel &M, int d, const double pos[3], TRIG &&trig, SINK &&sink)
 {
     Aff cur;
-    aff_global(cur, pos, t);
+    {
+        DigitTrig t;
+        trig(0, t.s[0], t.c[0]); trig(1, t.s[1], t.c[1]); trig(2, t.s[2], t.c[2]);
+        aff_global(cur, pos, t);
+    }
     // cur <- cur * base[d]   (general 3x4 product; base has r[2][*] = (0,0,1), t.z = 0)
     {
         const double *b = M.base[d];
@@ -115,17 +125,17 @@ __device__ __forceinline__ void fk_digit_trig(const DevModel &M, int d, const do
         cur.tz += cur.r20 * b[3] + cur.r21 * b[7];
         cur.r00 = n00; cur.r01 = n01; cur.r10 = n10; cur.r11 = n11; cur.r20 = n20; cur.r21 = n21;
     }
-    J[1][0] = cur.tx; J[1][1] = cur.ty; J[1][2] = cur.tz;
+    sink(1, cur.tx, cur.ty, cur.tz);
     {   // joint 0 = (cur * T10).col(3)
         double bx = M.backt[d][0], by = M.backt[d][1];
-        J[0][0] = cur.r00 * bx + cur.r01 * by + cur.tx;
-        J[0][1] = cur.r10 * bx + cur.r11 * by + cur.ty;
-        J[0][2] = cur.r20 * bx + cur.r21 * by + cur.tz;
+        sink(0, cur.r00 * bx + cur.r01 * by + cur.tx, cur.r10 * bx + cur.r11 * by + cur.ty, cur.r20 * bx + cur.r21 * by + cur.tz);
     }
     const double *L = M.geo + 4 * d;
-    const double s1 = t.s[3], c1 = t.c[3], s2 = t.s[4], c2 = t.c[4];
     double cp = d == 0 ? M.tc : 1.0, sp = d == 0 ? M.ts : 0.0;
     {   // S = twist(a0) * X(a1), X = [[c2,-s2 cp, s2 sp, L c2],[s2, c2 cp, -c2 sp, L s2],[0, sp, cp, 0]]
+        double s1, c1, s2, c2;
+        trig(3, s1, c1);
+        trig(4, s2, c2);
         double x00 = c2, x01 = -s2 * cp, x02 = s2 * sp, x03 = L[1] * c2;
         double x10 = s2, x11 = c2 * cp, x12 = -c2 * sp, x13 = L[1] * s2;
         double x21 = sp, x22 = cp;
@@ -148,14 +158,27 @@ __device__ __forceinline__ void fk_digit_trig(const DevModel &M, int d, const do
         n.tz  = cur.r20 * s03 + cur.r21 * s13 + cur.r22 * s23 + cur.tz;
         cur = n;
     }
-    J[2][0] = cur.tx; J[2][1] = cur.ty; J[2][2] = cur.tz;
-    const double s3 = t.s[5], c3 = t.c[5], s4 = t.s[6], c4 = t.c[6];
-    aff_planar(cur, c3, s3, L[2]);
-    J[3][0] = cur.tx; J[3][1] = cur.ty; J[3][2] = cur.tz;
-    // last link: only the translation is needed
-    J[4][0] = cur.tx + L[3] * (cur.r00 * c4 + cur.r01 * s4);
-    J[4][1] = cur.ty + L[3] * (cur.r10 * c4 + cur.r11 * s4);
-    J[4][2] = cur.tz + L[3] * (cur.r20 * c4 + cur.r21 * s4);
+    sink(2, cur.tx, cur.ty, cur.tz);
+    {
+        double s3, c3;
+        trig(5, s3, c3);
+        aff_planar(cur, c3, s3, L[2]);
+    }
+    sink(3, cur.tx, cur.ty, cur.tz);
+    {   // last link: only the translation is needed
+        double s4, c4;
+        trig(6, s4, c4);
+        sink(4, cur.tx + L[3] * (cur.r00 * c4 + cur.r01 * s4), cur.ty + L[3] * (cur.r10 * c4 + cur.r11 * s4),
+             cur.tz + L[3] * (cur.r20 * c4 + cur.r21 * s4));
+    }
+}
+
+// joints J[0..4] of digit d from precomputed sines / cosines
+__device__ __forceinline__ void fk_digit_trig(const DevModel &M, int d, const double pos[3], const DigitTrig &t,
+                                              double J[5][3])
+{
+    fk_chain(M, d, pos, [&](int k, double &sn, double &cs) { sn = t.s[k]; cs = t.c[k]; },
+             [&](int i, double x, double y, double z) { J[i][0] = x; J[i][1] = y; J[i][2] = z; });
 }
 
 // sine and cosine of an angle in degrees.  One out-of-line copy for the seven (or 23) call sites of a kernel: the
@@ -174,11 +197,62 @@ static __device__ __noinline__ void sincos_deg(double deg, double *sn, double *c
 // joints J[0..4] of digit d (0 = thumb) for pose th[26]: the lane computes its seven sincos itself
 __device__ __forceinline__ void fk_digit(const DevModel &M, int d, const double *th, double J[5][3])
 {
-    DigitTrig t;
     double pos[3] = {th[3], th[4], th[5]};
-#pragma unroll
-    for (int k = 0; k < 7; ++k) sincos_deg(trig_angle_deg(th, d, k), &t.s[k], &t.c[k]);
-    fk_digit_trig(M, d, pos, t, J);
+    fk_chain(M, d, pos, [&](int k, double &sn, double &cs) { sincos_deg(trig_angle_deg(th, d, k), &sn, &cs); },
+             [&](int i, double x, double y, double z) { J[i][0] = x; J[i][1] = y; J[i][2] = z; });
+}
+
+// The same chain writing the digit's sphere centres straight to sd[48][3] (un-negated frame) as soon as the two joints
+// of a segment are final -- no joint or sphere arrays stay live, the sincos are taken when the chain needs them.
+// Same interpolation arithmetic as digit_spheres().
+struct SphereSink {
+    double *sd;       // [48][3] of the pose
+    int d;
+    double jx, jy, jz;            // previous joint of the chain (joint 1 while joint 0 is pending)
+    __device__ __forceinline__ void put(int i, double x, double y, double z) const
+    {
+        double *p = sd + 3 * i;
+        p[0] = x; p[1] = y; p[2] = z;
+    }
+    __device__ __forceinline__ void operator()(int i, double x, double y, double z)
+    {
+        const int first = d == 0 ? 0 : 8 + 10 * (d - 1);
+        if (i == 1) { jx = x; jy = y; jz = z; return; }
+        if (i == 0) {             // segment 0 runs from joint 0 (x, y, z) to joint 1 (jx, jy, jz)
+            if (d == 0) {
+                put(first, mix2(0.5, x, 0.5, jx), mix2(0.5, y, 0.5, jy), mix2(0.5, z, 0.5, jz));
+                put(first + 1, jx, jy, jz);
+            } else {
+                const double t = 1. / 3.;
+                put(first, x, y, z);
+                put(first + 1, mix2(1. - t, x, t, jx), mix2(1. - t, y, t, jy), mix2(1. - t, z, t, jz));
+                put(first + 2, mix2(1. - t * 2, x, t * 2, jx), mix2(1. - t * 2, y, t * 2, jy), mix2(1. - t * 2, z, t * 2, jz));
+                put(first + 3, jx, jy, jz);
+            }
+            return;
+        }
+        // segment i - 1 -> i (i = 2, 3, 4): its midpoint and its end
+        const int at = first + (d == 0 ? 2 * (i - 1) : 2 + 2 * (i - 1));
+        put(at, mix2(0.5, jx, 0.5, x), mix2(0.5, jy, 0.5, y), mix2(0.5, jz, 0.5, z));
+        put(at + 1, x, y, z);
+        jx = x; jy = y; jz = z;
+    }
+};
+
+template <bool CG>
+__device__ __forceinline__ void fk_digit_emit(const DevModel &M, int d, const double *th, double *sd)
+{
+    double pos[3];
+    pos[0] = CG ? __ldcg(th + 3) : th[3]; pos[1] = CG ? __ldcg(th + 4) : th[4]; pos[2] = CG ? __ldcg(th + 5) : th[5];
+    SphereSink sink{sd, d, 0.0, 0.0, 0.0};
+    fk_chain(M, d, pos,
+             [&](int k, double &sn, double &cs) {
+                 const double *p = k < 3 ? th + k : th + 6 + 4 * d + (k - 3);
+                 double deg = CG ? __ldcg(p) : *p;
+                 if (k == 0) deg += 180.0;
+                 sincos_deg(deg, &sn, &cs);
+             },
+             sink);
 }
 
 // the same for a pose that may have been written while this kernel runs (chunks landing by DMA under a
@@ -234,12 +308,12 @@ __device__ __forceinline__ int digit_spheres(int d, const double J[5][3], double
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (d == 0) {
-            S[0][k] = 0.5 * J[0][k] + 0.5 * J[1][k];
+            S[0][k] = mix2(0.5, J[0][k], 0.5, J[1][k]);
             S[1][k] = J[1][k];
         } else {
             S[0][k] = J[0][k];
-            S[1][k] = (1. - t) * J[0][k] + t * J[1][k];
-            S[2][k] = (1. - t * 2) * J[0][k] + (t * 2) * J[1][k];
+            S[1][k] = mix2(1. - t, J[0][k], t, J[1][k]);
+            S[2][k] = mix2(1. - t * 2, J[0][k], t * 2, J[1][k]);
             S[3][k] = J[1][k];
         }
     }
@@ -247,7 +321,7 @@ __device__ __forceinline__ int digit_spheres(int d, const double J[5][3], double
     for (int i = 1; i < 4; ++i) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            double mid = 0.5 * J[i][k] + 0.5 * J[i + 1][k];
+            double mid = mix2(0.5, J[i][k], 0.5, J[i + 1][k]);
             if (d == 0) { S[2 * i][k] = mid; S[2 * i + 1][k] = J[i + 1][k]; }
             else        { S[2 + 2 * i][k] = mid; S[3 + 2 * i][k] = J[i + 1][k]; }
         }

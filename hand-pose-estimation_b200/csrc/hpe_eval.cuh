@@ -786,22 +786,7 @@ __device__ __forceinline__ void group_fk(const DevModel &M, ThetaAt theta, int n
         __syncwarp();
         return;
     }
-    if (g < n) {
-        double J[5][3], S[10][3];
-        if (CG) fk_digit_cg(M, d, theta(g), J);
-        else fk_digit(M, d, theta(g), J);
-        int cnt = digit_spheres(d, J, S);
-        int first = digit_first_sphere(d);
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            if (i < cnt) {
-                double *sd = ws.sphd + ((size_t)g * HPE_NSPH + first + i) * 3;
-                sd[0] = S[i][0];
-                sd[1] = S[i][1];
-                sd[2] = S[i][2];
-            }
-        }
-    }
+    if (g < n) fk_digit_emit<CG>(M, d, theta(g), ws.sphd + (size_t)g * HPE_NSPH * 3);
     __syncwarp();
 }
 
