@@ -86,48 +86,52 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
     const int64_t total_warps = (int64_t)gridDim.x * COST_WARPS;
     const int64_t gw = (int64_t)blockIdx.x * COST_WARPS + warp;
     const int64_t lo = n * gw / total_warps, hi = n * (gw + 1) / total_warps;
-    // this warp's poses [lo, hi): everything below is relative to lo (32-bit loop control)
-    const int mine = (int)(hi - lo);
-    theta += lo * HPE_NDOF;
-    if (cost) cost += lo;
-    if (terms) terms += lo;
-    if (AUX && match_out) match_out += lo * n_pts;
-
-#if HPE_STAGGER
-    // warps of an SM start with first groups of different sizes so that their FP64 / gather phases
-    // do not line up in time
-    int first_cnt = 1 + (int)(gw % HPE_GROUP);
-#else
-    int first_cnt = HPE_GROUP;
-#endif
-    for (int p0 = 0; p0 < mine;) {
-        const int cnt = min(p0 == 0 ? first_cnt : HPE_GROUP, mine - p0);
-        group_fk(sm.fs.M, [&](int g) { return theta + (p0 + g) * HPE_NDOF; }, cnt, ws, lane);
+    // this warp's poses [lo, hi): 32-bit indices (a launch scores < 2^31 poses, hpe_launch_cost splits larger batches)
+    // against the kernel's pointer parameters, which stay in the constant bank.  The two loop variables live in the warp's
+    // shared-memory scratch and are re-read where they are used: every register is taken inside the matching phases, and
+    // a loop counter spilled to local memory costs an L1 miss per pose (ncu: 3.5 % of the kernel's stall samples).
+    volatile int *wl = reinterpret_cast<volatile int *>(ws.dep + 6);      // [0] = next pose, [1] = end, [2] = group size, [3] = g
+    if (lane == 0) { wl[0] = (int)lo; wl[1] = (int)hi; }
+    __syncwarp();
+#pragma unroll 1
+    for (;;) {
+        if (lane == 0) { wl[2] = min(HPE_GROUP, wl[1] - wl[0]); wl[3] = 0; }
+        __syncwarp();
+        if (wl[2] <= 0) break;
+        group_fk(sm.fs.M, [&](int g) { return theta + (size_t)(wl[0] + g) * HPE_NDOF; }, wl[2], ws, lane);
 #if HPE_GROUP_DEPTH
-        group_depth<HPE_GROUP>(sm.fs, ws, cnt, lane);
+        group_depth<HPE_GROUP>(sm.fs, ws, wl[2], lane);
 #endif
 #pragma unroll 1
-        for (int g = 0; g < cnt; ++g) {
+        while (wl[3] < wl[2]) {
 #if HPE_GROUP_DEPTH
-            const double depth = ws.dep[g];
-            stage_pose(sm.fs, ws, g, lane);
+            stage_pose(sm.fs, ws, wl[3], lane);
 #else
-            const double depth = depth_and_stage(sm.fs, ws, g, lane);
-#endif
-            double align = match_align<MATCHER, AUX>(sm.fs, ws, g, lane, AUX ? frozen : nullptr,
-                                                AUX && match_out ? match_out + (size_t)(p0 + g) * n_pts : nullptr);
-            double colli = 0.0;
-            if (WITH_COLLI) colli = warp_sum(collision_lane(sm.fs.rad, ws.sphd + (size_t)g * HPE_NSPH * 3, lane));
-            if (lane == 0) {
-                if (cost) cost[p0 + g] = WITH_COLLI ? align + depth + colli : align + depth;
-                if (terms) {
-                    terms[p0 + g] = align;           // SoA: align | depth | colli, tstride apart
-                    terms[tstride + p0 + g] = depth;
-                    terms[2 * tstride + p0 + g] = colli;
-                }
+            {
+                const double depth = depth_and_stage(sm.fs, ws, wl[3], lane);
+                if (lane == 0) reinterpret_cast<volatile double *>(ws.dep)[wl[3]] = depth;     // parked like the loop variables
             }
+#endif
+            double align = match_align<MATCHER, AUX>(sm.fs, ws, wl[3], lane, AUX ? frozen : nullptr,
+                                                     AUX && match_out ? match_out + (size_t)(wl[0] + wl[3]) * n_pts : nullptr);
+            double colli = 0.0;
+            if (WITH_COLLI) colli = warp_sum(collision_lane(sm.fs.rad, ws.sphd + (size_t)wl[3] * HPE_NSPH * 3, lane));
+            __syncwarp();
+            if (lane == 0) {
+                const int64_t at = wl[0] + wl[3];
+                const double depth = reinterpret_cast<volatile double *>(ws.dep)[wl[3]];
+                if (cost) cost[at] = WITH_COLLI ? align + depth + colli : align + depth;
+                if (terms) {
+                    terms[at] = align;           // SoA: align | depth | colli, tstride apart
+                    terms[tstride + at] = depth;
+                    terms[2 * tstride + at] = colli;
+                }
+                wl[3] = wl[3] + 1;
+            }
+            __syncwarp();
         }
-        p0 += cnt;
+        if (lane == 0) wl[0] = wl[0] + wl[2];
+        __syncwarp();
     }
 }
 
@@ -703,6 +707,15 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
 {
     if (n <= 0) return cudaSuccess;
     if (terms_stride <= 0) terms_stride = n;
+    if (n > 0x40000000) {          // the kernel indexes poses with 32 bits: split (2^30 poses are 223 GB, more than a B200 holds)
+        const int64_t half = n / 2;
+        cudaError_t e = hpe_launch_cost(m, o, slot, theta_dev, half, with_colli, cost_dev, terms_dev, frozen_match_dev,
+                                        match_out_dev, st, terms_stride);
+        if (e != cudaSuccess) return e;
+        return hpe_launch_cost(m, o, slot, theta_dev + half * HPE_NDOF, n - half, with_colli, cost_dev ? cost_dev + half : nullptr,
+                               terms_dev ? terms_dev + half : nullptr, frozen_match_dev,
+                               match_out_dev ? match_out_dev + half * o.n_pts : nullptr, st, terms_stride);
+    }
     const int sms = hpe_sm_count();
     int64_t groups = (n + HPE_GROUP - 1) / HPE_GROUP;
     int64_t want = (groups + COST_WARPS - 1) / COST_WARPS;

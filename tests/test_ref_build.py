@@ -176,18 +176,60 @@ def test_pso_evolve_on_replayed_streams(orc, omodel, R, D, num_p, maxiter, seed)
 
 
 def test_shim_primitives_against_numpy():
-    """the stand-in headers themselves: matcher and chamfer transform equal the oracle's restatements
-    (which tests/test_oracle_pins.py pins bit-for-bit against cv2)"""
+    """the stand-in Armadillo header itself, op by op, against numpy on random inputs: the dense product (left-to-right
+    dot products: equal to numpy up to summation order), accu / mean / dot (Armadillo's two-accumulator order, restated
+    here), min / max / floor / repmat / sum(A, dim) (exact).  The matcher and the chamfer transform of the OpenCV stand-in
+    are pinned through test_observation_bit_exact / test_cost_terms_bit_exact and, bit for bit against cv2, in
+    tests/test_oracle_pins.py."""
+    import ctypes as C
     import ref
     if not ref.available():
         pytest.skip("oracle/_ref not built")
-    # exercised through test_observation_bit_exact / test_cost_terms_bit_exact: this test only records
-    # that the library exports the entry points the other tests use
     L = ref.lib()
     for n in ("ref_create", "ref_load_frame", "ref_fk", "ref_cal_cost", "ref_cal_cost2", "ref_cost_terms",
               "ref_cost_batch", "ref_set_pso_params", "ref_pso_evolve", "ref_pso_optimise",
               "ref_refine_init_pose", "ref_gnd_truth_err", "ref_dim_restore", "ref_set_rng"):
         assert hasattr(L, n)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rng = np.random.default_rng(71)
+    # dense products of the shapes the hot files use (4x4 chains, 3x3 K times 3xN, Nx3 times 3x3)
+    for m, k, n in ((4, 4, 4), (3, 3, 48), (250, 3, 3), (1, 26, 1), (7, 5, 9)):
+        a, b = rng.normal(size=(m, k)) * 30, rng.normal(size=(k, n)) * 30
+        out = np.empty((m, n))
+        L.ref_shim_matmul(dp(a), m, k, dp(b), n, dp(out))
+        want = a @ b
+        assert np.allclose(out, want, rtol=1e-13, atol=1e-11 * np.abs(a).max() * np.abs(b).max())
+        # the stated order: plain left-to-right dot products, no FMA (oracle/Makefile: -ffp-contract=off)
+        ref_lr = np.array([[np.cumsum(a[i] * b[:, j])[-1] for j in range(n)] for i in range(m)])
+        assert np.array_equal(out, ref_lr)
+
+    def two_acc(x):        # arrayops::accumulate: even and odd elements in two accumulators, then their sum
+        v1 = v2 = 0.0
+        n2 = len(x) // 2 * 2
+        for i in range(0, n2, 2):
+            v1 += x[i]
+            v2 += x[i + 1]
+        if n2 < len(x):
+            v1 += x[n2]
+        return v1 + v2
+
+    for n in (1, 2, 3, 48, 250, 1001):
+        x = rng.normal(size=n) * 100
+        out = np.empty(5)
+        L.ref_shim_reduce(dp(x), n, dp(out))
+        assert out[0] == two_acc(x) and abs(out[0] - np.sum(x)) <= 1e-12 * np.abs(x).sum()
+        assert out[1] == two_acc(x) / n and abs(out[1] - x.mean()) <= 1e-12 * np.abs(x).mean() + 1e-300
+        assert out[2] == x.min() and out[3] == x.max()
+        assert out[4] == two_acc(x * x) and abs(out[4] - x @ x) <= 1e-12 * (x @ x)
+    for m, k, nr, nc in ((1, 3, 5, 1), (6, 1, 1, 6), (3, 4, 2, 3)):
+        a = rng.normal(size=(m, k)) * 50
+        a.flat[0] = -3.0; a.flat[-1] = 7.0                          # exact integers: floor keeps them
+        rep, fl = np.empty((m * nr, k * nc)), np.empty((m, k))
+        L.ref_shim_repmat_floor(dp(a), m, k, nr, nc, dp(rep), dp(fl))
+        assert np.array_equal(rep, np.tile(a, (nr, nc))) and np.array_equal(fl, np.floor(a))
+        cs, rs = np.empty(k), np.empty(m)
+        L.ref_shim_sums(dp(a), m, k, dp(cs), dp(rs))
+        assert np.allclose(cs, a.sum(0), rtol=1e-13, atol=1e-11) and np.allclose(rs, a.sum(1), rtol=1e-13, atol=1e-11)
 
 
 # ---------------------------------------------------------------- SURVEY 8(f) rank 3: PSO::pso_optimise
