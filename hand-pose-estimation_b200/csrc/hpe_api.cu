@@ -153,6 +153,24 @@ int hpe_debug_fallback_points(unsigned long long *count, int reset)
     return HPE_OK;
 }
 
+// page-locked host memory for the streaming entry points: cudaMemcpyAsync from / to pageable memory is staged by the
+// driver and blocks the caller, so the uploads of hpe_cost_batch_submit only overlap with kernels when the caller's
+// buffers are pinned
+int hpe_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return hpe_set_error(HPE_ERR_ARG, "hpe_host_alloc: NULL output");
+    *out = nullptr;
+    if (int rc = check_device()) return rc;
+    HPE_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return HPE_OK;
+}
+
+int hpe_host_free(void *p)
+{
+    if (p) HPE_CUDA(cudaFreeHost(p));
+    return HPE_OK;
+}
+
 int hpe_device_count(void)
 {
     int n = 0;

@@ -301,22 +301,73 @@ class costfunc:
                                         C.c_void_p(terms_dev_ptr or 0), C.c_void_p(stream or 0)))
 
 
+class _Pinned:
+    """numpy view of a page-locked host buffer owned by the library (hpe_host_alloc / hpe_host_free)"""
+
+    def __init__(self, shape, dtype=np.float64):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = C.c_void_p()
+        _check(lib().hpe_host_alloc(C.c_size_t(n), C.byref(self._p)))
+        buf = (C.c_ubyte * max(n, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if getattr(self, "_p", None) is not None and self._p.value and _LIB is not None:
+            self.array = None
+            _LIB.hpe_host_free(self._p)
+            self._p = None
+
+    __del__ = free
+
+
 class CostJob:
-    """one batch in flight (hpe_cost_batch_submit / hpe_cost_batch_wait); keeps its buffers alive until wait()"""
+    """one batch in flight (hpe_cost_batch_submit / hpe_cost_batch_wait).  The poses are copied into page-locked host
+    buffers and the results land in page-locked buffers, so submit() returns while the upload is still running
+    (a copy from pageable memory would block the caller); the buffers live until wait() -- or until the job is
+    dropped, which waits first: a job must never outlive its buffers or keep its slot busy for ever."""
 
     def __init__(self, cf, thetas, slot, with_collision):
-        self.th = _f64(thetas).reshape(-1, 26)
-        n = self.th.shape[0]
-        self.a, self.d = np.empty(n), np.empty(n)
-        self.c = np.zeros(n) if with_collision else None
+        th = _f64(thetas).reshape(-1, 26)
+        n = th.shape[0]
+        self._bufs = [_Pinned((max(n, 1), 26)), _Pinned((max(n, 1),)), _Pinned((max(n, 1),))]
+        self.th, self.a, self.d = self._bufs[0].array[:n], self._bufs[1].array[:n], self._bufs[2].array[:n]
+        self.th[:] = th
+        self.c = None
+        if with_collision:
+            self._bufs.append(_Pinned((max(n, 1),)))
+            self.c = self._bufs[3].array[:n]
+            self.c[:] = 0.0
+        self.id = None
         job = C.c_int(-1)
         _check(lib().hpe_cost_batch_submit(cf.hand._h, cf.observation._h, int(slot), _p(self.th), C.c_int64(n),
                                            _p(self.a), _p(self.d), _p(self.c), C.byref(job)))
         self.id = job.value
+        self._keep = cf
 
     def wait(self):
-        _check(lib().hpe_cost_batch_wait(int(self.id)))
-        return self.a, self.d, (np.zeros_like(self.a) if self.c is None else self.c)
+        """blocks until the batch is done; returns copies (align, depth, collision) and releases the job"""
+        if self.id is None:
+            raise HpeError(4, "CostJob.wait: the job was already waited on")
+        jid, self.id = self.id, None
+        _check(lib().hpe_cost_batch_wait(int(jid)))
+        out = (self.a.copy(), self.d.copy(), np.zeros(len(self.a)) if self.c is None else self.c.copy())
+        self._release()
+        return out
+
+    def _release(self):
+        self.th = self.a = self.d = self.c = None
+        for b in self._bufs:
+            b.free()
+        self._bufs = []
+
+    def __del__(self):
+        try:
+            if getattr(self, "id", None) is not None and _LIB is not None:
+                _LIB.hpe_cost_batch_wait(int(self.id))       # in-flight DMA must finish before its buffers go away
+                self.id = None
+            self._release()
+        except Exception:
+            pass
 
 
 class PSO:

@@ -30,6 +30,7 @@
 #ifndef HPE_B200_ABI_H
 #define HPE_B200_ABI_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -270,6 +271,13 @@ int hpe_render_dev(const hpe_model *m, const double *theta_dev, int64_t n, doubl
                    float *depth_mm_dev, void *stream);
 /* host convenience: theta host n*26 -> depth_mm host n*240*320 */
 int hpe_render(const hpe_model *m, const double *theta, int64_t n, double focal, float *depth_mm);
+
+/* Page-locked host buffers for the streaming entry points (hpe_cost_batch_submit, hpe_fit_frames): copies from / to
+ * pageable memory are staged by the driver and block the calling thread, so uploads only run under kernels when the
+ * caller's buffers are pinned.  Any pinned memory works (cudaHostAlloc, torch pin_memory); these two are for callers
+ * without a CUDA runtime of their own.  A buffer must outlive the jobs that use it. */
+int hpe_host_alloc(size_t bytes, void **out);
+int hpe_host_free(void *p);
 
 /* ---- diagnostics ---- */
 /* Nearest-centre search used by the cost kernels launched through hpe_cost_batch*,
