@@ -418,10 +418,10 @@ def main():
         extras["pso_evals_per_sec"] = world * n_fr * 64 * 30 / dt
         extras["pso_batch"] = f"{n_fr} frames x 64 particles x 30 generations per GPU, host x0 in, best pose out"
         extras["pso_median_final_cost"] = float(np.median(best))
-        # the same end to end from HOST frames (pinned): hpe_fit_frames streams them through a buffer of 592 slots,
+        # the same end to end from HOST frames (pinned): hpe_fit_frames streams them through a buffer of 888 slots (two halves of 444 = one full wave of swarm CTAs each),
         # the upload of a chunk (307 KB per frame) overlapped with the observation + swarms of the previous one
         frames_host = frames_dev.cpu().pin_memory()
-        obse = hpe_b200.observedmodel(capacity=592, num_samples=250)
+        obse = hpe_b200.observedmodel(capacity=888, num_samples=250)
         cfe = hpe_b200.costfunc(hand, obse)
         pso.fit_frames(cfe, frames_host.numpy(), x0, 64)
         barrier()

@@ -424,6 +424,11 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
                 }
             }
         }
+        // release the rows this warp stored into the peers' tables at system scope (the flag that announces them is
+        // written by CTA 0 after the grid barrier below; release / acquire order is cumulative across the barrier).
+        // Only the warps that stored anything, and only when there are peers: a system-scope fence is slow (it was 30 % of
+        // this kernel's stall samples when every thread executed the sequentially consistent form)
+        if (a.world > 1 && plo < phi) asm volatile("fence.acq_rel.sys;" ::: "memory");
         // this CTA's minimum -> cta_key / cta_idx (the global argmin is then a reduction over CTAs and ranks)
         if (lane == 0) { skey[warp] = wkey; sidx[warp] = widx; }
         __syncthreads();
@@ -436,7 +441,6 @@ swarm_run_kernel(DevModel m, ObsView o, int slot, SwarmRunArgs a)
             a.cta_idx[blockIdx.x] = ii;
         }
         RUN_STAMP(3);
-        __threadfence_system();
         grid.sync();
         RUN_STAMP(4);
         // the keys of this generation have been consumed; its buffer is next used two generations from now
