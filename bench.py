@@ -513,6 +513,19 @@ def main():
                            f"init; median final cost {float(np.median(costs)):.3f}; track_joint_err_mm = gnd_truth_err / 6 "
                            "against the rendered poses")
 
+        # the reference driver's own swarm: 32 particles x 200 iterations per frame (src/testmodel.cpp:104-105), on the first
+        # 444 frames of the batch (one CTA per frame)
+        pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, 200, 1e-8, 1e-8)
+        pso.pso_evolve_batch(cfb, x0[:444], 32, want_trace=False)
+        barrier()
+        t0 = time.perf_counter()
+        _, best200, _ = pso.pso_evolve_batch(cfb, x0[:444], 32, want_trace=False)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        extras["pso32x200_frames_per_sec"] = world * 444 / dt
+        extras["pso32x200"] = (f"444 frames per GPU x 32 particles x 200 iterations (test_full's parameters, 6,400 evaluations per "
+                               f"frame): {world * 444 * 6400 / dt:.3g} evaluations/s; median final cost {float(np.median(best200)):.3f}")
+        pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, GEN, 1e-8, 1e-8)
         # batched sequence tracking (hpe_track_sequences): the same loop over several independent sequences in ONE launch,
         # one thread-block cluster (9 sequences: 16-CTA clusters, one CTA per SM) or one CTA (444 sequences) per sequence
         nb, fb = 9, 100                                   # 9 sequences x 100 frames = frames [0, 900) of the walk above
@@ -684,7 +697,7 @@ def main():
         # the side measurements the metric's second half and the sharded configurations are read from, under a key that
         # survives the driver's parsing (`extras` carries the full set with their descriptions)
         keep = ("track_frames_per_sec", "track9_frames_per_sec", "track444_frames_per_sec", "track_refined_frames_per_sec",
-                "pso_frames_per_sec", "pso_e2e_frames_per_sec", "offline_frames_per_sec", "offline_fit_frames_per_sec",
+                "pso_frames_per_sec", "pso32x200_frames_per_sec", "pso_e2e_frames_per_sec", "offline_frames_per_sec", "offline_fit_frames_per_sec",
                 "observe_frames_per_sec", "swarm16k_ms", "swarm16k_allgather_ms", "swarm16k_best_cost", "evals_per_sec_250pts")
         line["config"]["side_measurements"] = {k: extras[k] for k in keep if k in extras}
         if "swarm16k_best_cost" in extras:

@@ -107,6 +107,11 @@ PsoDev make_pso(const hpe_pso_params *p, int num_p)
 
 }  // namespace
 
+// process-wide debug / cross-check switches (hpe_set_pso_path, hpe_set_cost_pipeline): C++ linkage like their declarations
+int g_hpe_pso_path = 0;
+int g_hpe_cost_pipeline = 0;   // 0 = one launch per uploaded chunk (default), 1 = chase kernel for large host batches
+int g_hpe_cost_chunk = 0;      // poses per upload chunk of the chase path (0 = default)
+
 extern "C" {
 
 const char *hpe_last_error_string(void) { return g_err; }
@@ -119,9 +124,6 @@ int hpe_set_matcher(int mode)
     return HPE_OK;
 }
 
-int g_hpe_pso_path = 0;
-int g_hpe_cost_pipeline = 0;   // 0 = one launch per uploaded chunk (default), 1 = chase kernel for large host batches
-int g_hpe_cost_chunk = 0;      // poses per upload chunk of the chase path (0 = default)
 int hpe_set_cost_pipeline(int mode, int chunk_poses)
 {
     if (mode < 0 || mode > 1 || chunk_poses < 0) return hpe_set_error(HPE_ERR_ARG, "hpe_set_cost_pipeline: bad argument");
@@ -806,6 +808,67 @@ int hpe_track_sequences(const hpe_model *m, const hpe_obs *o, const hpe_pso_para
         for (int k = 0; k < n_frames; ++k) sd[(size_t)q * n_frames + k] = seeds ? seeds[q] : 1000ull;
     return pso_host(m, o, p, num_particles, x0, n_seq, first, n_seq * n_frames, sd.data(), poses, costs, nullptr, n_frames,
                     seq_stride, frame_stride);
+}
+
+// Asynchronous device-pointer forms ("every entry takes a stream"): nothing is copied, nothing is
+// synchronised; inputs must be valid on `stream` when the call is made, results are valid once `stream` reaches the
+// end of the queued work.  The slots must hold usable observations (not checked here: that would need a read-back).
+int hpe_pso_evolve_dev(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                       const double *x0_dev, int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
+                       double *best_cost_dev, double *trace_dev, void *stream)
+{
+    if (!m || !p || !x0_dev || !bestp_dev || !best_cost_dev || num_particles < 1 || p->maxiter < 1)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_pso_evolve_dev: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
+    if (int rc = check_slot(o, first, count)) return rc;
+    if (count == 0) return HPE_OK;
+    const bool use_cluster = g_hpe_pso_path == 2 || (g_hpe_pso_path == 0 && count <= 222);
+    cudaError_t e = use_cluster
+        ? hpe_launch_pso_cluster(m->dm, o->v, make_pso(p, num_particles), x0_dev, first, count, seeds_dev, bestp_dev,
+                                 best_cost_dev, trace_dev, 0, (cudaStream_t)stream)
+        : hpe_launch_pso(m->dm, o->v, make_pso(p, num_particles), x0_dev, first, count, seeds_dev, bestp_dev,
+                         best_cost_dev, trace_dev, 0, (cudaStream_t)stream);
+    if (e != cudaSuccess)
+        return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
+                             "pso launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));
+    return HPE_OK;
+}
+
+int hpe_track_sequences_dev(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                            const double *x0_dev, int first, int n_seq, int n_frames, int seq_stride, int frame_stride,
+                            const uint64_t *seeds_dev, double *poses_dev, double *costs_dev, void *stream)
+{
+    if (!m || !p || !x0_dev || !poses_dev || !costs_dev || num_particles < 1 || p->maxiter < 1 || n_seq < 0 || n_frames < 0 ||
+        (int64_t)n_seq * n_frames > 0x7fffffff)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_track_sequences_dev: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
+    if (n_seq == 0 || n_frames == 0) return HPE_OK;
+    const bool seq_major = seq_stride == n_frames && frame_stride == 1, frame_major = seq_stride == 1 && frame_stride == n_seq;
+    if (!seq_major && !frame_major)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_track_sequences_dev: (seq_stride, frame_stride) must be (n_frames, 1) or (1, n_seq)");
+    if (int rc = check_slot(o, first, n_seq * n_frames)) return rc;
+    const bool use_cluster = g_hpe_pso_path == 2 || (g_hpe_pso_path == 0 && n_seq <= 222);
+    const int count = n_seq * n_frames;
+    cudaError_t e = use_cluster
+        ? hpe_launch_pso_cluster(m->dm, o->v, make_pso(p, num_particles), x0_dev, first, count, seeds_dev, poses_dev, costs_dev,
+                                 nullptr, n_frames, (cudaStream_t)stream, seq_stride, frame_stride)
+        : hpe_launch_pso(m->dm, o->v, make_pso(p, num_particles), x0_dev, first, count, seeds_dev, poses_dev, costs_dev, nullptr,
+                         n_frames, (cudaStream_t)stream, seq_stride, frame_stride);
+    if (e != cudaSuccess)
+        return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
+                             "pso launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));
+    return HPE_OK;
+}
+
+int hpe_refine_init_pose_dev(const hpe_model *m, const hpe_obs *o, double *x0_dev, int first, int count, int *evals_dev,
+                             void *stream)
+{
+    if (!m || !x0_dev) return hpe_set_error(HPE_ERR_ARG, "hpe_refine_init_pose_dev: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
+    if (int rc = check_slot(o, first, count)) return rc;
+    if (count == 0) return HPE_OK;
+    HPE_CUDA(hpe_launch_refine(m->dm, o->v, first, count, x0_dev, evals_dev, (cudaStream_t)stream));
+    return HPE_OK;
 }
 
 // PSO::refine_init_pose for `count` frames (hpe_refine.cu)

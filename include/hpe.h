@@ -184,6 +184,19 @@ int hpe_track_sequence(const hpe_model *m, const hpe_obs *o, const hpe_pso_param
 int hpe_track_sequences(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
                         const double *x0, int first, int n_seq, int n_frames, int seq_stride, int frame_stride,
                         const uint64_t *seeds, double *poses, double *costs);
+/* Asynchronous device-pointer forms of the three calls above (and of hpe_refine_init_pose below): every pointer is a
+ * device pointer, nothing is copied or synchronised, the work is queued on `stream` (a cudaStream_t; NULL = the default
+ * stream).  seeds_dev of hpe_track_sequences_dev holds one value per FRAME (n_seq*n_frames, sequence-major) or is NULL.
+ * The slots must already hold usable observations. */
+int hpe_pso_evolve_dev(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                       const double *x0_dev, int first, int count, const uint64_t *seeds_dev,
+                       double *bestp_dev, double *best_cost_dev, double *trace_dev, void *stream);
+int hpe_track_sequences_dev(const hpe_model *m, const hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                            const double *x0_dev, int first, int n_seq, int n_frames, int seq_stride,
+                            int frame_stride, const uint64_t *seeds_dev, double *poses_dev, double *costs_dev,
+                            void *stream);
+int hpe_refine_init_pose_dev(const hpe_model *m, const hpe_obs *o, double *x0_dev, int first, int count,
+                             int *evals_dev, void *stream);
 /* PSO::refine_init_pose (src/PSO.cpp:216-266) with cal_grad (:183-214) and goldstein (:438-480) for
  * `count` frames: x0 (host, count*26) is refined in place against frame slot first+b -- gradient
  * descent with a Goldstein line search on theta[0:3], then on theta[3:6], every evaluation a

@@ -84,3 +84,44 @@ def test_track_sequences_rejects_overlapping_layouts(hpe, D):
     rc = hpe.lib().hpe_track_sequences(hand._h, obs._h, C.byref(pso.params), 16, np.tile(D.X0, (2, 1)).ctypes.data_as(C.c_void_p),
                                        0, 2, 4, 2, 1, None, out.ctypes.data_as(C.c_void_p), None)
     assert rc == 1          # HPE_ERR_ARG
+
+
+def test_async_device_pointer_entry_points(hpe, D):
+    """hpe_pso_evolve_dev / hpe_track_sequences_dev / hpe_refine_init_pose_dev: everything on a caller's stream, device
+    pointers in and out, no synchronisation inside; same bits as the blocking host-pointer calls"""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    n_seq, n_frames, num_p, maxiter = 3, 5, 32, 8
+    walks, x0 = _walks(D, n_seq, n_frames, 77)
+    hand = hpe.handmodel()
+    obs = hpe.observedmodel(capacity=n_seq * n_frames)
+    obs.upload(hpe.render_frames(hand, walks.reshape(-1, 26)))
+    cf, pso = hpe.costfunc(hand, obs), hpe.PSO()
+    pso.set_pso_params(D.UB, D.LB, D.STD, 0.7298, 1.49618, 1.49618, maxiter, 1e-8, 1e-8)
+    lib = hpe.lib()
+    st = torch.cuda.Stream()
+    n = n_seq * n_frames
+    xall = walks.reshape(-1, 26) + np.random.default_rng(78).normal(size=(n, 26)) * D.STD * 0.2
+    with torch.cuda.stream(st):
+        x_dev = torch.from_numpy(xall).cuda()
+        bp_dev = torch.empty(n, 26, dtype=torch.float64, device="cuda")
+        bc_dev = torch.empty(n, dtype=torch.float64, device="cuda")
+        # refine in place, then one swarm per frame from the refined poses, all queued on `st`
+        assert lib.hpe_refine_init_pose_dev(hand._h, obs._h, C.c_void_p(x_dev.data_ptr()), 0, n, None, C.c_void_p(st.cuda_stream)) == 0
+        assert lib.hpe_pso_evolve_dev(hand._h, obs._h, C.byref(pso.params), num_p, C.c_void_p(x_dev.data_ptr()), 0, n, None,
+                                      C.c_void_p(bp_dev.data_ptr()), C.c_void_p(bc_dev.data_ptr()), None,
+                                      C.c_void_p(st.cuda_stream)) == 0
+        xs_dev = torch.from_numpy(x0).cuda()
+        ps_dev = torch.empty(n, 26, dtype=torch.float64, device="cuda")
+        cs_dev = torch.empty(n, dtype=torch.float64, device="cuda")
+        assert lib.hpe_track_sequences_dev(hand._h, obs._h, C.byref(pso.params), num_p, C.c_void_p(xs_dev.data_ptr()), 0, n_seq,
+                                           n_frames, n_frames, 1, None, C.c_void_p(ps_dev.data_ptr()),
+                                           C.c_void_p(cs_dev.data_ptr()), C.c_void_p(st.cuda_stream)) == 0
+    st.synchronize()
+    xr, _ = pso.refine_init_pose_batch(xall, cf)
+    assert np.array_equal(x_dev.cpu().numpy(), xr)
+    bp, bc, _ = pso.pso_evolve_batch(cf, xr, num_p, want_trace=False)
+    assert np.array_equal(bp_dev.cpu().numpy(), bp) and np.array_equal(bc_dev.cpu().numpy(), bc)
+    poses, costs = pso.track_sequences(cf, x0, num_p, n_seq, n_frames)
+    assert np.array_equal(ps_dev.cpu().numpy().reshape(n_seq, n_frames, 26), poses)
+    assert np.array_equal(cs_dev.cpu().numpy().reshape(n_seq, n_frames), costs)
