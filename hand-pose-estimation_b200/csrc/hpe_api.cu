@@ -293,6 +293,25 @@ int hpe_gnd_truth_err(const hpe_model *m, const double *theta, const double *gt_
 }
 
 // costfunc::bincomp_penalty for n poses against one frame (hpe_bincomp.cu)
+int hpe_depthmatch_batch(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n, double *image)
+{
+    if (!m || n < 0 || ((!theta || !image) && n > 0)) return hpe_set_error(HPE_ERR_ARG, "hpe_depthmatch_batch: bad argument");
+    if (int rc = hpe_check_device_of(m->device, "model")) return rc;
+    if (int rc = check_slot(o, slot, 1)) return rc;
+    if (n == 0) return HPE_OK;
+    if (int rc = check_filled(o, slot, 1)) return rc;
+    const size_t npix = (size_t)HPE_W * HPE_H;
+    size_t b_th = align_up(sizeof(double) * n * HPE_NDOF), b_out = align_up(sizeof(double) * n * npix);
+    HPE_CUDA(g_ws.reserve(b_th + b_out));
+    char *base = (char *)g_ws.p;
+    double *d_th = (double *)base, *d_out = (double *)(base + b_th);
+    HPE_CUDA(cudaMemcpyAsync(d_th, theta, sizeof(double) * n * HPE_NDOF, cudaMemcpyHostToDevice, 0));
+    HPE_CUDA(hpe_launch_depthmatch(m->dm, o->v, slot, d_th, n, d_out, 0));
+    HPE_CUDA(cudaMemcpyAsync(image, d_out, sizeof(double) * n * npix, cudaMemcpyDeviceToHost, 0));
+    HPE_CUDA(cudaStreamSynchronize(0));
+    return HPE_OK;
+}
+
 int hpe_bincomp_batch(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n, double *penalty,
                       uint32_t *silhouette)
 {

@@ -204,6 +204,9 @@ unsigned long long hpe_fallbacks_pso_opt(int reset);
 // costfunc::bincomp_penalty of n poses against frame `slot` (hpe_bincomp.cu); silhouette_dev: n*2400 words or NULL
 cudaError_t hpe_launch_bincomp(const DevModel &m, const ObsView &o, int slot, const double *theta_dev, int64_t n,
                                double *out_dev, unsigned *silhouette_dev, cudaStream_t st);
+// costfunc::depthMatch_penalty of n poses against frame `slot` (hpe_depthmatch.cu); out_dev: n*240*320 doubles
+cudaError_t hpe_launch_depthmatch(const DevModel &m, const ObsView &o, int slot, const double *theta_dev, int64_t n,
+                                  double *out_dev, cudaStream_t st);
 cudaError_t hpe_launch_render(const DevModel &m, const double *theta_dev, int64_t n, double focal,
                               float *depth_dev, cudaStream_t st);
 size_t hpe_observe_scratch_bytes(int count);

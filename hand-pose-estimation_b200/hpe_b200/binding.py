@@ -249,6 +249,18 @@ class costfunc:
         previous.  Pass page-locked arrays for real overlap."""
         return CostJob(self, thetas, slot, with_collision)
 
+    def depthMatch_penalty(self, theta, slot=0):
+        """costfunc::depthMatch_penalty (src/costfunc.cpp:439-473) of the spheres of pose theta: the depth map (cm) with the
+        outlines of the projected spheres, (240, 320)"""
+        return self.depthMatch_penalty_batch(np.asarray(theta, dtype=np.float64).reshape(1, 26), slot=slot)[0]
+
+    def depthMatch_penalty_batch(self, thetas, slot=0):
+        th = _f64(thetas).reshape(-1, 26)
+        n = th.shape[0]
+        img = np.empty((n, D.H, D.W))
+        _check(lib().hpe_depthmatch_batch(self.hand._h, self.observation._h, int(slot), _p(th), C.c_int64(n), _p(img)))
+        return img
+
     def bincomp_penalty(self, theta, slot=0):
         """costfunc::bincomp_penalty (src/costfunc.cpp:384-436) of the spheres of pose theta: pixels where the
         silhouette of the projected spheres and the observed one differ"""

@@ -160,6 +160,13 @@ int hpe_gnd_truth_err(const hpe_model *m, const double *theta, const double *gt_
 int hpe_bincomp_batch(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
                       double *penalty, uint32_t *silhouette);
 
+/* costfunc::depthMatch_penalty (src/costfunc.cpp:439-473) for n poses against frame `slot`: image[i] (240*320 doubles,
+ * row-major) = the observed depth map in cm with the OUTLINE of every projected sphere of theta[i] drawn into it in
+ * sphere order -- centre = trunc(K c / c_z), radius = trunc(r / img_scale), cv::circle with thickness 2, value = the
+ * sphere's depth c_z.  The reference returns this cv::Mat for its debug views; bit-identical. */
+int hpe_depthmatch_batch(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
+                         double *image);
+
 /* ---- PSO (src/PSO.h:56-68) -------------------------------------------- */
 /* PSO::pso_evolve (src/PSO.cpp:717-886) for `count` independent swarms, swarm b fitted to
  * frame slot first+b with initial pose x0[b].  seeds: count values or NULL (every swarm

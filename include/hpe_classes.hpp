@@ -199,6 +199,15 @@ public:
         check(hpe_correspondences(hand->c_handle(), observation->c_handle(), slot, theta.data(), 1, matchId.data()));
     }
 
+    // cv::Mat depthMatch_penalty(spheres), src/costfunc.cpp:439-473: the depth map (cm) with the outlines of the projected
+    // spheres (cv::circle, thickness 2), 240 x 320 row-major; takes the pose like bincomp_penalty
+    std::vector<double> depthMatch_penalty(const vec &theta, int slot = 0)
+    {
+        if (theta.size() != HPE_NDOF) throw error(HPE_ERR_ARG, "depthMatch_penalty: theta must have 26 entries");
+        std::vector<double> img((size_t)HPE_IMG_W * HPE_IMG_H);
+        check(hpe_depthmatch_batch(hand->c_handle(), observation->c_handle(), slot, theta.data(), 1, img.data()));
+        return img;
+    }
     // double bincomp_penalty(spheres), src/costfunc.cpp:384-436: silhouette mismatch in pixels; takes the pose
     // (the reference takes the spheres build_hand_model made of it)
     double bincomp_penalty(const vec &theta, int slot = 0)

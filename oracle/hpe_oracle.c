@@ -14,6 +14,7 @@
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
+#include "orc_draw.h"
 #endif
 
 /* ------------------------------------------------------------------ */
@@ -1116,6 +1117,46 @@ double orc_bincomp_penalty(const orc_model *m, const orc_obs *o, const double *s
     if (silhouette) memcpy(silhouette, mask, (size_t)ORC_W * ORC_H);
     free(mask);
     return (double)c;
+}
+
+/* cv::circle(img, (cx, cy), radius, colour, thickness >= 2): OpenCV's outlined circle (oracle/orc_draw.h), as a mask;
+ * pinned bit for bit against cv2.circle (4.13) in tests/test_oracle_pins.py */
+typedef struct { uint8_t *mask; int w; } mask_ctx;
+static void mask_run2(void *ctx, int y, int x1, int x2)
+{
+    mask_ctx *c = (mask_ctx *)ctx;
+    for (int x = x1; x <= x2; ++x) c->mask[(long)y * c->w + x] = 1;
+}
+void orc_circle_outline(uint8_t *mask, int w, int h, int cx, int cy, int radius, int thickness)
+{
+    mask_ctx c = {mask, w};
+    orcd_target t = {w, h, &c, mask_run2};
+    orcd_circle_outline(&t, cx, cy, radius, thickness);
+}
+
+/* costfunc::depthMatch_penalty, src/costfunc.cpp:439-473: the observed depth map (cm) with the outline of every
+ * projected sphere drawn into it -- centre = trunc(K c / c_z), radius = trunc(r / scale), cv::circle(..., thickness 2),
+ * value = the sphere's depth c_z -- in sphere order (a later outline overwrites an earlier one).
+ * spheres: 48x3 as build_hand_model returns them (negated y, z; un-negated at :449).  out: H*W doubles. */
+typedef struct { double *img; double value; } dm_ctx;
+static void dm_run(void *ctx, int y, int x1, int x2)
+{
+    dm_ctx *c = (dm_ctx *)ctx;
+    for (int x = x1; x <= x2; ++x) c->img[(long)y * ORC_W + x] = c->value;
+}
+void orc_depthmatch_penalty(const orc_model *m, const orc_obs *o, const double *spheres, double *out)
+{
+    memcpy(out, o->depth, sizeof(double) * ORC_W * ORC_H);
+    for (int i = 0; i < ORC_NSPH; ++i) {
+        const double x = spheres[i * 3], y = -spheres[i * 3 + 1], z = -spheres[i * 3 + 2];
+        const double pu = (o->focal * x + o->cx * z) / z;
+        const double pv = (o->focal * y + o->cy * z) / z;
+        const int rad = trunc_to_int(m->rad[i] / o->scale);
+        if (rad < 0) continue;                    /* cv::circle asserts radius >= 0 */
+        dm_ctx c = {out, z};
+        orcd_target t = {ORC_W, ORC_H, &c, dm_run};
+        orcd_circle_outline(&t, trunc_to_int(pu), trunc_to_int(pv), rad, 2);
+    }
 }
 
 /* PSO::dim_restore, src/PSO.cpp:160-180: 22 -> 26 parameters with DIP = 2/3 PIP */

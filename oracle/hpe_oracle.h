@@ -125,6 +125,9 @@ void orc_cal_grad(const orc_model *m, const orc_obs *o, const double theta[ORC_N
                   const int sel[ORC_NDOF], int32_t *match, double grad[ORC_NDOF]);
 int  orc_goldstein(const orc_model *m, const orc_obs *o, const double theta[ORC_NDOF],
                    const double g_k[ORC_NDOF], int32_t *match, double f_k, double *tk, int maxiter);
+/* cv::circle with thickness >= 2 (outline) as a mask, and costfunc::depthMatch_penalty (src/costfunc.cpp:439-473) */
+void orc_circle_outline(uint8_t *mask, int w, int h, int cx, int cy, int radius, int thickness);
+void orc_depthmatch_penalty(const orc_model *m, const orc_obs *o, const double *spheres, double *out);
 /* smallest relative gap of a line-search comparison since the last reset (test instrumentation) */
 void orc_margin_reset(void);
 double orc_margin_min(void);

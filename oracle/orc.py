@@ -238,6 +238,21 @@ def bincomp_penalty(model, obs, theta, want_silhouette=False):
     return (v, sil) if want_silhouette else v
 
 
+def circle_outline(w, h, cx, cy, radius, thickness=2):
+    """cv::circle(..., thickness >= 2) restated (OpenCV drawing.cpp EllipseEx / ThickLine / FillConvexPoly); uint8 mask (h, w)"""
+    mask = np.zeros((h, w), dtype=np.uint8)
+    lib().orc_circle_outline(_p(mask, C.c_uint8), int(w), int(h), int(cx), int(cy), int(radius), int(thickness))
+    return mask
+
+
+def depthmatch_penalty(model, obs, theta):
+    """costfunc::depthMatch_penalty (src/costfunc.cpp:439-473): depth map (cm) with the outlines of the projected spheres"""
+    S, _ = fk(model, theta)
+    out = np.empty((H, W))
+    lib().orc_depthmatch_penalty(C.byref(model), C.byref(obs.o), _p(f64(S)), _p(out))
+    return out
+
+
 def philox(seed, c0, c1, c2, c3):
     out = (C.c_uint32 * 4)()
     lib().orc_philox(C.c_uint64(seed), c0, c1, c2, c3, out)

@@ -125,6 +125,12 @@ class Reference:
         lib().ref_cost_terms(self.h, _p(f64(theta)), _p(t), _p(m, C.c_int))
         return t, m
 
+    def depthmatch_penalty(self, theta):
+        """costfunc::depthMatch_penalty (src/costfunc.cpp:439-473): the depth map (cm) with the sphere outlines, (240, 320)"""
+        out = np.empty((240, 320))
+        lib().ref_depthmatch_penalty(self.h, _p(f64(theta)), _p(out))
+        return out
+
     def bincomp_penalty(self, theta):
         """costfunc::bincomp_penalty (src/costfunc.cpp:384-436) of the spheres build_hand_model gives for theta"""
         return lib().ref_bincomp_penalty(self.h, _p(f64(theta)))

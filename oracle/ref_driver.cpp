@@ -169,6 +169,19 @@ double ref_bincomp_penalty(void *h, const double theta[26])
     return c->cost->bincomp_penalty(Sm);
 }
 
+// costfunc::depthMatch_penalty (src/costfunc.cpp:439-473) of the spheres of pose theta: out = 240 x 320 doubles, row-major
+void ref_depthmatch_penalty(void *h, const double theta[26], double *out)
+{
+    ref_ctx *c = (ref_ctx *)h;
+    vec th = to_vec(theta, 26);
+    mat::fixed<48, 3> S;
+    c->hand->build_hand_model(th, S);
+    mat Sm = S;
+    cv::Mat img = c->cost->depthMatch_penalty(Sm);
+    for (int y = 0; y < img.rows; ++y)
+        for (int x = 0; x < img.cols; ++x) out[(long)y * img.cols + x] = img.at<double>(y, x);
+}
+
 // n poses through costfunc::cal_cost, parallelised over poses the way PSO::pso_evolve does
 // (#pragma omp parallel for around cal_cost, src/PSO.cpp:848-852); used as the CPU baseline
 void ref_cost_batch(void *h, const double *theta, long n, double *total)

@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 
+#include "../../orc_draw.h"      // OpenCV's outlined circle, restated (shared with the C oracle)
+
 #define CV_8U 0
 #define CV_32F 5
 #define CV_64F 6
@@ -230,13 +232,30 @@ inline void distanceTransform(const Mat &src, Mat &dst, int distanceType, int ma
 inline void namedWindow(const std::string &, int = 1) { shim_unreachable("namedWindow"); }
 inline void imshow(const std::string &, const Mat &) { shim_unreachable("imshow"); }
 inline int waitKey(int = 0) { shim_unreachable("waitKey"); }
-// cv::circle: only the filled disc (thickness < 0, line_type 8, shift 0) that costfunc::bincomp_penalty draws
-// (src/costfunc.cpp:423) on a CV_64F image -- OpenCV's midpoint walk `Circle(..., fill)` of imgproc/drawing.cpp,
-// the same restatement as oracle/hpe_oracle.c:orc_fill_circle (pinned against cv2.circle in
-// tests/test_oracle_pins.py).  Outlines (thickness >= 0: depthMatch_penalty, the viewer) stay unreachable.
+// cv::circle on a CV_64F image, line_type 8, shift 0:
+//  * thickness < 0, the filled disc costfunc::bincomp_penalty draws (src/costfunc.cpp:423): OpenCV's midpoint walk
+//    `Circle(..., fill)` of imgproc/drawing.cpp, the same restatement as oracle/hpe_oracle.c:orc_fill_circle;
+//  * thickness >= 2, the outline costfunc::depthMatch_penalty draws (src/costfunc.cpp:468): OpenCV's EllipseEx / PolyLine /
+//    ThickLine / FillConvexPoly path, restated in oracle/orc_draw.h.
+// Both are pinned bit for bit against cv2.circle (4.13) in tests/test_oracle_pins.py.  Thin outlines (thickness 0, 1: the
+// viewer) stay unreachable.
+struct shim_circle_ctx { Mat *img; double value; };
+inline void shim_circle_run(void *ctx, int y, int x1, int x2)
+{
+    shim_circle_ctx *c = static_cast<shim_circle_ctx *>(ctx);
+    double *line = c->img->ptr<double>(y);
+    for (int x = x1; x <= x2; ++x) line[x] = c->value;
+}
 inline void circle(Mat &img, Point c, int radius, const Scalar &colour, int thickness = 1, int line_type = 8, int shift = 0)
 {
-    if (thickness >= 0 || line_type != 8 || shift != 0 || img.type() != CV_64F || radius < 0) shim_unreachable("circle (outline)");
+    if (line_type != 8 || shift != 0 || img.type() != CV_64F || radius < 0 || thickness == 0 || thickness == 1)
+        shim_unreachable("circle (thin outline, other image types)");
+    if (thickness >= 2) {
+        shim_circle_ctx ctx = {&img, colour.val[0]};
+        orcd_target t = {img.cols, img.rows, &ctx, shim_circle_run};
+        orcd_circle_outline(&t, c.x, c.y, radius, thickness);
+        return;
+    }
     int e = 0, dx = radius, dy = 0, up = 1, down = 2 * radius - 1;
     for (; dx >= dy; ++dy) {
         for (int pass = 0; pass < 4; ++pass) {

@@ -204,3 +204,26 @@ def test_fill_circle_equals_cv2_circle(orc):
         img = np.zeros((h, w), dtype=np.float64)
         cv2.circle(img, (cx, cy), r, 7.5, -1)
         assert np.array_equal(img != 0, orc.fill_circle(w, h, cx, cy, r) != 0), (w, h, cx, cy, r)
+
+
+def test_circle_outline_equals_cv2_circle(orc):
+    """cv::circle(..., thickness=2), the third-party call of costfunc::depthMatch_penalty (src/costfunc.cpp:468): OpenCV
+    draws an outline of thickness > 1 through EllipseEx -> ellipse2Poly -> PolyLine -> ThickLine -> FillConvexPoly (+ Line2
+    after clipLine, + filled end caps); the oracle's restatement (oracle/orc_draw.h) covers exactly cv2.circle's pixels on
+    a CV_64F image -- clipped by the border, outside the image, radius 0, small images -- for thickness 2 (the
+    reference's) and 3"""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(18)
+    for t in range(2500):
+        w, h = (320, 240) if t % 3 else (int(rng.integers(1, 90)), int(rng.integers(1, 90)))
+        r = int(rng.integers(0, 90 if t % 5 else 4))
+        cx, cy = int(rng.integers(-120, w + 120)), int(rng.integers(-120, h + 120))
+        th = 2 if t % 4 else 3
+        img = np.zeros((h, w), dtype=np.float64)
+        cv2.circle(img, (cx, cy), r, 7.5, th)
+        assert np.array_equal(img != 0, orc.circle_outline(w, h, cx, cy, r, th) != 0), (w, h, cx, cy, r, th)
+    # every radius the sphere model can produce at the reference's depths, centred
+    for r in range(0, 140):
+        img = np.zeros((240, 320), dtype=np.float64)
+        cv2.circle(img, (160, 120), r, 1.0, 2)
+        assert np.array_equal(img != 0, orc.circle_outline(320, 240, 160, 120, r, 2) != 0), r

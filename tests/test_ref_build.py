@@ -298,3 +298,24 @@ def test_bincomp_penalty_bit_exact(orc, omodel, R, D):
         assert R.bincomp_penalty(th) == orc.bincomp_penalty(omodel, oo, th)
     v, sil = orc.bincomp_penalty(omodel, oo, truth, want_silhouette=True)
     assert v == np.count_nonzero((sil != 0) != (depth != 0))
+
+
+def test_depthmatch_penalty_bit_exact(orc, omodel, D):
+    """costfunc::depthMatch_penalty (src/costfunc.cpp:439-473) -- the reference's own function, compiled from its source
+    against the stand-in headers -- returns exactly the image orc_depthmatch_penalty returns: near the truth, far from it,
+    outlines clipped by the border and outside the image"""
+    import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(91)
+    truth = np.clip(D.X0 + rng.normal(size=26) * D.STD * 0.5, D.LB, D.UB)
+    depth = orc.render_depth(omodel, truth)
+    oo = orc.Observation(depth)
+    R = ref.Reference(threads=1)
+    R.load_depth(depth)
+    for k in range(30):
+        th = truth + rng.normal(size=26) * D.STD * (0.05, 1.0, 3.0)[k % 3]
+        a, b = orc.depthmatch_penalty(omodel, oo, th), R.depthmatch_penalty(th)
+        assert np.array_equal(a, b), (k, int((a != b).sum()))
+        if k % 3 == 0:
+            assert (a != oo.depth).sum() > 50         # near the truth the outlines are inside the image

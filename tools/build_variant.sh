@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../hand-pose-estimation_b200"
 name=$1; shift
 mkdir -p build/variants/$name
-for f in hpe_api hpe_cost hpe_obs hpe_pso hpe_pso_cluster hpe_swarm hpe_refine hpe_pso_opt hpe_bincomp hpe_bench; do
+for f in hpe_api hpe_cost hpe_obs hpe_pso hpe_pso_cluster hpe_swarm hpe_refine hpe_pso_opt hpe_bincomp hpe_depthmatch hpe_bench; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC \
      -ccbin /usr/bin/g++ "$@" -c csrc/$f.cu -o build/variants/$name/$f.o &
 done
