@@ -8,8 +8,8 @@
 // table of float sines of whole degrees) -> vertices rounded to Q16 fixed point -> PolyLine -> per segment ThickLine: the
 // segment widened to a quadrilateral (FillConvexPoly: its four edges as Q16 DDA lines after clipLine, then the span
 // between the two active edges of every scan line) plus a filled circle of radius 1 at the capped ends.  All of it is
-// integer work after a handful of correctly rounded FP64 operations, restated here operation by operation, so the image
-// equals the reference's bit for bit (tests/test_gpu_depthmatch.py: against the CPU restatement, which the CPU tests pin
+// integer work after a handful of correctly rounded FP64 operations, restated here operation by operation, so the raster
+// equals the reference's bit for bit; the value drawn is the sphere's depth, an FK output (tests/test_gpu_depthmatch.py: against the CPU restatement, which the CPU tests pin
 // against cv2.circle and against the reference's own depthMatch_penalty in the test build of its sources).
 //
 // One CTA per pose: warp 0 runs the forward kinematics, all threads copy the depth map, then the 48 spheres in order;

@@ -163,7 +163,8 @@ int hpe_bincomp_batch(const hpe_model *m, const hpe_obs *o, int slot, const doub
 /* costfunc::depthMatch_penalty (src/costfunc.cpp:439-473) for n poses against frame `slot`: image[i] (240*320 doubles,
  * row-major) = the observed depth map in cm with the OUTLINE of every projected sphere of theta[i] drawn into it in
  * sphere order -- centre = trunc(K c / c_z), radius = trunc(r / img_scale), cv::circle with thickness 2, value = the
- * sphere's depth c_z.  The reference returns this cv::Mat for its debug views; bit-identical. */
+ * sphere's depth c_z.  The reference returns this cv::Mat for its debug views.  The raster (which pixels, overwritten in
+ * which order) is bit-identical; the drawn values are forward-kinematics outputs (1e-15 relative). */
 int hpe_depthmatch_batch(const hpe_model *m, const hpe_obs *o, int slot, const double *theta, int64_t n,
                          double *image);
 

@@ -105,3 +105,23 @@ def test_refine_init_pose_matches_the_reference_code(hpe, orc, omodel, R, D):
             agree += 1
         assert R.cal_cost2(xg)[0] <= R.cal_cost2(x0)[0] * (1 + 1e-9)
     assert agree >= 7, agree
+
+
+def test_depthmatch_matches_the_reference_code(hpe, orc, omodel, R, D):
+    """costfunc::depthMatch_penalty (src/costfunc.cpp:439-473), the reference's own function called live: same pixels
+    drawn, background untouched, drawn values (the spheres' depths) within FK accuracy"""
+    rng = np.random.default_rng(73)
+    truth = synth_pose(D, rng)
+    depth = orc.render_depth(omodel, truth)
+    R.load_depth(depth)
+    hand, obs = hpe.handmodel(), hpe.observedmodel(capacity=1)
+    obs.upload(depth[None])
+    cf = hpe.costfunc(hand, obs)
+    th = np.concatenate([truth[None], truth + rng.normal(size=(20, 26)) * D.STD * 0.2, truth + rng.normal(size=(20, 26)) * D.STD * 2.0])
+    img = cf.depthMatch_penalty_batch(th)
+    _, dcm, _ = R.observation()
+    for i in range(len(th)):
+        want = R.depthmatch_penalty(th[i])
+        hit = want != dcm
+        assert np.array_equal(img[i] != dcm, hit), i
+        assert np.array_equal(img[i][~hit], dcm[~hit]) and np.allclose(img[i][hit], want[hit], rtol=1e-12, atol=0), i
