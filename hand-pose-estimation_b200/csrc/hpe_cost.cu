@@ -1,5 +1,6 @@
 // hpe_cost.cu -- batched handmodel::build_hand_model and costfunc::cal_cost/cal_cost2 kernels,
 // plus the sphere-model ray-caster used to synthesise Subject1-format frames.
+#include <atomic>
 #include <cooperative_groups.h>
 
 #include "hpe_eval.cuh"
@@ -62,6 +63,22 @@ __global__ void __launch_bounds__(160) fk_kernel(DevModel m, const double *__res
 // cal_cost / cal_cost2 for n poses against one frame.  Poses are split evenly over all
 // warps of the grid; a warp walks its range in groups of HPE_GROUP.
 // ---------------------------------------------------------------------------------------
+// Self-scheduling counters of cost_kernel: one slot per launch in flight.  The launcher hands the slots out round-robin;
+// HPE_SCHED_SLOTS exceeds the number of kernels a device runs concurrently (128), so two launches that share a slot are
+// ordered, and the last warp of a launch leaves its slot zeroed.
+struct SchedSlot { int next, tail, done, pad; };
+constexpr int HPE_SCHED_SLOTS = 256;
+__device__ SchedSlot g_sched[HPE_SCHED_SLOTS];
+#ifndef HPE_TAIL_R1
+#define HPE_TAIL_R1 2.5f     // poses per warp handed out in units smaller than a group (the warps leave their last group over a window of HPE_GROUP poses)
+#endif
+#ifndef HPE_TAIL_R2
+#define HPE_TAIL_R2 1.0f     // ... of these, poses per warp handed out one by one
+#endif
+#ifndef HPE_TAIL_C2
+#define HPE_TAIL_C2 2
+#endif
+
 struct __align__(16) CostSmem {
     FrameSmem fs;
     __align__(16) unsigned char ws[COST_WARPS * HPE_WS_BYTES(HPE_GROUP)];
@@ -73,7 +90,7 @@ template <bool WITH_COLLI, int MATCHER, bool AUX>
 __global__ void __launch_bounds__(COST_WARPS * 32, HPE_MINBLOCKS)
 cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, int64_t n,
             double *__restrict__ cost, double *__restrict__ terms, int64_t tstride,
-            const int32_t *__restrict__ frozen, int32_t *__restrict__ match_out)
+            const int32_t *__restrict__ frozen, int32_t *__restrict__ match_out, int sched_slot, int n1, int n2, int t2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
@@ -83,19 +100,36 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
     const WarpScratch ws = warp_scratch(sm.ws, warp, HPE_GROUP);
     const int n_pts = sm.fs.n_pts;
 
-    const int64_t total_warps = (int64_t)gridDim.x * COST_WARPS;
-    const int64_t gw = (int64_t)blockIdx.x * COST_WARPS + warp;
-    const int64_t lo = n * gw / total_warps, hi = n * (gw + 1) / total_warps;
-    // this warp's poses [lo, hi): 32-bit indices (a launch scores < 2^31 poses, hpe_launch_cost splits larger batches)
-    // against the kernel's pointer parameters, which stay in the constant bank.  The two loop variables live in the warp's
-    // shared-memory scratch and are re-read where they are used: every register is taken inside the matching phases, and
-    // a loop counter spilled to local memory costs an L1 miss per pose (ncu: 3.5 % of the kernel's stall samples).
-    volatile int *wl = reinterpret_cast<volatile int *>(ws.dep + 6);      // [0] = next pose, [1] = end, [2] = group size, [3] = g
-    if (lane == 0) { wl[0] = (int)lo; wl[1] = (int)hi; }
+    // Work distribution.  Poses are handed out through two counters in global memory (self-scheduling): groups of HPE_GROUP
+    // from [0, n1), then -- once these run out -- pairs from [n1, n2) and single poses from [n2, n).  A static split
+    // (round 1: n / warps poses each) leaves the warps of a scheduler finishing at very different times: ncu showed 20.2 of
+    // 24 warps resident on average and the last sixth of the kernel running with too few warps to hide the FP64 / gather
+    // latencies.  With the counters every warp works until the pool is empty; the shrinking units keep the final idle
+    // window below one pose (a group costs ~55 us, a pose ~11 us of a 216 us kernel).  32-bit pose indices (a launch
+    // scores < 2^31 poses, hpe_launch_cost splits larger batches).  The loop variables live in the warp's shared-memory
+    // scratch and are re-read where they are used: every register is taken inside the matching phases, and a loop counter
+    // spilled to local memory costs an L1 miss per pose (ncu: 3.5 % of the kernel's stall samples).
+    const int total_warps = (int)gridDim.x * COST_WARPS;
+    SchedSlot *const S = g_sched + sched_slot;
+    volatile int *wl = reinterpret_cast<volatile int *>(ws.dep + 6);      // [0] = first pose of the group, [1] = main range exhausted, [2] = group size, [3] = g
+    if (lane == 0) wl[1] = 0;
     __syncwarp();
 #pragma unroll 1
     for (;;) {
-        if (lane == 0) { wl[2] = min(HPE_GROUP, wl[1] - wl[0]); wl[3] = 0; }
+        if (lane == 0) {
+            int s = 0, cnt = 0;
+            if (!wl[1]) {
+                s = atomicAdd(&S->next, HPE_GROUP);
+                cnt = min(HPE_GROUP, n1 - s);
+                if (cnt <= 0) wl[1] = 1;
+            }
+            if (cnt <= 0) {
+                const int t = atomicAdd(&S->tail, 1);
+                if (t < t2) { s = n1 + HPE_TAIL_C2 * t; cnt = min(HPE_TAIL_C2, n2 - s); }
+                else { s = n2 + (t - t2); cnt = s < (int)n ? 1 : 0; }
+            }
+            wl[0] = s; wl[2] = cnt; wl[3] = 0;
+        }
         __syncwarp();
         if (wl[2] <= 0) break;
         group_fk(sm.fs.M, [&](int g) { return theta + (size_t)(wl[0] + g) * HPE_NDOF; }, wl[2], ws, lane);
@@ -132,8 +166,15 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
             }
             __syncwarp();
         }
-        if (lane == 0) wl[0] = wl[0] + wl[2];
-        __syncwarp();
+    }
+    // the last warp out re-arms the counters for the next launch that is given this slot
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(&S->done, 1) == total_warps - 1) {
+            S->next = 0; S->tail = 0;
+            __threadfence();
+            S->done = 0;
+        }
     }
 }
 
@@ -738,9 +779,18 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
         cudaFuncSetAttribute(cost_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr = true;
     }
+    // self-scheduling plan (cost_kernel): groups from [0, n1), units of HPE_TAIL_C2 from [n1, n2), single poses from [n2, n);
+    // batches with fewer than two groups per warp are handed out in groups only
+    const int64_t warps = (int64_t)blocks * COST_WARPS;
+    int64_t r1 = n >= 2 * HPE_GROUP * warps ? (int64_t)(HPE_TAIL_R1 * (float)warps) : 0, r2 = (int64_t)(HPE_TAIL_R2 * (float)warps);
+    if (r2 > r1) r2 = r1;
+    const int n1 = (int)(n - r1), t2 = (int)((r1 - r2 + HPE_TAIL_C2 - 1) / HPE_TAIL_C2);
+    const int n2 = (int)(n - r2);
+    static std::atomic<unsigned> next_slot{0};
+    const int sched_slot = (int)(next_slot.fetch_add(1, std::memory_order_relaxed) % HPE_SCHED_SLOTS);
     auto launch = [&](auto kern) {
         kern<<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev, terms_dev,
-                                                                 terms_stride, frozen_match_dev, match_out_dev);
+                                                                 terms_stride, frozen_match_dev, match_out_dev, sched_slot, n1, n2, t2);
     };
     const bool aux = frozen_match_dev || match_out_dev;
     if (g_hpe_matcher == 1) launch(with_colli ? cost_kernel<true, 1, true> : cost_kernel<false, 1, true>);

@@ -80,7 +80,8 @@ static __device__ unsigned long long g_hpe_fallback_points;
 
 // per-warp shared-memory scratch
 struct WarpScratch {
-    double *dep;    // [8] depth terms of the group's poses (group_depth -> the per-pose loop)
+    double *dep;    // [8] depth terms of the group's poses (group_depth -> the per-pose loop); [6], [7]: the cost kernel's loop variables
+    unsigned *slots; // [8] (cluster << 12 | block mask) of the cluster matched in slot 4 pass + quarter (match_align)
     double *sphd;   // [slot][48][3] un-negated FP64 centres of the group's poses
     float4 *cf;     // [48] (x,-y,-z,0): the float32 centres cv::BFMatcher sees, pose being matched
     float4 *ex;     // [12][5] (-2c'x, -2c'y, -2c'z, |c'|^2), c' = cf - q, pose being matched; blocks of 4 spheres
@@ -89,7 +90,7 @@ struct WarpScratch {
 #define HPE_EX_PITCH (HPE_BLK + 1)
 #define HPE_EX_AT(j) (((j) / HPE_BLK) * HPE_EX_PITCH + ((j) % HPE_BLK))
 #define HPE_EX_BLOCKS (HPE_NBLK + 1)      // + the "no block" entry a lane sweeps once its cluster's list is exhausted
-#define HPE_WS_BYTES(slots) ((slots) * HPE_NSPH * 24 + HPE_NSPH * 16 + HPE_EX_BLOCKS * HPE_EX_PITCH * 16 + 64)
+#define HPE_WS_BYTES(slots) ((slots) * HPE_NSPH * 24 + HPE_NSPH * 16 + HPE_EX_BLOCKS * HPE_EX_PITCH * 16 + 64 + 32)
 
 __device__ __forceinline__ WarpScratch warp_scratch(unsigned char *base, int warp, int slots)
 {
@@ -98,7 +99,8 @@ __device__ __forceinline__ WarpScratch warp_scratch(unsigned char *base, int war
     w.cf = reinterpret_cast<float4 *>(p);
     w.ex = w.cf + HPE_NSPH;
     w.dep = reinterpret_cast<double *>(p + HPE_NSPH * 16 + HPE_EX_BLOCKS * HPE_EX_PITCH * 16);
-    w.sphd = w.dep + 8;
+    w.slots = reinterpret_cast<unsigned *>(w.dep + 8);
+    w.sphd = w.dep + 12;
     return w;
 }
 
@@ -341,7 +343,7 @@ __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsign
 //   bound itself is below 16u(w_j + w_k + |p'|^2): in total < 100u(w_j + w_k) + 400u max|p'|^2, and the margin is
 //   4e-5 (w_j + w_k + 2 max|p'|^2) = 671u(...).  A block is skipped when all four of its spheres are excluded; the block
 //   of k itself never is, and the true nearest sphere of a point cannot be excluded (it is not farther than k).
-//   NaN / inf operands fail the comparison and keep the block.
+//   NaN / inf operands keep the blocks of the lane that meets them.
 __device__ __forceinline__ unsigned prune_blocks(const FrameSmem &fs, const WarpScratch &ws, int lane)
 {
     const int c = lane >> 2, sub = lane & 3;
@@ -375,11 +377,11 @@ __device__ __forceinline__ unsigned prune_blocks(const FrameSmem &fs, const Warp
     const unsigned long long nrx = dup32(-rx), nry = dup32(-ry), nrz = dup32(-rz), nsref = dup32(-sref),
                              wk = dup32(rw + bc.w), nmrg = dup32(-4e-5f);
     unsigned mask = 0u;
+    float poison = 0.0f;       // NaN as soon as one bound of this lane is NaN or infinite (0 * x accumulated on the FMA pipe)
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
         const ulonglong2 *blk = reinterpret_cast<const ulonglong2 *>(ws.ex + (3 * sub + t) * HPE_EX_PITCH);
         float tmin = __int_as_float(0x7f800000);
-        bool bad = false;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const ulonglong2 xy = blk[2 * q], zw = blk[2 * q + 1];
@@ -392,11 +394,12 @@ __device__ __forceinline__ unsigned prune_blocks(const FrameSmem &fs, const Warp
             split32(fadd2(zw.x, nrz), dz0, dz1);
             a0 = fmaf(-fabsf(dz0), hc.z, fmaf(-fabsf(dy0), hc.y, fmaf(-fabsf(dx0), hc.x, a0)));
             a1 = fmaf(-fabsf(dz1), hc.z, fmaf(-fabsf(dy1), hc.y, fmaf(-fabsf(dx1), hc.x, a1)));
-            bad = bad || !(a0 == a0) || !(a1 == a1);
+            poison = fmaf(a0, 0.0f, fmaf(a1, 0.0f, poison));
             tmin = fmin3(tmin, a0, a1);
         }
-        if (bad || !(tmin > 0.0f)) mask |= 1u << (3 * sub + t);
+        if (!(tmin > 0.0f)) mask |= 1u << (3 * sub + t);
     }
+    if (!(poison == poison)) mask = 7u << (3 * sub);        // keeps all three blocks of the lane: conservative
     mask |= __shfl_xor_sync(0xffffffffu, mask, 1);
     mask |= __shfl_xor_sync(0xffffffffu, mask, 2);
     return mask;
@@ -405,7 +408,7 @@ __device__ __forceinline__ unsigned prune_blocks(const FrameSmem &fs, const Warp
 // phase 3a for 4 points of the lane, k = k0 + 32 m (see the header comment).  ws.cf / ws.ex must
 // hold the pose being matched.
 __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratch &ws, int k0, int lane,
-                                           unsigned qmask, int idx[HPE_PASS])
+                                           unsigned mk, int idx[HPE_PASS])
 {
     const float INF = __int_as_float(0x7f800000);
 #if HPE_FFMA2
@@ -420,11 +423,10 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
         M1[m] = INF; M2[m] = INF; g1[m] = 0;
     }
 #if HPE_PRUNE && HPE_PACKED_INDEX
-    // pruned sweep A: the eight lanes of quarter q hold the 32 points of cluster 4 pass + q (cluster_storage), whose
-    // block mask sits on the quad of lanes 4 * cluster (prune_blocks).  Every quarter walks its own list -- the block
-    // address differs per quarter, the control flow does not: all lanes run max(list length) steps, a lane whose list
-    // is exhausted sweeps the "no block" entry (s = 3e38, changes neither M1 nor a certified M2).
-    unsigned mk = __shfl_sync(0xffffffffu, qmask, 4 * (((k0 - lane) >> 5) + (lane >> 3)));
+    // pruned sweep A: the eight lanes of a quarter hold the 32 points of ONE cluster (cluster_storage; match_align says
+    // which) and mk is that cluster's block mask.  Every quarter walks its own list -- the block address differs per
+    // quarter, the control flow does not: all lanes run max(list length) steps, a lane whose list is exhausted sweeps
+    // the "no block" entry (s = 3e38, changes neither M1 nor a certified M2).
     const int nit = __reduce_max_sync(0xffffffffu, __popc(mk));
 #ifdef HPE_COUNT_ITERS      // measurement build: the fallback counter counts sweep steps instead (tools/fallback_rate.py)
     if (lane == 0) atomicAdd(&g_hpe_fallback_points, (unsigned long long)nit);
@@ -655,14 +657,15 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
     if (__any_sync(0xffffffffu, slow != 0u)) {
 #pragma unroll
         for (int m = 0; m < HPE_PASS; ++m) {
-            unsigned todo = __ballot_sync(0xffffffffu, (slow >> m) & 1u) & fs.valid[(k0 + 32 * m) >> 5];
+            const int km = k0 + 32 * m;
+            unsigned todo = __ballot_sync(0xffffffffu, ((slow >> m) & 1u) && (fs.valid[km >> 5] >> (km & 31) & 1u));
 #ifndef HPE_COUNT_ITERS
             if (todo && lane == 0) atomicAdd(&g_hpe_fallback_points, (unsigned long long)__popc(todo));
 #endif
             while (todo) {
                 int src = __ffs(todo) - 1;
                 todo &= todo - 1;
-                int k = k0 - lane + src + 32 * m;
+                int k = __shfl_sync(0xffffffffu, km, src);
                 int e = match_point_exact_warp(ws.cf, (float)fs.cloud[k], (float)fs.cloud[HPE_MAXPTS + k],
                                                (float)fs.cloud[2 * HPE_MAXPTS + k], lane);
                 if (lane == src) idx[m] = e;
@@ -674,9 +677,15 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
 // phase 3 of pose g: both passes; returns the warp-reduced align_models value
 // (src/costfunc.cpp:346-377), valid on all lanes.  frozen: optional fixed correspondences
 // (n_pts ints); match_row: optional output row (n_pts ints).
-// sqrt of a non-negative finite double without the library's special-case branch: rsqrt seed (2^-22), two coupled
-// Newton steps and the FMA-residual correction -- within one ulp of the rounded root (almost always equal to it);
-// 0 and inputs below 1e-280 map to 0.  The alignment sums agree with the oracle to ~1e-15 relative either way (summation order).
+// sqrt of a non-negative finite double without the library's special-case branch: rsqrt seed (the upper word of the
+// reciprocal root, relative error < 2^-20), ONE coupled Newton step (g ~ sqrt x and h ~ 1 / (2 sqrt x) to ~2^-39) and the
+// FMA-residual correction g + (x - g^2) h, whose only rounding is the last one -- within one ulp of the rounded root and
+// equal to it except about once in 10^7 arguments (checked on the CPU with a perturbed, truncated seed; a second Newton
+// step, round 2's form, removes those cases and costs 3 DFMA per point).  0 and inputs below 1e-280 map to 0.  The
+// alignment sums agree with the oracle to ~1e-15 relative either way (summation order).
+#ifndef HPE_SQRT_STEPS
+#define HPE_SQRT_STEPS 1
+#endif
 __device__ __forceinline__ double sqrt_pos(double x)
 {
     double y;
@@ -685,29 +694,67 @@ __device__ __forceinline__ double sqrt_pos(double x)
     double r = __fma_rn(-h, g, 0.5);
     g = __fma_rn(g, r, g);
     h = __fma_rn(h, r, h);
+#if HPE_SQRT_STEPS > 1
     r = __fma_rn(-h, g, 0.5);
     g = __fma_rn(g, r, g);
     h = __fma_rn(h, r, h);
+#endif
     const double d = __fma_rn(-g, g, x);
     g = __fma_rn(d, h, g);
     return x > 1e-280 ? g : 0.0;      // 0 (seed = inf) and denormal-range inputs: the root is below 1e-140
 }
 
-// qmask_in: the block masks of prune_blocks() when the caller has computed them already (HPE_QMASK_NONE: not yet)
-#define HPE_QMASK_NONE 0xffffffffu
+#ifndef HPE_SORT_SLOTS
+#define HPE_SORT_SLOTS 1     // 1: the clusters with the four longest block lists are matched in pass 0, the other four in pass 1
+#endif
 template <int MATCHER, bool AUX = true>
 __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScratch &ws, int g, int lane,
-                                              const int32_t *frozen, int32_t *match_row, unsigned qmask_in = HPE_QMASK_NONE)
+                                              const int32_t *frozen, int32_t *match_row)
 {
     const double *sd = ws.sphd + (size_t)g * HPE_NSPH * 3;
     double acc = 0.0;
-    unsigned qmask = qmask_in == HPE_QMASK_NONE ? 0xfffu : qmask_in;
 #if HPE_PRUNE && HPE_FFMA2 && HPE_PACKED_INDEX
-    if (qmask_in == HPE_QMASK_NONE && !(AUX && frozen) && MATCHER == 0) qmask = prune_blocks(fs, ws, lane);
+    const bool pruned = !(AUX && frozen) && MATCHER == 0;
+    if (pruned) {
+        // Which cluster goes to which (pass, quarter) slot.  A pass costs max(list length) over its four quarters, so the
+        // clusters are ranked by list length (ties by index) and slot r = 4 pass + quarter takes the cluster of rank r:
+        // the two passes then cost l(1) + l(5) steps, the minimum over all assignments (11.1 instead of 12.7 steps per
+        // evaluation on the benchmark's poses, tools/prune_sim.py).  Which lane sums which point depends on the pose only,
+        // so every kernel still returns the same bits for the same pose and frame.
+        const unsigned qmask = prune_blocks(fs, ws, lane);        // mask of cluster lane / 4 on the lanes of its quad
+        const int c = lane >> 2, sub = lane & 3;
+#if HPE_SORT_SLOTS
+        const int cnt = __popc(qmask);
+        int rank = 0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {                             // the quad shares the seven comparisons
+            const int d = 2 * sub + t;
+            const int other = __shfl_sync(0xffffffffu, cnt, (lane + 4 * d) & 31), c2 = (c + d) & 7;
+            rank += (d != 0 && (other > cnt || (other == cnt && c2 < c))) ? 1 : 0;
+        }
+        rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+        rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+#else
+        const int rank = c;
+#endif
+        __syncwarp();
+        if (sub == 0) ws.slots[rank] = qmask | (unsigned)c << 12;
+        __syncwarp();
+    }
+#else
+    const bool pruned = false;
 #endif
 #pragma unroll 1
     for (int pass = 0; pass < HPE_PPL / HPE_PASS; ++pass) {
-        const int k0 = lane + 32 * HPE_PASS * pass;      // storage positions (stage_frame)
+        // storage positions k0 + 32 m of the lane's four points (stage_frame): member (lane & 7) + 8 m of the quarter's cluster
+        int k0 = lane + 32 * HPE_PASS * pass;
+        unsigned mk = 0xfffu;
+        if (pruned) {
+            const unsigned sl = ws.slots[4 * pass + (lane >> 3)];
+            const int c = (int)(sl >> 12);
+            mk = sl & 0xfffu;
+            k0 = 128 * (c >> 2) + 8 * (c & 3) + (lane & 7);
+        }
         int idx[HPE_PASS];
         if (AUX && frozen) {
 #pragma unroll
@@ -715,13 +762,14 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
         } else if (MATCHER == 1) {
             match_pass_direct(fs, ws, k0, lane, idx);
         } else {
-            match_pass(fs, ws, k0, lane, qmask, idx);
+            match_pass(fs, ws, k0, lane, mk, idx);
         }
         // align_models for these 4 points, FP64, the reference's operation order.  Branch-free: positions that only
         // repeat a point (fs.valid clear) are computed like the others and dropped by a select, the square root is the
         // straight-line Newton sequence below, so the four chains interleave.
-        const unsigned vbits = (fs.valid[HPE_PASS * pass] >> lane & 1u) | (fs.valid[HPE_PASS * pass + 1] >> lane & 1u) << 1 |
-                               (fs.valid[HPE_PASS * pass + 2] >> lane & 1u) << 2 | (fs.valid[HPE_PASS * pass + 3] >> lane & 1u) << 3;
+        const int w0 = k0 >> 5, bit = k0 & 31;
+        const unsigned vbits = (fs.valid[w0] >> bit & 1u) | (fs.valid[w0 + 1] >> bit & 1u) << 1 |
+                               (fs.valid[w0 + 2] >> bit & 1u) << 2 | (fs.valid[w0 + 3] >> bit & 1u) << 3;
         double n2[HPE_PASS], rj[HPE_PASS];
 #pragma unroll
         for (int m = 0; m < HPE_PASS; ++m) {
