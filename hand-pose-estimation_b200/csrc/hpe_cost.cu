@@ -70,13 +70,13 @@ struct SchedSlot { int next, tail, done, pad; };
 constexpr int HPE_SCHED_SLOTS = 256;
 __device__ SchedSlot g_sched[HPE_SCHED_SLOTS];
 #ifndef HPE_TAIL_R1
-#define HPE_TAIL_R1 2.5f     // poses per warp handed out in units smaller than a group (the warps leave their last group over a window of HPE_GROUP poses)
+#define HPE_TAIL_R1 3.0f     // poses per warp handed out in units smaller than a group (the warps leave their last group over a window of HPE_GROUP poses)
 #endif
 #ifndef HPE_TAIL_R2
 #define HPE_TAIL_R2 1.0f     // ... of these, poses per warp handed out one by one
 #endif
 #ifndef HPE_TAIL_C2
-#define HPE_TAIL_C2 2
+#define HPE_TAIL_C2 3
 #endif
 
 struct __align__(16) CostSmem {
@@ -101,7 +101,7 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
     const int n_pts = sm.fs.n_pts;
 
     // Work distribution.  Poses are handed out through two counters in global memory (self-scheduling): groups of HPE_GROUP
-    // from [0, n1), then -- once these run out -- pairs from [n1, n2) and single poses from [n2, n).  A static split
+    // from [0, n1), then -- once these run out -- units of HPE_TAIL_C2 from [n1, n2) and single poses from [n2, n).  A static split
     // (round 1: n / warps poses each) leaves the warps of a scheduler finishing at very different times: ncu showed 20.2 of
     // 24 warps resident on average and the last sixth of the kernel running with too few warps to hide the FP64 / gather
     // latencies.  With the counters every warp works until the pool is empty; the shrinking units keep the final idle

@@ -129,3 +129,42 @@ def test_cuda_path_reproduces_reference_fixtures(hpe, D):
         # 1 mm joint criterion of the north star, on the reference's final pose
         _, Jg = hand.build_hand_models(np.stack([bp[0], g[tag + "_bestp"]]))
         assert np.abs(Jg[0] - Jg[1]).max() * 10.0 < 1e-3
+
+
+def test_cost_kernel_self_scheduling(hpe, golden, D):
+    """cost_kernel hands its poses out through counters in device memory (groups, then shrinking units) and the last
+    warp re-arms the slot it used: every batch size must give the bits of the one big batch, also after more launches
+    than there are slots (256), from two streams at once, and with NaN poses in the batch."""
+    import torch
+    g = golden
+    rng = np.random.default_rng(11)
+    n = 40000                                        # > 10 poses per warp: groups + units of three + single poses
+    th = g["truth"] + rng.normal(size=(n, 26)) * D.STD
+    th[777] = np.nan
+    hand, obs = hpe.handmodel(), hpe.observedmodel(capacity=1)
+    obs.upload(golden_frame(g)[None])
+    cf = hpe.costfunc(hand, obs)
+    a, d, _ = cf.cal_cost_batch(th)
+    ok = np.ones(n, bool); ok[777] = False          # the NaN pose only has to come out the same way every time
+    assert np.isfinite(a[ok]).all() and np.isfinite(d[ok]).all()
+    sizes = [1, 2, 3, 4, 5, 6, 7, 31, 250, 3551, 3552, 3553, 17760, 35519, 35520, 35521]
+    for k, m in enumerate(sizes):
+        lo = (97 * k) % (n - m)
+        a2, d2, _ = cf.cal_cost_batch(th[lo:lo + m])
+        assert np.array_equal(a2, a[lo:lo + m], equal_nan=True) and np.array_equal(d2, d[lo:lo + m], equal_nan=True), m
+    for rep in range(300):                           # slot reuse
+        m = 1 + (rep * 37) % 200
+        a2, d2, _ = cf.cal_cost_batch(th[rep:rep + m])
+        assert np.array_equal(a2, a[rep:rep + m], equal_nan=True), rep
+    # two launches in flight on different streams (different slots)
+    th_dev = torch.from_numpy(th).cuda()
+    outs = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for o_, s_ in zip(outs, streams):
+            cf.cal_cost_dev(th_dev.data_ptr(), n, o_.data_ptr(), stream=s_.cuda_stream)
+    torch.cuda.synchronize()
+    want = a + d
+    for o_ in outs:
+        assert np.array_equal(o_.cpu().numpy(), want, equal_nan=True)
