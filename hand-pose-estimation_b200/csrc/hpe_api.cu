@@ -362,6 +362,8 @@ int hpe_obs_create(int capacity, int num_samples, double focal, hpe_obs **out)
     if (e == cudaSuccess) e = cudaMalloc(&v.wf_halo, sizeof(unsigned) * 2 * HPE_W * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&v.mask, sizeof(unsigned) * (npix / 32) * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&v.perm, (size_t)HPE_MAXPTS * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&v.image, (size_t)HPE_IMAGE_BYTES * capacity);
+    if (e == cudaSuccess) e = cudaMemset(v.image, 0, (size_t)HPE_IMAGE_BYTES * capacity);     // slots never observed: zeros, not garbage
     if (e == cudaSuccess) e = cudaMemset(v.meta, 0, sizeof(FrameMeta) * capacity);
     if (e != cudaSuccess) {
         hpe_obs_destroy(o);
@@ -374,7 +376,7 @@ int hpe_obs_create(int capacity, int num_samples, double focal, hpe_obs **out)
 int hpe_obs_destroy(hpe_obs *o)
 {
     if (!o) return HPE_OK;
-    cudaFree(o->v.depth_mm); cudaFree(o->v.dt_px); cudaFree(o->v.cloud); cudaFree(o->v.meta); cudaFree(o->v.wf_halo); cudaFree(o->v.mask); cudaFree(o->v.perm);
+    cudaFree(o->v.depth_mm); cudaFree(o->v.dt_px); cudaFree(o->v.cloud); cudaFree(o->v.meta); cudaFree(o->v.wf_halo); cudaFree(o->v.mask); cudaFree(o->v.perm); cudaFree(o->v.image);
     delete o;
     return HPE_OK;
 }

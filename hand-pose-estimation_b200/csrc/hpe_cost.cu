@@ -8,9 +8,6 @@
 
 namespace {
 
-#ifndef HPE_STAGGER
-#define HPE_STAGGER 0      // staggered first groups: measured -1 % with the packed sweeps
-#endif
 constexpr int COST_WARPS = 8;
 #ifndef HPE_GROUP_DEPTH
 #define HPE_GROUP_DEPTH 0  // 1: depth term of a whole group of poses at once (group_depth: fewer instructions, but its unrolled

@@ -21,6 +21,8 @@
                              // 6 would fill 30 lanes but its scratch leaves room for 2 CTAs per SM, not 3
 #define HPE_MAXPTS 256       // 8 points per lane
 #define HPE_PPL 8
+// staging image of a frame: float4 pre[256] | float4 cbox[8] | float4 chalf[8] | double cloud[3][256] | valid[8] | perm[256] | q, n_pts
+#define HPE_IMAGE_BYTES (HPE_MAXPTS * 16 + 2 * (HPE_MAXPTS / 32) * 16 + 3 * HPE_MAXPTS * 8 + (HPE_MAXPTS / 32) * 4 + HPE_MAXPTS + 16)
 
 struct DevModel {
     double base[5][12];      // pose-independent CMC link (finger T01 / thumb Trf), 3x4 row-major
@@ -37,6 +39,7 @@ struct FrameView {
     const float  *dt_px;     // [240][320]
     const double *cloud;     // [3][n_pts] SoA: X, -Y, -Z
     const unsigned char *perm;  // [HPE_MAXPTS] cluster order of the cloud (cluster_kernel): sorted position -> point index
+    const uint4 *image;      // staging image of the frame (FrameSmem's frame-dependent head, written by cluster_kernel)
     double scale;            // cm per pixel
     double dt_max;           // disttrans.max()
     double focal, cx, cy;

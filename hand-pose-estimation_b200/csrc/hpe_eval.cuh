@@ -37,6 +37,7 @@
 // Compile-time switches kept for cross-checks and measurements: HPE_FFMA2=0 (scalar FFMA sweeps),
 // HPE_PACKED_INDEX=0 (compare + select for the best block), HPE_PAIR_BLOCKS=0.
 #pragma once
+#include <cstddef>
 #include "hpe_device.cuh"
 
 // diagnostics: points sent to the exact fallback (hpe_debug_fallback_points); one copy per
@@ -64,7 +65,8 @@ static __device__ unsigned long long g_hpe_fallback_points;
 #define HPE_PAIR_BLOCKS 1      // 1: two sweep-A blocks per step share the runner-up update (needs HPE_PACKED_INDEX)
 #endif
 #ifndef HPE_SWEEP_UNROLL
-#define HPE_SWEEP_UNROLL 2   // sweep-A steps per loop body
+#define HPE_SWEEP_UNROLL 1   // sweep-A steps per loop body (1: the ranked lists of pass 1 are 2-3 steps long, a two-step body plus its
+                             // remainder copy measured 1.6 % slower)
 #endif
 #define HPE_STR2(x) #x
 #define HPE_STR(x) HPE_STR2(x)
@@ -125,23 +127,27 @@ __device__ __forceinline__ int sphere_slot(int j)
     return 4 * (10 + (f >> 1)) + (f & 1) * 2 + (i - 8);
 }
 
-// model + frame data every CTA stages once
+// model + frame data every CTA stages once.  The members up to n_pts are the frame's STAGING IMAGE (HPE_IMAGE_BYTES):
+// they depend on the cloud only, so cluster_kernel builds them once per observation (stage_frame_build) and every consumer
+// CTA copies them (stage_frame) instead of redoing the cluster gather, the centroid and the bounding boxes behind five barriers.
 struct __align__(16) FrameSmem {
     float4 pre[HPE_MAXPTS];          // (260u|p'|^2, x', y', z'): float32 points recentred on q, CLUSTER ORDER
     float4 cbox[HPE_NCL];            // per cluster of 32 points: centre of the bounding box of p', w = 2 max|p'|^2
     float4 chalf[HPE_NCL];           // ... its half extents (rounded outwards)
-    DevModel M;
-    double rad[HPE_NSPH];
     double cloud[3 * HPE_MAXPTS];    // FP64 cloud, SoA with stride HPE_MAXPTS (X | -Y | -Z), CLUSTER ORDER
-    double scale, dt_max, focal, cx, cy, lambda;
-    const float *depth_mm, *dt_px;
-    float qx, qy, qz;
-    int n_pts;
     unsigned valid[HPE_MAXPTS / 32]; // bit k & 31 of word k / 32: storage position k holds a point (not a repeat)
     unsigned char perm[HPE_MAXPTS];  // storage position -> point index of the observation
+    float qx, qy, qz;
+    int n_pts;
+    // ---- end of the staging image ----
+    DevModel M;
+    double rad[HPE_NSPH];
+    double scale, dt_max, focal, cx, cy, lambda;
+    const float *depth_mm, *dt_px;
     unsigned char slot_of[HPE_NSPH]; // sphere -> matcher slot
     unsigned char sph_of[HPE_NSPH];  // matcher slot -> sphere
 };
+static_assert(offsetof(FrameSmem, M) == HPE_IMAGE_BYTES && HPE_IMAGE_BYTES % 16 == 0, "staging image layout");
 
 // all threads of the CTA; caller syncs afterwards
 __device__ __forceinline__ void stage_model(FrameSmem &fs, const DevModel &m)
@@ -160,7 +166,7 @@ __device__ __forceinline__ void stage_model(FrameSmem &fs, const DevModel &m)
 // The cloud is staged in the CLUSTER ORDER of the observation (F.perm, cluster_kernel): member i of cluster c is point
 // perm[32 c + i] and lives at storage position cluster_storage(c, i); members beyond n_pts repeat the last point, so all
 // HPE_NCL clusters are well defined (fs.valid tells the alignment which positions count).
-__device__ __forceinline__ void stage_frame(FrameSmem &fs, const FrameView &F)
+__device__ __forceinline__ void stage_frame_build(FrameSmem &fs, const FrameView &F)
 {
     __syncthreads();
     for (int t = threadIdx.x; t < HPE_MAXPTS; t += blockDim.x) {
@@ -222,6 +228,21 @@ __device__ __forceinline__ void stage_frame(FrameSmem &fs, const FrameView &F)
                                       fmaf(0.5f * (hy - ly), 1.00001f, 1e-6f * fabsf(by) + 1e-30f),
                                       fmaf(0.5f * (hz - lz), 1.00001f, 1e-6f * fabsf(bz) + 1e-30f), 0.f);
         }
+    }
+    __syncthreads();
+}
+
+// all threads of the CTA; contains __syncthreads, ends synchronised.  Copies the frame's staging image (cluster_kernel)
+// and sets the per-frame scalars, which the observation kernels may have written after the image (dt_max).
+__device__ __forceinline__ void stage_frame(FrameSmem &fs, const FrameView &F)
+{
+    __syncthreads();
+    uint4 *dst = reinterpret_cast<uint4 *>(&fs);
+    for (int i = threadIdx.x; i < HPE_IMAGE_BYTES / 16; i += blockDim.x) dst[i] = __ldg(F.image + i);
+    if (threadIdx.x == 0) {
+        fs.scale = F.scale; fs.dt_max = F.dt_max; fs.focal = F.focal; fs.cx = F.cx; fs.cy = F.cy;
+        fs.lambda = (double)HPE_NSPH / (double)F.n_pts;       // |M|/|P|, src/costfunc.cpp:372
+        fs.depth_mm = F.depth_mm; fs.dt_px = F.dt_px;
     }
     __syncthreads();
 }

@@ -23,6 +23,7 @@ struct ObsView {
     unsigned  *wf_halo;   // [capacity][2][320] scratch of the wavefront chamfer (band halo rows)
     unsigned  *mask;      // [capacity][2400] hand-pixel bits, 32 consecutive pixels per word (cloud_kernel -> chamfer_scan_kernel)
     unsigned char *perm;  // [capacity][HPE_MAXPTS] cluster order of the cloud: sorted position -> point index (cluster_kernel)
+    unsigned char *image; // [capacity][HPE_IMAGE_BYTES] what every consumer CTA stages of the frame's cloud (cluster_kernel)
     double focal, cx, cy;
     int n_pts;
     int capacity;
@@ -35,6 +36,7 @@ __device__ __forceinline__ FrameView frame_view(const ObsView &o, int slot)
     f.dt_px = o.dt_px + (size_t)slot * HPE_W * HPE_H;
     f.cloud = o.cloud + (size_t)slot * 3 * o.n_pts;
     f.perm = o.perm + (size_t)slot * HPE_MAXPTS;
+    f.image = reinterpret_cast<const uint4 *>(o.image + (size_t)slot * HPE_IMAGE_BYTES);
     f.scale = o.meta[slot].scale;
     f.dt_max = o.meta[slot].dt_max;
     f.focal = o.focal; f.cx = o.cx; f.cy = o.cy;

@@ -5,6 +5,7 @@
 // One CTA per frame; frames are independent.
 #include <cstdlib>
 
+#include "hpe_eval.cuh"
 #include "hpe_internal.h"
 
 namespace {
@@ -206,7 +207,19 @@ __global__ void __launch_bounds__(HPE_MAXPTS) cluster_kernel(ObsView o, int firs
             if (t < mid) hi = mid; else lo = mid;
         }
     }
-    perm[t] = ord[cur][t < n ? t : n - 1];
+    const unsigned char mine = ord[cur][t < n ? t : n - 1];
+    perm[t] = mine;
+    // the frame's staging image (hpe_eval.cuh): built once here with the code every consumer used to run per CTA, so the
+    // bits (centroid, recentred points, cluster boxes) are the ones round 2's kernels computed
+    __shared__ FrameSmem fs;
+    __shared__ unsigned char final_perm[HPE_MAXPTS];
+    final_perm[t] = mine;
+    FrameView F = frame_view(o, slot);
+    F.perm = final_perm;                                        // generic pointer into shared memory
+    stage_frame_build(fs, F);                                   // starts and ends with a barrier
+    uint4 *img = reinterpret_cast<uint4 *>(o.image + (size_t)slot * HPE_IMAGE_BYTES);
+    const uint4 *src = reinterpret_cast<const uint4 *>(&fs);
+    for (int i = t; i < HPE_IMAGE_BYTES / 16; i += HPE_MAXPTS) img[i] = src[i];
 }
 
 // 5x5 chamfer metric in OpenCV's Q16 fixed point: a = 65536 (axis), b = 91750 (diagonal),
