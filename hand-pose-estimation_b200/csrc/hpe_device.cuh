@@ -21,8 +21,8 @@
                              // 6 would fill 30 lanes but its scratch leaves room for 2 CTAs per SM, not 3
 #define HPE_MAXPTS 256       // 8 points per lane
 #define HPE_PPL 8
-// staging image of a frame: float4 pre[256] | float4 cbox[8] | float4 chalf[8] | double cloud[3][256] | valid[8] | perm[256] | q, n_pts
-#define HPE_IMAGE_BYTES (HPE_MAXPTS * 16 + 2 * (HPE_MAXPTS / 32) * 16 + 3 * HPE_MAXPTS * 8 + (HPE_MAXPTS / 32) * 4 + HPE_MAXPTS + 16)
+// staging image of a frame: float4 pre[256] | float4 cbox[8] | float4 chalf[8] | double cloud[3][256] | vq[64] | perm[256] | q, n_pts
+#define HPE_IMAGE_BYTES (HPE_MAXPTS * 16 + 2 * (HPE_MAXPTS / 32) * 16 + 3 * HPE_MAXPTS * 8 + HPE_MAXPTS / 4 + HPE_MAXPTS + 16)
 
 struct DevModel {
     double base[5][12];      // pose-independent CMC link (finger T01 / thumb Trf), 3x4 row-major

@@ -135,7 +135,8 @@ struct __align__(16) FrameSmem {
     float4 cbox[HPE_NCL];            // per cluster of 32 points: centre of the bounding box of p', w = 2 max|p'|^2
     float4 chalf[HPE_NCL];           // ... its half extents (rounded outwards)
     double cloud[3 * HPE_MAXPTS];    // FP64 cloud, SoA with stride HPE_MAXPTS (X | -Y | -Z), CLUSTER ORDER
-    unsigned valid[HPE_MAXPTS / 32]; // bit k & 31 of word k / 32: storage position k holds a point (not a repeat)
+    unsigned char vq[HPE_MAXPTS / 4]; // [8 c + i] bit m: storage position cluster_storage(c, i + 8 m) holds a point (not a repeat): the four
+                                     // positions k0 + 32 m of a lane in one byte
     unsigned char perm[HPE_MAXPTS];  // storage position -> point index of the observation
     float qx, qy, qz;
     int n_pts;
@@ -176,17 +177,18 @@ __device__ __forceinline__ void stage_frame_build(FrameSmem &fs, const FrameView
         fs.cloud[HPE_MAXPTS + k] = F.cloud[F.n_pts + src];
         fs.cloud[2 * HPE_MAXPTS + k] = F.cloud[2 * F.n_pts + src];
     }
-    if (threadIdx.x < HPE_MAXPTS / 32) fs.valid[threadIdx.x] = 0u;
+    if (threadIdx.x < HPE_MAXPTS / 4) {
+        const int c = threadIdx.x >> 3, i = threadIdx.x & 7;
+        unsigned v = 0u;
+        for (int mm = 0; mm < 4; ++mm) v |= (32 * c + i + 8 * mm < F.n_pts ? 1u : 0u) << mm;
+        fs.vq[threadIdx.x] = (unsigned char)v;
+    }
     if (threadIdx.x == 0) {
         fs.scale = F.scale; fs.dt_max = F.dt_max; fs.focal = F.focal; fs.cx = F.cx; fs.cy = F.cy;
         fs.lambda = (double)HPE_NSPH / (double)F.n_pts;       // |M|/|P|, src/costfunc.cpp:372
         fs.depth_mm = F.depth_mm; fs.dt_px = F.dt_px; fs.n_pts = F.n_pts;
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < F.n_pts; t += blockDim.x) {
-        const int k = cluster_storage(t >> 5, t & 31);
-        atomicOr(&fs.valid[k >> 5], 1u << (k & 31));
-    }
     if (threadIdx.x < 32) {     // centroid of the float32 cloud (any float origin is valid)
         float sx = 0.f, sy = 0.f, sz = 0.f;
         for (int t = threadIdx.x; t < F.n_pts; t += 32) {
@@ -452,10 +454,11 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
 #ifdef HPE_COUNT_ITERS      // measurement build: the fallback counter counts sweep steps instead (tools/fallback_rate.py)
     if (lane == 0) atomicAdd(&g_hpe_fallback_points, (unsigned long long)nit);
 #endif
+    mk |= 1u << HPE_NBLK;          // sentinel above the 12 block bits: an exhausted list yields the "no block" entry
     HPE_UNROLL_SWEEP
     for (int it = 0; it < nit; ++it) {
-        const int g = mk ? __ffs(mk) - 1 : HPE_NBLK;
-        mk &= mk - 1u;
+        const int g = __ffs(mk) - 1;
+        mk = (mk & (mk - 1u)) | 1u << HPE_NBLK;
         const ulonglong2 *blk = reinterpret_cast<const ulonglong2 *>(ws.ex + g * HPE_EX_PITCH);
         const ulonglong2 a0 = blk[0], a1 = blk[1], b0 = blk[2], b1 = blk[3];
         unsigned long long sa[HPE_PASS], sb[HPE_PASS];
@@ -679,7 +682,9 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
 #pragma unroll
         for (int m = 0; m < HPE_PASS; ++m) {
             const int km = k0 + 32 * m;
-            unsigned todo = __ballot_sync(0xffffffffu, ((slow >> m) & 1u) && (fs.valid[km >> 5] >> (km & 31) & 1u));
+            // valid bit of position km = cluster_storage(c, i + 8 m): c = 4 (km >> 7) + ((km >> 3) & 3), i = km & 7
+            unsigned todo = __ballot_sync(0xffffffffu, ((slow >> m) & 1u) &&
+                                          (fs.vq[8 * (4 * (km >> 7) + ((km >> 3) & 3)) + (km & 7)] >> m & 1u));
 #ifndef HPE_COUNT_ITERS
             if (todo && lane == 0) atomicAdd(&g_hpe_fallback_points, (unsigned long long)__popc(todo));
 #endif
@@ -768,13 +773,14 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
 #pragma unroll 1
     for (int pass = 0; pass < HPE_PPL / HPE_PASS; ++pass) {
         // storage positions k0 + 32 m of the lane's four points (stage_frame): member (lane & 7) + 8 m of the quarter's cluster
-        int k0 = lane + 32 * HPE_PASS * pass;
+        int k0 = lane + 32 * HPE_PASS * pass, vidx = lane + 32 * pass;      // vidx = 8 cluster + member: the lane's byte of fs.vq
         unsigned mk = 0xfffu;
         if (pruned) {
             const unsigned sl = ws.slots[4 * pass + (lane >> 3)];
             const int c = (int)(sl >> 12);
             mk = sl & 0xfffu;
             k0 = 128 * (c >> 2) + 8 * (c & 3) + (lane & 7);
+            vidx = 8 * c + (lane & 7);
         }
         int idx[HPE_PASS];
         if (AUX && frozen) {
@@ -786,11 +792,9 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
             match_pass(fs, ws, k0, lane, mk, idx);
         }
         // align_models for these 4 points, FP64, the reference's operation order.  Branch-free: positions that only
-        // repeat a point (fs.valid clear) are computed like the others and dropped by a select, the square root is the
+        // repeat a point (fs.vq bit clear) are computed like the others and dropped by a select, the square root is the
         // straight-line Newton sequence below, so the four chains interleave.
-        const int w0 = k0 >> 5, bit = k0 & 31;
-        const unsigned vbits = (fs.valid[w0] >> bit & 1u) | (fs.valid[w0 + 1] >> bit & 1u) << 1 |
-                               (fs.valid[w0 + 2] >> bit & 1u) << 2 | (fs.valid[w0 + 3] >> bit & 1u) << 3;
+        const unsigned vbits = fs.vq[vidx];
         double n2[HPE_PASS], rj[HPE_PASS];
 #pragma unroll
         for (int m = 0; m < HPE_PASS; ++m) {
