@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(160) fk_kernel(DevModel m, const double *__res
 }
 
 // ---------------------------------------------------------------------------------------
-// cal_cost / cal_cost2 for n poses against one frame.  Poses are split evenly over all
-// warps of the grid; a warp walks its range in groups of HPE_GROUP.
+// cal_cost / cal_cost2 for n poses against one frame.  One CTA of SCORE_WARPS warps per SM; the warps take
+// groups of SCORE_GROUP poses (then smaller units) from counters in global memory until the batch is used up.
 // ---------------------------------------------------------------------------------------
 // Self-scheduling counters of cost_kernel: one slot per launch in flight.  The launcher hands the slots out round-robin;
 // HPE_SCHED_SLOTS exceeds the number of kernels a device runs concurrently (128), so two launches that share a slot are
@@ -80,21 +80,41 @@ struct __align__(16) CostSmem {
     FrameSmem fs;
     __align__(16) unsigned char ws[COST_WARPS * HPE_WS_BYTES(HPE_GROUP)];
 };
+// cost_kernel's own shape (the other kernels of this file keep COST_WARPS x HPE_MINBLOCKS and groups of HPE_GROUP): ONE CTA of
+// 24 warps per SM.  With self-scheduling there is nothing to balance between CTAs, one copy of the frame per SM instead of
+// three frees 25 KB of shared memory, and that pays for groups of SIX poses: the forward kinematics then runs on 30 of 32 lanes.
+// Measured (evaluations/s): 8 x 3, groups of 5: 3.357e8; 12 x 2: 3.365e8; 24 x 1: 3.373e8; 24 x 1, groups of 6: 3.403e8;
+// 25 x 1 (the register file would hold it): ptxas caps the kernel at 72 registers, 3.31e8.
+#ifndef HPE_SCORE_WARPS
+#define HPE_SCORE_WARPS 24
+#endif
+#ifndef HPE_SCORE_CTAS
+#define HPE_SCORE_CTAS 1
+#endif
+#ifndef HPE_SCORE_GROUP
+#define HPE_SCORE_GROUP 6
+#endif
+constexpr int SCORE_WARPS = HPE_SCORE_WARPS, SCORE_CTAS = HPE_SCORE_CTAS, SCORE_GROUP = HPE_SCORE_GROUP;
+static_assert(SCORE_GROUP <= 6, "five lanes per pose, dep[] holds six values");
+struct __align__(16) ScoreSmem {
+    FrameSmem fs;
+    __align__(16) unsigned char ws[SCORE_WARPS * HPE_WS_BYTES(SCORE_GROUP)];
+};
 
 // AUX: frozen correspondences in and / or correspondences out (cal_cost2's matchId); the plain scoring kernel is
 // compiled without them (fewer live registers and no per-point predicates in the alignment loop)
 template <bool WITH_COLLI, int MATCHER, bool AUX>
-__global__ void __launch_bounds__(COST_WARPS * 32, HPE_MINBLOCKS)
+__global__ void __launch_bounds__(SCORE_WARPS * 32, SCORE_CTAS)
 cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, int64_t n,
             double *__restrict__ cost, double *__restrict__ terms, int64_t tstride,
             const int32_t *__restrict__ frozen, int32_t *__restrict__ match_out, int sched_slot, int n1, int n2, int t2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CostSmem &sm = *reinterpret_cast<CostSmem *>(smem_raw);
+    ScoreSmem &sm = *reinterpret_cast<ScoreSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     stage_model(sm.fs, m);
     stage_frame(sm.fs, frame_view(o, slot));     // ends synchronised
-    const WarpScratch ws = warp_scratch(sm.ws, warp, HPE_GROUP);
+    const WarpScratch ws = warp_scratch(sm.ws, warp, SCORE_GROUP);
     const int n_pts = sm.fs.n_pts;
 
     // Work distribution.  Poses are handed out through two counters in global memory (self-scheduling): groups of HPE_GROUP
@@ -106,7 +126,7 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
     // scores < 2^31 poses, hpe_launch_cost splits larger batches).  The loop variables live in the warp's shared-memory
     // scratch and are re-read where they are used: every register is taken inside the matching phases, and a loop counter
     // spilled to local memory costs an L1 miss per pose (ncu: 3.5 % of the kernel's stall samples).
-    const int total_warps = (int)gridDim.x * COST_WARPS;
+    const int total_warps = (int)gridDim.x * SCORE_WARPS;
     SchedSlot *const S = g_sched + sched_slot;
     volatile int *wl = reinterpret_cast<volatile int *>(ws.dep + 6);      // [0] = first pose of the group, [1] = main range exhausted, [2] = group size, [3] = g
     if (lane == 0) wl[1] = 0;
@@ -116,8 +136,8 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
         if (lane == 0) {
             int s = 0, cnt = 0;
             if (!wl[1]) {
-                s = atomicAdd(&S->next, HPE_GROUP);
-                cnt = min(HPE_GROUP, n1 - s);
+                s = atomicAdd(&S->next, SCORE_GROUP);
+                cnt = min(SCORE_GROUP, n1 - s);
                 if (cnt <= 0) wl[1] = 1;
             }
             if (cnt <= 0) {
@@ -131,7 +151,7 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
         if (wl[2] <= 0) break;
         group_fk(sm.fs.M, [&](int g) { return theta + (size_t)(wl[0] + g) * HPE_NDOF; }, wl[2], ws, lane);
 #if HPE_GROUP_DEPTH
-        group_depth<HPE_GROUP>(sm.fs, ws, wl[2], lane);
+        group_depth<SCORE_GROUP>(sm.fs, ws, wl[2], lane);
 #endif
 #pragma unroll 1
         while (wl[3] < wl[2]) {
@@ -761,13 +781,14 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
                                match_out_dev ? match_out_dev + half * o.n_pts : nullptr, st, terms_stride);
     }
     const int sms = hpe_sm_count();
-    int64_t groups = (n + HPE_GROUP - 1) / HPE_GROUP;
-    int64_t want = (groups + COST_WARPS - 1) / COST_WARPS;
-    int blocks = (int)(want < (long long)HPE_MINBLOCKS * sms ? want : (long long)HPE_MINBLOCKS * sms);
+    // a batch with fewer groups than the device has warps is spread over as many SMs as it has groups (the warps of a CTA
+    // that find the counters empty leave at once)
+    int64_t groups = (n + SCORE_GROUP - 1) / SCORE_GROUP;
+    int blocks = (int)(groups < (long long)SCORE_CTAS * sms ? groups : (long long)SCORE_CTAS * sms);
     static PerDevice<bool> attr_pd;
     bool &attr = attr_pd.get();
     if (!attr) {
-        const int smem = (int)sizeof(CostSmem);
+        const int smem = (int)sizeof(ScoreSmem);
         cudaFuncSetAttribute(cost_kernel<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(cost_kernel<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(cost_kernel<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -778,15 +799,15 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
     }
     // self-scheduling plan (cost_kernel): groups from [0, n1), units of HPE_TAIL_C2 from [n1, n2), single poses from [n2, n);
     // batches with fewer than two groups per warp are handed out in groups only
-    const int64_t warps = (int64_t)blocks * COST_WARPS;
-    int64_t r1 = n >= 2 * HPE_GROUP * warps ? (int64_t)(HPE_TAIL_R1 * (float)warps) : 0, r2 = (int64_t)(HPE_TAIL_R2 * (float)warps);
+    const int64_t warps = (int64_t)blocks * SCORE_WARPS;
+    int64_t r1 = n >= 2 * SCORE_GROUP * warps ? (int64_t)(HPE_TAIL_R1 * (float)warps) : 0, r2 = (int64_t)(HPE_TAIL_R2 * (float)warps);
     if (r2 > r1) r2 = r1;
     const int n1 = (int)(n - r1), t2 = (int)((r1 - r2 + HPE_TAIL_C2 - 1) / HPE_TAIL_C2);
     const int n2 = (int)(n - r2);
     static std::atomic<unsigned> next_slot{0};
     const int sched_slot = (int)(next_slot.fetch_add(1, std::memory_order_relaxed) % HPE_SCHED_SLOTS);
     auto launch = [&](auto kern) {
-        kern<<<blocks, COST_WARPS * 32, sizeof(CostSmem), st>>>(m, o, slot, theta_dev, n, cost_dev, terms_dev,
+        kern<<<blocks, SCORE_WARPS * 32, sizeof(ScoreSmem), st>>>(m, o, slot, theta_dev, n, cost_dev, terms_dev,
                                                                  terms_stride, frozen_match_dev, match_out_dev, sched_slot, n1, n2, t2);
     };
     const bool aux = frozen_match_dev || match_out_dev;
