@@ -134,7 +134,10 @@ struct __align__(16) FrameSmem {
     float4 pre[HPE_MAXPTS];          // (260u|p'|^2, x', y', z'): float32 points recentred on q, CLUSTER ORDER
     float4 cbox[HPE_NCL];            // per cluster of 32 points: centre of the bounding box of p', w = 2 max|p'|^2
     float4 chalf[HPE_NCL];           // ... its half extents (rounded outwards)
-    double cloud[3 * HPE_MAXPTS];    // FP64 cloud, SoA with stride HPE_MAXPTS (X | -Y | -Z), CLUSTER ORDER
+    double2 cxy[HPE_MAXPTS];         // FP64 cloud (X, -Y), CLUSTER ORDER: one 128-bit load per point, which the eight lanes of a quarter
+                                     // fetch in one wavefront whatever cluster the quarter holds (three 64-bit arrays cost a two-way
+                                     // bank conflict whenever the two quarters of a half-warp hold clusters of the same parity)
+    double cz[HPE_MAXPTS];           // ... -Z
     unsigned char vq[HPE_MAXPTS / 4]; // [8 c + i] bit m: storage position cluster_storage(c, i + 8 m) holds a point (not a repeat): the four
                                      // positions k0 + 32 m of a lane in one byte
     unsigned char perm[HPE_MAXPTS];  // storage position -> point index of the observation
@@ -173,9 +176,8 @@ __device__ __forceinline__ void stage_frame_build(FrameSmem &fs, const FrameView
     for (int t = threadIdx.x; t < HPE_MAXPTS; t += blockDim.x) {
         const int k = cluster_storage(t >> 5, t & 31), src = F.perm[t];
         fs.perm[k] = (unsigned char)src;
-        fs.cloud[k] = F.cloud[src];
-        fs.cloud[HPE_MAXPTS + k] = F.cloud[F.n_pts + src];
-        fs.cloud[2 * HPE_MAXPTS + k] = F.cloud[2 * F.n_pts + src];
+        fs.cxy[k] = make_double2(F.cloud[src], F.cloud[F.n_pts + src]);
+        fs.cz[k] = F.cloud[2 * F.n_pts + src];
     }
     if (threadIdx.x < HPE_MAXPTS / 4) {
         const int c = threadIdx.x >> 3, i = threadIdx.x & 7;
@@ -193,7 +195,7 @@ __device__ __forceinline__ void stage_frame_build(FrameSmem &fs, const FrameView
         float sx = 0.f, sy = 0.f, sz = 0.f;
         for (int t = threadIdx.x; t < F.n_pts; t += 32) {
             const int k = cluster_storage(t >> 5, t & 31);
-            sx += (float)fs.cloud[k]; sy += (float)fs.cloud[HPE_MAXPTS + k]; sz += (float)fs.cloud[2 * HPE_MAXPTS + k];
+            sx += (float)fs.cxy[k].x; sy += (float)fs.cxy[k].y; sz += (float)fs.cz[k];
         }
         for (int o = 16; o > 0; o >>= 1) {
             sx += __shfl_xor_sync(0xffffffffu, sx, o);
@@ -205,8 +207,8 @@ __device__ __forceinline__ void stage_frame_build(FrameSmem &fs, const FrameView
     __syncthreads();
     for (int k = threadIdx.x; k < HPE_MAXPTS; k += blockDim.x) {
         // conv_to<fmat> (src/costfunc.cpp:322), then p' = fl(pf - q)
-        float x = __fsub_rn((float)fs.cloud[k], fs.qx), y = __fsub_rn((float)fs.cloud[HPE_MAXPTS + k], fs.qy),
-              z = __fsub_rn((float)fs.cloud[2 * HPE_MAXPTS + k], fs.qz);
+        float x = __fsub_rn((float)fs.cxy[k].x, fs.qx), y = __fsub_rn((float)fs.cxy[k].y, fs.qy),
+              z = __fsub_rn((float)fs.cz[k], fs.qz);
         float pp = x * x + y * y + z * z;
         fs.pre[k] = make_float4(1.56e-5f * pp, x, y, z);      // (260 * 2^-24 |p'|^2 rounded up, x', y', z'): the coordinates sit in
                                                               // register banks 1,2,3, the sphere operands they meet in 0,1,2
@@ -324,7 +326,7 @@ __device__ __forceinline__ void match_pass_direct(const FrameSmem &fs, const War
 #pragma unroll
     for (int m = 0; m < HPE_PASS; ++m) {
         int k = k0 + 32 * m;
-        px[m] = (float)fs.cloud[k]; py[m] = (float)fs.cloud[HPE_MAXPTS + k]; pz[m] = (float)fs.cloud[2 * HPE_MAXPTS + k];
+        px[m] = (float)fs.cxy[k].x; py[m] = (float)fs.cxy[k].y; pz[m] = (float)fs.cz[k];
         b1[m] = INF;
         idx[m] = 0;
     }
@@ -437,11 +439,13 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
 #if HPE_FFMA2
     // ---- packed variant: spheres are staged in pairs (see depth_and_stage), point coordinates duplicated ----
     unsigned long long px[HPE_PASS], py[HPE_PASS], pz[HPE_PASS];
+    float pxf[HPE_PASS], pyf[HPE_PASS], pzf[HPE_PASS];
     float M1[HPE_PASS], M2[HPE_PASS];
     int g1[HPE_PASS];
 #pragma unroll
     for (int m = 0; m < HPE_PASS; ++m) {
         const float4 q = fs.pre[k0 + 32 * m];
+        pxf[m] = q.y; pyf[m] = q.z; pzf[m] = q.w;
         px[m] = dup32(q.y); py[m] = dup32(q.z); pz[m] = dup32(q.w);
         M1[m] = INF; M2[m] = INF; g1[m] = 0;
     }
@@ -562,7 +566,9 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
 #if HPE_PACKED_INDEX
         // exact minimum of the best block; M2 carries an index in its low bits: |M2 - true| < 32u|M2|
         const float m1 = fminf(lo01, lo23);
-        const float tau = fmaf(7.2e-6f, fabsf(m1), fs.pre[k0 + 32 * m].x);      // (52 + 2*32) * 2^-24 = 6.9e-6
+        // (52 + 2*32) * 2^-24 = 6.9e-6; 260u|p'|^2 <= 1.56e-5 |p'|^2 from the coordinates in registers (a load of the staged
+        // value would cost four shared-memory wavefronts per pass: the float4 rows sit 16 bytes apart)
+        const float tau = fmaf(7.2e-6f, fabsf(m1), 1.56e-5f * fmaf(pzf[m], pzf[m], fmaf(pyf[m], pyf[m], pxf[m] * pxf[m])));
         bool cert = fminf(M2[m], r) - m1 > tau;                           // false on NaN
 #else
         const float tau = fmaf(3.2e-6f, fabsf(M1[m]), fs.pre[k0 + 32 * m].x);   // 52 * 2^-24 = 3.0994e-6
@@ -692,8 +698,7 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
                 int src = __ffs(todo) - 1;
                 todo &= todo - 1;
                 int k = __shfl_sync(0xffffffffu, km, src);
-                int e = match_point_exact_warp(ws.cf, (float)fs.cloud[k], (float)fs.cloud[HPE_MAXPTS + k],
-                                               (float)fs.cloud[2 * HPE_MAXPTS + k], lane);
+                int e = match_point_exact_warp(ws.cf, (float)fs.cxy[k].x, (float)fs.cxy[k].y, (float)fs.cz[k], lane);
                 if (lane == src) idx[m] = e;
             }
         }
@@ -801,9 +806,10 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
             const int k = k0 + 32 * m, j = idx[m];
             if (AUX && match_row && (vbits >> m & 1u)) match_row[fs.perm[k]] = j;
             // negated-frame centre = (cx, -cy, -cz)
-            const double a = fs.cloud[k] - sd[j * 3 + 0];
-            const double b = fs.cloud[HPE_MAXPTS + k] + sd[j * 3 + 1];
-            const double e = fs.cloud[2 * HPE_MAXPTS + k] + sd[j * 3 + 2];
+            const double2 pxy = fs.cxy[k];
+            const double a = pxy.x - sd[j * 3 + 0];
+            const double b = pxy.y + sd[j * 3 + 1];
+            const double e = fs.cz[k] + sd[j * 3 + 2];
             n2[m] = __dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(e, e));
             rj[m] = fs.rad[j];
         }
