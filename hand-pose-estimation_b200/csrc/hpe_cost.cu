@@ -165,7 +165,7 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
                 if (lane == 0) reinterpret_cast<volatile double *>(ws.dep)[wl[3]] = depth;     // parked like the loop variables
             }
 #endif
-            double align = match_align<MATCHER, AUX>(sm.fs, ws, wl[3], lane, AUX ? frozen : nullptr,
+            double align = match_align<MATCHER, AUX, 1>(sm.fs, ws, wl[3], lane, AUX ? frozen : nullptr,
                                                      AUX && match_out ? match_out + (size_t)(wl[0] + wl[3]) * n_pts : nullptr);
             double colli = 0.0;
             if (WITH_COLLI) colli = warp_sum(collision_lane(sm.fs.rad, ws.sphd + (size_t)wl[3] * HPE_NSPH * 3, lane));

@@ -65,8 +65,10 @@ static __device__ unsigned long long g_hpe_fallback_points;
 #define HPE_PAIR_BLOCKS 1      // 1: two sweep-A blocks per step share the runner-up update (needs HPE_PACKED_INDEX)
 #endif
 #ifndef HPE_SWEEP_UNROLL
-#define HPE_SWEEP_UNROLL 1   // sweep-A steps per loop body (1: the ranked lists of pass 1 are 2-3 steps long, a two-step body plus its
-                             // remainder copy measured 1.6 % slower)
+#define HPE_SWEEP_UNROLL 2   // sweep-A steps per loop body of the unpruned variants and, by default, of the pruned sweep (UNROLL of
+                             // match_align: the throughput kernel asks for 1 -- the ranked lists of pass 1 are 2-3 steps long and a
+                             // two-step body plus its remainder copy measured 1.6 % slower there; a warp that has its scheduler
+                             // to itself, as in the one-particle-per-warp kernels, wants the two independent steps)
 #endif
 #define HPE_STR2(x) #x
 #define HPE_STR(x) HPE_STR2(x)
@@ -432,6 +434,7 @@ __device__ __forceinline__ unsigned prune_blocks(const FrameSmem &fs, const Warp
 
 // phase 3a for 4 points of the lane, k = k0 + 32 m (see the header comment).  ws.cf / ws.ex must
 // hold the pose being matched.
+template <int UNROLL = HPE_SWEEP_UNROLL>
 __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratch &ws, int k0, int lane,
                                            unsigned mk, int idx[HPE_PASS])
 {
@@ -459,7 +462,7 @@ __device__ __forceinline__ void match_pass(const FrameSmem &fs, const WarpScratc
     if (lane == 0) atomicAdd(&g_hpe_fallback_points, (unsigned long long)nit);
 #endif
     mk |= 1u << HPE_NBLK;          // sentinel above the 12 block bits: an exhausted list yields the "no block" entry
-    HPE_UNROLL_SWEEP
+#pragma unroll UNROLL
     for (int it = 0; it < nit; ++it) {
         const int g = __ffs(mk) - 1;
         mk = (mk & (mk - 1u)) | 1u << HPE_NBLK;
@@ -738,7 +741,7 @@ __device__ __forceinline__ double sqrt_pos(double x)
 #ifndef HPE_SORT_SLOTS
 #define HPE_SORT_SLOTS 1     // 1: the clusters with the four longest block lists are matched in pass 0, the other four in pass 1
 #endif
-template <int MATCHER, bool AUX = true>
+template <int MATCHER, bool AUX = true, int UNROLL = HPE_SWEEP_UNROLL>
 __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScratch &ws, int g, int lane,
                                               const int32_t *frozen, int32_t *match_row)
 {
@@ -794,7 +797,7 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
         } else if (MATCHER == 1) {
             match_pass_direct(fs, ws, k0, lane, idx);
         } else {
-            match_pass(fs, ws, k0, lane, mk, idx);
+            match_pass<UNROLL>(fs, ws, k0, lane, mk, idx);
         }
         // align_models for these 4 points, FP64, the reference's operation order.  Branch-free: positions that only
         // repeat a point (fs.vq bit clear) are computed like the others and dropped by a select, the square root is the

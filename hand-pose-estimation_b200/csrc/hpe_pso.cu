@@ -8,6 +8,13 @@
 
 namespace {
 
+#ifndef HPE_PSO_UNROLL
+#define HPE_PSO_UNROLL 2      // sweep-A steps per loop body in pso_kernel
+#endif
+#ifndef HPE_PSO_DYN
+#define HPE_PSO_DYN 1         // 1: the warps of a CTA take the particle groups of a generation from a counter in shared memory
+                              // (a warp whose particles were cheap takes the next group instead of waiting at the barrier)
+#endif
 #ifndef HPE_PSO_WARPS
 #define HPE_PSO_WARPS 8
 #endif
@@ -21,7 +28,7 @@ struct __align__(16) PsoSmemHead {
     double gbest_cost;
     int count;
     int fmin_id;
-    int pad;
+    int next_group;      // first particle of the next group to hand out (HPE_PSO_DYN)
     // followed by: warp scratch [PSO_WARPS][gsz] slots; double pcost[num_p];
     //              double fx[num_p]; int informant[num_p]; int R[num_p][3];
 };
@@ -95,24 +102,34 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
             v[i * D + 2 * dp] = 0.0;
             v[i * D + 2 * dp + 1] = 0.0;
         }
-        if (tid == 0) { sm.gbest_cost = 1e100; sm.count = 100; }
+        if (tid == 0) { sm.gbest_cost = 1e100; sm.count = 100; sm.next_group = 0; }
         __syncthreads();
 
         for (int iter = 1;; ++iter) {
             // ---- evaluate every particle: cal_cost (src/PSO.cpp:748-752, 848-852) ----
+#if HPE_PSO_DYN
+            for (;;) {
+                int p0 = 0;
+                if (lane == 0) p0 = atomicAdd(&sm.next_group, gsz);
+                p0 = __shfl_sync(0xffffffffu, p0, 0);
+                if (p0 >= num_p) break;
+                int cnt = min(gsz, num_p - p0);
+#else
             const int per_round = PSO_WARPS * gsz;
             for (int p0 = warp * gsz; p0 < num_p; p0 += per_round) {
                 int cnt = min(gsz, num_p - p0);
+#endif
                 const WarpScratch ws = warp_scratch(ws_base, warp, gsz);
                 group_fk(sm.fs.M, [&](int g) { return x + (size_t)(p0 + g) * D; }, cnt, ws, lane);
                 for (int g = 0; g < cnt; ++g) {
                     double depth = depth_and_stage(sm.fs, ws, g, lane);
-                    double align = match_align<0>(sm.fs, ws, g, lane, nullptr, nullptr);
+                    double align = match_align<0, true, HPE_PSO_UNROLL>(sm.fs, ws, g, lane, nullptr, nullptr);
                     if (lane == 0) fx[p0 + g] = align + depth;
                 }
                 __syncwarp();
             }
             __syncthreads();
+            if (tid == 0) sm.next_group = 0;       // every warp has left the loop above; the next fetch is several barriers away
             // ---- pbest (:753, :855-860) ----
             for (int it = tid; it < num_p * D; it += nthr) {
                 int i = it / D;

@@ -9,7 +9,7 @@ src=${SRC:-hpe_cost}
 mkdir -p build/variants/$name
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC \
    -ccbin /usr/bin/g++ "$@" -c csrc/$src.cu -o build/variants/$name/$src.o
-objs=$(ls build/*.o | grep -v $src.o)
+objs=$(ls build/*.o | grep -v "/$src\.o$")
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static \
    -o build/variants/libhpe_b200_$name.so build/variants/$name/$src.o $objs
 echo built build/variants/libhpe_b200_$name.so
