@@ -435,6 +435,7 @@ int hpe_obs_set(hpe_obs *o, int slot, const float *depth_mm, const float *dt_px,
     HPE_CUDA(cudaMemcpy(o->v.cloud + (size_t)3 * np * slot, soa.data(), sizeof(double) * 3 * np, cudaMemcpyHostToDevice));
     HPE_CUDA(cudaMemcpy(o->v.meta + slot, &meta, sizeof meta, cudaMemcpyHostToDevice));
     HPE_CUDA(hpe_launch_dtmax(o->v, slot, 0));
+    HPE_CUDA(hpe_launch_fold_depth(o->v, slot, 0));      // after the maximum: hand pixels become -depth
     HPE_CUDA(hpe_launch_cluster(o->v, slot, 1, 0));
     HPE_CUDA(cudaStreamSynchronize(0));
     return HPE_OK;
@@ -457,7 +458,11 @@ int hpe_obs_get(const hpe_obs *o, int slot, double *cloud, float *dt_px, double 
         for (int k = 0; k < np; ++k)
             for (int c = 0; c < 3; ++c) cloud[k * 3 + c] = soa[(size_t)c * np + k];
     }
-    if (dt_px) HPE_CUDA(cudaMemcpy(dt_px, o->v.dt_px + npix * slot, sizeof(float) * npix, cudaMemcpyDeviceToHost));
+    if (dt_px) {
+        HPE_CUDA(cudaMemcpy(dt_px, o->v.dt_px + npix * slot, sizeof(float) * npix, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < npix; ++k)
+            if (dt_px[k] < 0.0f) dt_px[k] = 0.0f;      // the device map is folded: hand pixels hold minus their depth
+    }
     return HPE_OK;
 }
 

@@ -36,7 +36,7 @@ struct DevModel {
 // One observed frame (observedmodel after next_frame), device pointers.
 struct FrameView {
     const float  *depth_mm;  // [240][320]
-    const float  *dt_px;     // [240][320]
+    const float  *dt_px;     // [240][320] FOLDED map: distance transform (px) on the background, minus the depth (mm) on hand pixels
     const double *cloud;     // [3][n_pts] SoA: X, -Y, -Z
     const unsigned char *perm;  // [HPE_MAXPTS] cluster order of the cloud (cluster_kernel): sorted position -> point index
     const uint4 *image;      // staging image of the frame (FrameSmem's frame-dependent head, written by cluster_kernel)
@@ -368,30 +368,6 @@ __device__ __forceinline__ double floor_div(double a, double z, double rz)
     double frac = q - f;
     if (!(frac > 1e-6 && frac < 1.0 - 1e-6) || !(fabs(q) < 1e9)) f = floor(__ddiv_rn(a, z));
     return f;
-}
-
-template <class FrameT>
-__device__ __forceinline__ double depth_term(const FrameT &F, double x, double y, double z, double r)
-{
-    // K*c without FMA contraction: row0 = f*x + cx*z, row1 = f*y + cy*z, row2 = z; then the
-    // reference's floor(row / z) (src/costfunc.cpp:251-255)
-    const double rz = __drcp_rn(z);
-    double dx = floor_div(__dadd_rn(__dmul_rn(F.focal, x), __dmul_rn(F.cx, z)), z, rz);
-    double dy = floor_div(__dadd_rn(__dmul_rn(F.focal, y), __dmul_rn(F.cy, z)), z, rz);
-    bool inside = dx >= 0.0 && dx < (double)HPE_W && dy >= 0.0 && dy < (double)HPE_H;
-    double v;
-    if (inside) {
-        int at = (int)dy * HPE_W + (int)dx;
-        float mm = __ldg(F.depth_mm + at);
-        if (mm != 0.0f) {
-            v = fmax(0.0, div10_exact(mm) - z);       // depthmp is the file value / 10 (src/observedmodel.cpp:300-303)
-        } else {
-            v = __dadd_rn(__dmul_rn((double)__ldg(F.dt_px + at), F.scale), r);
-        }
-    } else {
-        v = __dadd_rn(__dmul_rn(F.dt_max, F.scale), r);
-    }
-    return __dmul_rn(v, v);
 }
 
 // ---------------------------------------------------------------------------------------

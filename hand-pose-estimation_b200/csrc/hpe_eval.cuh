@@ -971,7 +971,10 @@ __device__ __forceinline__ DepthInFlight depth_issue(const FrameSmem &fs, const 
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         f.mm[h] = 0.f; f.dtv[h] = 0.f;
-        if (f.at[h] >= 0) { f.mm[h] = __ldg(fs.depth_mm + f.at[h]); f.dtv[h] = __ldg(fs.dt_px + f.at[h]); }
+        // ONE gather per projection: the observation folds the depth map into the distance transform (fold_depth_kernel:
+        // hand pixel -> minus its depth in mm, background -> its distance), which halves the sectors an evaluation pulls
+        // through the L2 and the footprint of a frame in it
+        if (f.at[h] >= 0) { const float v = __ldg(fs.dt_px + f.at[h]); f.mm[h] = v < 0.0f ? -v : 0.0f; f.dtv[h] = v; }
     }
     return f;
 }
@@ -1023,7 +1026,7 @@ __device__ __forceinline__ void group_depth(const FrameSmem &fs, const WarpScrat
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
         mm[r] = 0.f; dtv[r] = 0.f;
-        if (at[r] >= 0 && lane + 32 * r < n_items) { mm[r] = __ldg(fs.depth_mm + at[r]); dtv[r] = __ldg(fs.dt_px + at[r]); }
+        if (at[r] >= 0 && lane + 32 * r < n_items) { const float v = __ldg(fs.dt_px + at[r]); mm[r] = v < 0.0f ? -v : 0.0f; dtv[r] = v; }
     }
     double acc[GROUP];
 #pragma unroll

@@ -17,7 +17,7 @@ struct FrameMeta {
 // device view of an hpe_obs, passed to kernels by value
 struct ObsView {
     float     *depth_mm;  // [capacity][240][320]
-    float     *dt_px;     // [capacity][240][320]
+    float     *dt_px;     // [capacity][240][320] folded: distance transform on the background, -depth_mm on hand pixels (fold_depth_kernel)
     double    *cloud;     // [capacity][3][n_pts]
     FrameMeta *meta;      // [capacity]
     unsigned  *wf_halo;   // [capacity][2][320] scratch of the wavefront chamfer (band halo rows)
@@ -181,6 +181,7 @@ cudaError_t hpe_launch_observe(const ObsView &o, int first, int count, void *scr
 cudaError_t hpe_launch_dtmax(const ObsView &o, int slot, cudaStream_t st);
 // cluster order of the clouds of slots [first, first+count) (run by hpe_launch_observe; separately for injected clouds)
 cudaError_t hpe_launch_cluster(const ObsView &o, int first, int count, cudaStream_t st);
+cudaError_t hpe_launch_fold_depth(const ObsView &o, int slot, cudaStream_t st);     // injected maps: dt_px becomes the folded map
 cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
                            int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
                            double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st, int seq_stride = 0,
