@@ -176,14 +176,36 @@ pso_kernel(DevModel m, ObsView o, PsoDev prm, const double *__restrict__ x0_in, 
             }
             __syncthreads();
             // ---- informant = first minimum of pcost over {s : L(s,i) = 1} (:810-812) ----
-            for (int i = tid; i < num_p; i += nthr) {
-                int best = -1;
-                double bc = 0.0;
-                for (int s = 0; s < num_p; ++s) {
-                    bool linked = (s == i) | (R[s * PSO_NK] == i) | (R[s * PSO_NK + 1] == i) | (R[s * PSO_NK + 2] == i);
-                    if (linked && (best < 0 || pcost[s] < bc)) { best = s; bc = pcost[s]; }
+            // Four threads per particle, each scanning every fourth s (round 2: one thread per particle, i.e. two warps of
+            // a 64-particle swarm worked while six waited at the barrier -- 6 % of the kernel's stall samples).  The
+            // reference's scan takes the first linked s whatever its cost and replaces it only by a strictly smaller cost:
+            // that is the first linked s if its cost is NaN (or if no linked cost compares below +inf), else the
+            // lexicographic minimum of (cost, s) over the linked s -- which is what the quad combines.
+            for (int base = 0; base < num_p; base += nthr >> 2) {
+                const int i = base + (tid >> 2), sub = tid & 3;
+                int first = 0x7fffffff, best = 0x7fffffff;
+                double bc = __longlong_as_double(0x7ff0000000000000LL);
+                if (i < num_p) {
+                    for (int s = sub; s < num_p; s += 4) {
+                        const bool linked = (s == i) | (R[s * PSO_NK] == i) | (R[s * PSO_NK + 1] == i) | (R[s * PSO_NK + 2] == i);
+                        if (linked) {
+                            first = min(first, s);
+                            const double c = pcost[s];
+                            if (c < bc) { bc = c; best = s; }
+                        }
+                    }
                 }
-                informant[i] = best;
+#pragma unroll
+                for (int o = 1; o < 4; o <<= 1) {
+                    first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+                    const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    if (oc < bc || (oc == bc && ob < best)) { bc = oc; best = ob; }
+                }
+                if (i < num_p && sub == 0) {
+                    const double cf0 = pcost[first];
+                    informant[i] = (cf0 != cf0 || best == 0x7fffffff) ? first : best;
+                }
             }
             __syncthreads();
             // ---- velocity, position, check_constraints (:824-840, :358-377) ----
