@@ -95,12 +95,15 @@ int hpe_obs_destroy(hpe_obs *o);
 /* observedmodel::next_frame for `count` frames (src/observedmodel.cpp:420-430 =
  * load_data :272-310 + depth_to_ptncloud :110-219 + dist_transform :340-369), all on
  * the device.  depth_mm: HOST float32 [count][240][320] in the file layout
- * (value at y*320+x, mm, 0 = background).  Frames are stored in slots first..first+count-1. */
+ * (value at y*320+x, mm >= 0 as in the unsigned file format, 0 = background).  Frames are stored in slots
+ * first..first+count-1.  On the device the distance transform is kept FOLDED with the depth map (hand pixel -> minus
+ * its depth, background -> its distance: one gather per projected sphere in the depth term); hpe_obs_get returns the
+ * plain transform. */
 int hpe_obs_upload(hpe_obs *o, const float *depth_mm, int first, int count);
 /* same with the frames already in device memory */
 int hpe_obs_upload_dev(hpe_obs *o, const float *depth_mm_dev, int first, int count);
 /* inject an externally preprocessed observation into one slot (host pointers):
- * depth_mm [240*320], dt_px [240*320], cloud [n_pts*3] = (X,-Y,-Z), scale. */
+ * depth_mm [240*320], dt_px [240*320] (the plain transform; folded on the device), cloud [n_pts*3] = (X,-Y,-Z), scale. */
 int hpe_obs_set(hpe_obs *o, int slot, const float *depth_mm, const float *dt_px, const double *cloud,
                 double scale);
 /* getters: get_ptncloud / get_disttran / get_img_scale (src/observedmodel.cpp:375-417).
