@@ -418,10 +418,11 @@ def main():
         extras["pso_evals_per_sec"] = world * n_fr * 64 * 30 / dt
         extras["pso_batch"] = f"{n_fr} frames x 64 particles x 30 generations per GPU, host x0 in, best pose out"
         extras["pso_median_final_cost"] = float(np.median(best))
-        # the same end to end from HOST frames (pinned): hpe_fit_frames streams them through a buffer of 888 slots (two halves of 444 = one full wave of swarm CTAs each),
-        # the upload of a chunk (307 KB per frame) overlapped with the observation + swarms of the previous one
+        # the same end to end from HOST frames (pinned): hpe_fit_frames streams them through a buffer of 1,776 slots (six chunks of 296 = two swarm
+        # CTAs per SM, rotating over three compute streams), the upload of a chunk (307 KB per frame) overlapped with the observation + swarms of
+        # the chunks before it
         frames_host = frames_dev.cpu().pin_memory()
-        obse = hpe_b200.observedmodel(capacity=888, num_samples=250)
+        obse = hpe_b200.observedmodel(capacity=1776, num_samples=250)
         cfe = hpe_b200.costfunc(hand, obse)
         pso.fit_frames(cfe, frames_host.numpy(), x0, 64)
         barrier()
@@ -433,8 +434,7 @@ def main():
         extras["pso_e2e_frames_per_sec"] = world * n_fr / dt
         extras["pso_e2e"] = (f"{n_fr} host frames per GPU ({n_fr * 307200 / 1e6:.0f} MB) uploaded, observed and fitted (64 x 30) by "
                              "hpe_fit_frames, uploads overlapped with the fits")
-        # the same call on 4x the frames (the first chunk's upload and the last chunk's fit are the part of a call that
-        # cannot overlap: 2 of 3 waves at 1,184 frames, 2 of 11 here)
+        # the same call on 4x the frames (the first chunk's upload and the last chunk's fit are the part of a call that cannot overlap)
         big_host = frames_host.repeat(4, 1, 1).pin_memory()
         x0_big = np.tile(x0, (4, 1))
         barrier()

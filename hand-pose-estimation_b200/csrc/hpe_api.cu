@@ -1028,9 +1028,12 @@ int hpe_track_sequences_refined(const hpe_model *m, const hpe_obs *o, const hpe_
     return track_refined(m, o, p, num_particles, x0, first, n_seq, n_frames, seeds, poses, costs, refined);
 }
 
-// Offline batch from HOST frames (BASELINE "offline batch"): count frames stream through the observation
-// buffer in chunks of capacity/2 -- the upload of chunk k+1 (307 KB per frame over PCIe) runs under the
-// observation + swarms of chunk k; initial poses go up and results come back once.
+// Offline batch from HOST frames (BASELINE "offline batch"): count frames stream through the observation buffer in
+// chunks -- the upload of a chunk (307 KB per frame over PCIe) runs under the observation + swarms of the chunks before
+// it; initial poses go up and results come back once.  A buffer of at least 8 (12) swarm CTAs per SM is cut into FOUR (SIX)
+// chunks whose swarms rotate over two (three) compute streams: only a quarter (sixth) of the buffer's upload is exposed at the
+// start of a call, and the swarm kernels of consecutive chunks (such a chunk does not fill the device on its own) run
+// concurrently, each with its own state scratch.  Smaller buffers keep two halves on one compute stream.
 int hpe_fit_frames(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles, const float *depth_mm,
                    const double *x0, int64_t count, const uint64_t *seeds, double *bestp, double *best_cost)
 {
@@ -1039,55 +1042,73 @@ int hpe_fit_frames(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int 
     if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (count == 0) return HPE_OK;
     if (int rc = check_device()) return rc;
-    const int half = o->v.capacity >= 2 ? o->v.capacity / 2 : 1;
-    const bool twobuf = o->v.capacity >= 2;
+    constexpr int MAXB = 6, MAXS = 3;
+    const int cap = o->v.capacity, wave = 2 * hpe_sm_count();           // chunks of two to three swarm CTAs per SM
+    const int nstreams = cap >= 6 * wave ? 3 : (cap >= 4 * wave ? 2 : 1);
+    const int nbuf = nstreams > 1 ? 2 * nstreams : (cap >= 2 ? 2 : 1);
+    // chunks of two swarm CTAs per SM measured best with concurrent kernels (1,184 / 4,736 host frames, frames/s: 6 x 296 on
+    // three streams 101k / 123k, 6 x 444: 97k / 109k, 4 x 296 on two streams 101k / 109k, two halves of 444 on one stream
+    // 95k / 108-113k, two halves of 592: 81k / 97k -- tools/fit_probe.py); a larger buffer is not used in full
+    const int csize = nstreams > 1 && cap / nbuf > wave ? wave : cap / nbuf;
     const size_t row = sizeof(double) * HPE_NDOF, npix = (size_t)HPE_W * HPE_H;
     size_t b_x = align_up(row * count), b_bc = align_up(sizeof(double) * count), b_sd = align_up(sizeof(uint64_t) * count);
     HPE_CUDA(g_ws.reserve(2 * b_x + b_bc + b_sd));
     char *base = (char *)g_ws.p;
     double *d_x0 = (double *)base, *d_bp = (double *)(base + b_x), *d_bc = (double *)(base + 2 * b_x);
     uint64_t *d_sd = (uint64_t *)(base + 2 * b_x + b_bc);
-    struct Fit { cudaStream_t up, comp; cudaEvent_t landed[2], fitted[2], ready; };
+    struct Fit { cudaStream_t up, comp[MAXS]; cudaEvent_t landed[MAXB], fitted[MAXB], ready, poses_up, other_done[MAXS]; };
     static PerDevice<Fit> fit_pd;                                      // per device (hpe_internal.h)
     Fit &F = fit_pd.get();
-    cudaStream_t &up = F.up, &comp = F.comp;
-    cudaEvent_t *landed = F.landed, *fitted = F.fitted, &ready = F.ready;
-    if (!up) {
-        HPE_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
-        HPE_CUDA(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            HPE_CUDA(cudaEventCreateWithFlags(&landed[i], cudaEventDisableTiming));
-            HPE_CUDA(cudaEventCreateWithFlags(&fitted[i], cudaEventDisableTiming));
+    if (!F.up) {
+        HPE_CUDA(cudaStreamCreateWithFlags(&F.up, cudaStreamNonBlocking));
+        for (int i = 0; i < MAXS; ++i) {
+            HPE_CUDA(cudaStreamCreateWithFlags(&F.comp[i], cudaStreamNonBlocking));
+            HPE_CUDA(cudaEventCreateWithFlags(&F.other_done[i], cudaEventDisableTiming));
         }
-        HPE_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        for (int i = 0; i < MAXB; ++i) {
+            HPE_CUDA(cudaEventCreateWithFlags(&F.landed[i], cudaEventDisableTiming));
+            HPE_CUDA(cudaEventCreateWithFlags(&F.fitted[i], cudaEventDisableTiming));
+        }
+        HPE_CUDA(cudaEventCreateWithFlags(&F.ready, cudaEventDisableTiming));
+        HPE_CUDA(cudaEventCreateWithFlags(&F.poses_up, cudaEventDisableTiming));
     }
-    HPE_CUDA(cudaEventRecord(ready, 0));
-    HPE_CUDA(cudaStreamWaitEvent(up, ready, 0));
-    HPE_CUDA(cudaStreamWaitEvent(comp, ready, 0));
-    HPE_CUDA(cudaMemcpyAsync(d_x0, x0, row * count, cudaMemcpyHostToDevice, comp));
-    if (seeds) HPE_CUDA(cudaMemcpyAsync(d_sd, seeds, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, comp));
+    HPE_CUDA(cudaEventRecord(F.ready, 0));
+    HPE_CUDA(cudaStreamWaitEvent(F.up, F.ready, 0));
+    for (int i = 0; i < MAXS; ++i) HPE_CUDA(cudaStreamWaitEvent(F.comp[i], F.ready, 0));
+    HPE_CUDA(cudaMemcpyAsync(d_x0, x0, row * count, cudaMemcpyHostToDevice, F.comp[0]));
+    if (seeds) HPE_CUDA(cudaMemcpyAsync(d_sd, seeds, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, F.comp[0]));
+    HPE_CUDA(cudaEventRecord(F.poses_up, F.comp[0]));
+    for (int i = 1; i < MAXS; ++i) HPE_CUDA(cudaStreamWaitEvent(F.comp[i], F.poses_up, 0));
     const PsoDev prm = make_pso(p, num_particles);
     int k = 0;
-    for (int64_t c0 = 0; c0 < count; c0 += half, ++k) {
-        const int n = (int)(count - c0 < half ? count - c0 : half);
-        const int h = twobuf ? (k & 1) : 0, first = h * half;
-        if (k >= (twobuf ? 2 : 1)) HPE_CUDA(cudaStreamWaitEvent(up, fitted[h], 0));      // the half is free again
+    for (int64_t c0 = 0; c0 < count; c0 += csize, ++k) {
+        const int n = (int)(count - c0 < csize ? count - c0 : csize);
+        const int b = k % nbuf, first = b * csize, sid = k % nstreams;
+        cudaStream_t comp = F.comp[sid];
+        if (k >= nbuf) HPE_CUDA(cudaStreamWaitEvent(F.up, F.fitted[b], 0));      // the chunk's slots are free again
         HPE_CUDA(cudaMemcpyAsync(o->v.depth_mm + npix * first, depth_mm + npix * c0, sizeof(float) * npix * n,
-                                 cudaMemcpyHostToDevice, up));
-        HPE_CUDA(cudaEventRecord(landed[h], up));
-        HPE_CUDA(cudaStreamWaitEvent(comp, landed[h], 0));
+                                 cudaMemcpyHostToDevice, F.up));
+        HPE_CUDA(cudaEventRecord(F.landed[b], F.up));
+        HPE_CUDA(cudaStreamWaitEvent(comp, F.landed[b], 0));
         HPE_CUDA(hpe_launch_observe(o->v, first, n, nullptr, comp));
         cudaError_t e = hpe_launch_pso(m->dm, o->v, prm, d_x0 + c0 * HPE_NDOF, first, n, seeds ? d_sd + c0 : nullptr,
-                                       d_bp + c0 * HPE_NDOF, d_bc + c0, nullptr, 0, comp);
-        if (e != cudaSuccess)
+                                       d_bp + c0 * HPE_NDOF, d_bc + c0, nullptr, 0, comp, 0, 1, sid);
+        if (e != cudaSuccess) {
+            cudaStreamSynchronize(F.up);
+            for (int i = 0; i < MAXS; ++i) cudaStreamSynchronize(F.comp[i]);
             return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
                                  "pso launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));
-        HPE_CUDA(cudaEventRecord(fitted[h], comp));
+        }
+        HPE_CUDA(cudaEventRecord(F.fitted[b], comp));
     }
-    HPE_CUDA(cudaMemcpyAsync(bestp, d_bp, row * count, cudaMemcpyDeviceToHost, comp));
-    if (best_cost) HPE_CUDA(cudaMemcpyAsync(best_cost, d_bc, sizeof(double) * count, cudaMemcpyDeviceToHost, comp));
-    HPE_CUDA(cudaStreamSynchronize(up));
-    HPE_CUDA(cudaStreamSynchronize(comp));
+    for (int i = 1; i < MAXS; ++i) {
+        HPE_CUDA(cudaEventRecord(F.other_done[i], F.comp[i]));
+        HPE_CUDA(cudaStreamWaitEvent(F.comp[0], F.other_done[i], 0));
+    }
+    HPE_CUDA(cudaMemcpyAsync(bestp, d_bp, row * count, cudaMemcpyDeviceToHost, F.comp[0]));
+    if (best_cost) HPE_CUDA(cudaMemcpyAsync(best_cost, d_bc, sizeof(double) * count, cudaMemcpyDeviceToHost, F.comp[0]));
+    HPE_CUDA(cudaStreamSynchronize(F.up));
+    for (int i = MAXS - 1; i >= 0; --i) HPE_CUDA(cudaStreamSynchronize(F.comp[i]));
     return HPE_OK;
 }
 

@@ -185,7 +185,9 @@ cudaError_t hpe_launch_fold_depth(const ObsView &o, int slot, cudaStream_t st); 
 cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
                            int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
                            double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st, int seq_stride = 0,
-                           int frame_stride = 1);
+                           int frame_stride = 1, int scratch_id = 0);
+// scratch_id (0..2): which of the device's three swarm-state scratch buffers the launch uses -- launches that may run
+// concurrently (hpe_fit_frames' compute streams) must not share one
 // chain: 0 = `count` independent swarms on slots first + b; L > 0 = count / L sequences of L frames (count a multiple of
 // L): frame k of sequence q is swarm q * L + k on slot first + q * seq_stride + k * frame_stride (seq_stride 0 = L), starts
 // from the best pose of frame k - 1, and x0_dev holds one pose per SEQUENCE

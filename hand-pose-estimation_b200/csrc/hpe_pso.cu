@@ -243,8 +243,10 @@ HPE_DEFINE_FALLBACK_GETTER(hpe_fallbacks_pso)
 
 cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p, const double *x0_dev,
                            int first, int count, const uint64_t *seeds_dev, double *bestp_dev,
-                           double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st, int seq_stride, int frame_stride)
+                           double *best_cost_dev, double *trace_dev, int chain, cudaStream_t st, int seq_stride, int frame_stride,
+                           int scratch_id)
 {
+    if (scratch_id < 0 || scratch_id > 2) return cudaErrorInvalidValue;
     if (count <= 0) return cudaSuccess;
     if (chain < 0 || (chain > 0 && count % chain != 0)) return cudaErrorInvalidValue;
     if (seq_stride == 0) seq_stride = chain;
@@ -269,10 +271,10 @@ cudaError_t hpe_launch_pso(const DevModel &m, const ObsView &o, const PsoDev &p,
     if (resident < 1) resident = 1;
     int blocks = units < resident * sms ? units : resident * sms;
     // velocity + pbest of the resident swarms: grow-only scratch (L2-resident, 27 KB per swarm)
-    static PerDevice<double *> scratch_pd;
-    static PerDevice<size_t> scratch_bytes_pd;
-    double *&scratch = scratch_pd.get();
-    size_t &scratch_bytes = scratch_bytes_pd.get();
+    static PerDevice<double *> scratch_pd[3];
+    static PerDevice<size_t> scratch_bytes_pd[3];
+    double *&scratch = scratch_pd[scratch_id].get();
+    size_t &scratch_bytes = scratch_bytes_pd[scratch_id].get();
     size_t per = (size_t)p.num_p * HPE_NDOF * sizeof(double);
     if (3 * per * blocks > scratch_bytes) {
         if (scratch) cudaFree(scratch);

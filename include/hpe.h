@@ -240,8 +240,9 @@ int hpe_track_sequences_refined(const hpe_model *m, const hpe_obs *o, const hpe_
 
 /* Offline batch from HOST frames: count Subject1-format frames (float32 mm, count*240*320) are uploaded,
  * observed (observedmodel::next_frame) and fitted with one pso_evolve swarm each (x0: count*26), streaming
- * through the observation buffer `o` in chunks of capacity/2 so that the upload of the next chunk runs under
- * the fit of the current one.  bestp: count*26, best_cost: count (NaN for a frame without hand pixels, whose
+ * through the observation buffer `o` in chunks so that the upload of a chunk runs under the fits of the chunks
+ * before it: two halves of the buffer, or -- from a capacity of 8 (12) swarm CTAs per SM, 1,184 (1,776) frames on a
+ * B200 -- four (six) chunks of two CTAs per SM whose swarm kernels run concurrently on two (three) streams.  bestp: count*26, best_cost: count (NaN for a frame without hand pixels, whose
  * bestp is its x0).  Afterwards `o` holds the last chunks.  HOST pointers (pinned memory makes the overlap real). */
 int hpe_fit_frames(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles,
                    const float *depth_mm, const double *x0, int64_t count, const uint64_t *seeds,

@@ -123,7 +123,7 @@ def test_streaming_fit_from_host_frames(hpe, D):
     big = hpe.observedmodel(capacity=n)
     big.upload(frames)
     bp, bc, _ = pso.pso_evolve_batch(hpe.costfunc(hand, big), x0, 32, seeds=seeds, want_trace=False)
-    for cap in (256, 2 * n, 77, 1):
+    for cap in (256, 2 * n, 1300, 77, 1):        # two halves | six chunks on three streams | four on two | halves | one slot
         m = n if cap > 1 else 5
         small = hpe.observedmodel(capacity=cap)
         bp2, bc2 = pso.fit_frames(hpe.costfunc(hand, small), frames[:m], x0[:m], 32, seeds=seeds[:m])
