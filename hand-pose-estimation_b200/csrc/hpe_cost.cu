@@ -60,11 +60,13 @@ __global__ void __launch_bounds__(160) fk_kernel(DevModel m, const double *__res
 // cal_cost / cal_cost2 for n poses against one frame.  One CTA of SCORE_WARPS warps per SM; the warps take
 // groups of SCORE_GROUP poses (then smaller units) from counters in global memory until the batch is used up.
 // ---------------------------------------------------------------------------------------
-// Self-scheduling counters of cost_kernel: one slot per launch in flight.  The launcher hands the slots out round-robin;
-// HPE_SCHED_SLOTS exceeds the number of kernels a device runs concurrently (128), so two launches that share a slot are
-// ordered, and the last warp of a launch leaves its slot zeroed.
-struct SchedSlot { int next, tail, done, pad; };
-constexpr int HPE_SCHED_SLOTS = 256;
+// Self-scheduling counters of cost_kernel: a ring of slots, one per launch in flight.  The launcher hands out (slot, ticket)
+// round-robin; thread 0 of every CTA CLAIMS the slot for the launch's ticket before the CTA touches the counters (a slot
+// still owned by an older launch that is running -- possible when a long launch on one stream is lapped by a ring's worth
+// of short ones on another -- is waited for: its owner is running), and the last warp of a launch zeroes the counters and
+// then releases the slot.
+struct SchedSlot { int next, tail, done; unsigned owner; };
+constexpr int HPE_SCHED_SLOTS = 4096;
 __device__ SchedSlot g_sched[HPE_SCHED_SLOTS];
 #ifndef HPE_TAIL_R1
 #define HPE_TAIL_R1 3.0f     // poses per warp handed out in units smaller than a group (the warps leave their last group over a window of HPE_GROUP poses)
@@ -107,11 +109,16 @@ template <bool WITH_COLLI, int MATCHER, bool AUX>
 __global__ void __launch_bounds__(SCORE_WARPS * 32, SCORE_CTAS)
 cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, int64_t n,
             double *__restrict__ cost, double *__restrict__ terms, int64_t tstride,
-            const int32_t *__restrict__ frozen, int32_t *__restrict__ match_out, int sched_slot, int n1, int n2, int t2)
+            const int32_t *__restrict__ frozen, int32_t *__restrict__ match_out, int sched_slot, unsigned ticket, int n1, int n2, int t2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScoreSmem &sm = *reinterpret_cast<ScoreSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {                      // claim the counters for this launch (ordered before their use by the barriers below)
+        unsigned *owner = &g_sched[sched_slot].owner;
+        unsigned cur = atomicCAS(owner, 0u, ticket);
+        while (cur != 0u && cur != ticket) { __nanosleep(256); cur = atomicCAS(owner, 0u, ticket); }
+    }
     stage_model(sm.fs, m);
     stage_frame(sm.fs, frame_view(o, slot));     // ends synchronised
     const WarpScratch ws = warp_scratch(sm.ws, warp, SCORE_GROUP);
@@ -188,9 +195,9 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
     if (lane == 0) {
         __threadfence();
         if (atomicAdd(&S->done, 1) == total_warps - 1) {
-            S->next = 0; S->tail = 0;
+            S->next = 0; S->tail = 0; S->done = 0;
             __threadfence();
-            S->done = 0;
+            atomicExch(&S->owner, 0u);           // released only once the counters read zero
         }
     }
 }
@@ -804,11 +811,13 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
     if (r2 > r1) r2 = r1;
     const int n1 = (int)(n - r1), t2 = (int)((r1 - r2 + HPE_TAIL_C2 - 1) / HPE_TAIL_C2);
     const int n2 = (int)(n - r2);
-    static std::atomic<unsigned> next_slot{0};
-    const int sched_slot = (int)(next_slot.fetch_add(1, std::memory_order_relaxed) % HPE_SCHED_SLOTS);
+    static std::atomic<unsigned> next_ticket{0};
+    unsigned ticket = next_ticket.fetch_add(1, std::memory_order_relaxed) + 1u;
+    if (ticket == 0u) ticket = next_ticket.fetch_add(1, std::memory_order_relaxed) + 1u;      // 0 means "free"
+    const int sched_slot = (int)(ticket % HPE_SCHED_SLOTS);
     auto launch = [&](auto kern) {
         kern<<<blocks, SCORE_WARPS * 32, sizeof(ScoreSmem), st>>>(m, o, slot, theta_dev, n, cost_dev, terms_dev,
-                                                                 terms_stride, frozen_match_dev, match_out_dev, sched_slot, n1, n2, t2);
+                                                                 terms_stride, frozen_match_dev, match_out_dev, sched_slot, ticket, n1, n2, t2);
     };
     const bool aux = frozen_match_dev || match_out_dev;
     if (g_hpe_matcher == 1) launch(with_colli ? cost_kernel<true, 1, true> : cost_kernel<false, 1, true>);

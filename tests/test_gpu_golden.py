@@ -134,11 +134,11 @@ def test_cuda_path_reproduces_reference_fixtures(hpe, D):
 def test_cost_kernel_self_scheduling(hpe, golden, D):
     """cost_kernel hands its poses out through counters in device memory (groups, then shrinking units) and the last
     warp re-arms the slot it used: every batch size must give the bits of the one big batch, also after more launches
-    than there are slots (256), from two streams at once, and with NaN poses in the batch."""
+    than there are slots, from two streams at once, and with NaN poses in the batch."""
     import torch
     g = golden
     rng = np.random.default_rng(11)
-    n = 40000                                        # > 10 poses per warp: groups + units of three + single poses
+    n = 60000                                        # > 12 poses per warp (3,552 warps): groups + units of three + single poses
     th = g["truth"] + rng.normal(size=(n, 26)) * D.STD
     th[777] = np.nan
     hand, obs = hpe.handmodel(), hpe.observedmodel(capacity=1)
@@ -147,7 +147,7 @@ def test_cost_kernel_self_scheduling(hpe, golden, D):
     a, d, _ = cf.cal_cost_batch(th)
     ok = np.ones(n, bool); ok[777] = False          # the NaN pose only has to come out the same way every time
     assert np.isfinite(a[ok]).all() and np.isfinite(d[ok]).all()
-    sizes = [1, 2, 3, 4, 5, 6, 7, 31, 250, 3551, 3552, 3553, 17760, 35519, 35520, 35521]
+    sizes = [1, 2, 3, 4, 5, 6, 7, 31, 250, 3551, 3552, 3553, 21311, 21312, 21313, 42623, 42624, 42625, 50001]
     for k, m in enumerate(sizes):
         lo = (97 * k) % (n - m)
         a2, d2, _ = cf.cal_cost_batch(th[lo:lo + m])
@@ -156,6 +156,13 @@ def test_cost_kernel_self_scheduling(hpe, golden, D):
         m = 1 + (rep * 37) % 200
         a2, d2, _ = cf.cal_cost_batch(th[rep:rep + m])
         assert np.array_equal(a2, a[rep:rep + m], equal_nan=True), rep
+    # more launches than the ring has slots (4,096), queued without a host round trip in between
+    th_small = torch.from_numpy(th[:64]).cuda()
+    out_small = torch.empty(64, dtype=torch.float64, device="cuda")
+    for rep in range(4500):
+        cf.cal_cost_dev(th_small.data_ptr(), 64, out_small.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(out_small.cpu().numpy(), (a + d)[:64], equal_nan=True)
     # two launches in flight on different streams (different slots)
     th_dev = torch.from_numpy(th).cuda()
     outs = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(2)]
