@@ -1034,58 +1034,115 @@ int hpe_track_sequences_refined(const hpe_model *m, const hpe_obs *o, const hpe_
 // chunks whose swarms rotate over two (three) compute streams: only a quarter (sixth) of the buffer's upload is exposed at the
 // start of a call, and the swarm kernels of consecutive chunks (such a chunk does not fill the device on its own) run
 // concurrently, each with its own state scratch.  Smaller buffers keep two halves on one compute stream.
-int hpe_fit_frames(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles, const float *depth_mm,
-                   const double *x0, int64_t count, const uint64_t *seeds, double *bestp, double *best_cost)
+// Submit / wait form: up to two calls in flight per device.  The chunk events outlive a call, so the first uploads of call
+// j + 1 run under the last fits of call j (same observation buffer, same chunking) instead of after its results are back.
+namespace {
+constexpr int FIT_MAXB = 6, FIT_MAXS = 3, FIT_JOBS = 2;
+struct FitJob {
+    bool busy = false;
+    Workspace ws;                       // poses in, poses / costs out, seeds
+    void *stage = nullptr;              // page-locked copy of the caller's initial poses and seeds: an asynchronous copy from
+    size_t stage_bytes = 0;             // pageable memory would block the submitting thread behind the uploads already queued
+    cudaEvent_t done = nullptr;
+};
+struct Fit {
+    cudaStream_t up = nullptr, comp[FIT_MAXS] = {};
+    cudaEvent_t landed[FIT_MAXB] = {}, fitted[FIT_MAXB] = {}, ready = nullptr, poses_up = nullptr, other_done[FIT_MAXS] = {};
+    bool used[FIT_MAXB] = {};           // the chunk buffer has been fitted on before: an upload into it waits for fitted[b]
+    const hpe_obs *last_obs = nullptr;  // what `used` / `fitted` refer to
+    int last_nbuf = 0, last_csize = 0;
+    int next_chunk = 0;                 // chunk counter across calls (buffer and stream rotation continue from call to call)
+    FitJob jobs[FIT_JOBS];
+};
+PerDevice<Fit> g_fit;
+
+int fit_drain(Fit &F)
 {
-    if (!m || !o || !p || !depth_mm || !x0 || !bestp || num_particles < 1 || p->maxiter < 1 || count < 0)
-        return hpe_set_error(HPE_ERR_ARG, "hpe_fit_frames: bad argument");
+    HPE_CUDA(cudaStreamSynchronize(F.up));
+    for (int i = 0; i < FIT_MAXS; ++i) HPE_CUDA(cudaStreamSynchronize(F.comp[i]));
+    return HPE_OK;
+}
+}  // namespace
+
+int hpe_fit_frames_submit(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles, const float *depth_mm,
+                          const double *x0, int64_t count, const uint64_t *seeds, double *bestp, double *best_cost, int *job)
+{
+    if (!m || !o || !p || !depth_mm || !x0 || !bestp || !job || num_particles < 1 || p->maxiter < 1 || count < 0)
+        return hpe_set_error(HPE_ERR_ARG, "hpe_fit_frames_submit: bad argument");
+    *job = -1;
     if (int rc = hpe_check_device_of(m->device, "model")) return rc;
-    if (count == 0) return HPE_OK;
     if (int rc = check_device()) return rc;
-    constexpr int MAXB = 6, MAXS = 3;
-    const int cap = o->v.capacity, wave = 2 * hpe_sm_count();           // chunks of two to three swarm CTAs per SM
+    Fit &F = g_fit.get();
+    int j = 0;
+    while (j < FIT_JOBS && F.jobs[j].busy) ++j;
+    if (j == FIT_JOBS) return hpe_set_error(HPE_ERR_STATE, "hpe_fit_frames_submit: %d calls already in flight", FIT_JOBS);
+    FitJob &J = F.jobs[j];
+    if (!F.up) {
+        HPE_CUDA(cudaStreamCreateWithFlags(&F.up, cudaStreamNonBlocking));
+        for (int i = 0; i < FIT_MAXS; ++i) {
+            HPE_CUDA(cudaStreamCreateWithFlags(&F.comp[i], cudaStreamNonBlocking));
+            HPE_CUDA(cudaEventCreateWithFlags(&F.other_done[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < FIT_MAXB; ++i) {
+            HPE_CUDA(cudaEventCreateWithFlags(&F.landed[i], cudaEventDisableTiming));
+            HPE_CUDA(cudaEventCreateWithFlags(&F.fitted[i], cudaEventDisableTiming));
+        }
+        HPE_CUDA(cudaEventCreateWithFlags(&F.ready, cudaEventDisableTiming));
+        HPE_CUDA(cudaEventCreateWithFlags(&F.poses_up, cudaEventDisableTiming));
+        for (int i = 0; i < FIT_JOBS; ++i) HPE_CUDA(cudaEventCreateWithFlags(&F.jobs[i].done, cudaEventDisableTiming));
+    }
+    if (count == 0) {                                   // nothing to do: a job that is already complete
+        HPE_CUDA(cudaEventRecord(J.done, F.comp[0]));
+        J.busy = true;
+        *job = j;
+        return HPE_OK;
+    }
+    const int cap = o->v.capacity, wave = 2 * hpe_sm_count();           // chunks of two swarm CTAs per SM
     const int nstreams = cap >= 6 * wave ? 3 : (cap >= 4 * wave ? 2 : 1);
     const int nbuf = nstreams > 1 ? 2 * nstreams : (cap >= 2 ? 2 : 1);
     // chunks of two swarm CTAs per SM measured best with concurrent kernels (1,184 / 4,736 host frames, frames/s: 6 x 296 on
     // three streams 101k / 123k, 6 x 444: 97k / 109k, 4 x 296 on two streams 101k / 109k, two halves of 444 on one stream
     // 95k / 108-113k, two halves of 592: 81k / 97k -- tools/fit_probe.py); a larger buffer is not used in full
     const int csize = nstreams > 1 && cap / nbuf > wave ? wave : cap / nbuf;
+    if (F.last_obs != o || F.last_nbuf != nbuf || F.last_csize != csize) {
+        // another buffer or another chunking: the chunk events of the calls before mean nothing here
+        if (int rc = fit_drain(F)) return rc;
+        for (int i = 0; i < FIT_MAXB; ++i) F.used[i] = false;
+        F.last_obs = o; F.last_nbuf = nbuf; F.last_csize = csize; F.next_chunk = 0;
+    }
     const size_t row = sizeof(double) * HPE_NDOF, npix = (size_t)HPE_W * HPE_H;
     size_t b_x = align_up(row * count), b_bc = align_up(sizeof(double) * count), b_sd = align_up(sizeof(uint64_t) * count);
-    HPE_CUDA(g_ws.reserve(2 * b_x + b_bc + b_sd));
-    char *base = (char *)g_ws.p;
+    HPE_CUDA(J.ws.reserve(2 * b_x + b_bc + b_sd));      // the job's own buffers (the previous user of this job slot has been waited for)
+    char *base = (char *)J.ws.p;
     double *d_x0 = (double *)base, *d_bp = (double *)(base + b_x), *d_bc = (double *)(base + 2 * b_x);
     uint64_t *d_sd = (uint64_t *)(base + 2 * b_x + b_bc);
-    struct Fit { cudaStream_t up, comp[MAXS]; cudaEvent_t landed[MAXB], fitted[MAXB], ready, poses_up, other_done[MAXS]; };
-    static PerDevice<Fit> fit_pd;                                      // per device (hpe_internal.h)
-    Fit &F = fit_pd.get();
-    if (!F.up) {
-        HPE_CUDA(cudaStreamCreateWithFlags(&F.up, cudaStreamNonBlocking));
-        for (int i = 0; i < MAXS; ++i) {
-            HPE_CUDA(cudaStreamCreateWithFlags(&F.comp[i], cudaStreamNonBlocking));
-            HPE_CUDA(cudaEventCreateWithFlags(&F.other_done[i], cudaEventDisableTiming));
-        }
-        for (int i = 0; i < MAXB; ++i) {
-            HPE_CUDA(cudaEventCreateWithFlags(&F.landed[i], cudaEventDisableTiming));
-            HPE_CUDA(cudaEventCreateWithFlags(&F.fitted[i], cudaEventDisableTiming));
-        }
-        HPE_CUDA(cudaEventCreateWithFlags(&F.ready, cudaEventDisableTiming));
-        HPE_CUDA(cudaEventCreateWithFlags(&F.poses_up, cudaEventDisableTiming));
-    }
     HPE_CUDA(cudaEventRecord(F.ready, 0));
     HPE_CUDA(cudaStreamWaitEvent(F.up, F.ready, 0));
-    for (int i = 0; i < MAXS; ++i) HPE_CUDA(cudaStreamWaitEvent(F.comp[i], F.ready, 0));
-    HPE_CUDA(cudaMemcpyAsync(d_x0, x0, row * count, cudaMemcpyHostToDevice, F.comp[0]));
-    if (seeds) HPE_CUDA(cudaMemcpyAsync(d_sd, seeds, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, F.comp[0]));
-    HPE_CUDA(cudaEventRecord(F.poses_up, F.comp[0]));
-    for (int i = 1; i < MAXS; ++i) HPE_CUDA(cudaStreamWaitEvent(F.comp[i], F.poses_up, 0));
+    for (int i = 0; i < FIT_MAXS; ++i) HPE_CUDA(cudaStreamWaitEvent(F.comp[i], F.ready, 0));
+    // the initial poses travel on the upload stream, ahead of the frames (not behind the results of the call before),
+    // from the job's page-locked staging copy
+    const size_t need = row * count + (seeds ? sizeof(uint64_t) * count : 0);
+    if (need > J.stage_bytes) {
+        if (J.stage) cudaFreeHost(J.stage);
+        J.stage = nullptr; J.stage_bytes = 0;
+        HPE_CUDA(cudaHostAlloc(&J.stage, need, cudaHostAllocDefault));
+        J.stage_bytes = need;
+    }
+    memcpy(J.stage, x0, row * count);
+    HPE_CUDA(cudaMemcpyAsync(d_x0, J.stage, row * count, cudaMemcpyHostToDevice, F.up));
+    if (seeds) {
+        memcpy((char *)J.stage + row * count, seeds, sizeof(uint64_t) * count);
+        HPE_CUDA(cudaMemcpyAsync(d_sd, (char *)J.stage + row * count, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, F.up));
+    }
+    HPE_CUDA(cudaEventRecord(F.poses_up, F.up));
+    for (int i = 0; i < FIT_MAXS; ++i) HPE_CUDA(cudaStreamWaitEvent(F.comp[i], F.poses_up, 0));
     const PsoDev prm = make_pso(p, num_particles);
-    int k = 0;
-    for (int64_t c0 = 0; c0 < count; c0 += csize, ++k) {
+    for (int64_t c0 = 0; c0 < count; c0 += csize) {
+        const int k = F.next_chunk++;
         const int n = (int)(count - c0 < csize ? count - c0 : csize);
         const int b = k % nbuf, first = b * csize, sid = k % nstreams;
         cudaStream_t comp = F.comp[sid];
-        if (k >= nbuf) HPE_CUDA(cudaStreamWaitEvent(F.up, F.fitted[b], 0));      // the chunk's slots are free again
+        if (F.used[b]) HPE_CUDA(cudaStreamWaitEvent(F.up, F.fitted[b], 0));      // the chunk's slots are free again
         HPE_CUDA(cudaMemcpyAsync(o->v.depth_mm + npix * first, depth_mm + npix * c0, sizeof(float) * npix * n,
                                  cudaMemcpyHostToDevice, F.up));
         HPE_CUDA(cudaEventRecord(F.landed[b], F.up));
@@ -1094,22 +1151,43 @@ int hpe_fit_frames(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int 
         cudaError_t e = hpe_launch_pso(m->dm, o->v, prm, d_x0 + c0 * HPE_NDOF, first, n, seeds ? d_sd + c0 : nullptr,
                                        d_bp + c0 * HPE_NDOF, d_bc + c0, nullptr, 0, comp, 0, 1, sid);
         if (e != cudaSuccess) {
-            cudaStreamSynchronize(F.up);
-            for (int i = 0; i < MAXS; ++i) cudaStreamSynchronize(F.comp[i]);
+            fit_drain(F);
+            for (int i = 0; i < FIT_MAXB; ++i) F.used[i] = false;
             return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
                                  "pso launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));
         }
         HPE_CUDA(cudaEventRecord(F.fitted[b], comp));
+        F.used[b] = true;
     }
-    for (int i = 1; i < MAXS; ++i) {
+    for (int i = 1; i < FIT_MAXS; ++i) {
         HPE_CUDA(cudaEventRecord(F.other_done[i], F.comp[i]));
         HPE_CUDA(cudaStreamWaitEvent(F.comp[0], F.other_done[i], 0));
     }
     HPE_CUDA(cudaMemcpyAsync(bestp, d_bp, row * count, cudaMemcpyDeviceToHost, F.comp[0]));
     if (best_cost) HPE_CUDA(cudaMemcpyAsync(best_cost, d_bc, sizeof(double) * count, cudaMemcpyDeviceToHost, F.comp[0]));
-    HPE_CUDA(cudaStreamSynchronize(F.up));
-    for (int i = MAXS - 1; i >= 0; --i) HPE_CUDA(cudaStreamSynchronize(F.comp[i]));
+    HPE_CUDA(cudaEventRecord(J.done, F.comp[0]));
+    J.busy = true;
+    *job = j;
     return HPE_OK;
+}
+
+int hpe_fit_frames_wait(int job)
+{
+    if (int rc = check_device()) return rc;
+    Fit &F = g_fit.get();
+    if (job < 0 || job >= FIT_JOBS || !F.jobs[job].busy) return hpe_set_error(HPE_ERR_ARG, "hpe_fit_frames_wait: no such job");
+    cudaError_t e = cudaEventSynchronize(F.jobs[job].done);
+    F.jobs[job].busy = false;
+    if (e != cudaSuccess) return hpe_set_error(HPE_ERR_CUDA, "hpe_fit_frames_wait: %s", cudaGetErrorString(e));
+    return HPE_OK;
+}
+
+int hpe_fit_frames(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles, const float *depth_mm,
+                   const double *x0, int64_t count, const uint64_t *seeds, double *bestp, double *best_cost)
+{
+    int job = -1;
+    if (int rc = hpe_fit_frames_submit(m, o, p, num_particles, depth_mm, x0, count, seeds, bestp, best_cost, &job)) return rc;
+    return hpe_fit_frames_wait(job);
 }
 
 // ------------------------------------------------------------------------------------------

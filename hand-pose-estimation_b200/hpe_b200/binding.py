@@ -313,6 +313,48 @@ class costfunc:
                                         C.c_void_p(terms_dev_ptr or 0), C.c_void_p(stream or 0)))
 
 
+_FIT_POOL = {}       # n -> [(bestp, best), ...] page-locked result buffers of finished fit jobs
+
+
+class FitJob:
+    """one hpe_fit_frames call in flight (hpe_fit_frames_submit / hpe_fit_frames_wait); keeps its host arrays alive.
+    The page-locked result buffers are recycled: allocating page-locked memory synchronises the device, which would
+    serialise the very calls this form is meant to overlap."""
+
+    def __init__(self, pso, optfunc, fr, x0, num_particles, sd):
+        n = fr.shape[0]
+        self.keep = (fr, x0, sd, optfunc)
+        self.n = n
+        free = _FIT_POOL.get(n)
+        self.bestp, self.best = free.pop() if free else (_Pinned((n, 26)), _Pinned((n,)))
+        jid = C.c_int(-1)
+        _check(lib().hpe_fit_frames_submit(optfunc.hand._h, optfunc.observation._h, C.byref(pso.params), int(num_particles),
+                                           _p(fr, C.c_float), _p(x0), C.c_int64(n), _p(sd, C.c_uint64),
+                                           _p(self.bestp.array), _p(self.best.array), C.byref(jid)))
+        self.id = jid.value
+
+    def wait(self):
+        jid, self.id = self.id, -1
+        if jid < 0:
+            raise HpeError(4, "fit job already waited for")
+        _check(lib().hpe_fit_frames_wait(int(jid)))
+        out = self.bestp.array.copy(), self.best.array.copy()
+        pool = _FIT_POOL.setdefault(self.n, [])
+        if len(pool) < 2:
+            pool.append((self.bestp, self.best))
+        else:
+            self.bestp.free(); self.best.free()
+        self.bestp = self.best = self.keep = None
+        return out
+
+    def __del__(self):
+        if getattr(self, "id", -1) >= 0 and _LIB is not None:
+            try:
+                _LIB.hpe_fit_frames_wait(int(self.id))       # in-flight DMA must finish before its buffers go away
+            except Exception:
+                pass
+
+
 class _Pinned:
     """numpy view of a page-locked host buffer owned by the library (hpe_host_alloc / hpe_host_free)"""
 
@@ -462,6 +504,16 @@ class PSO:
         _check(lib().hpe_fit_frames(optfunc.hand._h, optfunc.observation._h, C.byref(self.params), int(num_particles),
                                     _p(fr, C.c_float), _p(x0), C.c_int64(n), _p(sd, C.c_uint64), _p(bestp), _p(best)))
         return bestp, best
+
+    def fit_frames_submit(self, optfunc, frames_mm, x0, num_particles, seeds=None):
+        """submit / wait form of fit_frames (hpe_fit_frames_submit): returns a job whose wait() gives (bestp, best).
+        Two jobs may be in flight; the frames of the second start to upload under the last fits of the first.  The
+        arrays passed in are used as they are (page-locked ones make the overlap real) and must not change before wait()."""
+        fr = np.ascontiguousarray(frames_mm, dtype=np.float32).reshape(-1, D.H, D.W)
+        x0 = _f64(x0).reshape(-1, 26)
+        if x0.shape[0] != fr.shape[0]:
+            raise HpeError(1, "fit_frames: one initial pose per frame")
+        return FitJob(self, optfunc, fr, x0, num_particles, None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64))
 
     def refine_init_pose(self, x0, optfunc, slot=0):
         """PSO::refine_init_pose(x0, optfunc) (src/PSO.cpp:216-266); returns the refined pose (the

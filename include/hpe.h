@@ -247,6 +247,15 @@ int hpe_track_sequences_refined(const hpe_model *m, const hpe_obs *o, const hpe_
 int hpe_fit_frames(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles,
                    const float *depth_mm, const double *x0, int64_t count, const uint64_t *seeds,
                    double *bestp, double *best_cost);
+/* The same in two steps, up to two calls in flight per device: submit queues everything (uploads, observations, swarms,
+ * the copy of the results) and returns a job id, wait blocks until the job's results are in bestp / best_cost.  With a
+ * second call submitted before the first is waited for -- same `o`, whose frames neither call may touch meanwhile -- the
+ * first uploads of the second run under the last swarms of the first (src/testmodel.cpp:117-138 has no counterpart: the
+ * reference fits one frame at a time).  All host buffers must stay valid (and should be page-locked) until the wait. */
+int hpe_fit_frames_submit(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles,
+                          const float *depth_mm, const double *x0, int64_t count, const uint64_t *seeds,
+                          double *bestp, double *best_cost, int *job);
+int hpe_fit_frames_wait(int job);
 
 /* ---- one large swarm, particles [lo,hi) of num_particles owned by this GPU ---- */
 /* State lives on the device; the caller (one process per GPU) exchanges the

@@ -31,7 +31,7 @@ def test_header_declares_the_expected_surface():
                  "hpe_track_sequence", "hpe_swarm_create", "hpe_swarm_step", "hpe_swarm_reduce",
                  "hpe_render_dev", "hpe_last_error_string", "hpe_refine_init_pose", "hpe_pso_optimise",
                  "hpe_bincomp_batch", "hpe_gnd_truth_err", "hpe_cost_batch_submit", "hpe_cost_batch_wait", "hpe_fit_frames",
-                 "hpe_track_sequences", "hpe_track_sequences_refined"):
+                 "hpe_fit_frames_submit", "hpe_fit_frames_wait", "hpe_track_sequences", "hpe_track_sequences_refined"):
         assert must in names
 
 

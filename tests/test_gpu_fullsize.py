@@ -128,6 +128,21 @@ def test_streaming_fit_from_host_frames(hpe, D):
         small = hpe.observedmodel(capacity=cap)
         bp2, bc2 = pso.fit_frames(hpe.costfunc(hand, small), frames[:m], x0[:m], 32, seeds=seeds[:m])
         assert np.array_equal(bp2, bp[:m]) and np.array_equal(bc2, bc[:m]), cap
+    # submit / wait: two calls in flight through one buffer (the second call's uploads start under the first call's
+    # last fits), a third submit is refused, results are the blocking call's
+    for cap in (2 * n, 300):
+        cf2 = hpe.costfunc(hand, hpe.observedmodel(capacity=cap))
+        j1 = pso.fit_frames_submit(cf2, frames[:900], x0[:900], 32, seeds=seeds[:900])
+        j2 = pso.fit_frames_submit(cf2, frames[900:], x0[900:], 32, seeds=seeds[900:])
+        with pytest.raises(hpe.HpeError) as e:
+            pso.fit_frames_submit(cf2, frames[:5], x0[:5], 32, seeds=seeds[:5])
+        assert e.value.code == 4                      # HPE_ERR_STATE
+        p1, c1 = j1.wait()
+        j3 = pso.fit_frames_submit(cf2, frames[:700], x0[:700], 32, seeds=seeds[:700])
+        p2, c2 = j2.wait()
+        p3, c3 = j3.wait()
+        assert np.array_equal(np.concatenate([p1, p2]), bp) and np.array_equal(np.concatenate([c1, c2]), bc), cap
+        assert np.array_equal(p3, bp[:700]) and np.array_equal(c3, bc[:700]), cap
     fr = frames[:10].copy()
     fr[3] = 0.0
     bp3, bc3 = pso.fit_frames(hpe.costfunc(hand, hpe.observedmodel(capacity=4)), fr, x0[:10], 32, seeds=seeds[:10])
