@@ -303,6 +303,18 @@ public:
                              num_particles, depth_mm, x0,
                              count, seeds, bestp, best_cost));
     }
+    // the same in two steps (hpe_fit_frames_submit / hpe_fit_frames_wait): returns a job id; two calls may be in flight
+    // per device, the uploads of the second then run under the fits of the first.  All buffers (page-locked for real
+    // overlap) must outlive fit_frames_wait(job); the observedmodel must not be touched in between
+    int fit_frames_submit(costfunc &optfunc, const float *depth_mm, const double *x0, long count, int num_particles,
+                          double *bestp, double *best_cost, const uint64_t *seeds = nullptr)
+    {
+        int job = -1;
+        check(hpe_fit_frames_submit(optfunc.hand->c_handle(), const_cast<hpe_obs *>(optfunc.observation->c_handle()), &p_,
+                                    num_particles, depth_mm, x0, count, seeds, bestp, best_cost, &job));
+        return job;
+    }
+    static void fit_frames_wait(int job) { check(hpe_fit_frames_wait(job)); }
     // void refine_init_pose(x0, optfunc), src/PSO.cpp:216-266: x0 is updated in place
     void refine_init_pose(vec &x0, costfunc &optfunc, int slot = 0)
     {
