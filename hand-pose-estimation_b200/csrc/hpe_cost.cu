@@ -117,7 +117,13 @@ cost_kernel(DevModel m, ObsView o, int slot, const double *__restrict__ theta, i
     if (threadIdx.x == 0) {                      // claim the counters for this launch (ordered before their use by the barriers below)
         unsigned *owner = &g_sched[sched_slot].owner;
         unsigned cur = atomicCAS(owner, 0u, ticket);
-        while (cur != 0u && cur != ticket) { __nanosleep(256); cur = atomicCAS(owner, 0u, ticket); }
+        // bounded like every other wait in this library (~30 s): an owner that never releases means a launch died with the
+        // slot in its hands; the context is lost then anyway, and a trap is reported where a hang would not be
+        for (long long spins = 0; cur != 0u && cur != ticket; ++spins) {
+            if (spins > (1ll << 27)) __trap();
+            __nanosleep(256);
+            cur = atomicCAS(owner, 0u, ticket);
+        }
     }
     stage_model(sm.fs, m);
     stage_frame(sm.fs, frame_view(o, slot));     // ends synchronised
