@@ -1,16 +1,17 @@
 // hpe_eval.cuh -- the warp-level evaluation of costfunc::cal_cost / cal_cost2
-// (src/costfunc.cpp:31-127) for a group of up to HPE_GROUP poses against one frame.
+// (src/costfunc.cpp:31-127) for a group of poses (up to HPE_GROUP = 5; six in the scoring kernel) against one frame.
 //
 // Work split inside a warp:
 //   phase 1  lanes = (pose, digit): forward kinematics in FP64 -> FP64 sphere centres in shared memory
-//   phase 2  per pose, lanes = spheres: projection + depth-map / distance-transform gathers; the same
-//            lanes stage the pose's float32 centres for the matcher
-//   phase 3  per pose, lanes = points (two passes of 4 points per lane): nearest-centre search in
-//            FP32, then the FP64 alignment sum of those points
+//   phase 2  per pose, lanes = spheres: projection + ONE gather per pixel from the folded distance / depth map; the
+//            same lanes stage the pose's float32 centres for the matcher
+//   phase 3  per pose: which sphere blocks each cluster of 32 points has to look at (prune_blocks), clusters ranked by
+//            list length and dealt to the (pass, quarter) slots; then lanes = points (two passes of 4 points per lane):
+//            nearest-centre search in FP32 and the FP64 alignment sum of those points
 //   phase 4  (cal_cost2 only) lanes = sphere pairs: self-collision
-// Everything a warp needs between phases lives in shared memory (model, frame scalars, cloud,
-// recentred points), so the kernels stay under 85 registers and 3 CTAs of 8 warps fit per SM: the
-// FP64 / gather phases of some warps hide under the FP32 sweeps of the others.
+// Everything a warp needs between phases lives in shared memory (model, frame scalars and the frame's staging image:
+// cloud, recentred points, cluster boxes), so the kernels stay at 80 registers and 24 warps fit per SM (3 CTAs of 8, or
+// the scoring kernel's one CTA of 24): the FP64 / gather phases of some warps hide under the FP32 sweeps of the others.
 //
 // The nearest-centre search (compute_correspondences, src/costfunc.cpp:306-343) must return the
 // index cv::BFMatcher returns: first minimum over j of sqrtf(d_j), d_j = ((t0^2 + t1^2) + t2^2) in
