@@ -754,7 +754,7 @@ __device__ __forceinline__ double match_align(const FrameSmem &fs, const WarpScr
         // Which cluster goes to which (pass, quarter) slot.  A pass costs max(list length) over its four quarters, so the
         // clusters are ranked by list length (ties by index) and slot r = 4 pass + quarter takes the cluster of rank r:
         // the two passes then cost l(1) + l(5) steps, the minimum over all assignments (11.1 instead of 12.7 steps per
-        // evaluation on the benchmark's poses, tools/prune_sim.py).  Which lane sums which point depends on the pose only,
+        // evaluation on the benchmark's poses, tools/prune_balance_sim.py).  Which lane sums which point depends on the pose only,
         // so every kernel still returns the same bits for the same pose and frame.
         const unsigned qmask = prune_blocks(fs, ws, lane);        // mask of cluster lane / 4 on the lanes of its quad
         const int c = lane >> 2, sub = lane & 3;
