@@ -1064,6 +1064,9 @@ int fit_drain(Fit &F)
 }
 }  // namespace
 
+static int fit_submit(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles, const float *depth_mm,
+                      const double *x0, int64_t count, const uint64_t *seeds, double *bestp, double *best_cost, int *job);
+
 int hpe_fit_frames_submit(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles, const float *depth_mm,
                           const double *x0, int64_t count, const uint64_t *seeds, double *bestp, double *best_cost, int *job)
 {
@@ -1072,6 +1075,24 @@ int hpe_fit_frames_submit(const hpe_model *m, hpe_obs *o, const hpe_pso_params *
     *job = -1;
     if (int rc = hpe_check_device_of(m->device, "model")) return rc;
     if (int rc = check_device()) return rc;
+    const int rc = fit_submit(m, o, p, num_particles, depth_mm, x0, count, seeds, bestp, best_cost, job);
+    if (rc != HPE_OK && rc != HPE_ERR_STATE) {
+        // a failure half way leaves copies and kernels queued that nothing tracks: let them finish before the caller
+        // gets its buffers back, and forget the chunk history (the message of the failure stays the last error)
+        Fit &F = g_fit.get();
+        if (F.up) {
+            cudaStreamSynchronize(F.up);
+            for (int i = 0; i < FIT_MAXS; ++i) cudaStreamSynchronize(F.comp[i]);
+        }
+        for (int i = 0; i < FIT_MAXB; ++i) F.used[i] = false;
+        F.last_obs = nullptr;
+    }
+    return rc;
+}
+
+static int fit_submit(const hpe_model *m, hpe_obs *o, const hpe_pso_params *p, int num_particles, const float *depth_mm,
+                      const double *x0, int64_t count, const uint64_t *seeds, double *bestp, double *best_cost, int *job)
+{
     Fit &F = g_fit.get();
     int j = 0;
     while (j < FIT_JOBS && F.jobs[j].busy) ++j;
@@ -1151,8 +1172,6 @@ int hpe_fit_frames_submit(const hpe_model *m, hpe_obs *o, const hpe_pso_params *
         cudaError_t e = hpe_launch_pso(m->dm, o->v, prm, d_x0 + c0 * HPE_NDOF, first, n, seeds ? d_sd + c0 : nullptr,
                                        d_bp + c0 * HPE_NDOF, d_bc + c0, nullptr, 0, comp, 0, 1, sid);
         if (e != cudaSuccess) {
-            fit_drain(F);
-            for (int i = 0; i < FIT_MAXB; ++i) F.used[i] = false;
             return hpe_set_error(e == cudaErrorInvalidValue ? HPE_ERR_ARG : HPE_ERR_CUDA,
                                  "pso launch (num_particles=%d): %s", num_particles, cudaGetErrorString(e));
         }
