@@ -777,6 +777,34 @@ cudaError_t hpe_launch_gt_err(const double *joints_dev, const double *gt_dev, in
     return cudaGetLastError();
 }
 
+// Self-scheduling plan of cost_kernel for a batch of n poses on a device with `sms` SMs: groups of SCORE_GROUP from [0, n1),
+// units of HPE_TAIL_C2 from [n1, n2) (t2 of them), single poses from [n2, n); batches with fewer than two groups per warp
+// are handed out in groups only.  A batch with fewer groups than the device has CTAs is spread over as many SMs as it has
+// groups (the warps of a CTA that find the counters empty leave at once).
+struct CostPlan { int blocks, n1, n2, t2; };
+static CostPlan cost_plan(int64_t n, int sms)
+{
+    CostPlan pl;
+    const int64_t groups = (n + SCORE_GROUP - 1) / SCORE_GROUP;
+    pl.blocks = (int)(groups < (long long)SCORE_CTAS * sms ? groups : (long long)SCORE_CTAS * sms);
+    const int64_t warps = (int64_t)pl.blocks * SCORE_WARPS;
+    int64_t r1 = n >= 2 * SCORE_GROUP * warps ? (int64_t)(HPE_TAIL_R1 * (float)warps) : 0, r2 = (int64_t)(HPE_TAIL_R2 * (float)warps);
+    if (r2 > r1) r2 = r1;
+    pl.n1 = (int)(n - r1);
+    pl.t2 = (int)((r1 - r2 + HPE_TAIL_C2 - 1) / HPE_TAIL_C2);
+    pl.n2 = (int)(n - r2);
+    return pl;
+}
+
+extern "C" int hpe_debug_cost_plan(int64_t n, int sms, int plan[6])
+{
+    if (n < 0 || n > 0x40000000 || sms < 1 || !plan) return HPE_ERR_ARG;
+    const CostPlan pl = cost_plan(n, sms);
+    plan[0] = pl.blocks * SCORE_WARPS; plan[1] = SCORE_GROUP; plan[2] = HPE_TAIL_C2;
+    plan[3] = pl.n1; plan[4] = pl.n2; plan[5] = pl.t2;
+    return HPE_OK;
+}
+
 cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const double *theta_dev,
                             int64_t n, bool with_colli, double *cost_dev, double *terms_dev,
                             const int32_t *frozen_match_dev, int32_t *match_out_dev, cudaStream_t st,
@@ -794,10 +822,8 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
                                match_out_dev ? match_out_dev + half * o.n_pts : nullptr, st, terms_stride);
     }
     const int sms = hpe_sm_count();
-    // a batch with fewer groups than the device has warps is spread over as many SMs as it has groups (the warps of a CTA
-    // that find the counters empty leave at once)
-    int64_t groups = (n + SCORE_GROUP - 1) / SCORE_GROUP;
-    int blocks = (int)(groups < (long long)SCORE_CTAS * sms ? groups : (long long)SCORE_CTAS * sms);
+    const CostPlan plan = cost_plan(n, sms);
+    const int blocks = plan.blocks;
     static PerDevice<bool> attr_pd;
     bool &attr = attr_pd.get();
     if (!attr) {
@@ -810,13 +836,7 @@ cudaError_t hpe_launch_cost(const DevModel &m, const ObsView &o, int slot, const
         cudaFuncSetAttribute(cost_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr = true;
     }
-    // self-scheduling plan (cost_kernel): groups from [0, n1), units of HPE_TAIL_C2 from [n1, n2), single poses from [n2, n);
-    // batches with fewer than two groups per warp are handed out in groups only
-    const int64_t warps = (int64_t)blocks * SCORE_WARPS;
-    int64_t r1 = n >= 2 * SCORE_GROUP * warps ? (int64_t)(HPE_TAIL_R1 * (float)warps) : 0, r2 = (int64_t)(HPE_TAIL_R2 * (float)warps);
-    if (r2 > r1) r2 = r1;
-    const int n1 = (int)(n - r1), t2 = (int)((r1 - r2 + HPE_TAIL_C2 - 1) / HPE_TAIL_C2);
-    const int n2 = (int)(n - r2);
+    const int n1 = plan.n1, n2 = plan.n2, t2 = plan.t2;
     static std::atomic<unsigned> next_ticket{0};
     unsigned ticket = next_ticket.fetch_add(1, std::memory_order_relaxed) + 1u;
     if (ticket == 0u) ticket = next_ticket.fetch_add(1, std::memory_order_relaxed) + 1u;      // 0 means "free"

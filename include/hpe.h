@@ -339,6 +339,11 @@ int hpe_set_chamfer(int mode);
  * staging | matching + alignment (the latency that bounds the one-particle-per-warp paths) */
 int hpe_debug_eval_latency(const hpe_model *m, const hpe_obs *o, int slot, const double theta[HPE_NDOF],
                            long long cycles[3]);
+/* host only (no device needed): how hpe_cost_batch* hands n poses out to the warps of its kernel on a device with `sms`
+ * SMs -- plan = { warps, poses per group, poses per tail unit, n1, n2, t2 }: a warp takes groups from a counter that runs
+ * over [0, n1) and, once that is used up, tickets t from a second counter: ticket t < t2 is the unit of `poses per tail
+ * unit` poses starting at n1 + unit * t (cut at n2), later tickets are the single poses n2 + (t - t2) < n. */
+int hpe_debug_cost_plan(int64_t n, int sms, int plan[6]);
 /* number of points the certified search handed to its exact fallback since the last reset */
 int hpe_debug_fallback_points(unsigned long long *count, int reset);
 

@@ -119,3 +119,44 @@ def test_product_never_touches_the_oracle():
     import hpe_b200
     ldd = subprocess.run(["ldd", hpe_b200.library_path()], capture_output=True, text=True).stdout
     assert "oracle" not in ldd and "gomp" not in ldd
+
+
+def test_cost_kernel_plan_covers_every_pose_once(lib):
+    """The self-scheduling plan of the scoring kernel (hpe_debug_cost_plan, host only) replayed with the kernel's fetch
+    protocol and warps that arrive in random order: every pose must be handed out exactly once, whatever the batch size."""
+    import ctypes as C
+    import numpy as np
+    rng = np.random.default_rng(0)
+    sizes = [0, 1, 5, 6, 7, 35, 36, 3551, 3552, 21311, 21312, 42623, 42624, 42625, 65536, 100003, 1 << 20]
+    sizes += [int(v) for v in rng.integers(1, 200000, size=40)]
+    for sms in (148, 1, 7):
+        for n in sizes:
+            plan = (C.c_int * 6)()
+            assert lib.hpe_debug_cost_plan(C.c_int64(n), sms, plan) == 0
+            warps, group, unit, n1, n2, t2 = list(plan)
+            assert 0 <= n1 <= n2 <= n and (warps > 0 or n == 0)
+            seen = np.zeros(n, dtype=np.int32)
+            nxt, tail = 0, 0
+            exhausted = np.zeros(max(warps, 1), dtype=bool)
+            active = list(range(warps))
+            while active:
+                w = active[int(rng.integers(len(active)))]          # any interleaving of the warps
+                s = cnt = 0
+                if not exhausted[w]:
+                    s, nxt = nxt, nxt + group
+                    cnt = min(group, n1 - s)
+                    if cnt <= 0:
+                        exhausted[w] = True
+                if cnt <= 0:
+                    t, tail = tail, tail + 1
+                    if t < t2:
+                        s = n1 + unit * t
+                        cnt = min(unit, n2 - s)
+                    else:
+                        s = n2 + (t - t2)
+                        cnt = 1 if s < n else 0
+                if cnt <= 0:
+                    active.remove(w)
+                    continue
+                seen[s:s + cnt] += 1
+            assert (seen == 1).all(), (sms, n, list(plan))
